@@ -1,0 +1,89 @@
+"""ctypes binding of libercgraph.so (include/ercgraph.h).
+
+The library is the product: there is NO fallback.  If the shared object is missing or a call
+returns an error code this module raises -- it never routes to PyTorch or CPU code.
+PyTorch is used only for device memory, streams and autograd bookkeeping around these calls.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_int64, c_uint64, c_float, c_double, c_void_p, c_size_t, c_char_p, POINTER, Structure
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libercgraph.so")
+
+ACT_NONE, ACT_RELU, ACT_RELU_DROPOUT, ACT_MASK_POS = 0, 1, 2, 3
+
+
+class ErcgError(RuntimeError):
+    pass
+
+
+class GraphOut(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "node_off", "edge_off", "rowptr", "col", "etype", "t_rowptr", "t_col", "t_etype", "t_eid", "spk",
+        "node_dlg", "inv_cnt", "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row")]
+
+
+P, I, L, F, D, U64, SZ = c_void_p, c_int, c_int64, c_float, c_double, c_uint64, c_size_t
+
+# name -> (restype, argtypes); mirrors include/ercgraph.h one to one
+SIGNATURES = {
+    "ercg_strerror": (c_char_p, [I]),
+    "ercg_version": (I, []),
+    "ercg_launch_count": (ctypes.c_ulonglong, []),
+    "ercg_graphify_sizes_host": (I, [P, I, I, I, POINTER(L), POINTER(L)]),
+    "ercg_graphify_count": (I, [P, I, I, I, I, P, P]),
+    "ercg_graphify_workspace_bytes": (SZ, [I]),
+    "ercg_graphify_csr": (I, [P, I, I, P, I, L, I, I, I, L, L, POINTER(GraphOut), P, SZ, P]),
+    "ercg_pack_rows": (I, [P, L, L, I, I, P, P, P, L, L, I, P]),
+    "ercg_unpack_rows": (I, [P, L, P, P, P, L, L, I, I, L, I, P]),
+    "ercg_gemm_nn": (I, [P, L, P, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P]),
+    "ercg_gemm_tn_workspace_bytes": (SZ, [L, I, I]),
+    "ercg_gemm_tn": (I, [P, L, P, P, L, P, L, L, I, I, P, SZ, P]),
+    "ercg_mask_pos": (I, [P, L, P, L, F, P, L, L, I, P]),
+    "ercg_colsum_workspace_bytes": (SZ, [L, I]),
+    "ercg_colsum": (I, [P, L, L, I, P, P, SZ, P]),
+    "ercg_gather_fwd": (I, [P, L, P, P, P, P, I, P, P, L, L, I, P]),
+    "ercg_gather_bwd": (I, [P, L, P, L, P, P, P, P, P, I, I, P, L, P, L, I, P]),
+    "ercg_attn_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, L, I, P]),
+    "ercg_attn_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, L, I, P]),
+    "ercg_attn_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, L, I, P]),
+    "ercg_edgeatt_fwd": (I, [P, L, P, L, P, P, P, P, L, I, P]),
+    "ercg_edgeatt_bwd_src": (I, [P, P, P, L, P, P, P, P, P, L, L, I, P]),
+    "ercg_edgeatt_bwd_dst": (I, [P, P, L, P, P, P, L, L, I, P]),
+    "ercg_bn_workspace_bytes": (SZ, [L, I]),
+    "ercg_bn_stats": (I, [P, L, L, I, P, P, P, SZ, P]),
+    "ercg_bn_act_fwd": (I, [P, L, P, P, F, P, P, F, P, L, L, I, P]),
+    "ercg_bn_act_bwd_reduce": (I, [P, L, P, L, P, P, F, P, P, F, P, L, I, P, SZ, P]),
+    "ercg_bn_act_bwd_apply": (I, [P, L, P, L, P, P, F, P, P, F, P, D, I, P, L, L, I, P]),
+    "ercg_ce_workspace_bytes": (SZ, [L]),
+    "ercg_ce_fwd": (I, [P, L, P, P, P, P, L, L, I, P, SZ, P]),
+    "ercg_scale_by_ratio": (I, [P, L, P, P, P]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises ErcgError when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ErcgError(
+                "libercgraph.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C %s`; there is no CPU/PyTorch fallback" % (LIB_PATH, os.path.join(_HERE, "csrc")))
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise ErcgError("%s failed: %s (%d)" % (what, lib().ercg_strerror(rc).decode(), rc))
+
+
+def launch_count():
+    return int(lib().ercg_launch_count())

@@ -1,0 +1,392 @@
+// K4 / K5: fused edge attention over the packed CSR.
+//
+// K4 = PyG TransformerConv(heads=1) message/aggregate (track_mm/cogmen.py:66,72):
+//   sigma[j->i] = <q_i, k_j> * scale,  alpha = softmax over the in-edges of i (max-subtracted,
+//   denominator + 1e-16),  out_i = sum_j alpha[j->i] v_j + s_i.
+// K5 = EdgeAtt of DialogueGCN (track_mm/dgcn_models.py:121-152): the same score/softmax machinery
+//   normalised over the OUT-edges of each source (by-source traversal), no value aggregation.
+//
+// One warp per node, lane c owns float4 chunk(s) of the H-wide rows.  Scores of up to 32 edges are
+// kept one-per-lane in a register (deg <= 11 / 21 for the reference's windows); longer rows fall back
+// to an online (running max / rescale) chunked loop.  Score, softmax and aggregation are one kernel:
+// k_j and v_j rows are read once per edge from L1/L2, q_i/s_i/out_i once per node from HBM.
+// Algorithmic HBM bytes per node: 5*4H (q,k,v,s,out) + 4 (rowptr) + 8*deg (col, alpha).
+#include "common.cuh"
+#include <math.h>
+
+namespace ercg {
+
+constexpr int AW = 8;
+
+template <int NC>
+__device__ __forceinline__ void load_row(const float* p, int nch, int lane, float4 r[NC]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    r[c] = ch < nch ? ld4(p + 4 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int NC>
+__device__ __forceinline__ float row_dot(const float4 a[NC], const float* p, int nch, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) s += dot4(a[c], ld4(p + 4 * ch));
+  }
+  return warp_sum(s);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(AW * 32)
+attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                const float* __restrict__ s, long long ld, const int* __restrict__ rowptr,
+                const int* __restrict__ col, float scale, float* __restrict__ out, long long ldo,
+                float* __restrict__ alpha, long long N, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long node = (long long)blockIdx.x * AW + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int nch = H >> 2;
+  float4 qi[NC], acc[NC];
+  load_row<NC>(q + node * ld, nch, lane, qi);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  float run_max = -INFINITY, run_sum = 0.f;
+  for (int cb = beg; cb < end; cb += 32) {
+    const int cn = min(32, end - cb);
+    float my = -INFINITY;                       // score of edge cb + lane
+    for (int u = 0; u < cn; ++u) {
+      const float d = row_dot<NC>(qi, k + (long long)col[cb + u] * ld, nch, lane) * scale;
+      if (lane == u) my = d;
+    }
+    const float cmax = warp_max(my);
+    const float new_max = fmaxf(run_max, cmax);
+    const float resc = run_max == -INFINITY ? 0.f : expf(run_max - new_max);   // first chunk: nothing to rescale
+    const float ex = lane < cn ? expf(my - new_max) : 0.f;
+    run_sum = run_sum * resc + warp_sum(ex);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { acc[c].x *= resc; acc[c].y *= resc; acc[c].z *= resc; acc[c].w *= resc; }
+    if (alpha && lane < cn) alpha[cb + lane] = ex;        // un-normalised, relative to new_max; fixed below
+    if (alpha && cb > beg && resc != 1.f) {               // rescale earlier chunks (rare: deg > 32)
+      for (int e2 = beg + lane; e2 < cb; e2 += 32) alpha[e2] *= resc;
+    }
+    for (int u = 0; u < cn; ++u) {
+      const float a = __shfl_sync(0xffffffffu, ex, u);
+      const float* pv = v + (long long)col[cb + u] * ld;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nch) fma4(acc[c], a, ld4(pv + 4 * ch));
+      }
+    }
+    run_max = new_max;
+  }
+  const float inv = 1.f / (run_sum + 1e-16f);
+  if (alpha) {
+    __syncwarp();
+    for (int e2 = beg + lane; e2 < end; e2 += 32) alpha[e2] *= inv;
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      float4 r = acc[c];
+      r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+      if (s) {
+        const float4 sk = ld4(s + node * ld + 4 * ch);
+        r.x += sk.x; r.y += sk.y; r.z += sk.z; r.w += sk.w;
+      }
+      st4(out + node * ldo + 4 * ch, r);
+    }
+  }
+}
+
+// by-destination backward: dalpha_e = <dout_i, v_j>, D = sum alpha dalpha, dsig_e = alpha_e (dalpha_e - D),
+// dq_i = scale * sum dsig_e k_j, ds_i = dout_i
+template <int NC>
+__global__ void __launch_bounds__(AW * 32)
+attn_bwd_dst_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ k,
+                    const float* __restrict__ v, long long ld, const int* __restrict__ rowptr,
+                    const int* __restrict__ col, const float* __restrict__ alpha, float scale,
+                    float* __restrict__ dq, float* __restrict__ ds, long long ldd, float* __restrict__ dsig,
+                    long long N, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long node = (long long)blockIdx.x * AW + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int nch = H >> 2;
+  float4 go[NC], acc[NC];
+  load_row<NC>(dout + node * ldo, nch, lane, go);
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  // pass 1: dalpha per edge -> dsig buffer (temporarily), D
+  float D = 0.f;
+  for (int cb = beg; cb < end; cb += 32) {
+    const int cn = min(32, end - cb);
+    float my = 0.f;
+    for (int u = 0; u < cn; ++u) {
+      const float d = row_dot<NC>(go, v + (long long)col[cb + u] * ld, nch, lane);
+      if (lane == u) my = d;
+    }
+    const float a = lane < cn ? alpha[cb + lane] : 0.f;
+    D += warp_sum(a * my);
+    if (lane < cn) dsig[cb + lane] = my;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int cb = beg; cb < end; cb += 32) {
+    const int cn = min(32, end - cb);
+    float g = 0.f;
+    if (lane < cn) {
+      g = alpha[cb + lane] * (dsig[cb + lane] - D);
+      dsig[cb + lane] = g;
+    }
+    for (int u = 0; u < cn; ++u) {
+      const float gu = __shfl_sync(0xffffffffu, g, u) * scale;
+      const float* pk = k + (long long)col[cb + u] * ld;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nch) fma4(acc[c], gu, ld4(pk + 4 * ch));
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      st4(dq + node * ldd + 4 * ch, acc[c]);
+      if (ds) st4(ds + node * ldd + 4 * ch, go[c]);
+    }
+  }
+}
+
+// by-source backward: dk_j = scale * sum_i dsig[j->i] q_i,  dv_j = sum_i alpha[j->i] dout_i
+template <int NC>
+__global__ void __launch_bounds__(AW * 32)
+attn_bwd_src_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ q, long long ld,
+                    const int* __restrict__ t_rowptr, const int* __restrict__ t_col, const int* __restrict__ t_eid,
+                    const float* __restrict__ alpha, const float* __restrict__ dsig, float scale,
+                    float* __restrict__ dk, float* __restrict__ dv, long long ldd, long long N, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long node = (long long)blockIdx.x * AW + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int nch = H >> 2;
+  float4 ak[NC], av[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { ak[c] = make_float4(0.f, 0.f, 0.f, 0.f); av[c] = ak[c]; }
+  const int beg = t_rowptr[node], end = t_rowptr[node + 1];
+  for (int e = beg; e < end; ++e) {
+    const int i = t_col[e], id = t_eid[e];
+    const float a = alpha[id], g = dsig[id] * scale;
+    const float* pq = q + (long long)i * ld;
+    const float* pd = dout + (long long)i * ldo;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        fma4(ak[c], g, ld4(pq + 4 * ch));
+        fma4(av[c], a, ld4(pd + 4 * ch));
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      st4(dk + node * ldd + 4 * ch, ak[c]);
+      st4(dv + node * ldd + 4 * ch, av[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- K5 EdgeAtt
+// by-source softmax of <x_j, u_k> over k in out(j); result stored at the by-destination edge id.
+template <int NC>
+__global__ void __launch_bounds__(AW * 32)
+edgeatt_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ u, long long ldu,
+                   const int* __restrict__ t_rowptr, const int* __restrict__ t_col, const int* __restrict__ t_eid,
+                   float* __restrict__ nu, long long N, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long node = (long long)blockIdx.x * AW + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int nch = H >> 2;
+  float4 xj[NC];
+  load_row<NC>(x + node * ldx, nch, lane, xj);
+  const int beg = t_rowptr[node], end = t_rowptr[node + 1];
+  // pass 1: raw scores -> nu[t_eid], running max
+  float mx = -INFINITY;
+  for (int cb = beg; cb < end; cb += 32) {
+    const int cn = min(32, end - cb);
+    float my = -INFINITY;
+    for (int uu = 0; uu < cn; ++uu) {
+      const float d = row_dot<NC>(xj, u + (long long)t_col[cb + uu] * ldu, nch, lane);
+      if (lane == uu) my = d;
+    }
+    if (lane < cn) nu[t_eid[cb + lane]] = my;
+    mx = fmaxf(mx, warp_max(my));
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int e = beg + lane; e < end; e += 32) {
+    const int id = t_eid[e];
+    const float ex = expf(nu[id] - mx);
+    nu[id] = ex;
+    sum += ex;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int e = beg + lane; e < end; e += 32) nu[t_eid[e]] *= inv;
+}
+
+// by-source backward: dsig[e] = nu_e (dnu_e - sum nu dnu),  dx_j = sum_k dsig u_k   (dx is WRITTEN, not accumulated)
+template <int NC>
+__global__ void __launch_bounds__(AW * 32)
+edgeatt_bwd_src_kernel(const float* __restrict__ dnu, const float* __restrict__ nu, const float* __restrict__ u,
+                       long long ldu, const int* __restrict__ t_rowptr, const int* __restrict__ t_col,
+                       const int* __restrict__ t_eid, float* __restrict__ dsig, float* __restrict__ dx, long long lddx,
+                       long long N, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long node = (long long)blockIdx.x * AW + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int nch = H >> 2;
+  const int beg = t_rowptr[node], end = t_rowptr[node + 1];
+  float D = 0.f;
+  for (int e = beg + lane; e < end; e += 32) {
+    const int id = t_eid[e];
+    D += nu[id] * dnu[id];
+  }
+  D = warp_sum(D);
+  float4 acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = beg; e < end; ++e) {
+    const int id = t_eid[e];
+    const float g = nu[id] * (dnu[id] - D);
+    if (lane == 0) dsig[id] = g;
+    const float* pu = u + (long long)t_col[e] * ldu;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) fma4(acc[c], g, ld4(pu + 4 * ch));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) st4(dx + node * lddx + 4 * ch, acc[c]);
+  }
+}
+
+// by-destination backward: du_k = sum_{j in in(k)} dsig[j->k] x_j
+template <int NC>
+__global__ void __launch_bounds__(AW * 32)
+edgeatt_bwd_dst_kernel(const float* __restrict__ dsig, const float* __restrict__ x, long long ldx,
+                       const int* __restrict__ rowptr, const int* __restrict__ col, float* __restrict__ du,
+                       long long lddu, long long N, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long node = (long long)blockIdx.x * AW + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int nch = H >> 2;
+  float4 acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  for (int e = beg; e < end; ++e) {
+    const float g = dsig[e];
+    const float* px = x + (long long)col[e] * ldx;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) fma4(acc[c], g, ld4(px + 4 * ch));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) st4(du + node * lddu + 4 * ch, acc[c]);
+  }
+}
+
+static int chk(const void* p, long long ld, int H) {
+  if ((H & 3) || H <= 0 || H > 256) return ERCG_EINVAL;
+  if (!p) return ERCG_EINVAL;
+  if ((ld & 3) || !aligned16(p)) return ERCG_EALIGN;
+  return ERCG_OK;
+}
+
+}  // namespace ercg
+
+using namespace ercg;
+
+#define ERCG_CHK(p, ld) do { int rc_ = chk(p, ld, H); if (rc_) return rc_; } while (0)
+#define ERCG_LAUNCH_NC(kernel, ...)                                                            \
+  do {                                                                                         \
+    const unsigned blocks_ = (unsigned)((N + AW - 1) / AW);                                    \
+    if (H <= 128) kernel<1><<<blocks_, AW * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);       \
+    else kernel<2><<<blocks_, AW * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                \
+    return finish_launch();                                                                    \
+  } while (0)
+
+extern "C" int ercg_attn_fwd(const float* q, const float* k, const float* v, const float* s, int64_t ld,
+                             const int32_t* rowptr, const int32_t* col, float scale,
+                             float* out, int64_t ldo, float* alpha, int64_t N, int H, void* stream) {
+  if (N < 0) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!rowptr || !col) return ERCG_EINVAL;
+  ERCG_CHK(q, ld); ERCG_CHK(k, ld); ERCG_CHK(v, ld); ERCG_CHK(out, ldo);
+  if (s) ERCG_CHK(s, ld);
+  ERCG_LAUNCH_NC(attn_fwd_kernel, q, k, v, s, ld, rowptr, col, scale, out, ldo, alpha, N, H);
+}
+
+extern "C" int ercg_attn_bwd_dst(const float* dout, int64_t ldo, const float* k, const float* v, int64_t ld,
+                                 const int32_t* rowptr, const int32_t* col, const float* alpha, float scale,
+                                 float* dq, float* ds, int64_t ldd, float* dsig, int64_t N, int H, void* stream) {
+  if (N < 0) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!rowptr || !col || !alpha || !dsig) return ERCG_EINVAL;
+  ERCG_CHK(dout, ldo); ERCG_CHK(k, ld); ERCG_CHK(v, ld); ERCG_CHK(dq, ldd);
+  if (ds) ERCG_CHK(ds, ldd);
+  ERCG_LAUNCH_NC(attn_bwd_dst_kernel, dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, N, H);
+}
+
+extern "C" int ercg_attn_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld,
+                                 const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
+                                 const float* alpha, const float* dsig, float scale,
+                                 float* dk, float* dv, int64_t ldd, int64_t N, int H, void* stream) {
+  if (N < 0) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!t_rowptr || !t_col || !t_eid || !alpha || !dsig) return ERCG_EINVAL;
+  ERCG_CHK(dout, ldo); ERCG_CHK(q, ld); ERCG_CHK(dk, ldd); ERCG_CHK(dv, ldd);
+  ERCG_LAUNCH_NC(attn_bwd_src_kernel, dout, ldo, q, ld, t_rowptr, t_col, t_eid, alpha, dsig, scale, dk, dv, ldd, N, H);
+}
+
+extern "C" int ercg_edgeatt_fwd(const float* x, int64_t ldx, const float* u, int64_t ldu,
+                                const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
+                                float* nu, int64_t N, int H, void* stream) {
+  if (N < 0) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!t_rowptr || !t_col || !t_eid || !nu) return ERCG_EINVAL;
+  ERCG_CHK(x, ldx); ERCG_CHK(u, ldu);
+  ERCG_LAUNCH_NC(edgeatt_fwd_kernel, x, ldx, u, ldu, t_rowptr, t_col, t_eid, nu, N, H);
+}
+
+extern "C" int ercg_edgeatt_bwd_src(const float* dnu, const float* nu, const float* u, int64_t ldu,
+                                    const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
+                                    float* dsig, float* dx, int64_t lddx, int64_t N, int H, void* stream) {
+  if (N < 0) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!dnu || !nu || !t_rowptr || !t_col || !t_eid || !dsig) return ERCG_EINVAL;
+  ERCG_CHK(u, ldu); ERCG_CHK(dx, lddx);
+  ERCG_LAUNCH_NC(edgeatt_bwd_src_kernel, dnu, nu, u, ldu, t_rowptr, t_col, t_eid, dsig, dx, lddx, N, H);
+}
+
+extern "C" int ercg_edgeatt_bwd_dst(const float* dsig, const float* x, int64_t ldx,
+                                    const int32_t* rowptr, const int32_t* col,
+                                    float* du, int64_t lddu, int64_t N, int H, void* stream) {
+  if (N < 0) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!dsig || !rowptr || !col) return ERCG_EINVAL;
+  ERCG_CHK(x, ldx); ERCG_CHK(du, lddu);
+  ERCG_LAUNCH_NC(edgeatt_bwd_dst_kernel, dsig, x, ldx, rowptr, col, du, lddu, N, H);
+}

@@ -1,0 +1,344 @@
+// K1: batch_graphify as one cooperative integer kernel (sm_100a).
+//
+// Replaces the python loops of the reference:
+//   edge_perms      track_mm/cogmen_utils.py:147-172 (= dgcn_models.py:95-118)
+//   batch_graphify  track_mm/cogmen_utils.py:109-144, track_mm/dgcn_models.py:51-92
+// Everything is closed form: the in-edges of k are the window [max(0,k-wf), min(L-1,k+wp)], the
+// out-edges of j are [max(0,j-wp), min(L-1,j+wf)], and the prefix of window sizes has a formula
+// (deg_prefix), so no per-node scan is needed -- only a scan over the B dialogue lengths.
+//
+// One launch, three phases separated by grid.sync():
+//   1. per-tile (256 dialogues) sums of node and edge counts
+//   2. exclusive scan -> node_off[B+1], edge_off[B+1], edge_index_lengths[B]
+//   3. one warp per dialogue fills node arrays, then walks its by-destination edge range and its
+//      by-source edge range lane-per-edge (coalesced 4/1/8-byte stores).
+// HBM traffic (algorithmic): 8B(lengths) + N speakers + 8(N+1) rowptrs + E*(4+1+4+1+4) (+4E inv_cnt,
+// +24E when the reference-layout int64 edge_index/edge_type are requested).
+#include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace ercg {
+
+__host__ __device__ inline void eff_window(long long L, int wp, int wf, long long& P, long long& F) {
+  long long m = L > 0 ? L - 1 : 0;
+  P = (wp < 0 || wp > m) ? m : wp;
+  F = (wf < 0 || wf > m) ? m : wf;
+}
+
+__host__ __device__ inline long long dialog_edges(long long L, int wp, int wf) {
+  if (L <= 0) return 0;
+  long long P, F;
+  eff_window(L, wp, wf, P, F);
+  return L * (P + F + 1) - P * (P + 1) / 2 - F * (F + 1) / 2;
+}
+
+// sum_{k' < k} [ min(L-1, k'+A) - max(0, k'-Bk) + 1 ],  0 <= k <= L,  0 <= A,Bk <= L-1
+__host__ __device__ inline long long deg_prefix(long long L, long long A, long long Bk, long long k) {
+  long long t1 = L - A;                       // nodes k' < t1 are not clipped on the high side
+  long long a = k < t1 ? k : t1;
+  long long sum1 = a * A + a * (a - 1) / 2 + (k - a) * (L - 1);
+  long long b = k - 1 - Bk;
+  if (b < 0) b = 0;
+  return sum1 + k - b * (b + 1) / 2;
+}
+
+struct GraphifyParams {
+  const void* lengths; int len64; int B;
+  const void* speakers; int spk64; long long spk_ld;
+  int wp, wf, n_speakers;
+  long long N, E;
+  ercg_graph_out o;
+  long long* tile_agg;   // [2 * numTiles]
+};
+
+__device__ __forceinline__ long long load_len(const GraphifyParams& p, int b) {
+  long long L = p.len64 ? reinterpret_cast<const long long*>(p.lengths)[b]
+                        : (long long)reinterpret_cast<const int*>(p.lengths)[b];
+  return L < 0 ? 0 : L;
+}
+
+// block-wide inclusive scan of a pair of int64 (blockDim.x <= 1024, multiple of 32)
+__device__ inline void block_scan_pair(long long& a, long long& b, long long* sm /* [2*32+2] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
+    if (lane >= o) { a += ta; b += tb; }
+  }
+  __syncthreads();
+  if (lane == 31) { sm[2 * wid] = a; sm[2 * wid + 1] = b; }
+  __syncthreads();
+  if (wid == 0) {
+    long long wa = lane < nw ? sm[2 * lane] : 0, wb = lane < nw ? sm[2 * lane + 1] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long ta = __shfl_up_sync(0xffffffffu, wa, o), tb = __shfl_up_sync(0xffffffffu, wb, o);
+      if (lane >= o) { wa += ta; wb += tb; }
+    }
+    if (lane < nw) { sm[2 * lane] = wa; sm[2 * lane + 1] = wb; }
+  }
+  __syncthreads();
+  if (wid > 0) { a += sm[2 * (wid - 1)]; b += sm[2 * (wid - 1) + 1]; }
+}
+
+__global__ void __launch_bounds__(256) graphify_kernel(GraphifyParams p) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ long long sm[66];
+  const int T = blockDim.x;
+  const int numTiles = (p.B + T - 1) / T;
+
+  // ---- phase 1: tile aggregates
+  for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    int b = tile * T + threadIdx.x;
+    long long n = 0, e = 0;
+    if (b < p.B) { n = load_len(p, b); e = dialog_edges(n, p.wp, p.wf); }
+    block_scan_pair(n, e, sm);
+    if (threadIdx.x == T - 1) { p.tile_agg[2 * tile] = n; p.tile_agg[2 * tile + 1] = e; }
+    __syncthreads();
+  }
+  grid.sync();
+
+  // ---- phase 2: offsets
+  for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    long long pn = 0, pe = 0;
+    for (int t = threadIdx.x; t < tile; t += T) { pn += p.tile_agg[2 * t]; pe += p.tile_agg[2 * t + 1]; }
+    block_scan_pair(pn, pe, sm);      // last thread holds the totals of all previous tiles
+    __syncthreads();
+    if (threadIdx.x == T - 1) { sm[64] = pn; sm[65] = pe; }
+    __syncthreads();
+    const long long basen = sm[64], basee = sm[65];
+    int b = tile * T + threadIdx.x;
+    long long n = 0, e = 0;
+    if (b < p.B) { n = load_len(p, b); e = dialog_edges(n, p.wp, p.wf); }
+    long long n0 = n, e0 = e;
+    block_scan_pair(n, e, sm);
+    if (b < p.B) {
+      p.o.node_off[b] = (int)(basen + n - n0);
+      p.o.edge_off[b] = (int)(basee + e - e0);
+      if (p.o.edge_index_lengths) p.o.edge_index_lengths[b] = e0;
+      if (b == p.B - 1) {
+        long long Nt = basen + n, Et = basee + e;
+        p.o.node_off[p.B] = (int)Nt;
+        p.o.edge_off[p.B] = (int)Et;
+        if (Nt <= p.N) { p.o.rowptr[Nt] = (int)Et; p.o.t_rowptr[Nt] = (int)Et; }
+        if (p.o.totals) { p.o.totals[0] = Nt; p.o.totals[1] = Et; }
+      }
+    }
+    __syncthreads();
+  }
+  if (p.B == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.o.node_off[0] = 0; p.o.edge_off[0] = 0; p.o.rowptr[0] = 0; p.o.t_rowptr[0] = 0;
+    if (p.o.totals) { p.o.totals[0] = 0; p.o.totals[1] = 0; }
+  }
+  grid.sync();
+
+  // ---- phase 3: one warp per dialogue
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = T >> 5;
+  const long long gwarp = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * warps_per_block;
+  const int n_spk = p.n_speakers;
+  for (long long d = gwarp; d < p.B; d += nwarps) {
+    const long long L = load_len(p, (int)d);
+    if (L == 0) continue;
+    const long long o = p.o.node_off[d], eo = p.o.edge_off[d];
+    if (o + L > p.N) continue;                  // caller passed a too-small N: never write out of bounds
+    long long P, F;
+    eff_window(L, p.wp, p.wf, P, F);
+    if (eo + dialog_edges(L, p.wp, p.wf) > p.E) continue;
+    // (a) node arrays
+    for (long long k = lane; k < L; k += 32) {
+      long long s;
+      if (p.spk_ld > 0) {
+        long long idx = d * p.spk_ld + k;
+        s = p.spk64 ? reinterpret_cast<const long long*>(p.speakers)[idx]
+                    : (long long)reinterpret_cast<const int*>(p.speakers)[idx];
+      } else {
+        s = p.spk64 ? reinterpret_cast<const long long*>(p.speakers)[o + k]
+                    : (long long)reinterpret_cast<const int*>(p.speakers)[o + k];
+      }
+      p.o.spk[o + k] = (int)s;
+      p.o.node_dlg[o + k] = (int)d;
+      if (p.o.pad_row) p.o.pad_row[o + k] = (int)(p.spk_ld > 0 ? d * p.spk_ld + k : o + k);
+      p.o.rowptr[o + k] = (int)(eo + deg_prefix(L, P, F, k));
+      p.o.t_rowptr[o + k] = (int)(eo + deg_prefix(L, F, P, k));
+    }
+    __syncwarp();
+    const int* spk = p.o.spk + o;
+    // (b) by-destination edges, (c) by-source edges
+    for (int pass = 0; pass < 2; ++pass) {
+      const long long A = pass == 0 ? P : F;      // high-side reach of the row node
+      const long long Bk = pass == 0 ? F : P;     // low-side reach
+      for (long long k0 = 0; k0 < L; k0 += 32) {
+        long long kmine = k0 + lane;
+        if (kmine > L) kmine = L;
+        const long long myS = deg_prefix(L, A, Bk, kmine);
+        const long long base = __shfl_sync(0xffffffffu, myS, 0);
+        long long kend = k0 + 32 < L ? k0 + 32 : L;
+        const long long end = deg_prefix(L, A, Bk, kend);
+        for (long long xb = base; xb < end; xb += 32) {
+          const long long x = xb + lane;
+          const bool valid = x < end;
+          const long long xs = valid ? x : base;
+          int lo = 0, hi = 31;
+#pragma unroll
+          for (int it = 0; it < 5; ++it) {
+            int mid = (lo + hi + 1) >> 1;
+            long long v = __shfl_sync(0xffffffffu, myS, mid);
+            if (v <= xs) lo = mid; else hi = mid - 1;
+          }
+          const long long Srow = __shfl_sync(0xffffffffu, myS, lo);
+          if (!valid) continue;
+          const long long row = k0 + lo;                 // k (pass 0) or j (pass 1)
+          const long long rlo = row - Bk > 0 ? row - Bk : 0;
+          const long long other = rlo + (x - Srow);      // j (pass 0) or k (pass 1)
+          const long long j = pass == 0 ? other : row;
+          const long long k = pass == 0 ? row : other;
+          const int sj = spk[j], sk = spk[k];
+          const int ty = (sj * n_spk + sk) * 2 + (j >= k ? 1 : 0);
+          const long long e = eo + x;
+          if (pass == 0) {
+            p.o.col[e] = (int)(o + j);
+            p.o.etype[e] = (uint8_t)ty;
+            if (p.o.edge_index) { p.o.edge_index[e] = o + j; p.o.edge_index[p.E + e] = o + k; }
+            if (p.o.edge_type) p.o.edge_type[e] = ty;
+            if (p.o.inv_cnt) {
+              const long long rhi = k + P < L - 1 ? k + P : L - 1;
+              int c = 0;
+              const bool dirj = j >= k;
+              for (long long jj = rlo; jj <= rhi; ++jj) c += (spk[jj] == sj && ((jj >= k) == dirj)) ? 1 : 0;
+              p.o.inv_cnt[e] = 1.0f / (float)c;
+            }
+          } else {
+            p.o.t_col[e] = (int)(o + k);
+            p.o.t_etype[e] = (uint8_t)ty;
+            const long long klo = k - F > 0 ? k - F : 0;
+            p.o.t_eid[e] = (int)(eo + deg_prefix(L, P, F, k) + (j - klo));
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void graphify_count_kernel(const void* lengths, int len64, int B, int wp, int wf, long long* totals) {
+  __shared__ long long sm[66];
+  long long n = 0, e = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    long long L = len64 ? reinterpret_cast<const long long*>(lengths)[b] : (long long)reinterpret_cast<const int*>(lengths)[b];
+    if (L < 0) L = 0;
+    n += L; e += dialog_edges(L, wp, wf);
+  }
+  block_scan_pair(n, e, sm);
+  if (threadIdx.x == blockDim.x - 1) { totals[0] = n; totals[1] = e; }
+}
+
+__global__ void pack_rows_kernel(const float* __restrict__ padded, long long ld, long long Lmax, int B, int seq_first,
+                                 const int* __restrict__ node_off, const int* __restrict__ node_dlg,
+                                 float* __restrict__ packed, long long ldp, long long N, int D, int unpack) {
+  // one warp per node row
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int d = node_dlg[row];
+  const long long pos = row - node_off[d];
+  const long long prow = seq_first ? pos * B + d : (long long)d * Lmax + pos;
+  const float* src = padded + prow * ld;
+  float* dst = packed + row * ldp;
+  if (unpack) {
+    float* pd = const_cast<float*>(padded) + prow * ld;
+    for (int c = lane; c < D; c += 32) pd[c] = dst[c];
+  } else {
+    for (int c = lane; c < D; c += 32) dst[c] = src[c];
+  }
+}
+
+}  // namespace ercg
+
+using namespace ercg;
+
+extern "C" int ercg_graphify_sizes_host(const int64_t* lengths_host, int B, int wp, int wf, int64_t* N_out, int64_t* E_out) {
+  if (B < 0 || (B > 0 && !lengths_host) || !N_out || !E_out) return ERCG_EINVAL;
+  long long n = 0, e = 0;
+  for (int b = 0; b < B; ++b) {
+    long long L = lengths_host[b] < 0 ? 0 : lengths_host[b];
+    n += L; e += dialog_edges(L, wp, wf);
+  }
+  *N_out = n; *E_out = e;
+  return ERCG_OK;
+}
+
+extern "C" int ercg_graphify_count(const void* lengths_dev, int lengths_is_i64, int B, int wp, int wf,
+                                   int64_t* totals_dev, void* stream) {
+  if (B < 0 || !totals_dev || (B > 0 && !lengths_dev)) return ERCG_EINVAL;
+  graphify_count_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lengths_dev, lengths_is_i64, B, wp, wf,
+                                                              reinterpret_cast<long long*>(totals_dev));
+  return finish_launch();
+}
+
+extern "C" size_t ercg_graphify_workspace_bytes(int B) {
+  size_t tiles = (size_t)(B > 0 ? (B + 255) / 256 : 1);
+  return tiles * 2 * sizeof(long long);
+}
+
+extern "C" int ercg_graphify_csr(const void* lengths_dev, int lengths_is_i64, int B,
+                                 const void* speakers_dev, int speakers_is_i64, int64_t spk_ld,
+                                 int wp, int wf, int n_speakers, int64_t N, int64_t E,
+                                 const ercg_graph_out* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!out || B < 0 || N < 0 || E < 0 || n_speakers < 1 || spk_ld < 0) return ERCG_EINVAL;
+  if (!out->node_off || !out->edge_off || !out->rowptr || !out->col || !out->etype || !out->t_rowptr ||
+      !out->t_col || !out->t_etype || !out->t_eid || !out->spk || !out->node_dlg) return ERCG_EINVAL;
+  if (B > 0 && (!lengths_dev || !speakers_dev)) return ERCG_EINVAL;
+  if (2LL * n_speakers * n_speakers > 256) return ERCG_ERANGE;       // etype is uint8
+  if (N >= 2147483647LL || E >= 2147483647LL) return ERCG_ERANGE;    // packed int32 indices
+  if (workspace_bytes < ercg_graphify_workspace_bytes(B) || !workspace) return ERCG_EWORKSPACE;
+  GraphifyParams p;
+  p.lengths = lengths_dev; p.len64 = lengths_is_i64; p.B = B;
+  p.speakers = speakers_dev; p.spk64 = speakers_is_i64; p.spk_ld = spk_ld;
+  p.wp = wp; p.wf = wf; p.n_speakers = n_speakers; p.N = N; p.E = E; p.o = *out;
+  p.tile_agg = reinterpret_cast<long long*>(workspace);
+  static int max_blocks_per_sm = 0;
+  static int num_sms = 0;
+  if (!max_blocks_per_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, graphify_kernel, 256, 0);
+    if (max_blocks_per_sm < 1) max_blocks_per_sm = 1;
+    if (num_sms < 1) num_sms = kNumSMs;
+  }
+  long long want = (B + 7) / 8;                       // one warp per dialogue
+  long long cap = (long long)max_blocks_per_sm * num_sms;
+  int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  void* args[] = {&p};
+  cudaError_t err = cudaLaunchCooperativeKernel((const void*)graphify_kernel, dim3(grid), dim3(256), args, 0,
+                                                (cudaStream_t)stream);
+  ++g_launches;
+  return err == cudaSuccess ? ERCG_OK : ERCG_ECUDA;
+}
+
+static int pack_launch(const float* padded, int64_t ld, int64_t Lmax, int B, int seq_first,
+                       const int32_t* node_off, const int32_t* node_dlg, float* packed, int64_t ldp,
+                       int64_t N, int D, int unpack, void* stream) {
+  if (N < 0 || D < 0 || B < 0) return ERCG_EINVAL;
+  if (N == 0 || D == 0) return ERCG_OK;
+  if (!padded || !packed || !node_off || !node_dlg) return ERCG_EINVAL;
+  const int wpb = 8;
+  long long blocks = (N + wpb - 1) / wpb;
+  pack_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(padded, ld, Lmax, B, seq_first, node_off,
+                                                                            node_dlg, packed, ldp, N, D, unpack);
+  return finish_launch();
+}
+
+extern "C" int ercg_pack_rows(const float* padded, int64_t ld, int64_t Lmax, int B, int seq_first,
+                              const int32_t* node_off, const int32_t* node_dlg, float* packed, int64_t ldp,
+                              int64_t N, int D, void* stream) {
+  return pack_launch(padded, ld, Lmax, B, seq_first, node_off, node_dlg, packed, ldp, N, D, 0, stream);
+}
+
+extern "C" int ercg_unpack_rows(const float* packed, int64_t ldp, const int32_t* node_off, const int32_t* node_dlg,
+                                float* padded, int64_t ld, int64_t Lmax, int B, int seq_first, int64_t N, int D,
+                                void* stream) {
+  return pack_launch(padded, ld, Lmax, B, seq_first, node_off, node_dlg, const_cast<float*>(packed), ldp, N, D, 1, stream);
+}

@@ -1,0 +1,280 @@
+// BatchNorm1d(training statistics) + LeakyReLU (track_mm/cogmen.py:67-68,72) and the (class-weighted)
+// mean cross entropy of the train steps (cogmen.py:185, dgcn.py:124), forward and backward.
+// All reductions are two-level with a fixed order (per-block partials, then one thread per column
+// summing the partials in fp64) => bit-reproducible and independent of scheduling.
+#include "common.cuh"
+#include <math.h>
+
+namespace ercg {
+
+constexpr int RPB = 1024;   // rows per block in the column reductions
+
+// partial[b][0:H] = sum f0, partial[b][H:2H] = sum f1 over the block's rows
+template <int MODE>   // 0: (x, x^2)   1: (dy, dy*xhat) with dy = dout * lrelu'(gamma*xhat+beta)
+__global__ void __launch_bounds__(256)
+col_partials_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dout, long long ldo,
+                    const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                    long long N, int H, float* __restrict__ partial) {
+  __shared__ float sm0[8][33], sm1[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long rbeg = (long long)blockIdx.x * RPB;
+  long long rend = rbeg + RPB;
+  if (rend > N) rend = N;
+  for (int c0 = 0; c0 < H; c0 += 32) {
+    const int c = c0 + tx;
+    float s0 = 0.f, s1 = 0.f;
+    if (c < H) {
+      float mu = 0.f, istd = 0.f, g = 0.f, b = 0.f;
+      if (MODE == 1) { mu = mean[c]; istd = (1.0f / sqrtf(var[c] + eps)); g = gamma[c]; b = beta[c]; }
+      for (long long r = rbeg + ty; r < rend; r += 8) {
+        const float xv = x[r * ldx + c];
+        if (MODE == 0) {
+          s0 += xv; s1 = fmaf(xv, xv, s1);
+        } else {
+          const float xh = (xv - mu) * istd;
+          const float z = fmaf(g, xh, b);
+          const float dy = dout[r * ldo + c] * (z > 0.f ? 1.f : slope);
+          s0 += dy; s1 = fmaf(dy, xh, s1);
+        }
+      }
+    }
+    sm0[ty][tx] = s0; sm1[ty][tx] = s1;
+    __syncthreads();
+    if (ty == 0 && c < H) {
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) { t0 += sm0[y][tx]; t1 += sm1[y][tx]; }
+      partial[(long long)blockIdx.x * 2 * H + c] = t0;
+      partial[(long long)blockIdx.x * 2 * H + H + c] = t1;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nb, int H, long long N,
+                                      float* __restrict__ mean, float* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < nb; ++b) { s0 += (double)partial[(long long)b * 2 * H + c]; s1 += (double)partial[(long long)b * 2 * H + H + c]; }
+  const double m = s0 / (double)N;
+  double v = s1 / (double)N - m * m;
+  if (v < 0.0) v = 0.0;
+  mean[c] = (float)m; var[c] = (float)v;
+}
+
+__global__ void sums_final_kernel(const float* __restrict__ partial, int nb, int H, float* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * H) return;
+  double s = 0.0;
+  for (int b = 0; b < nb; ++b) s += (double)partial[(long long)b * 2 * H + c];
+  sums[c] = (float)s;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
+                  const float* __restrict__ var, float eps, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float slope, float* __restrict__ out, long long ldo,
+                  long long N, int H) {
+  const int nch = H >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nch) return;
+  const long long r = idx / nch;
+  const int c = (int)(idx % nch) * 4;
+  const float4 xv = ld4(x + r * ldx + c), mu = ld4(mean + c), vv = ld4(var + c), g = ld4(gamma + c), b = ld4(beta + c);
+  float4 y;
+  y.x = fmaf(g.x, (xv.x - mu.x) * (1.0f / sqrtf(vv.x + eps)), b.x);
+  y.y = fmaf(g.y, (xv.y - mu.y) * (1.0f / sqrtf(vv.y + eps)), b.y);
+  y.z = fmaf(g.z, (xv.z - mu.z) * (1.0f / sqrtf(vv.z + eps)), b.z);
+  y.w = fmaf(g.w, (xv.w - mu.w) * (1.0f / sqrtf(vv.w + eps)), b.w);
+  y.x = y.x > 0.f ? y.x : y.x * slope; y.y = y.y > 0.f ? y.y : y.y * slope;
+  y.z = y.z > 0.f ? y.z : y.z * slope; y.w = y.w > 0.f ? y.w : y.w * slope;
+  st4(out + r * ldo + c, y);
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ x, long long ldx,
+                        const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                        const float* __restrict__ sums, float inv_count, int use_batch_stats,
+                        float* __restrict__ dx, long long lddx, long long N, int H) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * H) return;
+  const long long r = idx / H;
+  const int c = (int)(idx % H);
+  const float istd = (1.0f / sqrtf(var[c] + eps)), g = gamma[c];
+  const float xh = (x[r * ldx + c] - mean[c]) * istd;
+  const float z = fmaf(g, xh, beta[c]);
+  const float dy = dout[r * ldo + c] * (z > 0.f ? 1.f : slope);
+  float v = dy;
+  if (use_batch_stats) v = dy - sums[c] * inv_count - xh * (sums[H + c] * inv_count);
+  dx[r * lddx + c] = g * istd * v;
+}
+
+// ------------------------------------------------------------------------------------------- CE
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+              const float* __restrict__ cw, float* __restrict__ dlogits, long long ldd, long long N, int C,
+              float* __restrict__ partial /* [blocks][2] */) {
+  __shared__ float s0[256], s1[256];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float num = 0.f, den = 0.f;
+  if (i < N) {
+    const float* z = logits + i * ld;
+    float m = z[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(z[c] - m);
+    const float lse = m + logf(se);
+    long long y = labels[i];
+    const bool ok = y >= 0 && y < C;
+    const float w = ok ? (cw ? cw[y] : 1.f) : 0.f;
+    if (ok) { num = w * (lse - z[y]); den = w; }
+    if (dlogits) {
+      const float inv = 1.f / se;
+      for (int c = 0; c < C; ++c) {
+        const float p = expf(z[c] - m) * inv;
+        dlogits[i * ldd + c] = w * (p - (c == y ? 1.f : 0.f));
+      }
+    }
+  }
+  s0[threadIdx.x] = num; s1[threadIdx.x] = den;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { partial[2 * (long long)blockIdx.x] = s0[0]; partial[2 * (long long)blockIdx.x + 1] = s1[0]; }
+}
+
+__global__ void ce_final_kernel(const float* __restrict__ partial, long long nb, float* __restrict__ out) {
+  // one warp; fixed order: lane-strided fp64 sums then a fixed shuffle tree
+  double a = 0.0, b = 0.0;
+  for (long long i = threadIdx.x; i < nb; i += 32) { a += (double)partial[2 * i]; b += (double)partial[2 * i + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (threadIdx.x == 0) { out[0] = (float)a; out[1] = (float)b; }
+}
+
+__global__ void scale_by_ratio_kernel(float* __restrict__ x, long long n, const float* __restrict__ num,
+                                      const float* __restrict__ den) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= num[0] / den[0];
+}
+
+__global__ void mask_pos_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ ref, long long ldr,
+                                float scale, float* __restrict__ out, long long ldo, long long M, int N) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const long long r = idx / N;
+  const int c = (int)(idx % N);
+  out[r * ldo + c] = ref[r * ldr + c] > 0.f ? x[r * ldx + c] * scale : 0.f;
+}
+
+}  // namespace ercg
+
+using namespace ercg;
+
+extern "C" int ercg_mask_pos(const float* x, int64_t ldx, const float* ref, int64_t ldr, float scale,
+                             float* out, int64_t ldo, int64_t M, int N, void* stream) {
+  if (M < 0 || N < 0) return ERCG_EINVAL;
+  if (M == 0 || N == 0) return ERCG_OK;
+  if (!x || !ref || !out) return ERCG_EINVAL;
+  const long long tot = M * N;
+  mask_pos_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, ref, ldr, scale, out, ldo, M, N);
+  return finish_launch();
+}
+
+extern "C" size_t ercg_bn_workspace_bytes(int64_t N, int H) {
+  if (N <= 0 || H <= 0) return 0;
+  return (size_t)((N + RPB - 1) / RPB) * 2 * H * sizeof(float);
+}
+
+extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, float* mean, float* var,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0 || H <= 0 || !x || !mean || !var || ldx < H) return ERCG_EINVAL;
+  if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
+  const int nb = (int)((N + RPB - 1) / RPB);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(workspace);
+  col_partials_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
+  int rc = finish_launch();
+  if (rc) return rc;
+  bn_stats_final_kernel<<<(H + 127) / 128, 128, 0, st>>>(part, nb, H, N, mean, var);
+  return finish_launch();
+}
+
+extern "C" int ercg_bn_act_fwd(const float* x, int64_t ldx, const float* mean, const float* var, float eps,
+                               const float* gamma, const float* beta, float slope,
+                               float* out, int64_t ldo, int64_t N, int H, void* stream) {
+  if (N < 0 || H <= 0 || (H & 3)) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!x || !mean || !var || !gamma || !beta || !out) return ERCG_EINVAL;
+  if ((ldx & 3) || (ldo & 3) || !aligned16(x) || !aligned16(out) || !aligned16(mean) || !aligned16(var) ||
+      !aligned16(gamma) || !aligned16(beta)) return ERCG_EALIGN;
+  const long long tot = N * (H >> 2);
+  bn_act_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean, var, eps, gamma, beta,
+                                                                                     slope, out, ldo, N, H);
+  return finish_launch();
+}
+
+extern "C" int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const float* x, int64_t ldx,
+                                      const float* mean, const float* var, float eps,
+                                      const float* gamma, const float* beta, float slope,
+                                      float* sums, int64_t N, int H, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0 || H <= 0 || !dout || !x || !mean || !var || !gamma || !beta || !sums) return ERCG_EINVAL;
+  if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
+  const int nb = (int)((N + RPB - 1) / RPB);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(workspace);
+  col_partials_kernel<1><<<nb, 256, 0, st>>>(x, ldx, dout, ldo, mean, var, eps, gamma, beta, slope, N, H, part);
+  int rc = finish_launch();
+  if (rc) return rc;
+  sums_final_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(part, nb, H, sums);
+  return finish_launch();
+}
+
+extern "C" int ercg_bn_act_bwd_apply(const float* dout, int64_t ldo, const float* x, int64_t ldx,
+                                     const float* mean, const float* var, float eps,
+                                     const float* gamma, const float* beta, float slope,
+                                     const float* sums, double count, int use_batch_stats,
+                                     float* dx, int64_t lddx, int64_t N, int H, void* stream) {
+  if (N < 0 || H <= 0) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!dout || !x || !mean || !var || !gamma || !beta || !dx || (use_batch_stats && (!sums || count <= 0))) return ERCG_EINVAL;
+  const long long tot = N * H;
+  bn_act_bwd_apply_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      dout, ldo, x, ldx, mean, var, eps, gamma, beta, slope, sums, use_batch_stats ? (float)(1.0 / count) : 0.f,
+      use_batch_stats, dx, lddx, N, H);
+  return finish_launch();
+}
+
+extern "C" size_t ercg_ce_workspace_bytes(int64_t N) {
+  if (N <= 0) return 2 * sizeof(float);
+  return (size_t)((N + 255) / 256) * 2 * sizeof(float);
+}
+
+extern "C" int ercg_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, const float* class_weight,
+                           float* lossnum_den, float* dlogits, int64_t ldd, int64_t N, int C,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0 || C <= 0 || !logits || !labels || !lossnum_den || ld < C || (dlogits && ldd < C)) return ERCG_EINVAL;
+  if (workspace_bytes < ercg_ce_workspace_bytes(N) || !workspace) return ERCG_EWORKSPACE;
+  const long long nb = (N + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(workspace);
+  ce_fwd_kernel<<<(unsigned)nb, 256, 0, st>>>(logits, ld, reinterpret_cast<const long long*>(labels), class_weight, dlogits,
+                                             ldd, N, C, part);
+  int rc = finish_launch();
+  if (rc) return rc;
+  ce_final_kernel<<<1, 32, 0, st>>>(part, nb, lossnum_den);
+  return finish_launch();
+}
+
+extern "C" int ercg_scale_by_ratio(float* x, int64_t n, const float* num, const float* den, void* stream) {
+  if (n < 0) return ERCG_EINVAL;
+  if (n == 0) return ERCG_OK;
+  if (!x || !num || !den) return ERCG_EINVAL;
+  scale_by_ratio_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, num, den);
+  return finish_launch();
+}

@@ -1,0 +1,182 @@
+"""Packed conversation graph (CSR by destination + by-source transpose) built by kernel K1.
+
+Host-side mirror of the reference's graph construction:
+  batch_graphify / edge_perms   track_mm/cogmen_utils.py:109-172, track_mm/dgcn_models.py:51-118
+The per-edge python loop (2 device syncs per edge in the reference) becomes one cooperative
+integer kernel launch (csrc/graphify.cu).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, GraphOut
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class PackedGraph:
+    """All arrays live on the GPU.  Canonical edge order: dialogue, then destination, then source."""
+
+    __slots__ = ("B", "N", "E", "wp", "wf", "n_speakers", "num_relations", "device", "node_off", "edge_off",
+                 "rowptr", "col", "etype", "t_rowptr", "t_col", "t_etype", "t_eid", "spk", "node_dlg", "inv_cnt",
+                 "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row", "perm", "Lpad")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+    def mean_weight(self):
+        """1/|N_r(k)| per edge -- the aggr='mean' weight of PyG RGCNConv."""
+        if self.inv_cnt is None:
+            self.inv_cnt = _inv_count_from_csr(self)
+        return self.inv_cnt
+
+
+def graph_sizes(lengths_cpu, wp, wf):
+    """Closed-form (N, E) from a CPU int64 lengths tensor (no device work, no sync)."""
+    lengths_cpu = lengths_cpu.to(torch.int64).contiguous()
+    n, e = ctypes.c_int64(), ctypes.c_int64()
+    check(lib().ercg_graphify_sizes_host(lengths_cpu.data_ptr(), lengths_cpu.numel(), wp, wf, ctypes.byref(n),
+                                         ctypes.byref(e)), "ercg_graphify_sizes_host")
+    return n.value, e.value
+
+
+def build_graph(lengths, speakers, wp, wf, n_speakers, device=None, reference_layout=True, mean_weight=True,
+                sizes=None):
+    """Run K1.
+
+    lengths   [B] int64/int32 (CPU or CUDA).  A CPU tensor avoids the single size sync.
+    speakers  padded [B,Lmax] or packed [N] int64/int32 speaker ids
+    sizes     optional (N, E) if the caller already knows them
+    """
+    if device is None:
+        device = speakers.device if speakers.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    B = lengths.numel()
+    if sizes is None:
+        if lengths.is_cuda:
+            tot = torch.empty(2, dtype=torch.int64, device=device)
+            ldev = lengths.contiguous()
+            check(lib().ercg_graphify_count(_p(ldev), 1 if ldev.dtype == torch.int64 else 0, B, wp, wf, _p(tot), _stream()),
+                  "ercg_graphify_count")
+            N, E = (int(v) for v in tot.tolist())      # the one host sync of the graph build
+        else:
+            N, E = graph_sizes(lengths, wp, wf)
+    else:
+        N, E = sizes
+    ldev = lengths.to(device=device, non_blocking=True).contiguous()
+    assert ldev.dtype in (torch.int64, torch.int32)
+    sdev = speakers.to(device=device, non_blocking=True)
+    assert sdev.dtype in (torch.int64, torch.int32)
+    if sdev.dim() == 2:
+        sdev = sdev.contiguous()
+        spk_ld = sdev.size(1)
+        assert sdev.size(0) == B
+    else:
+        sdev = sdev.contiguous()
+        spk_ld = 0
+        assert sdev.numel() == N
+
+    g = PackedGraph()
+    g.B, g.N, g.E, g.wp, g.wf, g.n_speakers, g.device = B, N, E, wp, wf, n_speakers, device
+    g.num_relations = 2 * n_speakers * n_speakers
+    i32 = dict(dtype=torch.int32, device=device)
+    g.node_off = torch.empty(B + 1, **i32)
+    g.edge_off = torch.empty(B + 1, **i32)
+    g.rowptr = torch.empty(N + 1, **i32)
+    g.t_rowptr = torch.empty(N + 1, **i32)
+    g.col = torch.empty(E, **i32)
+    g.t_col = torch.empty(E, **i32)
+    g.t_eid = torch.empty(E, **i32)
+    g.etype = torch.empty(E, dtype=torch.uint8, device=device)
+    g.t_etype = torch.empty(E, dtype=torch.uint8, device=device)
+    g.spk = torch.empty(N, **i32)
+    g.node_dlg = torch.empty(N, **i32)
+    g.totals = torch.empty(2, dtype=torch.int64, device=device)
+    g.pad_row = torch.empty(N, **i32)
+    g.Lpad = spk_ld
+    if mean_weight:
+        g.inv_cnt = torch.empty(E, dtype=torch.float32, device=device)
+    if reference_layout:
+        g.edge_index = torch.empty((2, E), dtype=torch.int64, device=device)
+        g.edge_type = torch.empty(E, dtype=torch.int64, device=device)
+        g.edge_index_lengths = torch.empty(B, dtype=torch.int64, device=device)
+    out = GraphOut(*[_p(getattr(g, n)) for n, _ in GraphOut._fields_])
+    ws_bytes = lib().ercg_graphify_workspace_bytes(B)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
+    check(lib().ercg_graphify_csr(_p(ldev), 1 if ldev.dtype == torch.int64 else 0, B, _p(sdev),
+                                  1 if sdev.dtype == torch.int64 else 0, spk_ld, wp, wf, n_speakers, N, E,
+                                  ctypes.byref(out), _p(ws), ws.numel(), _stream()), "ercg_graphify_csr")
+    return g
+
+
+def _inv_count_from_csr(g):
+    """Mean weights for a graph that did not come from K1 (generic edge_index path); O(E) torch ops."""
+    dst = torch.repeat_interleave(torch.arange(g.N, device=g.device), (g.rowptr[1:] - g.rowptr[:-1]).long())
+    key = dst * g.num_relations + g.etype.long()
+    _, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
+    return (1.0 / cnt[inv].float()).contiguous()
+
+
+def graph_from_edge_index(edge_index, edge_type, num_nodes, num_relations=1):
+    """Compatibility path: arbitrary COO edge_index [2,E] (+ edge_type) -> PackedGraph.
+
+    Used when the drop-in layers are handed an edge_index that did not come from our batch_graphify.
+    The sort runs on the GPU through torch.sort (plumbing, not the hot path); the result feeds the
+    same kernels.  Canonical order = (dst, src) stable.
+    """
+    g = getattr(edge_index, "_ercg_graph", None)
+    if g is not None:
+        return g
+    dev = edge_index.device
+    assert dev.type == "cuda", "libercgraph has no CPU path"
+    src, dst = edge_index[0].long(), edge_index[1].long()
+    E = src.numel()
+    et = edge_type.long() if edge_type is not None else torch.zeros(E, dtype=torch.int64, device=dev)
+    order = torch.argsort(dst * num_nodes + src, stable=True)
+    g = PackedGraph()
+    g.B, g.N, g.E, g.device, g.num_relations = 0, num_nodes, E, dev, num_relations
+    s, d, t = src[order], dst[order], et[order]
+    g.col = s.int().contiguous()
+    g.etype = t.to(torch.uint8).contiguous()
+    g.rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=dev)
+    g.rowptr[1:] = torch.cumsum(torch.bincount(d, minlength=num_nodes), 0)
+    g.rowptr = g.rowptr.int().contiguous()
+    torder = torch.argsort(s * num_nodes + d, stable=True)        # positions in by-dst order, sorted by (src,dst)
+    g.t_eid = torder.int().contiguous()
+    g.t_col = d[torder].int().contiguous()
+    g.t_etype = t[torder].to(torch.uint8).contiguous()
+    g.t_rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=dev)
+    g.t_rowptr[1:] = torch.cumsum(torch.bincount(s, minlength=num_nodes), 0)
+    g.t_rowptr = g.t_rowptr.int().contiguous()
+    g.edge_index = torch.stack([s, d]).contiguous()
+    g.edge_type = t.contiguous()
+    # map from the caller's edge order to canonical order, for per-edge inputs such as edge_norm
+    g.perm = order
+    return g
+
+
+def standard_edge_dict(n_speakers):
+    """edge_type_to_idx exactly as the reference builds it (track_mm/cogmen.py:124-129, dgcn.py:72-77)."""
+    d = {}
+    for j in range(n_speakers):
+        for k in range(n_speakers):
+            d[str(j) + str(k) + "0"] = len(d)
+            d[str(j) + str(k) + "1"] = len(d)
+    return d
+
+
+def speakers_from_edge_dict(edge_type_to_idx):
+    n = 1
+    while 2 * n * n < len(edge_type_to_idx):
+        n += 1
+    if edge_type_to_idx != standard_edge_dict(n):
+        raise ValueError("edge_type_to_idx is not the reference's numbering ((s_j*n+s_k)*2+[j>=k]); "
+                         "the graph kernel only implements that one")
+    return n

@@ -1,0 +1,349 @@
+"""torch.autograd wrappers around the C ABI (include/ercgraph.h).
+
+Every forward/backward here is one or more calls into libercgraph.so on the current CUDA stream;
+PyTorch only owns the buffers.  Nothing in this file computes on the CPU or through ATen kernels
+except O(parameters) re-layouts of weights (transposes / concatenations of <= 600 KB tensors).
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ACT_NONE, ACT_RELU, ACT_RELU_DROPOUT, ACT_MASK_POS
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _rows(t):
+    """2-D fp32 CUDA tensor with unit inner stride -> (tensor, leading dimension)."""
+    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2, (t.device, t.dtype, t.shape)
+    if t.stride(1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t, (t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0)))
+
+
+# ------------------------------------------------------------------------------------------- raw calls
+def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_scale=1.0, drop_p=0.0, seed=0, out=None):
+    A, lda = _rows(A)
+    Bm, ldb = _rows(Bm)
+    K, N = Bm.shape
+    assert A.size(1) == K, (A.shape, Bm.shape)
+    if M is None:
+        M = a_rows.numel() if a_rows is not None else A.size(0)
+    C = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ldaux = 0
+    if aux is not None:
+        aux, ldaux = _rows(aux)
+    check(lib().ercg_gemm_nn(_p(A), lda, _p(a_rows), _p(Bm), ldb, _p(bias), _p(C), C.stride(0) if M > 1 else N, M, N, K,
+                             act, _p(aux), ldaux, float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _stream()),
+          "ercg_gemm_nn")
+    return C
+
+
+def gemm_tn(A, Bm, a_rows=None, M=None):
+    """A[M,K1]^T @ B[M,N1] -> [K1,N1]"""
+    A, lda = _rows(A)
+    Bm, ldb = _rows(Bm)
+    if M is None:
+        M = Bm.size(0)
+    K1, N1 = A.size(1), Bm.size(1)
+    C = torch.empty((K1, N1), dtype=torch.float32, device=A.device)
+    nbytes = lib().ercg_gemm_tn_workspace_bytes(M, K1, N1)
+    ws = _ws(nbytes, A.device)
+    check(lib().ercg_gemm_tn(_p(A), lda, _p(a_rows), _p(Bm), ldb, _p(C), N1, M, K1, N1, _p(ws), ws.numel(), _stream()),
+          "ercg_gemm_tn")
+    return C
+
+
+def colsum(A):
+    A, lda = _rows(A)
+    M, N = A.shape
+    out = torch.empty(N, dtype=torch.float32, device=A.device)
+    ws = _ws(lib().ercg_colsum_workspace_bytes(M, N), A.device)
+    check(lib().ercg_colsum(_p(A), lda, M, N, _p(out), _p(ws), ws.numel(), _stream()), "ercg_colsum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- Linear
+class _LinearAct(torch.autograd.Function):
+    """C = act(A[a_rows] @ Bm + bias); Bm is [K,N] (already transposed weight)."""
+
+    @staticmethod
+    def forward(ctx, A, Bm, bias, act, a_rows, drop_p, seed):
+        C = gemm_nn(A, Bm, bias, act=act, a_rows=a_rows, drop_p=drop_p, seed=seed)
+        ctx.act, ctx.drop_p, ctx.has_bias = act, drop_p, bias is not None
+        ctx.a_rows = a_rows
+        ctx.save_for_backward(A, Bm, C if act != ACT_NONE else None)
+        return C
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, Bm, C = ctx.saved_tensors
+        dC = dC.contiguous()
+        if ctx.act != ACT_NONE:
+            scale = 1.0 / (1.0 - ctx.drop_p) if ctx.act == ACT_RELU_DROPOUT else 1.0
+            dZ = mask_pos(dC, C, scale)
+        else:
+            dZ = dC
+        dA = dB = dbias = None
+        if ctx.needs_input_grad[0]:
+            assert ctx.a_rows is None, "input gradient through a row gather is not needed by any reference path"
+            dA = gemm_nn(dZ, Bm.t().contiguous())
+        if ctx.needs_input_grad[1]:
+            dB = gemm_tn(A, dZ, a_rows=ctx.a_rows, M=dZ.size(0))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dbias = colsum(dZ)
+        return dA, dB, dbias, None, None, None, None
+
+
+def mask_pos(x, ref, scale=1.0):
+    """x * (ref > 0 ? scale : 0) -- relu / relu+dropout backward.  Implemented with the GEMM epilogue
+    (identity contraction is wasteful), so use the dedicated elementwise entry point instead."""
+    x, ldx = _rows(x)
+    ref, ldr = _rows(ref)
+    out = torch.empty_like(x)
+    check(lib().ercg_mask_pos(_p(x), ldx, _p(ref), ldr, float(scale), _p(out), out.stride(0), x.size(0), x.size(1), _stream()),
+          "ercg_mask_pos")
+    return out
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, a_rows=None, drop_p=0.0, seed=0):
+    """nn.Linear semantics (weight [out,in]) on 2-D row-major input."""
+    return _LinearAct.apply(x, weight.t().contiguous(), bias, act, a_rows, drop_p, seed)
+
+
+def matmul_kn(x, w_kn, bias=None, act=ACT_NONE, a_rows=None):
+    """x @ w_kn (+bias) with w_kn already [K,N]."""
+    return _LinearAct.apply(x, w_kn if w_kn.is_contiguous() else w_kn.contiguous(), bias, act, a_rows, 0.0, 0)
+
+
+# ------------------------------------------------------------------------------------------- K3 gather
+class _Gather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Y, w, bias, graph, H, R, root_off, use_types):
+        Y, ldy = _rows(Y)
+        N = Y.size(0)
+        out = torch.empty((N, H), dtype=torch.float32, device=Y.device)
+        check(lib().ercg_gather_fwd(_p(Y), ldy, _p(graph.rowptr), _p(graph.col), _p(graph.etype) if use_types else None,
+                                    _p(w), root_off, _p(bias), _p(out), H, N, H, _stream()), "ercg_gather_fwd")
+        ctx.graph, ctx.H, ctx.R, ctx.root_off, ctx.use_types = graph, H, R, root_off, use_types
+        ctx.has_bias = bias is not None
+        ctx.w_grad = w is not None and w.requires_grad
+        ctx.save_for_backward(Y if ctx.w_grad else None, w)
+        ctx.ycols = Y.size(1)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Y, w = ctx.saved_tensors
+        g, H, R = ctx.graph, ctx.H, ctx.R
+        dout, ldo = _rows(dout)
+        N = dout.size(0)
+        dY = torch.empty((N, ctx.ycols), dtype=torch.float32, device=dout.device)
+        dw = torch.empty(g.E, dtype=torch.float32, device=dout.device) if ctx.w_grad else None
+        ldy = Y.stride(0) if Y is not None else 0
+        check(lib().ercg_gather_bwd(_p(dout), ldo, _p(Y), ldy, _p(g.t_rowptr), _p(g.t_col),
+                                    _p(g.t_etype) if ctx.use_types else None, _p(g.t_eid), _p(w), R, ctx.root_off,
+                                    _p(dY), ctx.ycols, _p(dw), N, H, _stream()), "ercg_gather_bwd")
+        dbias = colsum(dout) if ctx.has_bias else None
+        return dY, dw, dbias, None, None, None, None, None
+
+
+def gather(Y, graph, H, R, w=None, bias=None, root_off=-1, use_types=True):
+    """out[k] = sum_e w[e] * Y[col[e], etype[e]*H:+H] (+ Y[k, root_off:+H]) (+ bias)."""
+    assert Y.size(1) == (R * H + (H if root_off >= 0 else 0)), (Y.shape, R, H, root_off)
+    return _Gather.apply(Y, w, bias, graph, H, R, root_off, use_types)
+
+
+# ------------------------------------------------------------------------------------------- K4 attention
+class _Attn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkvs, graph, H, scale):
+        qkvs, ld = _rows(qkvs)
+        N = qkvs.size(0)
+        out = torch.empty((N, H), dtype=torch.float32, device=qkvs.device)
+        alpha = torch.empty(graph.E, dtype=torch.float32, device=qkvs.device)
+        b = qkvs.data_ptr()
+        check(lib().ercg_attn_fwd(b, b + 4 * H, b + 8 * H, b + 12 * H, ld, _p(graph.rowptr), _p(graph.col), scale,
+                                  _p(out), H, _p(alpha), N, H, _stream()), "ercg_attn_fwd")
+        ctx.graph, ctx.H, ctx.scale = graph, H, scale
+        ctx.save_for_backward(qkvs, alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkvs, alpha = ctx.saved_tensors
+        g, H, scale = ctx.graph, ctx.H, ctx.scale
+        dout, ldo = _rows(dout)
+        N, ld = qkvs.size(0), qkvs.stride(0)
+        d = torch.empty((N, 4 * H), dtype=torch.float32, device=dout.device)
+        dsig = torch.empty(g.E, dtype=torch.float32, device=dout.device)
+        b, db = qkvs.data_ptr(), d.data_ptr()
+        check(lib().ercg_attn_bwd_dst(_p(dout), ldo, b + 4 * H, b + 8 * H, ld, _p(g.rowptr), _p(g.col), _p(alpha), scale,
+                                      db, db + 12 * H, 4 * H, _p(dsig), N, H, _stream()), "ercg_attn_bwd_dst")
+        check(lib().ercg_attn_bwd_src(_p(dout), ldo, b, ld, _p(g.t_rowptr), _p(g.t_col), _p(g.t_eid), _p(alpha), _p(dsig),
+                                      scale, db + 4 * H, db + 8 * H, 4 * H, N, H, _stream()), "ercg_attn_bwd_src")
+        return d, None, None, None
+
+
+def edge_attention(qkvs, graph, H, scale):
+    """qkvs = [q | k | v | skip] (each H wide); TransformerConv(heads=1) message+aggregate+skip."""
+    assert qkvs.size(1) == 4 * H
+    return _Attn.apply(qkvs, graph, H, float(scale))
+
+
+# ------------------------------------------------------------------------------------------- K5 EdgeAtt
+class _EdgeAtt(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, u, graph):
+        x, ldx = _rows(x)
+        u, ldu = _rows(u)
+        N, H = x.shape
+        nu = torch.empty(graph.E, dtype=torch.float32, device=x.device)
+        check(lib().ercg_edgeatt_fwd(_p(x), ldx, _p(u), ldu, _p(graph.t_rowptr), _p(graph.t_col), _p(graph.t_eid), _p(nu),
+                                     N, H, _stream()), "ercg_edgeatt_fwd")
+        ctx.graph = graph
+        ctx.save_for_backward(x, u, nu)
+        return nu
+
+    @staticmethod
+    def backward(ctx, dnu):
+        x, u, nu = ctx.saved_tensors
+        g = ctx.graph
+        N, H = x.shape
+        dnu = dnu.contiguous()
+        dsig = torch.empty_like(nu)
+        dx = torch.empty((N, H), dtype=torch.float32, device=x.device)
+        du = torch.empty((N, H), dtype=torch.float32, device=x.device)
+        check(lib().ercg_edgeatt_bwd_src(_p(dnu), _p(nu), _p(u), u.stride(0), _p(g.t_rowptr), _p(g.t_col), _p(g.t_eid),
+                                         _p(dsig), _p(dx), H, N, H, _stream()), "ercg_edgeatt_bwd_src")
+        check(lib().ercg_edgeatt_bwd_dst(_p(dsig), _p(x), x.stride(0), _p(g.rowptr), _p(g.col), _p(du), H, N, H, _stream()),
+              "ercg_edgeatt_bwd_dst")
+        return dx, du, None
+
+
+def edge_att(x, u, graph):
+    """nu[j->k] = softmax over the out-edges of j of <x_j, u_k>, in by-destination edge order."""
+    return _EdgeAtt.apply(x, u, graph)
+
+
+# ------------------------------------------------------------------------------------------- BN + LeakyReLU
+class _BnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, var, eps, slope, use_batch_stats, count, stat_sync):
+        x, ldx = _rows(x)
+        N, H = x.shape
+        out = torch.empty((N, H), dtype=torch.float32, device=x.device)
+        check(lib().ercg_bn_act_fwd(_p(x), ldx, _p(mean), _p(var), eps, _p(gamma), _p(beta), slope, _p(out), H, N, H, _stream()),
+              "ercg_bn_act_fwd")
+        ctx.eps, ctx.slope, ctx.use_batch_stats, ctx.count, ctx.stat_sync = eps, slope, use_batch_stats, count, stat_sync
+        ctx.save_for_backward(x, gamma, beta, mean, var)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, gamma, beta, mean, var = ctx.saved_tensors
+        dout, ldo = _rows(dout)
+        N, H = x.shape
+        ldx = x.stride(0)
+        sums = torch.empty(2 * H, dtype=torch.float32, device=x.device)
+        ws = _ws(lib().ercg_bn_workspace_bytes(N, H), x.device)
+        check(lib().ercg_bn_act_bwd_reduce(_p(dout), ldo, _p(x), ldx, _p(mean), _p(var), ctx.eps, _p(gamma), _p(beta), ctx.slope,
+                                           _p(sums), N, H, _p(ws), ws.numel(), _stream()), "ercg_bn_act_bwd_reduce")
+        local = sums
+        if ctx.stat_sync is not None and ctx.use_batch_stats:
+            sums = ctx.stat_sync(sums.clone())         # all-reduce(sum) of (sum dy, sum dy*xhat) across ranks
+        dx = torch.empty((N, H), dtype=torch.float32, device=x.device)
+        check(lib().ercg_bn_act_bwd_apply(_p(dout), ldo, _p(x), ldx, _p(mean), _p(var), ctx.eps, _p(gamma), _p(beta), ctx.slope,
+                                          _p(sums), float(ctx.count), 1 if ctx.use_batch_stats else 0, _p(dx), H, N, H,
+                                          _stream()), "ercg_bn_act_bwd_apply")
+        return dx, local[H:], local[:H], None, None, None, None, None, None, None
+
+
+def bn_stats(x):
+    """(mean[H], biased var[H]) over the rows of x."""
+    x, ldx = _rows(x)
+    N, H = x.shape
+    mean = torch.empty(H, dtype=torch.float32, device=x.device)
+    var = torch.empty(H, dtype=torch.float32, device=x.device)
+    ws = _ws(lib().ercg_bn_workspace_bytes(N, H), x.device)
+    check(lib().ercg_bn_stats(_p(x), ldx, N, H, _p(mean), _p(var), _p(ws), ws.numel(), _stream()), "ercg_bn_stats")
+    return mean, var
+
+
+def bn_leaky_relu(x, gamma, beta, mean, var, eps, slope, use_batch_stats, count=None, stat_sync=None):
+    return _BnAct.apply(x, gamma, beta, mean, var, float(eps), float(slope), bool(use_batch_stats),
+                        float(count if count is not None else x.size(0)), stat_sync)
+
+
+# ------------------------------------------------------------------------------------------- cross entropy
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, class_weight, reduce_sync):
+        logits, ld = _rows(logits)
+        N, C = logits.shape
+        nd = torch.empty(2, dtype=torch.float32, device=logits.device)
+        dl = torch.empty((N, C), dtype=torch.float32, device=logits.device)
+        ws = _ws(lib().ercg_ce_workspace_bytes(N), logits.device)
+        check(lib().ercg_ce_fwd(_p(logits), ld, _p(labels), _p(class_weight), _p(nd), _p(dl), C, N, C, _p(ws), ws.numel(),
+                                _stream()), "ercg_ce_fwd")
+        if reduce_sync is not None:
+            nd = reduce_sync(nd)                       # global numerator / denominator across ranks
+        ctx.save_for_backward(dl, nd)
+        return nd[0] / nd[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        dl, nd = ctx.saved_tensors
+        out = dl.clone()
+        g = g.contiguous().reshape(1)
+        check(lib().ercg_scale_by_ratio(_p(out), out.numel(), _p(g), nd.data_ptr() + 4, _stream()), "ercg_scale_by_ratio")
+        return out, None, None, None
+
+
+def cross_entropy(logits, labels, class_weight=None, reduce_sync=None):
+    """F.cross_entropy(logits, labels, weight=class_weight) with mean reduction."""
+    assert labels.dtype == torch.int64 and labels.is_cuda
+    return _CrossEntropy.apply(logits, labels.contiguous(), class_weight, reduce_sync)
+
+
+# ------------------------------------------------------------------------------------------- pack rows
+class _PackRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, padded, graph, seq_first):
+        shape = padded.shape
+        D = shape[-1]
+        flat = padded.reshape(-1, D)
+        flat, ld = _rows(flat)
+        B = graph.B
+        Lmax = shape[0] if seq_first else shape[1]
+        out = torch.empty((graph.N, D), dtype=torch.float32, device=padded.device)
+        check(lib().ercg_pack_rows(_p(flat), ld, Lmax, B, 1 if seq_first else 0, _p(graph.node_off), _p(graph.node_dlg),
+                                   _p(out), D, graph.N, D, _stream()), "ercg_pack_rows")
+        ctx.graph, ctx.seq_first, ctx.shape, ctx.Lmax = graph, seq_first, shape, Lmax
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g = ctx.graph
+        dout, ldp = _rows(dout)
+        D = ctx.shape[-1]
+        dpad = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
+        check(lib().ercg_unpack_rows(_p(dout), ldp, _p(g.node_off), _p(g.node_dlg), _p(dpad), D, ctx.Lmax, g.B,
+                                     1 if ctx.seq_first else 0, g.N, D, _stream()), "ercg_unpack_rows")
+        return dpad, None, None
+
+
+def pack_rows(padded, graph, seq_first=False):
+    """[B,Lmax,D] (or [Lmax,B,D] when seq_first) -> packed [N,D], dialogue-major."""
+    return _PackRows.apply(padded, graph, seq_first)

@@ -1,0 +1,232 @@
+/*
+ * ercgraph.h -- C ABI of libercgraph.so: the B200 (sm_100a) conversation-graph hot path of
+ * sailist/emotion-recognition-in-conversation (track_mm COGMEN / DialogueGCN / MMGCN / DAG-ERC).
+ *
+ * The reference has NO FFI / plugin registry: its boundary is "Python imports a function and calls
+ * it with torch tensors" (SURVEY.md section 8b).  This header is therefore the boundary a binding
+ * would use: every entry point takes raw DEVICE pointers + sizes + a CUDA stream (as void*), never
+ * allocates, never synchronises, keeps no global state, launches on the stream it is given and
+ * returns 0 or a negative ERCG_E* code (text via ercg_strerror).  Outputs and workspaces are
+ * caller-allocated; the companion *_workspace_bytes functions say how much.
+ *
+ * Each entry point cites the reference code (path:line under the reference tree) it replaces.
+ * Graph convention everywhere (track_mm/cogmen_utils.py:125-140, models/rgcn.py:133,158):
+ *   edge (j -> k): j = source = edge_index[0], k = destination = edge_index[1]; messages are
+ *   aggregated at k.  "CSR" = by destination (rowptr/col/etype), "transpose" = by source
+ *   (t_rowptr/t_col/t_etype/t_eid, t_eid = position of that edge in the by-destination order).
+ * All feature matrices are row-major fp32 with an explicit leading dimension in ELEMENTS.
+ */
+#ifndef ERCGRAPH_H_
+#define ERCGRAPH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden: only this header is exported */
+#endif
+
+#define ERCG_OK 0
+#define ERCG_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported combination) */
+#define ERCG_EALIGN (-2)   /* pointer / leading dimension not aligned as the kernel requires */
+#define ERCG_ERANGE (-3)   /* size exceeds what the packed int32/uint8 formats can hold */
+#define ERCG_ECUDA (-4)    /* CUDA runtime reported an error at launch (cudaGetLastError) */
+#define ERCG_EWORKSPACE (-5) /* workspace too small */
+
+#define ERCG_ACT_NONE 0
+#define ERCG_ACT_RELU 1
+#define ERCG_ACT_RELU_DROPOUT 2   /* relu then inverted dropout (mask from a counter hash of seed,row,col) */
+#define ERCG_ACT_MASK_POS 3       /* C = (A@B) * (aux[m,n] > 0 ? aux_scale : 0): relu/dropout backward */
+
+const char* ercg_strerror(int code);
+int ercg_version(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+unsigned long long ercg_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  batch_graphify: window edges + speaker-pair/direction relation typing as ONE integer kernel
+ * emitting a packed CSR (and its by-source transpose) over the whole batch of dialogues.
+ * Replaces edge_perms (track_mm/cogmen_utils.py:147-172 = dgcn_models.py:95-118) and the per-edge
+ * python loop of batch_graphify (cogmen_utils.py:109-144, dgcn_models.py:51-92).
+ *   edges of dialogue d (length L): (j -> k) for max(0,j-wp) <= k <= min(L-1,j+wf); wp/wf = -1 unbounded
+ *   type(j -> k) = ((spk_j * n_speakers + spk_k) * 2) + (j >= k)         (cogmen.py:124-129)
+ * Canonical edge order = ascending dialogue, then destination k, then source j.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Host-side closed form: N = sum L, E = sum |E_d|.  lengths_host is a HOST array. */
+int ercg_graphify_sizes_host(const int64_t* lengths_host, int B, int wp, int wf, int64_t* N_out, int64_t* E_out);
+
+/* Device-side totals when lengths live on the GPU: totals_dev[0]=N, totals_dev[1]=E. */
+int ercg_graphify_count(const void* lengths_dev, int lengths_is_i64, int B, int wp, int wf,
+                        int64_t* totals_dev, void* stream);
+
+size_t ercg_graphify_workspace_bytes(int B);
+
+typedef struct ercg_graph_out {
+  /* required (device) */
+  int32_t* node_off;   /* [B+1] first node of each dialogue */
+  int32_t* edge_off;   /* [B+1] first edge of each dialogue */
+  int32_t* rowptr;     /* [N+1] CSR by destination */
+  int32_t* col;        /* [E]   source node of each edge */
+  uint8_t* etype;      /* [E]   relation id */
+  int32_t* t_rowptr;   /* [N+1] by source */
+  int32_t* t_col;      /* [E]   destination node */
+  uint8_t* t_etype;    /* [E] */
+  int32_t* t_eid;      /* [E]   index of the same edge in by-destination order */
+  int32_t* spk;        /* [N]   packed speaker ids */
+  int32_t* node_dlg;   /* [N]   dialogue of each node */
+  /* optional (may be NULL) */
+  float* inv_cnt;      /* [E]   1/|{e' : dst(e')=dst(e), type(e')=type(e)}| -- PyG RGCNConv aggr='mean' weight */
+  int64_t* edge_index; /* [2,E] reference layout (row0 = j, row1 = k), cogmen_utils.py:140 */
+  int64_t* edge_type;  /* [E]   cogmen_utils.py:141 */
+  int64_t* edge_index_lengths; /* [B] cogmen_utils.py:142 */
+  int64_t* totals;     /* [2]   N, E as computed on the device (for validation) */
+  int32_t* pad_row;    /* [N]   d*spk_ld + k: row of the node in a padded [B,spk_ld,*] tensor (node id if spk_ld=0) */
+} ercg_graph_out;
+
+/* speakers: padded [B, spk_ld] when spk_ld > 0 (reference layout), packed [N] when spk_ld == 0. */
+int ercg_graphify_csr(const void* lengths_dev, int lengths_is_i64, int B,
+                      const void* speakers_dev, int speakers_is_i64, int64_t spk_ld,
+                      int wp, int wf, int n_speakers, int64_t N, int64_t E,
+                      const ercg_graph_out* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* padded [B,Lmax,D] (row stride ld) -> packed [N,D]: the torch.cat of cogmen_utils.py:123,139 and
+ * simple_batch_graphify (track_mm/mmgcn_utils.py:5-21, seq_first=1 for its [L,B,D] layout). */
+int ercg_pack_rows(const float* padded, int64_t ld, int64_t Lmax, int B, int seq_first,
+                   const int32_t* node_off, const int32_t* node_dlg, float* packed, int64_t ldp,
+                   int64_t N, int D, void* stream);
+/* backward of the above: scatter packed gradients into a zero-initialised padded tensor */
+int ercg_unpack_rows(const float* packed, int64_t ldp, const int32_t* node_off, const int32_t* node_dlg,
+                     float* padded, int64_t ld, int64_t Lmax, int B, int seq_first, int64_t N, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  dense feature transforms.  C[M,N] = act(A[M,K] @ B[K,N] + bias[N]).
+ * Replaces nn.Linear (cogmen.py:103-105,116-122), the per-relation weights of PyG RGCNConv
+ * (cogmen.py:65) / vendored RGCNConv.message (models/rgcn.py:329-343) as one GEMM against the
+ * concatenated [K,(R+1)*out] matrix, and the four Linears of TransformerConv (cogmen.py:66).
+ * a_rows (optional): row m of the product reads A row a_rows[m] (fused padded->packed gather).
+ * act = ERCG_ACT_*; aux/ldaux/aux_scale used by RELU_DROPOUT (aux_scale = keep prob handled via
+ * drop_p) and MASK_POS.  fp32 in, fp32 accumulate, fp32 out.
+ * ------------------------------------------------------------------------------------------- */
+int ercg_gemm_nn(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb,
+                 const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int act,
+                 const float* aux, int64_t ldaux, float aux_scale, float drop_p, uint64_t seed, void* stream);
+
+/* C[K1,N1] = A[M,K1]^T @ B[M,N1]  (weight gradients; contraction over the M utterance rows, split
+ * across CTAs into fixed slabs and reduced in a fixed order => bit-reproducible). */
+size_t ercg_gemm_tn_workspace_bytes(int64_t M, int K1, int N1);
+int ercg_gemm_tn(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb,
+                 float* C, int64_t ldc, int64_t M, int K1, int N1,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* out = ref > 0 ? x * scale : 0  -- backward of ReLU / ReLU+inverted-dropout given the forward OUTPUT
+ * (cls of cogmen.py:116-122, Classifier of dgcn_models.py:163-170). */
+int ercg_mask_pos(const float* x, int64_t ldx, const float* ref, int64_t ldr, float scale,
+                  float* out, int64_t ldo, int64_t M, int N, void* stream);
+
+/* out[n] = sum_m A[m,n]  (bias gradients), fixed-order two-level reduction */
+size_t ercg_colsum_workspace_bytes(int64_t M, int N);
+int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float* out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  deterministic warp-segmented gather-reduce over the CSR (no atomics).
+ *   out[k,:] = sum_{e in row k} w[e] * Y[col[e], etype[e]*H : +H]  (+ Y[k, root_off : +H]) (+ bias)
+ * w == NULL -> 1, etype == NULL -> slot 0, root_off < 0 -> no root term, bias == NULL -> none.
+ * Replaces MessagePassing.propagate + scatter_add of models/rgcn.py:188-221,15-46 (w = edge_norm),
+ * PyG RGCNConv's per-relation mean (w = inv_cnt), and GraphConv's neighbour sum (dgcn_models.py:42,46).
+ * Backward (by-source traversal):
+ *   dY[j, r*H:+H] = sum_{e in out(j), type r} w[e] * dout[dst e]   for r in [0,R)   (all slots written)
+ *   dY[j, root_off:+H] = dout[j]                                     (if root_off >= 0)
+ *   dw[eid] = <dout[dst e], Y[src e, type e]>                        (if dw != NULL; needs Y)
+ * ------------------------------------------------------------------------------------------- */
+int ercg_gather_fwd(const float* Y, int64_t ldy, const int32_t* rowptr, const int32_t* col,
+                    const uint8_t* etype, const float* w, int root_off, const float* bias,
+                    float* out, int64_t ldo, int64_t N, int H, void* stream);
+int ercg_gather_bwd(const float* dout, int64_t ldo, const float* Y, int64_t ldy,
+                    const int32_t* t_rowptr, const int32_t* t_col, const uint8_t* t_etype,
+                    const int32_t* t_eid, const float* w, int R, int root_off,
+                    float* dY, int64_t lddy, float* dw, int64_t N, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  fused edge attention of PyG TransformerConv(heads=1) (cogmen.py:66,72): score, segment
+ * softmax over the in-edges of each destination (max-subtracted, denominator + 1e-16), weighted
+ * aggregate of v, plus the skip row:  out[i] = sum_j alpha[j->i] v[j] + s[i].
+ * alpha[E] (by-destination order) is saved for the backward.  q,k,v,s share one leading dimension.
+ * ------------------------------------------------------------------------------------------- */
+int ercg_attn_fwd(const float* q, const float* k, const float* v, const float* s, int64_t ld,
+                  const int32_t* rowptr, const int32_t* col, float scale,
+                  float* out, int64_t ldo, float* alpha, int64_t N, int H, void* stream);
+/* by-destination half: dq[i], ds[i] = dout[i], dsig[e] = alpha_e (dalpha_e - sum alpha dalpha) */
+int ercg_attn_bwd_dst(const float* dout, int64_t ldo, const float* k, const float* v, int64_t ld,
+                      const int32_t* rowptr, const int32_t* col, const float* alpha, float scale,
+                      float* dq, float* ds, int64_t ldd, float* dsig, int64_t N, int H, void* stream);
+/* by-source half: dk[j] = scale * sum_i dsig q[i], dv[j] = sum_i alpha dout[i] */
+int ercg_attn_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld,
+                      const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
+                      const float* alpha, const float* dsig, float scale,
+                      float* dk, float* dv, int64_t ldd, int64_t N, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  EdgeAtt of DialogueGCN (dgcn_models.py:121-152): per-SOURCE window softmax
+ *   nu[j->k] = softmax_{k in out(j)} <x_j, u_k>,  u = x @ W^T  (u computed by ercg_gemm_nn)
+ * written in by-destination edge order (nu[t_eid]).  Backward: dsig per edge, dx_j += sum dsig u_k
+ * (by source), du_k = sum_j dsig x_j (by destination).
+ * ------------------------------------------------------------------------------------------- */
+int ercg_edgeatt_fwd(const float* x, int64_t ldx, const float* u, int64_t ldu,
+                     const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
+                     float* nu, int64_t N, int H, void* stream);
+int ercg_edgeatt_bwd_src(const float* dnu, const float* nu, const float* u, int64_t ldu,
+                         const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
+                         float* dsig, float* dx, int64_t lddx, int64_t N, int H, void* stream);
+int ercg_edgeatt_bwd_dst(const float* dsig, const float* x, int64_t ldx,
+                         const int32_t* rowptr, const int32_t* col,
+                         float* du, int64_t lddu, int64_t N, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm1d (training statistics) + LeakyReLU of GNN.forward (cogmen.py:67-68,72).
+ * stats: mean[H], var[H] (biased) over the N rows, fixed-order reduction.
+ * ------------------------------------------------------------------------------------------- */
+size_t ercg_bn_workspace_bytes(int64_t N, int H);
+int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, float* mean, float* var,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int ercg_bn_act_fwd(const float* x, int64_t ldx, const float* mean, const float* var, float eps,
+                    const float* gamma, const float* beta, float slope,
+                    float* out, int64_t ldo, int64_t N, int H, void* stream);
+/* backward with batch statistics (train) or with fixed statistics (eval, use_batch_stats = 0).
+ * dgamma[H], dbeta[H], dx[N,H].  count = number of rows the statistics were taken over (N, or the
+ * global count when the statistics were all-reduced across ranks; sums[2H] then holds the
+ * all-reduced (sum dy, sum dy*xhat) produced by ercg_bn_act_bwd_reduce). */
+int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const float* x, int64_t ldx,
+                           const float* mean, const float* var, float eps,
+                           const float* gamma, const float* beta, float slope,
+                           float* sums /* [2H]: sum dy, sum dy*xhat */, int64_t N, int H,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int ercg_bn_act_bwd_apply(const float* dout, int64_t ldo, const float* x, int64_t ldx,
+                          const float* mean, const float* var, float eps,
+                          const float* gamma, const float* beta, float slope,
+                          const float* sums, double count, int use_batch_stats,
+                          float* dx, int64_t lddx, int64_t N, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (class-weighted) cross entropy, mean reduction (F.cross_entropy at cogmen.py:185, dgcn.py:124).
+ * fwd writes lossnum_den[0] = sum_i w[y_i] * nll_i, lossnum_den[1] = sum_i w[y_i] and the
+ * un-normalised dlogits[i,c] = w[y_i] (softmax_ic - [c == y_i]).  The caller divides (possibly after an
+ * all-reduce of lossnum_den across ranks); ercg_scale_by_ratio applies  x *= g[0] / den[0].
+ * ------------------------------------------------------------------------------------------- */
+size_t ercg_ce_workspace_bytes(int64_t N);
+int ercg_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, const float* class_weight,
+                float* lossnum_den, float* dlogits, int64_t ldd, int64_t N, int C,
+                void* workspace, size_t workspace_bytes, void* stream);
+int ercg_scale_by_ratio(float* x, int64_t n, const float* num, const float* den, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERCGRAPH_H_ */

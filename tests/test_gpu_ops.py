@@ -1,0 +1,237 @@
+"""Kernel-level parity: every libercgraph op against a plain fp32/fp64 PyTorch CPU expression."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import graph_np
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _graph(lengths, n=2, wp=5, wf=5, seed=0):
+    import erc_b200
+    from erc_b200.graph import build_graph
+    rng = np.random.default_rng(seed)
+    lengths = np.asarray(lengths)
+    spk = rng.integers(0, n, size=int(lengths.sum()))
+    g = build_graph(torch.as_tensor(lengths, dtype=torch.int64), torch.as_tensor(spk).cuda(), wp, wf, n)
+    return g, graph_np.batch_graphify_np(lengths, spk, wp, wf, n)
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 1, 1), (37, 100, 100), (300, 1380, 100), (257, 1443, 100), (130, 100, 900),
+                                   (64, 900, 100), (129, 100, 6), (200, 6, 100), (513, 200, 131)])
+def test_gemm_nn_tn_colsum(M, K, N):
+    import erc_b200
+    from erc_b200 import ops
+    g = torch.Generator().manual_seed(M * 7 + K)
+    A, B, bias = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g), torch.randn(N, generator=g)
+    want = A.double() @ B.double() + bias.double()
+    got = ops.gemm_nn(A.cuda(), B.cuda(), bias.cuda())
+    assert rel_err(got, want) < TOL
+    got = ops.gemm_nn(A.cuda(), B.cuda(), bias.cuda(), act=ops.ACT_RELU)
+    assert rel_err(got, want.clamp(min=0)) < TOL
+    dC = torch.randn(M, N, generator=g)
+    assert rel_err(ops.gemm_tn(A.cuda(), dC.cuda()), A.double().t() @ dC.double()) < TOL
+    assert rel_err(ops.colsum(dC.cuda()), dC.double().sum(0)) < TOL
+    aux = torch.randn(M, N, generator=g)
+    assert rel_err(ops.mask_pos(dC.cuda(), aux.cuda(), 2.0), torch.where(aux > 0, dC * 2.0, torch.zeros(()))) < 1e-7
+
+
+def test_gemm_row_gather_and_unaligned_lda():
+    import erc_b200
+    from erc_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(500, 1443, generator=g)               # 1443 floats per row: rows are not 16-byte aligned
+    B = torch.randn(1443, 100, generator=g)
+    rows = torch.randint(0, 500, (333,), generator=g).int()
+    want = A[rows.long()].double() @ B.double()
+    got = ops.gemm_nn(A.cuda(), B.cuda(), a_rows=rows.cuda())
+    assert rel_err(got, want) < TOL
+    dC = torch.randn(333, 100, generator=g)
+    got = ops.gemm_tn(A.cuda(), dC.cuda(), a_rows=rows.cuda(), M=333)
+    assert rel_err(got, A[rows.long()].double().t() @ dC.double()) < TOL
+
+
+def test_gemm_large_split_reduction_is_deterministic():
+    import erc_b200
+    from erc_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    A, dC = torch.randn(40_000, 200, generator=g).cuda(), torch.randn(40_000, 100, generator=g).cuda()
+    r1, r2 = ops.gemm_tn(A, dC), ops.gemm_tn(A, dC)
+    assert torch.equal(r1, r2)
+    assert rel_err(r1, A.double().cpu().t() @ dC.double().cpu()) < TOL
+
+
+def test_dropout_epilogue_statistics_and_backward():
+    import erc_b200
+    from erc_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4096, 100, generator=g).cuda().requires_grad_()
+    w = torch.randn(100, 100, generator=g).cuda().requires_grad_()
+    h = ops.linear(x, w, None, act=ops.ACT_RELU_DROPOUT, drop_p=0.5, seed=1234)
+    ref = torch.relu(x.detach() @ w.detach().t())
+    kept = h != 0
+    frac = float(kept.sum()) / float((ref > 0).sum())
+    assert 0.48 < frac < 0.52
+    assert rel_err(h[kept], (ref * 2.0)[kept]) < TOL
+    h2 = ops.linear(x, w, None, act=ops.ACT_RELU_DROPOUT, drop_p=0.5, seed=1234)
+    assert torch.equal(h, h2)                               # same seed => same mask
+    h.sum().backward()
+    mask = kept.float() * 2.0
+    assert rel_err(x.grad, mask @ w.detach()) < TOL
+    assert rel_err(w.grad, mask.t() @ x.detach()) < TOL
+
+
+@pytest.mark.parametrize("H,R,wp,wf", [(100, 8, 5, 5), (100, 8, 10, 10), (200, 8, 10, 10), (100, 2, -1, -1)])
+def test_gather_fwd_bwd(H, R, wp, wf):
+    import erc_b200
+    from erc_b200 import ops
+    n = 2 if R == 8 else 1
+    g, b = _graph([7, 1, 23, 60, 4], n=n, wp=wp, wf=wf)
+    N, E = b["N"], b["E"]
+    gen = torch.Generator().manual_seed(H + R)
+    Y = torch.randn(N, (R + 1) * H, generator=gen)
+    w = torch.rand(E, generator=gen) + 0.1
+    bias = torch.randn(H, generator=gen)
+    src, dst, et = (torch.from_numpy(b[k]).long() for k in ("col", "edge_index", "etype"))
+    dst = dst[1]
+    Yd, wd = Y.double().requires_grad_(), w.double().requires_grad_()
+    msg = Yd.view(N, R + 1, H)[src, et] * wd[:, None]
+    want = torch.zeros(N, H, dtype=torch.float64).index_add(0, dst, msg) + Yd[:, R * H:] + bias.double()
+    dout = torch.randn(N, H, generator=gen)
+    want.backward(dout.double())
+    Yc, wc, bc = Y.cuda().requires_grad_(), w.cuda().requires_grad_(), bias.cuda().requires_grad_()
+    got = ops.gather(Yc, g, H, R, w=wc, bias=bc, root_off=R * H)
+    got.backward(dout.cuda())
+    assert rel_err(got, want) < TOL
+    assert rel_err(Yc.grad, Yd.grad) < TOL
+    assert rel_err(wc.grad, wd.grad) < TOL
+    assert rel_err(bc.grad, dout.double().sum(0)) < TOL
+
+
+@pytest.mark.parametrize("wp,wf", [(5, 5), (-1, -1), (2, 40)])
+def test_edge_attention_fwd_bwd(wp, wf):
+    import erc_b200
+    from erc_b200 import ops
+    H = 100
+    g, b = _graph([9, 1, 50, 75, 3], wp=wp, wf=wf, seed=2)     # wp=wf=-1 gives rows longer than 32 edges
+    N = b["N"]
+    gen = torch.Generator().manual_seed(11)
+    qkvs = torch.randn(N, 4 * H, generator=gen)
+    src, dst = torch.from_numpy(b["edge_index"][0]), torch.from_numpy(b["edge_index"][1])
+    x = qkvs.double().requires_grad_()
+    q, k, v, s = x[:, :H], x[:, H:2 * H], x[:, 2 * H:3 * H], x[:, 3 * H:]
+    sc = (q[dst] * k[src]).sum(-1) / math.sqrt(H)
+    mx = torch.full((N,), -1e300, dtype=torch.float64).scatter_reduce(0, dst, sc, reduce="amax")
+    ex = (sc - mx[dst]).exp()
+    alpha = ex / (torch.zeros(N, dtype=torch.float64).index_add(0, dst, ex) + 1e-16)[dst]
+    want = torch.zeros(N, H, dtype=torch.float64).index_add(0, dst, alpha[:, None] * v[src]) + s
+    dout = torch.randn(N, H, generator=gen)
+    want.backward(dout.double())
+    xc = qkvs.cuda().requires_grad_()
+    got = ops.edge_attention(xc, g, H, 1.0 / math.sqrt(H))
+    got.backward(dout.cuda())
+    assert rel_err(got, want) < TOL
+    assert rel_err(xc.grad, x.grad) < TOL
+
+
+def test_edge_att_source_softmax_fwd_bwd():
+    import erc_b200
+    from erc_b200 import ops
+    H = 200
+    g, b = _graph([12, 1, 40, 110], wp=10, wf=10, seed=3)
+    N, E = b["N"], b["E"]
+    gen = torch.Generator().manual_seed(13)
+    x, u = torch.randn(N, H, generator=gen) * 0.3, torch.randn(N, H, generator=gen) * 0.3
+    src, dst = torch.from_numpy(b["edge_index"][0]), torch.from_numpy(b["edge_index"][1])
+    xd, ud = x.double().requires_grad_(), u.double().requires_grad_()
+    sc = (xd[src] * ud[dst]).sum(-1)
+    mx = torch.full((N,), -1e300, dtype=torch.float64).scatter_reduce(0, src, sc, reduce="amax")
+    ex = (sc - mx[src]).exp()
+    want = ex / torch.zeros(N, dtype=torch.float64).index_add(0, src, ex)[src]
+    dnu = torch.randn(E, generator=gen)
+    want.backward(dnu.double())
+    xc, uc = x.cuda().requires_grad_(), u.cuda().requires_grad_()
+    got = ops.edge_att(xc, uc, g)
+    got.backward(dnu.cuda())
+    assert rel_err(got, want) < TOL
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(uc.grad, ud.grad) < TOL
+
+
+@pytest.mark.parametrize("N", [1, 5, 1023, 5000])
+def test_bn_leaky_relu_fwd_bwd(N):
+    import erc_b200
+    from erc_b200 import ops
+    H = 100
+    gen = torch.Generator().manual_seed(N)
+    x = torch.randn(N, H, generator=gen) * 2 + 0.5
+    gamma, beta = torch.rand(H, generator=gen) + 0.5, torch.randn(H, generator=gen)
+    xd, gd, bd = x.double().requires_grad_(), gamma.double().requires_grad_(), beta.double().requires_grad_()
+    mean, var = xd.mean(0), xd.var(0, unbiased=False)
+    want = torch.nn.functional.leaky_relu((xd - mean) / (var + 1e-5).sqrt() * gd + bd, 0.01)
+    dout = torch.randn(N, H, generator=gen)
+    want.backward(dout.double())
+    xc, gc, bc = x.cuda().requires_grad_(), gamma.cuda().requires_grad_(), beta.cuda().requires_grad_()
+    m, v = ops.bn_stats(xc.detach())
+    assert rel_err(m, mean.detach()) < TOL and rel_err(v, var.detach(), floor=1e-12) < TOL
+    got = ops.bn_leaky_relu(xc, gc, bc, m, v, 1e-5, 0.01, True)
+    got.backward(dout.cuda())
+    assert rel_err(got, want) < TOL
+    scale = float(xd.grad.abs().max())
+    assert rel_err(xc.grad, xd.grad, floor=max(scale, 1e-3)) < 5 * TOL     # N=1: dx is exactly 0
+    assert rel_err(gc.grad, gd.grad, floor=1e-3) < TOL and rel_err(bc.grad, bd.grad) < TOL
+
+
+@pytest.mark.parametrize("C,weighted", [(4, False), (6, True), (1, False), (7, True)])
+def test_cross_entropy(C, weighted):
+    import erc_b200
+    from erc_b200 import ops
+    gen = torch.Generator().manual_seed(C)
+    N = 777
+    z = torch.randn(N, C, generator=gen) * 3
+    y = torch.randint(0, C, (N,), generator=gen)
+    w = torch.rand(C, generator=gen) + 0.2 if weighted else None
+    zd = z.double().requires_grad_()
+    want = torch.nn.functional.cross_entropy(zd, y, weight=None if w is None else w.double())
+    (want * 1.7).backward()
+    zc = z.cuda().requires_grad_()
+    got = ops.cross_entropy(zc, y.cuda(), None if w is None else w.cuda())
+    (got * 1.7).backward()
+    assert abs(float(got) - float(want)) < TOL * max(abs(float(want)), 1e-3)
+    assert rel_err(zc.grad, zd.grad, floor=1e-8) < TOL
+
+
+def test_pack_rows_roundtrip():
+    import erc_b200
+    from erc_b200 import ops
+    g, b = _graph([5, 1, 9])
+    gen = torch.Generator().manual_seed(1)
+    for seq_first in (False, True):
+        shape = (9, 3, 8) if seq_first else (3, 9, 8)
+        pad = torch.randn(*shape, generator=gen).cuda().requires_grad_()
+        got = ops.pack_rows(pad, g, seq_first)
+        p = pad.detach().cpu()
+        want = torch.cat([(p[:L, i] if seq_first else p[i, :L]) for i, L in enumerate([5, 1, 9])])
+        assert torch.equal(got.cpu(), want)
+        got.sum().backward()
+        mask = torch.zeros(shape)
+        for i, L in enumerate([5, 1, 9]):
+            if seq_first:
+                mask[:L, i] = 1
+            else:
+                mask[i, :L] = 1
+        assert torch.equal(pad.grad.cpu(), mask)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    import erc_b200
+    from erc_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libercgraph.so")
+    with pytest.raises(_lib.ErcgError):
+        _lib.lib()
