@@ -27,10 +27,12 @@ col_partials_kernel(const float* __restrict__ x, long long ldx, const float* __r
     if (c < H) {
       float mu = 0.f, istd = 0.f, g = 0.f, b = 0.f;
       if (MODE == 1) { mu = mean[c]; istd = (1.0f / sqrtf(var[c] + eps)); g = gamma[c]; b = beta[c]; }
+      const float shift = MODE == 0 ? x[c] : 0.f;   // row 0 as a per-column shift: kills the E[x^2]-E[x]^2 cancellation
       for (long long r = rbeg + ty; r < rend; r += 8) {
         const float xv = x[r * ldx + c];
         if (MODE == 0) {
-          s0 += xv; s1 = fmaf(xv, xv, s1);
+          const float xs = xv - shift;
+          s0 += xs; s1 = fmaf(xs, xs, s1);
         } else {
           const float xh = (xv - mu) * istd;
           const float z = fmaf(g, xh, b);
@@ -53,15 +55,15 @@ col_partials_kernel(const float* __restrict__ x, long long ldx, const float* __r
 }
 
 __global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nb, int H, long long N,
-                                      float* __restrict__ mean, float* __restrict__ var) {
+                                      const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= H) return;
   double s0 = 0.0, s1 = 0.0;
   for (int b = 0; b < nb; ++b) { s0 += (double)partial[(long long)b * 2 * H + c]; s1 += (double)partial[(long long)b * 2 * H + H + c]; }
-  const double m = s0 / (double)N;
+  const double m = s0 / (double)N;          // mean of (x - shift)
   double v = s1 / (double)N - m * m;
   if (v < 0.0) v = 0.0;
-  mean[c] = (float)m; var[c] = (float)v;
+  mean[c] = (float)(m + (double)x[c]); var[c] = (float)v;
 }
 
 __global__ void sums_final_kernel(const float* __restrict__ partial, int nb, int H, float* __restrict__ sums) {
@@ -201,7 +203,7 @@ extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, floa
   col_partials_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
   int rc = finish_launch();
   if (rc) return rc;
-  bn_stats_final_kernel<<<(H + 127) / 128, 128, 0, st>>>(part, nb, H, N, mean, var);
+  bn_stats_final_kernel<<<(H + 127) / 128, 128, 0, st>>>(part, nb, H, N, x, mean, var);
   return finish_launch();
 }
 

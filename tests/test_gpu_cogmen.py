@@ -20,7 +20,7 @@ def _run_ours(m, x, spk, lens, y, class_weight=None):
     loss.backward()
     torch.cuda.synchronize()
     grads = {k: p.grad.cpu().numpy() for k, p in m.named_parameters() if p.grad is not None}
-    return logits.detach().cpu(), feats.detach().cpu(), float(loss), grads
+    return logits.detach().cpu(), feats.detach().cpu(), float(loss.detach()), grads
 
 
 def test_cogmen_vs_reference_fixture(golden):

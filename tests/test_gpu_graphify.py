@@ -50,7 +50,7 @@ def test_reference_fixture_cases(golden):
 @pytest.mark.parametrize("wp,wf,n", [(5, 5, 2), (10, 10, 2), (0, 0, 1), (-1, -1, 2), (-1, 3, 3), (4, -1, 9), (2, 7, 2),
                                       (200, 200, 2)])
 def test_random_batches(wp, wf, n):
-    rng = np.random.default_rng(wp * 100 + wf * 10 + n)
+    rng = np.random.default_rng((wp + 1) * 1000 + (wf + 1) * 10 + n)
     for B in (1, 2, 33, 300):
         lengths = rng.integers(1, 111, size=B)
         lengths[rng.integers(0, B)] = 1

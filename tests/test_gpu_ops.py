@@ -202,7 +202,7 @@ def test_cross_entropy(C, weighted):
     zc = z.cuda().requires_grad_()
     got = ops.cross_entropy(zc, y.cuda(), None if w is None else w.cuda())
     (got * 1.7).backward()
-    assert abs(float(got) - float(want)) < TOL * max(abs(float(want)), 1e-3)
+    assert abs(float(got.detach()) - float(want.detach())) < TOL * max(abs(float(want.detach())), 1e-3)
     assert rel_err(zc.grad, zd.grad, floor=1e-8) < TOL
 
 
