@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- COGMEN fwd+bwd utterances/sec on the BASELINE.json config-5 workload.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (libercgraph kernels)
+  python bench.py --impl reference --gpus N ...            the reference's CPU path (oracle port), rank 0 only
+
+Workload ("config.workload"): COGMEN train step (graphify + forward + cross entropy + backward + gradient
+all-reduce + Adam) on ~2^20 synthetic MOSEI-shaped utterances (hidden_all = 768+640+35 = 1443, one speaker id,
+dialogue lengths 1+Geometric(1/7) clipped to 40, 6 classes), whole dialogues sharded across the N GPUs
+(strong scaling: the total is fixed).  One "step" = one pass over all ~2^20 utterances as ONE batch per GPU.
+``value`` = utterances / second with inputs resident in HBM; ``e2e`` = the same step fed from pinned HOST
+buffers (H2D of the inputs and D2H of the loss inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "COGMEN fwd+bwd utterances/sec"
+UNIT = "utterances/s"
+HIDDEN = 1443
+N_CLASSES = 6
+WORKLOAD = "cogmen-train-step mosei-emo-sbert-fbank-6 shape (hidden_all=1443, 1 speaker id, window 5/5), ~2^20 utterances/step sharded by dialogue"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for n, v in zip(names, s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_rate(budget_s, steps=None, warmup=1, batch_dialogues=32, skip_dead_encoder=False, seed=0):
+    """Times the reference's CPU COGMEN train step (oracle/ref_port.py, "port") on MOSEI-shaped batches of 32
+    dialogues (the reference's batch size, cogmen.py:43-45).  Returns (utt/s, description, seconds per batch)."""
+    from oracle import ref_port
+    import importlib
+    synth = importlib.import_module("erc_b200.synth")
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen = torch.Generator().manual_seed(seed)
+    model = ref_port.CogmenRefPort(HIDDEN, n_classes=N_CLASSES, skip_dead_encoder=skip_dead_encoder)
+    model.train()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8)     # cogmen.py:50
+
+    def batch():
+        L = synth.mosei_lengths(batch_dialogues * 8, gen)[:batch_dialogues]
+        return synth.padded_batch(L, HIDDEN, 2, N_CLASSES, gen, one_speaker=True)
+
+    for _ in range(warmup):
+        ref_port.train_step(model, optim, batch())
+    utts, t_total, n = 0, 0.0, 0
+    while True:
+        b = batch()
+        t0 = time.perf_counter()
+        ref_port.train_step(model, optim, b)
+        t_total += time.perf_counter() - t0
+        utts += int(b["text_length"].sum())
+        n += 1
+        if (steps is not None and n >= steps) or (steps is None and (t_total >= budget_s or n >= 64)):
+            break
+    return utts / t_total, "%d batches x %d dialogues (%d utterances), MOSEI-shaped" % (n, batch_dialogues, utts), t_total / n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import erc_b200  # noqa: F401  (synth only; no kernels run on this arm)
+    cores = os.cpu_count() or 1
+    # each "step" = a bounded sample of the workload: `bps` batches of 32 dialogues; sized so the run ends in minutes
+    probe_rate, _, t_batch = cpu_reference_rate(0.0, steps=1, warmup=1)
+    total_batches = max(1, int(150.0 / max(t_batch, 1e-3)))
+    bps = max(1, min(16, total_batches // max(args.steps + args.warmup, 1)))
+    from oracle import ref_port
+    import importlib
+    synth = importlib.import_module("erc_b200.synth")
+    gen = torch.Generator().manual_seed(0)
+    model = ref_port.CogmenRefPort(HIDDEN, n_classes=N_CLASSES)
+    model.train()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8)
+
+    def one_step():
+        u = 0
+        for _ in range(bps):
+            L = synth.mosei_lengths(32 * 8, gen)[:32]
+            b = synth.padded_batch(L, HIDDEN, 2, N_CLASSES, gen, one_speaker=True)
+            ref_port.train_step(model, optim, b)
+            u += int(L.sum())
+        return u
+
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    utts = sum(one_step() for _ in range(args.steps))
+    dt = time.perf_counter() - t0
+    value = utts / dt
+    sample = "%d steps x %d batches x 32 dialogues (%d utterances) of the MOSEI-shaped workload; throughput is per-batch, linear in dialogues" % (
+        args.steps, bps, utts)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reference_batch": "32 dialogues/batch (cogmen.py:43-45)", "device": "cpu"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def kernel_label(name, args):
+    try:
+        if name == "ercg_gemm_nn":
+            return "gemm_nn[K=%d,N=%d]" % (args[10], args[9])
+        if name == "ercg_gemm_tn":
+            return "gemm_tn[K1=%d,N1=%d]" % (args[8], args[9])
+    except Exception:
+        pass
+    return name[5:] if name.startswith("ercg_") else name
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import erc_b200
+    from erc_b200 import _lib, ops, synth
+    from erc_b200.graph import build_graph, graph_sizes
+    from erc_b200.track_mm.cogmen import COGMENModule
+    from erc_b200.dist import shard_dialogues, StatSync, LossSync, GradSync
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a GPU: libercgraph has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()                                            # fail loudly now if the .so is missing
+
+    # ---- workload
+    lengths_all = synth.config5_lengths(args.total_utts, seed=0)
+    total_utts = int(lengths_all.sum())
+    mine = shard_dialogues(lengths_all, world)[rank]
+    lengths = lengths_all[mine].contiguous()
+    N = int(lengths.sum())
+    ld = (HIDDEN + 3) // 4 * 4                            # 1444: rows 16-byte aligned in HBM
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_store = torch.empty((N, ld), dtype=torch.float32, device=dev)
+    x_store.normal_(generator=gen)
+    x = x_store[:, :HIDDEN]
+    spk = torch.zeros(N, dtype=torch.int64, device=dev)   # MOSEI: a single speaker id (mosei_feature.py:211)
+    labels = torch.randint(0, N_CLASSES, (N,), device=dev, generator=gen)
+    sizes = graph_sizes(lengths, 5, 5)
+
+    torch.manual_seed(0)
+    model = COGMENModule(HIDDEN, 100, 17, 2, N_CLASSES).to(dev)
+    model.train()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8)
+    loss_sync = grad_sync = None
+    if world > 1:
+        model.gcn.stat_sync = StatSync(global_count=total_utts)
+        loss_sync = LossSync()
+        grad_sync = GradSync(model)
+
+    def step(xi, spki, labi):
+        g = build_graph(lengths, spki, 5, 5, 2, device=dev, sizes=sizes)
+        logits, _ = model.forward_packed(xi, spki, lengths, graph=g)
+        loss = ops.cross_entropy(logits, labi, reduce_sync=loss_sync)
+        optim.zero_grad(set_to_none=True)
+        loss.backward()
+        if grad_sync is not None:
+            grad_sync()
+        optim.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x, spk, labels)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timer = _lib.KernelTimer(labeler=kernel_label)      # GEMM records are split by shape
+    with timer:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            loss = step(x, spk, labels)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.finish() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total_utts * args.steps / (ms / 1e3)
+    ksum = timer.summary()
+
+    # ---- e2e: same step fed from pinned host memory, loss read back
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    hx = torch.empty((N, ld), dtype=torch.float32, pin_memory=True)
+    hx.copy_(x_store)
+    hspk = torch.zeros(N, dtype=torch.int64).pin_memory()
+    hlab = labels.cpu().pin_memory()
+    dx = torch.empty_like(x_store)
+    dspk, dlab = torch.empty_like(spk), torch.empty_like(labels)
+
+    def e2e_step():
+        dx.copy_(hx, non_blocking=True)
+        dspk.copy_(hspk, non_blocking=True)
+        dlab.copy_(hlab, non_blocking=True)
+        return float(step(dx[:, :HIDDEN], dspk, dlab).item())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = total_utts * e2e_steps / (e2e_ms / 1e3)
+    h2d = hx.numel() * 4 + hspk.numel() * 8 + hlab.numel() * 8
+    if world > 1:
+        b = torch.tensor([h2d], dtype=torch.float64, device=dev)
+        dist.all_reduce(b)
+        h2d = int(b.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        E = sizes[1]
+        per = {k: (c, tot / c) for k, (c, tot) in ksum.items()}          # kernel label -> (calls, avg ms)
+        step_kernel_ms = sum(tot for _, tot in ksum.values()) / args.steps
+        H, P = 100, 2          # row width; distinct (source, relation) slots referenced per source (1 speaker id -> 2)
+
+        def alg_bytes(label):
+            """Algorithmic (unique) HBM bytes of ONE launch on this rank (weights ignored)."""
+            if label.startswith("gemm_nn[") or label.startswith("gemm_tn["):
+                a, b = (int(v.split("=")[1]) for v in label[label.index("[") + 1:-1].split(","))
+                return 4 * N * (a + b)
+            return {
+                "gather_fwd": 4 * H * P * N + 4 * H * N + 4 * H * N + 4 * (N + 1) + 9 * E,
+                "gather_bwd": 4 * H * N + 4 * H * 9 * N + 4 * (N + 1) + 13 * E,
+                "attn_fwd": 5 * 4 * H * N + 4 * (N + 1) + 8 * E,
+                "attn_bwd_dst": 5 * 4 * H * N + 4 * (N + 1) + 12 * E,
+                "attn_bwd_src": 4 * 4 * H * N + 4 * (N + 1) + 16 * E,
+                "graphify_csr": 8 * lengths.numel() + 8 * N + 8 * (N + 1) + 12 * N + E * (4 + 1 + 4 + 1 + 4 + 4 + 24),
+                "bn_stats": 4 * H * N, "bn_act_fwd": 8 * H * N, "bn_act_bwd_reduce": 8 * H * N, "bn_act_bwd_apply": 12 * H * N,
+                "mask_pos": 12 * H * N, "colsum": None, "ce_fwd": (4 * N_CLASSES * 2 + 8) * N,
+            }.get(label)
+
+        kernels = {}
+        for label, (calls, avg_ms) in sorted(per.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+            ab = alg_bytes(label)
+            ent = {"calls_per_step": calls / args.steps, "avg_ms": round(avg_ms, 4)}
+            if ab:
+                gbs = ab / (avg_ms * 1e-3) / 1e9
+                ent.update({"algorithmic_bytes": ab, "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)})
+            kernels[label] = ent
+        dom_label = max(ksum.items(), key=lambda kv: kv[1][1])[0]
+        dom_calls, dom_ms = per[dom_label]
+        dom_bytes = alg_bytes(dom_label) or 0
+        roof = {"bound": "hbm", "kernel": dom_label, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": dom_ms, "launches_timed": dom_calls, "algorithmic_bytes_per_launch": dom_bytes}
+        graph_kernels = {k: kernels[k] for k in ("gather_fwd", "gather_bwd", "attn_fwd", "attn_bwd_dst", "attn_bwd_src",
+                                                 "graphify_csr") if k in kernels}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "utterances_per_step": total_utts, "dialogues": int(lengths_all.numel()),
+                           "edges_per_step_rank0": E, "parallelism": "dp%d (whole dialogues per GPU)" % world,
+                           "l2": "inputs (%.1f GB/step/GPU) are larger than the 126 MB L2" % (x_store.numel() * 4 / 1e9),
+                           "dropout": "on (train mode)", "optimizer": "Adam inside the step", "dead_encoder": "not executed (cogmen.py:146-147 discards its output)"},
+                "roofline": roof, "graph_kernels": graph_kernels,
+                "kernels": kernels,
+                "kernel_time_share_of_step": round(step_kernel_ms / (ms / args.steps), 4),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
+                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                "gpu_launches": launches, "clocks": clocks, "loss": float(loss.item())}
+        if world == 1 and not args.no_cpu_baseline:
+            v, sample, _ = cpu_reference_rate(args.cpu_budget_s)
+            v2, sample2, _ = cpu_reference_rate(args.cpu_budget_s / 2, skip_dead_encoder=True)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample,
+                                    "value_dead_encoder_skipped": v2}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--total-utts", type=int, default=1 << 20)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-budget-s", type=float, default=16.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

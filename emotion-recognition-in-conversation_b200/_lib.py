@@ -62,6 +62,65 @@ SIGNATURES = {
 }
 
 _lib = None
+_timer = None          # active KernelTimer or None
+
+
+class KernelTimer:
+    """Times every libercgraph call with CUDA events on the launching (current) stream.
+
+    Used by bench.py to measure the per-kernel durations behind the roofline numbers live, inside the
+    timed region.  ``with KernelTimer() as kt: ...; kt.summary()`` -> {entry point: (calls, total ms)}."""
+
+    def __init__(self, labeler=None):
+        self.records = []
+        self.labeler = labeler        # optional (entry point, args) -> label, e.g. to split GEMMs by shape
+
+    def __enter__(self):
+        global _timer
+        _timer = self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.records:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+class _Timed:
+    """Attribute proxy over the CDLL handle that brackets calls with events when a KernelTimer is active."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if name.endswith("_bytes") or name in ("ercg_strerror", "ercg_version", "ercg_launch_count",
+                                               "ercg_graphify_sizes_host"):
+            setattr(self, name, fn)
+            return fn
+
+        def call(*args):
+            t = _timer
+            if t is None:
+                return fn(*args)
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            t.records.append((t.labeler(name, args) if t.labeler else name, e0, e1))
+            return rc
+
+        setattr(self, name, call)
+        return call
 
 
 def lib():
@@ -76,7 +135,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
-        _lib = handle
+        _lib = _Timed(handle)
     return _lib
 
 

@@ -1,0 +1,104 @@
+"""Dialogue-sharded data parallelism.
+
+The reference reaches NCCL only through HF accelerate -> DDP (lumo/trainer/trainer.py:60-67,315-327): a
+bucketed gradient all-reduce in ``accelerate.backward`` (track_mm/cogmen.py:188).  Dialogues are independent
+graphs (edges never cross dialogues, cogmen_utils.py:125-126), so the path shards by whole dialogues with
+no data-path exchange; what crosses GPUs per step is
+  1. ONE all-reduce (sum) of the flat buffer of LIVE gradients (COGMEN: 279 304 floats = 1.1 MB),
+  2. BatchNorm statistics: (sum x, sum x^2, count) = 2H+1 floats forward, (sum dy, sum dy*xhat) = 2H floats
+     backward, so that N-GPU results equal the 1-GPU result on the same global batch (the reference's DDP
+     uses per-rank statistics; ``global_stats=False`` reproduces that),
+  3. the loss numerator/denominator (2 floats) so the mean is over the global utterance count.
+All of them are torch.distributed collectives (NCCL on GPUs, gloo in the CPU tests); none is fused with
+compute because none follows a compute tile -- they are latency-bound scalars/vectors.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_dialogues(lengths, world_size):
+    """Greedy balance of whole dialogues by utterance count: longest first onto the lightest rank.
+
+    Returns a list (one entry per rank) of int64 index tensors into ``lengths`` (ascending, so every rank keeps
+    the original dialogue order).  Deterministic."""
+    lengths = torch.as_tensor(lengths, dtype=torch.int64)
+    if world_size == 1:
+        return [torch.arange(lengths.numel())]
+    order = torch.argsort(lengths, descending=True, stable=True).tolist()
+    loads = [0] * world_size
+    buckets = [[] for _ in range(world_size)]
+    # block-greedy: equal-length dialogues are dealt round-robin, which is what greedy does anyway and is O(B)
+    ll = lengths.tolist()
+    import heapq
+    heap = [(0, r) for r in range(world_size)]
+    heapq.heapify(heap)
+    for d in order:
+        load, r = heapq.heappop(heap)
+        buckets[r].append(d)
+        heapq.heappush(heap, (load + ll[d], r))
+        loads[r] = load + ll[d]
+    return [torch.tensor(sorted(b), dtype=torch.int64) for b in buckets]
+
+
+class StatSync:
+    """All-reduce hooks for BatchNorm statistics (see GNN._bn_relu in track_mm/cogmen.py of this package)."""
+
+    def __init__(self, group=None, global_count=None):
+        self.group = group
+        self.global_count = global_count       # host-known global utterance count: avoids a device sync
+
+    def stats(self, mean, var, n_local):
+        """local (mean, biased var, n) -> global (mean, biased var, count)."""
+        H = mean.numel()
+        buf = torch.empty(2 * H + 1, dtype=torch.float64, device=mean.device)
+        buf[:H] = mean.double() * n_local
+        buf[H:2 * H] = (var.double() + mean.double() ** 2) * n_local
+        buf[2 * H] = n_local
+        dist.all_reduce(buf, group=self.group)
+        count = buf[2 * H]
+        gmean = buf[:H] / count
+        gvar = (buf[H:2 * H] / count - gmean ** 2).clamp_(min=0)
+        return gmean.float(), gvar.float(), (float(self.global_count) if self.global_count else float(count.item()))
+
+    def grads(self, sums):
+        dist.all_reduce(sums, group=self.group)
+        return sums
+
+
+class LossSync:
+    def __init__(self, group=None):
+        self.group = group
+
+    def __call__(self, num_den):
+        out = num_den.clone()
+        dist.all_reduce(out, group=self.group)
+        return out
+
+
+class GradSync:
+    """One flat all-reduce(sum) of every parameter that received a gradient."""
+
+    def __init__(self, module, group=None, average=False):
+        self.module, self.group, self.average = module, group, average
+        self._flat = None
+        self._live = None
+
+    def __call__(self):
+        live = [p for p in self.module.parameters() if p.grad is not None]
+        n = sum(p.numel() for p in live)
+        if self._flat is None or self._flat.numel() != n or self._flat.device != live[0].device:
+            self._flat = torch.empty(n, dtype=torch.float32, device=live[0].device)
+        flat, off = self._flat, 0
+        torch._foreach_copy_([flat[o:o + p.numel()].view_as(p) for o, p in _offsets(live)], [p.grad for p in live])
+        dist.all_reduce(flat, group=self.group)
+        if self.average:
+            flat.div_(dist.get_world_size(self.group))
+        torch._foreach_copy_([p.grad for p in live], [flat[o:o + p.numel()].view_as(p) for o, p in _offsets(live)])
+        return n
+
+
+def _offsets(params):
+    off = 0
+    for p in params:
+        yield off, p
+        off += p.numel()
