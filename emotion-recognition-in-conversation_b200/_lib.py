@@ -51,6 +51,9 @@ SIGNATURES = {
     "ercg_edgeatt_fwd": (I, [P, L, P, L, P, P, P, P, L, I, P]),
     "ercg_edgeatt_bwd_src": (I, [P, P, P, L, P, P, P, P, P, L, L, I, P]),
     "ercg_edgeatt_bwd_dst": (I, [P, P, L, P, P, P, L, L, I, P]),
+    "ercg_lstm_fwd": (I, [P, L, P, P, I, I, P, L, P, P, P, P]),
+    "ercg_lstm_bwd": (I, [P, L, P, P, P, P, I, I, P, L, P]),
+    "ercg_dropout": (I, [P, P, L, F, U64, P]),
     "ercg_bn_workspace_bytes": (SZ, [L, I]),
     "ercg_bn_stats": (I, [P, L, L, I, P, P, P, SZ, P]),
     "ercg_bn_act_fwd": (I, [P, L, P, P, F, P, P, F, P, L, L, I, P]),

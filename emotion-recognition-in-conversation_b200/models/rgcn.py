@@ -43,9 +43,11 @@ class RGCNConv(nn.Module):
         if x is None:
             raise NotImplementedError("featureless (embedding-lookup) mode is not used by the reference's models")
         R, H, K = self.num_relations, self.out_channels, self.in_channels
+        attached = getattr(edge_index, "_ercg_graph", None)
+        n_graph = attached.N if attached is not None else (int(edge_index.max()) + 1 if edge_index.numel() else 0)
+        if (attached is not None and x.size(0) != n_graph) or x.size(0) < n_graph:   # models/rgcn.py:126-130
+            raise ValueError("Encountered node tensor with size %d in dimension 0, but expected size %d." % (x.size(0), n_graph))
         g = graph_from_edge_index(edge_index, edge_type, x.size(0), R)
-        if x.size(0) != g.N:
-            raise ValueError("Encountered node tensor with size %d in dimension 0, but expected size %d." % (x.size(0), g.N))
         w = ops.matmul_kn(self.att, self.basis.reshape(self.num_bases, K * H))          # [R, K*H]
         w = w.view(R, K, H).permute(1, 0, 2).reshape(K, R * H)
         root_off = -1

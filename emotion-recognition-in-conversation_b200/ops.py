@@ -347,3 +347,91 @@ class _PackRows(torch.autograd.Function):
 def pack_rows(padded, graph, seq_first=False):
     """[B,Lmax,D] (or [Lmax,B,D] when seq_first) -> packed [N,D], dialogue-major."""
     return _PackRows.apply(padded, graph, seq_first)
+
+
+# ------------------------------------------------------------------------------------------- K6 LSTM
+class _LstmLayer(torch.autograd.Function):
+    """One bidirectional layer on packed rows: gx [N, 8*Hd] (input transform already applied) -> out [N, 2*Hd]."""
+
+    @staticmethod
+    def forward(ctx, gx, whh, graph):
+        gx, ldgx = _rows(gx)
+        whh = whh.contiguous()
+        N, Hd = gx.size(0), whh.size(2)
+        dev = gx.device
+        out = torch.empty((N, 2 * Hd), dtype=torch.float32, device=dev)
+        gates = torch.empty((N, 8 * Hd), dtype=torch.float32, device=dev)
+        cells = torch.empty((N, 2 * Hd), dtype=torch.float32, device=dev)
+        hprev = torch.empty((N, 2 * Hd), dtype=torch.float32, device=dev)
+        check(lib().ercg_lstm_fwd(_p(gx), ldgx, _p(whh), _p(graph.node_off), graph.B, Hd, _p(out), 2 * Hd, _p(gates), _p(cells),
+                                  _p(hprev), _stream()), "ercg_lstm_fwd")
+        ctx.graph, ctx.Hd = graph, Hd
+        ctx.save_for_backward(whh, gates, cells, hprev)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        whh, gates, cells, hprev = ctx.saved_tensors
+        g, Hd = ctx.graph, ctx.Hd
+        dout, ldo = _rows(dout)
+        N = dout.size(0)
+        dgx = torch.empty((N, 8 * Hd), dtype=torch.float32, device=dout.device)
+        check(lib().ercg_lstm_bwd(_p(dout), ldo, _p(gates), _p(cells), _p(whh), _p(g.node_off), g.B, Hd, _p(dgx), 8 * Hd,
+                                  _stream()), "ercg_lstm_bwd")
+        dwhh = None
+        if ctx.needs_input_grad[1]:
+            dwhh = torch.stack([gemm_tn(dgx[:, d * 4 * Hd:(d + 1) * 4 * Hd], hprev[:, d * Hd:(d + 1) * Hd]) for d in range(2)])
+        return dgx, dwhh, None
+
+
+def lstm_layer(gx, whh, graph):
+    return _LstmLayer.apply(gx, whh, graph)
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        check(lib().ercg_dropout(_p(x), _p(out), x.numel(), p, seed & (2 ** 64 - 1), _stream()), "ercg_dropout")
+        ctx.p, ctx.seed = p, seed
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        dx = torch.empty_like(dout)
+        check(lib().ercg_dropout(_p(dout), _p(dx), dout.numel(), ctx.p, ctx.seed & (2 ** 64 - 1), _stream()), "ercg_dropout")
+        return dx, None, None
+
+
+def dropout(x, p, seed):
+    return _Dropout.apply(x, float(p), int(seed))
+
+
+def unpack_rows(packed, graph, Lmax, seq_first=False):
+    """packed [N,D] -> zero-padded [B,Lmax,D] (pad_packed_sequence layout); autograd via pack_rows' kernels."""
+    return _UnpackRows.apply(packed, graph, Lmax, seq_first)
+
+
+class _UnpackRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, packed, graph, Lmax, seq_first):
+        packed, ldp = _rows(packed)
+        D = packed.size(1)
+        shape = (Lmax, graph.B, D) if seq_first else (graph.B, Lmax, D)
+        out = torch.zeros(shape, dtype=torch.float32, device=packed.device)
+        check(lib().ercg_unpack_rows(_p(packed), ldp, _p(graph.node_off), _p(graph.node_dlg), _p(out), D, Lmax, graph.B,
+                                     1 if seq_first else 0, graph.N, D, _stream()), "ercg_unpack_rows")
+        ctx.graph, ctx.seq_first, ctx.Lmax, ctx.D = graph, seq_first, Lmax, D
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g = ctx.graph
+        dout = dout.contiguous()
+        flat = dout.reshape(-1, ctx.D)
+        dp = torch.empty((g.N, ctx.D), dtype=torch.float32, device=dout.device)
+        check(lib().ercg_pack_rows(_p(flat), ctx.D, ctx.Lmax, g.B, 1 if ctx.seq_first else 0, _p(g.node_off), _p(g.node_dlg),
+                                   _p(dp), ctx.D, g.N, ctx.D, _stream()), "ercg_pack_rows")
+        return dp, None, None, None

@@ -187,6 +187,24 @@ int ercg_edgeatt_bwd_dst(const float* dsig, const float* x, int64_t ldx,
                          float* du, int64_t lddu, int64_t N, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K6  packed bidirectional LSTM recurrence, one layer (SeqContext, track_mm/dgcn_models.py:10-33;
+ * MMGCN text LSTM, track_mm/mmgcn.py:69,114).  gx[N, 8*Hd] = x @ [W_ih; W_ih_reverse]^T + b_ih + b_hh is
+ * produced by ercg_gemm_nn (gate order i,f,g,o per direction); whh = [2][4*Hd][Hd] (forward, reverse).
+ * Dialogue d owns rows node_off[d]..node_off[d+1] (packed-sequence semantics, zero initial state).
+ * fwd writes out[N,2*Hd] and saves gates[N,8*Hd] (post-activation), cells[N,2*Hd], hprev[N,2*Hd] (= h_{t-1}).
+ * bwd writes dgx[N,8*Hd] (gradient w.r.t. the pre-activations); the caller forms
+ *   dW_hh = dgx^T @ hprev, dW_ih = dgx^T @ x, db = colsum(dgx), dx = dgx @ [W_ih; W_ih_reverse] with K2.
+ * Hd in {100 (the size the reference instantiates), 64, 48, 32, 24, 16, 8}; Hd % 4 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int ercg_lstm_fwd(const float* gx, int64_t ldgx, const float* whh, const int32_t* node_off, int B, int Hd,
+                  float* out, int64_t ldo, float* gates, float* cells, float* hprev, void* stream);
+int ercg_lstm_bwd(const float* dout, int64_t ldo, const float* gates, const float* cells, const float* whh,
+                  const int32_t* node_off, int B, int Hd, float* dgx, int64_t lddgx, void* stream);
+/* inverted dropout with a counter-hash mask (same (seed, index) -> same mask, so the backward re-applies it):
+ * out[i] = hash(seed, i) < p ? 0 : x[i] / (1 - p).  nn.LSTM(dropout=.4) between layers, dgcn_models.py:17. */
+int ercg_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * BatchNorm1d (training statistics) + LeakyReLU of GNN.forward (cogmen.py:67-68,72).
  * stats: mean[H], var[H] (biased) over the N rows, fixed-order reduction.
  * ------------------------------------------------------------------------------------------- */
