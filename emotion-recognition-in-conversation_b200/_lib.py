@@ -38,6 +38,9 @@ SIGNATURES = {
     "ercg_pack_rows": (I, [P, L, L, I, I, P, P, P, L, L, I, P]),
     "ercg_unpack_rows": (I, [P, L, P, P, P, L, L, I, I, L, I, P]),
     "ercg_gemm_nn": (I, [P, L, P, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P]),
+    "ercg_gemm_nn_tc_workspace_bytes": (SZ, [I, I]),
+    "ercg_gemm_nn_tc_supported": (I, [P, L, P, L, L, I, I]),
+    "ercg_gemm_nn_tc": (I, [P, L, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, SZ, P]),
     "ercg_gemm_tn_workspace_bytes": (SZ, [L, I, I]),
     "ercg_gemm_tn": (I, [P, L, P, P, L, P, L, L, I, I, P, SZ, P]),
     "ercg_mask_pos": (I, [P, L, P, L, F, P, L, L, I, P]),
@@ -105,7 +108,7 @@ class _Timed:
 
     def __getattr__(self, name):
         fn = getattr(self._h, name)
-        if name.endswith("_bytes") or name in ("ercg_strerror", "ercg_version", "ercg_launch_count",
+        if name.endswith("_bytes") or name.endswith("_supported") or name in ("ercg_strerror", "ercg_version", "ercg_launch_count",
                                                "ercg_graphify_sizes_host"):
             setattr(self, name, fn)
             return fn

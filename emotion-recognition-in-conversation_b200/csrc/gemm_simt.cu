@@ -261,36 +261,55 @@ __global__ void reduce_splits_kernel(const float* __restrict__ P, long long spli
   C[(long long)r * ldc + c] = s;
 }
 
-// column sums: block b sums rows [b*RPB, (b+1)*RPB) -> partial[b][N]
-constexpr int CS_RPB = 2048;
-__global__ void colsum_partial_kernel(const float* __restrict__ A, long long lda, long long M, int N, float* __restrict__ partial) {
-  // blockDim = (32, 8): x over columns (strided), y over rows
+// column sums: block b sums rows [b*CS_RPB, (b+1)*CS_RPB) -> partial[b][N]; the final kernel reduces the partials with
+// the same (32 columns x 8 row-lanes) pattern in fp64.  Fixed order => bit-reproducible.
+constexpr int CS_RPB = 256;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ A, long long lda, long long M, int N, float* __restrict__ partial) {
   __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long rbeg = (long long)blockIdx.x * CS_RPB;
   long long rend = rbeg + CS_RPB;
   if (rend > M) rend = M;
   for (int c0 = 0; c0 < N; c0 += 32) {
-    const int c = c0 + threadIdx.x;
+    const int c = c0 + tx;
     float s = 0.f;
-    if (c < N)
-      for (long long r = rbeg + threadIdx.y; r < rend; r += 8) s += A[r * lda + c];
-    sm[threadIdx.y][threadIdx.x] = s;
+    if (c < N) {
+      long long r = rbeg + ty;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (; r + 24 < rend; r += 32) {
+        s0 += A[r * lda + c]; s1 += A[(r + 8) * lda + c]; s2 += A[(r + 16) * lda + c]; s3 += A[(r + 24) * lda + c];
+      }
+      for (; r < rend; r += 8) s0 += A[r * lda + c];
+      s = (s0 + s1) + (s2 + s3);
+    }
+    sm[ty][tx] = s;
     __syncthreads();
-    if (threadIdx.y == 0 && c < N) {
+    if (ty == 0 && c < N) {
       float tot = 0.f;
 #pragma unroll
-      for (int y = 0; y < 8; ++y) tot += sm[y][threadIdx.x];
+      for (int y = 0; y < 8; ++y) tot += sm[y][tx];
       partial[(long long)blockIdx.x * N + c] = tot;
     }
     __syncthreads();
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ out) {
+  __shared__ double sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)partial[(long long)b * N + c];
-  out[c] = (float)s;
+  if (c < N)
+    for (int b = ty; b < nblocks; b += 8) s += (double)partial[(long long)b * N + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    double tot = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += sm[y][tx];
+    out[c] = (float)tot;
+  }
 }
 
 static void tn_plan(int64_t M, int K1, int N1, int& S, long long& rows_per_split) {
@@ -392,9 +411,9 @@ extern "C" int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float*
   const size_t need = ercg_colsum_workspace_bytes(M, N);
   if (need > workspace_bytes || !workspace) return ERCG_EWORKSPACE;
   const int nb = (int)((M + CS_RPB - 1) / CS_RPB);
-  colsum_partial_kernel<<<nb, dim3(32, 8), 0, st>>>(A, lda, M, N, reinterpret_cast<float*>(workspace));
+  colsum_partial_kernel<<<nb, 256, 0, st>>>(A, lda, M, N, reinterpret_cast<float*>(workspace));
   int rc = finish_launch();
   if (rc != ERCG_OK) return rc;
-  colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(workspace), nb, N, out);
+  colsum_final_kernel<<<(N + 31) / 32, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), nb, N, out);
   return finish_launch();
 }

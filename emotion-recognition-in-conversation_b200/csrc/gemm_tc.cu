@@ -1,0 +1,484 @@
+// K2 (tensor-core path): C[M,N] = act(A[M,K] @ B[K,N] + bias) on tcgen05 with fp32-grade accuracy (3xTF32).
+//
+// Replaces the same reference code as gemm_simt.cu (nn.Linear of cogmen.py:103-105,116-122, the relation
+// weights of RGCNConv cogmen.py:65 / models/rgcn.py:329-343, the Linears of TransformerConv cogmen.py:66).
+//
+// The reference is fp32 and BASELINE.json asks for 1e-5 relative parity, which plain TF32 (10-bit mantissa)
+// cannot give.  Every operand is therefore split x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi) and the
+// product is accumulated in fp32 TMEM as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is 2^-22
+// relative).  Weights (B) are split once per call on the device into K-major [N,K] hi/lo copies; activations (A)
+// are split on the fly in shared memory: the split is elementwise, so it preserves whatever (swizzled) layout
+// TMA wrote -- hi overwrites the raw tile in place, lo goes to a twin buffer at the same offsets.
+//
+// Persistent, warp-specialised CTA (320 threads, 1 CTA / SM):
+//   warps 0-3  splitter   : raw A tile -> hi (in place) + lo, fence.proxy.async, arrive split_done[s]
+//   warps 4-7  epilogue   : tcgen05.ld 32x32b accumulator rows -> bias/activation -> 16-byte global stores
+//   warp  8    TMA        : cp.async.bulk.tensor 2D boxes {32 k, 128 rows} (A) and {32 k, BN rows} (B hi, B lo),
+//                           128-byte swizzle, out-of-bounds rows/columns zero-filled (K and N tails for free)
+//   warp  9    MMA        : one elected lane issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per
+//                           stage, tcgen05.commit releases the smem stage / publishes the accumulator
+// 3 smem stages of (A_hi, A_lo, B_hi, B_lo) = 64 KB each; 2 TMEM accumulator stages of BN columns.
+//
+// Accumulation accuracy: the tensor core adds into TMEM with round-toward-zero, which on random-sign data shrinks
+// |D| by ~0.3 ulp per instruction (measured on B200: -8.8e-6 relative at K=1443 with one long chain -- see
+// DESIGN.md).  As in Ootomo & Yokota's error-corrected tensor-core GEMM, the long sum therefore lives OUTSIDE the
+// tensor core: the MMA warp accumulates only TC_GROUP k-chunks (128 k) into a TMEM stage, the epilogue warps add
+// each such partial into fp32 REGISTER accumulators with round-to-nearest, and the two TMEM stages ping-pong so
+// the drain of group g overlaps the MMAs of group g+1.  Every mbarrier wait is bounded: a protocol bug traps instead of
+// hanging the GPU.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace ercg {
+
+constexpr int TC_BM = 128;        // rows per tile (UMMA M)
+constexpr int TC_BN = 128;        // max output columns per tile (UMMA N, multiple of 16)
+constexpr int TC_BK = 32;         // k per stage: 32 floats = one 128-byte swizzle span
+constexpr int TC_GROUP = 4;         // k-chunks accumulated inside TMEM before a round-to-nearest flush to registers
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;      // 16 KB
+
+struct TcEpilogue {
+  const float* bias; int act; const float* aux; long long ldaux; float aux_scale; float drop_p; unsigned long long seed;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 24)) __trap();            // ~seconds: a broken pipeline must fail, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, 128-byte swizzle: rows are 128 B apart, 8-row atoms are 1024 B apart (SBO), LBO unused (=1), version 1
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+// Shared-memory plan (1 CTA / SM):
+//   raw ring  : TC_R stages x 16 KB   A tile as TMA wrote it; the splitter rewrites it in place as A_hi
+//   oper ring : TC_Q stages x 48 KB   A_lo (16 KB) + B_hi (16 KB) + B_lo (16 KB)
+// The raw ring is deeper than the operand ring so that enough HBM bytes are in flight per SM to cover the loaded
+// DRAM latency; B comes from L2.  Chunk i uses raw stage i % TC_R and operand stage i % TC_Q.
+constexpr int TC_R = 5;
+constexpr int TC_Q = 3;
+constexpr uint32_t TC_OPER_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;
+constexpr uint32_t TC_SMEM_BYTES = TC_R * TC_A_BYTES + TC_Q * TC_OPER_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int TC_THREADS = 352;   // 4 splitter + 4 epilogue warps, A producer, MMA, B producer
+
+// barrier indices
+constexpr int BAR_A_FULL = 0;                    // [TC_R] TMA bytes of the raw A tile landed
+constexpr int BAR_R_FREE = BAR_A_FULL + TC_R;    // [TC_R] MMAs that read A_hi of this raw stage retired
+constexpr int BAR_B_FULL = BAR_R_FREE + TC_R;    // [TC_Q] TMA bytes of B_hi/B_lo landed
+constexpr int BAR_SPLIT = BAR_B_FULL + TC_Q;     // [TC_Q] A_hi / A_lo written (128 arrivals)
+constexpr int BAR_Q_FREE = BAR_SPLIT + TC_Q;     // [TC_Q] MMAs that read this operand stage retired
+constexpr int BAR_ACC_FULL = BAR_Q_FREE + TC_Q;  // [2]
+constexpr int BAR_ACC_EMPTY = BAR_ACC_FULL + 2;  // [2]   (128 arrivals)
+constexpr int BAR_COUNT = BAR_ACC_EMPTY + 2;
+
+template <int ACT>
+__device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, long long m, int nn0, int N) {
+  if (ep.bias) {
+    if (nn0 + 4 <= N) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nn0));   // bias is 16-byte aligned (checked on host)
+      x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+    } else {
+      if (nn0 + 0 < N) x.x += __ldg(ep.bias + nn0 + 0);
+      if (nn0 + 1 < N) x.y += __ldg(ep.bias + nn0 + 1);
+      if (nn0 + 2 < N) x.z += __ldg(ep.bias + nn0 + 2);
+    }
+  }
+  if (ACT == ERCG_ACT_RELU || ACT == ERCG_ACT_RELU_DROPOUT) {
+    x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+  }
+  if (ACT == ERCG_ACT_RELU_DROPOUT) {
+    const float sc = 1.0f / (1.0f - ep.drop_p);
+    const unsigned long long base = (unsigned long long)m * (unsigned long long)N + (unsigned long long)nn0;
+    x.x = hash_uniform(ep.seed, base + 0) < ep.drop_p ? 0.f : x.x * sc;
+    x.y = hash_uniform(ep.seed, base + 1) < ep.drop_p ? 0.f : x.y * sc;
+    x.z = hash_uniform(ep.seed, base + 2) < ep.drop_p ? 0.f : x.z * sc;
+    x.w = hash_uniform(ep.seed, base + 3) < ep.drop_p ? 0.f : x.w * sc;
+  }
+  if (ACT == ERCG_ACT_MASK_POS) {
+    const float* a = ep.aux + m * ep.ldaux + nn0;
+    x.x = (nn0 + 0 < N && __ldg(a + 0) > 0.f) ? x.x * ep.aux_scale : 0.f;
+    x.y = (nn0 + 1 < N && __ldg(a + 1) > 0.f) ? x.y * ep.aux_scale : 0.f;
+    x.z = (nn0 + 2 < N && __ldg(a + 2) > 0.f) ? x.z * ep.aux_scale : 0.f;
+    x.w = (nn0 + 3 < N && __ldg(a + 3) > 0.f) ? x.w * ep.aux_scale : 0.f;
+  }
+  return x;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                  const __grid_constant__ CUtensorMap tmBl, float* __restrict__ C, long long ldc, long long M, int N,
+                  int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, TcEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* oper = smem + TC_R * TC_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(oper + TC_Q * TC_OPER_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_R; ++i) { mbar_init(BAR(BAR_A_FULL + i), 1); mbar_init(BAR(BAR_R_FREE + i), 1); }
+    for (int i = 0; i < TC_Q; ++i) {
+      mbar_init(BAR(BAR_B_FULL + i), 1);
+      mbar_init(BAR(BAR_SPLIT + i), 128);
+      mbar_init(BAR(BAR_Q_FREE + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_ACC_FULL + i), 1); mbar_init(BAR(BAR_ACC_EMPTY + i), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {   // TMEM: 2 accumulator stages x 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int n_tiles = (N + bn - 1) / bn;
+  const long long tiles = m_tiles * n_tiles;
+  const int k_chunks = (K + TC_BK - 1) / TC_BK;
+  const uint32_t raw_base = smem_u32(smem), oper_base = smem_u32(oper);
+  auto A_HI = [&](int r) { return raw_base + r * TC_A_BYTES; };
+  auto A_LO = [&](int q) { return oper_base + q * TC_OPER_BYTES; };
+  auto B_HI = [&](int q) { return oper_base + q * TC_OPER_BYTES + TC_A_BYTES; };
+  auto B_LO = [&](int q) { return oper_base + q * TC_OPER_BYTES + TC_A_BYTES + TC_B_BYTES; };
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ A producer (HBM stream, deep ring)
+    if (lane == 0) {
+      int r = 0;
+      uint32_t rph = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (int)(t / n_tiles) * TC_BM;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(BAR(BAR_R_FREE + r), rph ^ 1);
+          mbar_expect_tx(BAR(BAR_A_FULL + r), TC_A_BYTES);
+          tma_load_2d(A_HI(r), &tmA, kc * TC_BK, m0, BAR(BAR_A_FULL + r));
+          if (++r == TC_R) { r = 0; rph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ B producer (L2-resident weights)
+    if (lane == 0) {
+      int q = 0;
+      uint32_t qph = 0;
+      const uint32_t tx = 2u * (uint32_t)bn * TC_BK * 4u;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int n0 = (int)(t % n_tiles) * bn;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(BAR(BAR_Q_FREE + q), qph ^ 1);
+          mbar_expect_tx(BAR(BAR_B_FULL + q), tx);
+          tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, n0, BAR(BAR_B_FULL + q));
+          tma_load_2d(B_LO(q), &tmBl, kc * TC_BK, n0, BAR(BAR_B_FULL + q));
+          if (++q == TC_Q) { q = 0; qph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int r = 0, q = 0, a = 0;
+      uint32_t rph = 0, qph = 0, aph = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          const int in_group = kc % TC_GROUP;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
+          if (in_group == 0) {
+            mbar_wait(BAR(BAR_ACC_EMPTY + a), aph ^ 1);           // epilogue has drained this accumulator stage
+            tc_fence_after();
+          }
+          mbar_wait(BAR(BAR_B_FULL + q), qph);                    // B tiles landed
+          mbar_wait(BAR(BAR_SPLIT + q), qph);                     // A split into hi (raw stage r) / lo (operand stage q)
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t ah = make_desc_k_sw128(A_HI(r) + ks * 32), al = make_desc_k_sw128(A_LO(q) + ks * 32);
+            const uint64_t bh = make_desc_k_sw128(B_HI(q) + ks * 32), bl = make_desc_k_sw128(B_LO(q) + ks * 32);
+            tc_mma_tf32(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
+            tc_mma_tf32(d_tmem, ah, bl, idesc, 1u);
+            tc_mma_tf32(d_tmem, ah, bh, idesc, 1u);
+          }
+          tc_commit(BAR(BAR_R_FREE + r));                         // both smem stages are free once these MMAs retire
+          tc_commit(BAR(BAR_Q_FREE + q));
+          if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) {   // partial sum complete -> epilogue
+            tc_commit(BAR(BAR_ACC_FULL + a));
+            if (++a == 2) { a = 0; aph ^= 1; }
+          }
+          if (++r == TC_R) { r = 0; rph ^= 1; }
+          if (++q == TC_Q) { q = 0; qph ^= 1; }
+        }
+      }
+      (void)rph;
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ splitter (128 threads)
+    int r = 0, q = 0;
+    uint32_t rph = 0, qph = 0;
+    const int tid = threadIdx.x;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int kc = 0; kc < k_chunks; ++kc) {
+        mbar_wait(BAR(BAR_Q_FREE + q), qph ^ 1);       // A_lo slot of the operand stage is reusable
+        mbar_wait(BAR(BAR_A_FULL + r), rph);           // raw tile landed
+        float4* hi = reinterpret_cast<float4*>(smem + r * TC_A_BYTES);
+        float4* lo = reinterpret_cast<float4*>(oper + q * TC_OPER_BYTES);
+#pragma unroll
+        for (int i = 0; i < (int)(TC_A_BYTES / 16 / 128); ++i) {
+          const int idx = tid + 128 * i;
+          const float4 x = hi[idx];
+          float4 h, l;
+          h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
+          l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(BAR(BAR_SPLIT + q));
+        if (++r == TC_R) { r = 0; rph ^= 1; }
+        if (++q == TC_Q) { q = 0; qph ^= 1; }
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue (warps 4-7 -> TMEM lanes 32*(warp%4))
+    int a = 0;
+    uint32_t aph = 0;
+    const int ew = warp & 3;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const int n_groups = (k_chunks + TC_GROUP - 1) / TC_GROUP;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const long long m0 = (t / n_tiles) * TC_BM;
+      const int n0 = (int)(t % n_tiles) * bn;
+      const long long m = m0 + ew * 32 + lane;
+      float acc[TC_BN];
+#pragma unroll
+      for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
+      for (int g = 0; g < n_groups; ++g) {
+        mbar_wait(BAR(BAR_ACC_FULL + a), aph);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < TC_BN; c += 32) {
+          if (c < bn) {
+            uint32_t rr[32];
+            tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN + c), rr);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(rr[j]);     // round-to-nearest accumulation
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(BAR_ACC_EMPTY + a));
+        if (++a == 2) { a = 0; aph ^= 1; }
+      }
+      if (m < M) {
+        float* crow = C + m * ldc + n0;
+#pragma unroll
+        for (int j = 0; j < TC_BN; j += 4) {
+          const int nn0 = n0 + j;
+          if (j < bn && nn0 < N) {
+            const float4 v = tc_finish4<ACT>(make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), ep, m, nn0, N);
+            if (vec_ok && nn0 + 4 <= N) {
+              st4(crow + j, v);
+            } else {
+              if (nn0 + 0 < N) crow[j + 0] = v.x;
+              if (nn0 + 1 < N) crow[j + 1] = v.y;
+              if (nn0 + 2 < N) crow[j + 2] = v.z;
+              if (nn0 + 3 < N) crow[j + 3] = v.w;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// B[K,N] (row-major, ldb) -> Bt_hi, Bt_lo [N, Kp] (K-major, pitch Kp floats), tf32 split
+__global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int K, int N, int Kp, float* __restrict__ hi,
+                                float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? B[(long long)k * ldb + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < Kp) {
+      const float x = tile[threadIdx.x][i];
+      const float h = rn_tf32(x);
+      hi[(long long)n * Kp + k] = h;
+      lo[(long long)n * Kp + k] = rn_tf32(x - h);
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with row pitch `ld` floats; box {32 cols, box_rows}; 128-byte swizzle
+static bool make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace ercg
+
+using namespace ercg;
+
+extern "C" size_t ercg_gemm_nn_tc_workspace_bytes(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  const size_t Kp = (size_t)(K + 3) / 4 * 4;
+  return 2 * (size_t)N * Kp * sizeof(float) + 256;
+}
+
+// returns 1 when this shape/alignment can run on the tensor-core path
+extern "C" int ercg_gemm_nn_tc_supported(const float* A, int64_t lda, const float* C, int64_t ldc, int64_t M, int N, int K) {
+  if (M < 1 || N < 1 || K < 1) return 0;
+  if ((lda & 3) || (ldc & 3) || !aligned16(A) || !aligned16(C)) return 0;
+  if (M >= 2147483647LL || K >= (1 << 30)) return 0;
+  return 1;
+}
+
+extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                               int64_t ldc, int64_t M, int N, int K, int act, const float* aux, int64_t ldaux,
+                               float aux_scale, float drop_p, uint64_t seed, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (M < 0 || N < 0 || K < 0) return ERCG_EINVAL;
+  if (M == 0 || N == 0) return ERCG_OK;
+  if (!A || !B || !C || lda < K || ldb < N || ldc < N || K == 0) return ERCG_EINVAL;
+  if (act < 0 || act > 3 || (act == ERCG_ACT_MASK_POS && !aux)) return ERCG_EINVAL;
+  if (act == ERCG_ACT_RELU_DROPOUT && !(drop_p >= 0.f && drop_p < 1.f)) return ERCG_EINVAL;
+  if (!ercg_gemm_nn_tc_supported(A, lda, C, ldc, M, N, K) || (bias && !aligned16(bias))) return ERCG_EALIGN;
+  if (workspace_bytes < ercg_gemm_nn_tc_workspace_bytes(N, K) || !workspace) return ERCG_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = (K + 3) / 4 * 4;
+  float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  float* blo = bhi + (size_t)N * Kp;
+  split_bt_kernel<<<dim3((Kp + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Kp, bhi, blo);
+  int rc = finish_launch();
+  if (rc) return rc;
+  // UMMA N: multiple of 16, <= 128, chosen to waste the fewest columns
+  int bn = 128;
+  if (N <= 128) bn = (N + 15) / 16 * 16;
+  CUtensorMap tmA, tmBh, tmBl;
+  if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, bn) || !make_map(&tmBl, blo, N, K, Kp, bn))
+    return ERCG_ECUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_nn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_nn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_nn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_nn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+      return ERCG_ECUDA;
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms < 1) num_sms = kNumSMs;
+  }
+  const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed};
+  switch (act) {
+    case 0: gemm_tc_nn_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
+    case 1: gemm_tc_nn_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
+    case 2: gemm_tc_nn_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
+    default: gemm_tc_nn_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
+  }
+  return finish_launch();
+}

@@ -7,7 +7,7 @@
 
 namespace ercg {
 
-constexpr int RPB = 1024;   // rows per block in the column reductions
+constexpr int RPB = 256;    // rows per block in the column reductions
 
 // partial[b][0:H] = sum f0, partial[b][H:2H] = sum f1 over the block's rows
 template <int MODE>   // 0: (x, x^2)   1: (dy, dy*xhat) with dy = dout * lrelu'(gamma*xhat+beta)
@@ -54,24 +54,44 @@ col_partials_kernel(const float* __restrict__ x, long long ldx, const float* __r
   }
 }
 
-__global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nb, int H, long long N,
-                                      const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= H) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < nb; ++b) { s0 += (double)partial[(long long)b * 2 * H + c]; s1 += (double)partial[(long long)b * 2 * H + H + c]; }
+// fixed-order fp64 reduction of partial[nb][2H] column c: 8 row-lanes per column, then a fixed 8-term sum
+__device__ __forceinline__ double reduce_partials(const float* __restrict__ partial, int nb, int width, int c, bool ok,
+                                                  double (*sm)[33]) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double s = 0.0;
+  if (ok)
+    for (int b = ty; b < nb; b += 8) s += (double)partial[(long long)b * width + c];
+  __syncthreads();
+  sm[ty][tx] = s;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) tot += sm[y][tx];
+  return tot;
+}
+
+__global__ void __launch_bounds__(256)
+bn_stats_final_kernel(const float* __restrict__ partial, int nb, int H, long long N,
+                      const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var) {
+  __shared__ double sm[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool ok = c < H;
+  const double s0 = reduce_partials(partial, nb, 2 * H, c, ok, sm);
+  const double s1 = reduce_partials(partial, nb, 2 * H, H + c, ok, sm);
+  if (!ok || (threadIdx.x >> 5) != 0) return;
   const double m = s0 / (double)N;          // mean of (x - shift)
   double v = s1 / (double)N - m * m;
   if (v < 0.0) v = 0.0;
   mean[c] = (float)(m + (double)x[c]); var[c] = (float)v;
 }
 
-__global__ void sums_final_kernel(const float* __restrict__ partial, int nb, int H, float* __restrict__ sums) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * H) return;
-  double s = 0.0;
-  for (int b = 0; b < nb; ++b) s += (double)partial[(long long)b * 2 * H + c];
-  sums[c] = (float)s;
+__global__ void __launch_bounds__(256)
+sums_final_kernel(const float* __restrict__ partial, int nb, int H, float* __restrict__ sums) {
+  __shared__ double sm[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool ok = c < 2 * H;
+  const double s = reduce_partials(partial, nb, 2 * H, c, ok, sm);
+  if (ok && (threadIdx.x >> 5) == 0) sums[c] = (float)s;
 }
 
 __global__ void __launch_bounds__(256)
@@ -203,7 +223,7 @@ extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, floa
   col_partials_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
   int rc = finish_launch();
   if (rc) return rc;
-  bn_stats_final_kernel<<<(H + 127) / 128, 128, 0, st>>>(part, nb, H, N, x, mean, var);
+  bn_stats_final_kernel<<<(H + 31) / 32, 256, 0, st>>>(part, nb, H, N, x, mean, var);
   return finish_launch();
 }
 
@@ -233,7 +253,7 @@ extern "C" int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const floa
   col_partials_kernel<1><<<nb, 256, 0, st>>>(x, ldx, dout, ldo, mean, var, eps, gamma, beta, slope, N, H, part);
   int rc = finish_launch();
   if (rc) return rc;
-  sums_final_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(part, nb, H, sums);
+  sums_final_kernel<<<(2 * H + 31) / 32, 256, 0, st>>>(part, nb, H, sums);
   return finish_launch();
 }
 

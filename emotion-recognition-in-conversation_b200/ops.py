@@ -33,6 +33,14 @@ def _rows(t):
 
 
 # ------------------------------------------------------------------------------------------- raw calls
+# Dense-transform engine: "tc" = tcgen05 3xTF32 tensor-core kernels where the operands qualify (16-byte aligned rows,
+# no row gather, enough rows to fill a tile), exact-fp32 SIMT kernels otherwise; "simt" forces the SIMT kernels.
+# Both meet the 1e-5 fp32 parity bound; this is a kernel choice inside one CUDA library, not a backend dispatch.
+import os as _os
+GEMM_ENGINE = _os.environ.get("ERCG_GEMM", "tc")
+TC_MIN_ROWS = 256
+
+
 def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_scale=1.0, drop_p=0.0, seed=0, out=None):
     A, lda = _rows(A)
     Bm, ldb = _rows(Bm)
@@ -44,6 +52,14 @@ def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_s
     ldaux = 0
     if aux is not None:
         aux, ldaux = _rows(aux)
+    ldc = C.stride(0) if M > 1 else N
+    if (GEMM_ENGINE == "tc" and a_rows is None and M >= TC_MIN_ROWS and K > 0
+            and lib().ercg_gemm_nn_tc_supported(_p(A), lda, _p(C), ldc, M, N, K)):
+        ws = _ws(lib().ercg_gemm_nn_tc_workspace_bytes(N, K), A.device)
+        check(lib().ercg_gemm_nn_tc(_p(A), lda, _p(Bm), ldb, _p(bias), _p(C), ldc, M, N, K, act, _p(aux), ldaux,
+                                    float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _p(ws), ws.numel(), _stream()),
+              "ercg_gemm_nn_tc")
+        return C
     check(lib().ercg_gemm_nn(_p(A), lda, _p(a_rows), _p(Bm), ldb, _p(bias), _p(C), C.stride(0) if M > 1 else N, M, N, K,
                              act, _p(aux), ldaux, float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _stream()),
           "ercg_gemm_nn")

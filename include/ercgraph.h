@@ -115,6 +115,17 @@ int ercg_gemm_nn(const float* A, int64_t lda, const int32_t* a_rows, const float
                  const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int act,
                  const float* aux, int64_t ldaux, float aux_scale, float drop_p, uint64_t seed, void* stream);
 
+/* Tensor-core variant of ercg_gemm_nn (tcgen05 kind::tf32, TMA-staged 128-byte-swizzled tiles, TMEM
+ * accumulators).  fp32-grade accuracy through the 3xTF32 split (hi/lo of both operands, fp32 accumulate);
+ * same arguments and epilogues, plus a workspace for the K-major hi/lo copies of B.  Requirements
+ * (ercg_gemm_nn_tc_supported): A and C 16-byte aligned with lda, ldc multiples of 4, no row gather. */
+size_t ercg_gemm_nn_tc_workspace_bytes(int N, int K);
+int ercg_gemm_nn_tc_supported(const float* A, int64_t lda, const float* C, int64_t ldc, int64_t M, int N, int K);
+int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                    int64_t ldc, int64_t M, int N, int K, int act, const float* aux, int64_t ldaux,
+                    float aux_scale, float drop_p, uint64_t seed, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 /* C[K1,N1] = A[M,K1]^T @ B[M,N1]  (weight gradients; contraction over the M utterance rows, split
  * across CTAs into fixed slabs and reduced in a fixed order => bit-reproducible). */
 size_t ercg_gemm_tn_workspace_bytes(int64_t M, int K1, int N1);

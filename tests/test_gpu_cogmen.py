@@ -88,7 +88,7 @@ def test_cogmen_packed_entry_point_equals_padded():
     with torch.no_grad():
         a = m(x.cuda(), spk.cuda(), lens)[0]
         b = m.forward_packed(x[mask].contiguous().cuda(), spk[mask].contiguous().cuda(), lens)[0]
-    assert torch.equal(a, b)
+    assert rel_err(b, a) < 1e-5       # padded path gathers rows in the SIMT GEMM, packed path runs the tcgen05 GEMM
 
 
 def test_cogmen_generic_edge_index_path_matches_attached_graph():
