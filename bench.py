@@ -168,6 +168,8 @@ def kernel_label(name, args):
             return "gemm_nn[K=%d,N=%d]" % (args[10], args[9])
         if name == "ercg_gemm_nn_tc":
             return "gemm_nn_tc[K=%d,N=%d]" % (args[9], args[8])
+        if name == "ercg_gemm_tn_tc":
+            return "gemm_tn_tc[K1=%d,N1=%d]" % (args[7], args[8])
         if name == "ercg_gemm_tn":
             return "gemm_tn[K1=%d,N1=%d]" % (args[8], args[9])
     except Exception:
@@ -304,7 +306,7 @@ def run_ours(args):
 
         def alg_bytes(label):
             """Algorithmic (unique) HBM bytes of ONE launch on this rank (weights ignored)."""
-            if label.startswith("gemm_nn[") or label.startswith("gemm_tn[") or label.startswith("gemm_nn_tc["):
+            if label.startswith("gemm_"):
                 a, b = (int(v.split("=")[1]) for v in label[label.index("[") + 1:-1].split(","))
                 return 4 * N * (a + b)
             return {

@@ -43,6 +43,9 @@ SIGNATURES = {
     "ercg_gemm_nn_tc": (I, [P, L, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, SZ, P]),
     "ercg_gemm_tn_workspace_bytes": (SZ, [L, I, I]),
     "ercg_gemm_tn": (I, [P, L, P, P, L, P, L, L, I, I, P, SZ, P]),
+    "ercg_gemm_tn_tc_workspace_bytes": (SZ, [L, I, I]),
+    "ercg_gemm_tn_tc_supported": (I, [P, L, P, L, L, I, I]),
+    "ercg_gemm_tn_tc": (I, [P, L, P, L, P, L, L, I, I, P, SZ, P]),
     "ercg_mask_pos": (I, [P, L, P, L, F, P, L, L, I, P]),
     "ercg_colsum_workspace_bytes": (SZ, [L, I]),
     "ercg_colsum": (I, [P, L, L, I, P, P, SZ, P]),

@@ -361,6 +361,236 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------- TN (weight gradients)
+// C[K1,N1] = A[M,K1]^T @ B[M,N1]: the contraction runs over the M utterance rows, so both operands are "MN-major"
+// for the tensor core (the non-contracted index is the contiguous one).  Per chunk of 32 rows TMA brings
+//   A boxes {32 k1, 32 rows} x 4  -> [k1-block][row][32]   (LBO = 4096 B between k1 blocks, SBO = 1024 B per 8 rows)
+//   B boxes {32 n1, 32 rows} x nb -> [n1-block][row][32]
+// both are activations, so both are hi/lo-split in shared memory (in place + twin buffer).  Work unit = (k1 tile,
+// n1 tile, row slab); each unit writes its [128 x bn] partial to the workspace and a fixed-order reduction sums the
+// slabs (bit-reproducible).  Same grouped-TMEM / register accumulation as the NN kernel.
+constexpr int TN_R = 4;           // raw stages (A_hi | B_hi), 32 KB each
+constexpr int TN_Q = 3;           // lo stages  (A_lo | B_lo), 32 KB each
+constexpr uint32_t TN_STAGE = TC_A_BYTES + TC_B_BYTES;
+constexpr uint32_t TN_SMEM_BYTES = (TN_R + TN_Q) * TN_STAGE + 1024 + 512;
+constexpr int TN_FULL = 0, TN_RFREE = TN_FULL + TN_R, TN_SPLIT = TN_RFREE + TN_R, TN_QFREE = TN_SPLIT + TN_Q,
+              TN_ACC_FULL = TN_QFREE + TN_Q, TN_ACC_EMPTY = TN_ACC_FULL + 2, TN_BARS = TN_ACC_EMPTY + 2;
+constexpr int TN_THREADS = 320;
+
+// MN-major tf32 operands only exist in the "128-byte swizzle, 32-byte atom" layout (UMMA layout type 1; TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B (32 MN elements), the four 32-byte chunks of a row XOR-ed with
+// (row & 3), atoms of 4 K-rows = 512 B.  SBO = 512 B between 4-row K groups, LBO = 4096 B between 32-wide MN blocks.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 1)
+gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  float* __restrict__ P /* [S][K1][N1] */, long long M, int K1, int N1, int bn, int k1_tiles, int n1_tiles,
+                  int S, long long rows_per_slab) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* lo_ring = smem + TN_R * TN_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + TN_Q * TN_STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TN_BARS);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TN_R; ++i) { mbar_init(BAR(TN_FULL + i), 1); mbar_init(BAR(TN_RFREE + i), 1); }
+    for (int i = 0; i < TN_Q; ++i) { mbar_init(BAR(TN_SPLIT + i), 128); mbar_init(BAR(TN_QFREE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(TN_ACC_FULL + i), 1); mbar_init(BAR(TN_ACC_EMPTY + i), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long units = (long long)k1_tiles * n1_tiles * S;
+  const int nb = (bn + 31) / 32;                       // 32-wide n1 boxes per B tile
+  const uint32_t raw_base = smem_u32(smem), lo_base = smem_u32(lo_ring);
+  auto A_HI = [&](int r) { return raw_base + r * TN_STAGE; };
+  auto B_HI = [&](int r) { return raw_base + r * TN_STAGE + TC_A_BYTES; };
+  auto A_LO = [&](int q) { return lo_base + q * TN_STAGE; };
+  auto B_LO = [&](int q) { return lo_base + q * TN_STAGE + TC_A_BYTES; };
+  // unit -> (k1 tile, n1 tile, slab); slab fastest so that concurrently running CTAs stream different rows
+  auto decode = [&](long long u, int& k1_0, int& n1_0, long long& mbeg, long long& mend, int& slab) {
+    slab = (int)(u % S);
+    const long long kn = u / S;
+    k1_0 = (int)(kn / n1_tiles) * TC_BM;
+    n1_0 = (int)(kn % n1_tiles) * bn;
+    mbeg = (long long)slab * rows_per_slab;
+    mend = mbeg + rows_per_slab < M ? mbeg + rows_per_slab : M;
+    if (mbeg > M) mbeg = M;
+  };
+
+  if (warp == 8) {
+    if (lane == 0) {   // ---------------------------------------------------- TMA producer
+      int r = 0;
+      uint32_t rph = 0;
+      const uint32_t tx = TC_A_BYTES + (uint32_t)nb * 4096u;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        int k1_0, n1_0, slab; long long mbeg, mend;
+        decode(u, k1_0, n1_0, mbeg, mend, slab);
+        for (long long m = mbeg; m < mend; m += TC_BK) {
+          mbar_wait(BAR(TN_RFREE + r), rph ^ 1);
+          mbar_expect_tx(BAR(TN_FULL + r), tx);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_2d(A_HI(r) + i * 4096, &tmA, k1_0 + 32 * i, (int)m, BAR(TN_FULL + r));
+          for (int i = 0; i < nb; ++i) tma_load_2d(B_HI(r) + i * 4096, &tmB, n1_0 + 32 * i, (int)m, BAR(TN_FULL + r));
+          if (++r == TN_R) { r = 0; rph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {   // ---------------------------------------------------- MMA issuer
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int r = 0, q = 0, a = 0;
+      uint32_t qph = 0, aph = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        int k1_0, n1_0, slab; long long mbeg, mend;
+        decode(u, k1_0, n1_0, mbeg, mend, slab);
+        const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
+        for (long long kc = 0; kc < chunks; ++kc) {
+          const int in_group = (int)(kc % TC_GROUP);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
+          if (in_group == 0) {
+            mbar_wait(BAR(TN_ACC_EMPTY + a), aph ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(BAR(TN_SPLIT + q), qph);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t ah = make_desc_mn_sw128(A_HI(r) + ks * 1024), al = make_desc_mn_sw128(A_LO(q) + ks * 1024);
+            const uint64_t bh = make_desc_mn_sw128(B_HI(r) + ks * 1024), bl = make_desc_mn_sw128(B_LO(q) + ks * 1024);
+            tc_mma_tf32(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
+            tc_mma_tf32(d_tmem, ah, bl, idesc, 1u);
+            tc_mma_tf32(d_tmem, ah, bh, idesc, 1u);
+          }
+          tc_commit(BAR(TN_RFREE + r));
+          tc_commit(BAR(TN_QFREE + q));
+          if (in_group == TC_GROUP - 1 || kc == chunks - 1) {
+            tc_commit(BAR(TN_ACC_FULL + a));
+            if (++a == 2) { a = 0; aph ^= 1; }
+          }
+          if (++r == TN_R) r = 0;
+          if (++q == TN_Q) { q = 0; qph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------------ splitter: A tile and B tile
+    int r = 0, q = 0;
+    uint32_t rph = 0, qph = 0;
+    const int tid = threadIdx.x;
+    const int b_vec = nb * 256;                        // float4s in the B tile
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      int k1_0, n1_0, slab; long long mbeg, mend;
+      decode(u, k1_0, n1_0, mbeg, mend, slab);
+      for (long long m = mbeg; m < mend; m += TC_BK) {
+        mbar_wait(BAR(TN_QFREE + q), qph ^ 1);
+        mbar_wait(BAR(TN_FULL + r), rph);
+        float4* hi = reinterpret_cast<float4*>(smem + r * TN_STAGE);
+        float4* lo = reinterpret_cast<float4*>(lo_ring + q * TN_STAGE);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {                 // 2048 float4 slots: A (1024) then B (up to 1024)
+          const int idx = tid + 128 * i;
+          if (i < 8 || idx - 1024 < b_vec) {
+            const float4 x = hi[idx];
+            float4 h, l;
+            h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
+            l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
+            hi[idx] = h;
+            lo[idx] = l;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(BAR(TN_SPLIT + q));
+        if (++r == TN_R) { r = 0; rph ^= 1; }
+        if (++q == TN_Q) { q = 0; qph ^= 1; }
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------------ epilogue: partial [128 x bn] per unit
+    int a = 0;
+    uint32_t aph = 0;
+    const int ew = warp & 3;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      int k1_0, n1_0, slab; long long mbeg, mend;
+      decode(u, k1_0, n1_0, mbeg, mend, slab);
+      const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
+      const long long n_groups = (chunks + TC_GROUP - 1) / TC_GROUP;
+      float acc[TC_BN];
+#pragma unroll
+      for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
+      for (long long g = 0; g < n_groups; ++g) {
+        mbar_wait(BAR(TN_ACC_FULL + a), aph);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < TC_BN; c += 32) {
+          if (c < bn) {
+            uint32_t rr[32];
+            tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN + c), rr);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(rr[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(TN_ACC_EMPTY + a));
+        if (++a == 2) { a = 0; aph ^= 1; }
+      }
+      const int k1 = k1_0 + ew * 32 + lane;
+      if (k1 < K1) {
+        float* prow = P + ((long long)slab * K1 + k1) * N1 + n1_0;
+#pragma unroll
+        for (int j = 0; j < TC_BN; ++j)
+          if (j < bn && n1_0 + j < N1) prow[j] = acc[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+__global__ void tn_reduce_kernel(const float* __restrict__ P, long long stride, int S, float* __restrict__ C, long long ldc,
+                                 int rows, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += P[(long long)z * stride + idx];
+  C[(idx / cols) * ldc + (idx % cols)] = s;
+}
+
+static void tn_tc_plan(int64_t M, int K1, int N1, int& bn, int& k1_tiles, int& n1_tiles, int& S, long long& rps) {
+  n1_tiles = (N1 + 127) / 128;
+  bn = ((N1 + n1_tiles - 1) / n1_tiles + 31) / 32 * 32;      // whole 32-wide boxes
+  if (bn > 128) bn = 128;
+  n1_tiles = (N1 + bn - 1) / bn;
+  k1_tiles = (K1 + TC_BM - 1) / TC_BM;
+  const int kn = k1_tiles * n1_tiles;
+  S = kNumSMs / kn;
+  if (S < 1) S = 1;
+  const long long quantum = (long long)TC_BK * TC_GROUP;
+  long long maxS = (M + quantum - 1) / quantum;
+  if (maxS < 1) maxS = 1;
+  if (S > maxS) S = (int)maxS;
+  rps = ((M + S - 1) / S + quantum - 1) / quantum * quantum;
+  S = (int)((M + rps - 1) / rps);
+}
+
 // B[K,N] (row-major, ldb) -> Bt_hi, Bt_lo [N, Kp] (K-major, pitch Kp floats), tf32 split
 __global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int K, int N, int Kp, float* __restrict__ hi,
                                 float* __restrict__ lo) {
@@ -401,7 +631,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 row-major [rows, cols] with row pitch `ld` floats; box {32 cols, box_rows}; 128-byte swizzle
-static bool make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+static bool make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
+                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -409,7 +640,7 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -480,5 +711,47 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
     case 2: gemm_tc_nn_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
     default: gemm_tc_nn_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
   }
+  return finish_launch();
+}
+
+extern "C" size_t ercg_gemm_tn_tc_workspace_bytes(int64_t M, int K1, int N1) {
+  if (M <= 0 || K1 <= 0 || N1 <= 0) return 0;
+  int bn, kt, nt, S; long long rps;
+  tn_tc_plan(M, K1, N1, bn, kt, nt, S, rps);
+  return (size_t)S * K1 * N1 * sizeof(float) + 256;
+}
+
+extern "C" int ercg_gemm_tn_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int K1, int N1) {
+  if (M < 1 || K1 < 1 || N1 < 1) return 0;
+  if ((lda & 3) || (ldb & 3) || !aligned16(A) || !aligned16(B)) return 0;
+  if (M >= 2147483647LL) return 0;
+  return 1;
+}
+
+extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                               int K1, int N1, void* workspace, size_t workspace_bytes, void* stream) {
+  if (M < 1 || K1 < 1 || N1 < 1 || !A || !B || !C || lda < K1 || ldb < N1 || ldc < N1) return ERCG_EINVAL;
+  if (!ercg_gemm_tn_tc_supported(A, lda, B, ldb, M, K1, N1)) return ERCG_EALIGN;
+  if (workspace_bytes < ercg_gemm_tn_tc_workspace_bytes(M, K1, N1) || !workspace) return ERCG_EWORKSPACE;
+  int bn, kt, nt, S; long long rps;
+  tn_tc_plan(M, K1, N1, bn, kt, nt, S, rps);
+  float* P = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  CUtensorMap tmA, tmB;
+  if (!make_map(&tmA, A, M, K1, lda, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map(&tmB, B, M, N1, ldb, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ERCG_ECUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
+      return ERCG_ECUDA;
+    attr_set = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long units = (long long)kt * nt * S;
+  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
+  gemm_tc_tn_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmA, tmB, P, M, K1, N1, bn, kt, nt, S, rps);
+  int rc = finish_launch();
+  if (rc) return rc;
+  const long long tot = (long long)K1 * N1;
+  tn_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tot, S, C, ldc, K1, N1);
   return finish_launch();
 }

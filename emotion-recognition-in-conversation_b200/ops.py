@@ -74,6 +74,12 @@ def gemm_tn(A, Bm, a_rows=None, M=None):
         M = Bm.size(0)
     K1, N1 = A.size(1), Bm.size(1)
     C = torch.empty((K1, N1), dtype=torch.float32, device=A.device)
+    if (GEMM_ENGINE == "tc" and a_rows is None and M >= 4 * TC_MIN_ROWS
+            and lib().ercg_gemm_tn_tc_supported(_p(A), lda, _p(Bm), ldb, M, K1, N1)):
+        ws = _ws(lib().ercg_gemm_tn_tc_workspace_bytes(M, K1, N1), A.device)
+        check(lib().ercg_gemm_tn_tc(_p(A), lda, _p(Bm), ldb, _p(C), N1, M, K1, N1, _p(ws), ws.numel(), _stream()),
+              "ercg_gemm_tn_tc")
+        return C
     nbytes = lib().ercg_gemm_tn_workspace_bytes(M, K1, N1)
     ws = _ws(nbytes, A.device)
     check(lib().ercg_gemm_tn(_p(A), lda, _p(a_rows), _p(Bm), ldb, _p(C), N1, M, K1, N1, _p(ws), ws.numel(), _stream()),

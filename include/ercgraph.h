@@ -133,6 +133,12 @@ int ercg_gemm_tn(const float* A, int64_t lda, const int32_t* a_rows, const float
                  float* C, int64_t ldc, int64_t M, int K1, int N1,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core variant of ercg_gemm_tn (both operands MN-major for tcgen05, both hi/lo-split in shared memory). */
+size_t ercg_gemm_tn_tc_workspace_bytes(int64_t M, int K1, int N1);
+int ercg_gemm_tn_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int K1, int N1);
+int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                    int K1, int N1, void* workspace, size_t workspace_bytes, void* stream);
+
 /* out = ref > 0 ? x * scale : 0  -- backward of ReLU / ReLU+inverted-dropout given the forward OUTPUT
  * (cls of cogmen.py:116-122, Classifier of dgcn_models.py:163-170). */
 int ercg_mask_pos(const float* x, int64_t ldx, const float* ref, int64_t ldr, float scale,

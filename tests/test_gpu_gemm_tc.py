@@ -63,3 +63,28 @@ def test_tc_gemm_adversarial_magnitudes():
     want = A.double() @ B.double()
     out = _tc(lambda o: o.gemm_nn(A.cuda(), B.cuda()))
     assert rel_err(out, want) < TOL
+
+
+@pytest.mark.parametrize("M,K1,N1", [(1024, 100, 100), (5000, 1443, 100), (4100, 100, 900), (2048, 100, 400), (40000, 1380, 100),
+                                     (3000, 200, 800), (1500, 300, 100), (1111, 32, 32)])
+def test_tc_gemm_tn_matches_fp64(M, K1, N1):
+    import erc_b200
+    from erc_b200 import _lib
+    g = torch.Generator().manual_seed(M + K1 + N1)
+    lda = (K1 + 3) // 4 * 4
+    store = torch.randn(M, lda, generator=g)
+    A, dC = store[:, :K1], torch.randn(M, N1, generator=g)
+    want = A.double().t() @ dC.double()
+
+    def run(ops):
+        Ad, Bd = store.cuda()[:, :K1], dC.cuda()
+        assert _lib.lib().ercg_gemm_tn_tc_supported(Ad.data_ptr(), lda, Bd.data_ptr(), N1, M, K1, N1)
+        with _lib.KernelTimer() as kt:
+            r1 = ops.gemm_tn(Ad, Bd)
+            r2 = ops.gemm_tn(Ad, Bd)
+        assert "ercg_gemm_tn_tc" in kt.summary()
+        return r1, r2
+
+    r1, r2 = _tc(run)
+    assert torch.equal(r1, r2)
+    assert rel_err(r1, want) < TOL
