@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import ref_loader, graph_np
+from . import ref_loader, graph_np, seeded
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -155,16 +155,128 @@ def dgcn_fixture(ref):
     print("dgcn_small.npz loss", float(loss), "live grads", len(grads))
 
 
+def _store_grads(out, grads, big=4096):
+    """Small gradients whole; large ones as a strided sample + max-abs + sum (oracle/seeded.py)."""
+    for k, v in grads.items():
+        if v.size <= big:
+            out["grad/" + k] = v
+        else:
+            s, mx, tot = seeded.digest(v)
+            out["gsample/" + k] = s
+            out["gmax/" + k] = mx
+            out["gsum/" + k] = tot
+
+
+MMGCN_SEED, DAGERC_SEED = 31, 41
+
+
+def mmgcn_inputs(lengths, dims, n_classes, seed):
+    """Seq-first batch as ERCCollate builds it for MMGCN (batch_first=False, speaker_onehot=True; mmgcn.py:39-40)."""
+    dt, da, dv = dims
+    B, Lmax = len(lengths), max(lengths)
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(Lmax, B, dt, generator=g)
+    a = torch.randn(Lmax, B, da, generator=g)
+    v = torch.randn(Lmax, B, dv, generator=g)
+    spk = torch.randint(0, 2, (Lmax, B), generator=g)
+    for b, L in enumerate(lengths):
+        t[L:, b] = 0
+        a[L:, b] = 0
+        v[L:, b] = 0
+        spk[L:, b] = 0
+    y = torch.randint(0, n_classes, (sum(lengths),), generator=g)
+    return dict(text_feature=t, audio_feature=a, visual_feature=v, speaker_tensor=F.one_hot(spk, 2).float(),
+                text_length=torch.tensor(lengths), label=y)
+
+
+def mmgcn_fixture(ref):
+    """Real MMGCNModule (mmgcn.py:56-122, 64 GCNII layers of width 200) on a tiny batch.  Weights are NOT stored:
+    both sides call seeded.fill_by_name(module, MMGCN_SEED)."""
+    dims, C, lengths = (24, 10, 12), 6, [5, 1, 9, 3]
+    torch.manual_seed(0)
+    m = ref.mmgcn.MMGCNModule(hidden_text=dims[0], hidden_audio=dims[1], hidden_visual=dims[2], n_speakers=2, n_classes=C,
+                              modals="atv")
+    seeded.fill_by_name(m, MMGCN_SEED)
+    m.lstm_l.dropout = 0.0
+    m.graph_model.graph_net.dropout = 0.0
+    m.dropout_.p = 0.0
+    m.train()
+    b = mmgcn_inputs(lengths, dims, C, seed=32)
+    # intermediate pins: packed per-modality features and the normalised adjacency (create_big_adj)
+    with torch.no_grad():
+        fa = ref.mmgcn_utils.simple_batch_graphify(m.linear_a(b["audio_feature"]), b["text_length"])[0]
+        fv = ref.mmgcn_utils.simple_batch_graphify(m.linear_v(b["visual_feature"]), b["text_length"])[0]
+        fl = ref.mmgcn_utils.simple_batch_graphify(m.lstm_l(m.linear_l(b["text_feature"]))[0], b["text_length"])[0]
+        qm = torch.cat([b["speaker_tensor"][:x, i, :] for i, x in enumerate(lengths)], 0)
+        fl = fl + m.graph_model.speaker_embeddings(qm.argmax(-1))
+        adj = m.graph_model.create_big_adj(fa, fv, fl, b["text_length"], "atv")
+    logits, _ = m(**{k: v for k, v in b.items() if k != "label"})
+    loss = F.cross_entropy(logits, b["label"])
+    loss.backward()
+    grads = _grads(m)
+    out = {k: _np(v) for k, v in b.items()}
+    out.update(logits=_np(logits), loss=_np(loss), feat_a=_np(fa), feat_v=_np(fv), feat_l=_np(fl), adj=_np(adj),
+               dims=np.array(dims), live=np.array(sorted(grads)))
+    _store_grads(out, grads)
+    np.savez_compressed(os.path.join(OUT, "mmgcn_small.npz"), **out)
+    print("mmgcn_small.npz loss", float(loss), "live grads", len(grads), "max grad",
+          max(float(np.abs(v).max()) for v in grads.values()))
+
+
+def dagerc_inputs(lengths, emb, n_classes, seed):
+    """Batch-first batch with one-hot speakers (dagerc.py:41-42); padded speaker id 0 (mmbase.py:420,431-432)."""
+    B, Lmax = len(lengths), max(lengths)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Lmax, emb, generator=g)
+    spk = torch.randint(0, 2, (B, Lmax), generator=g)
+    mask = torch.zeros(B, Lmax)
+    for b, L in enumerate(lengths):
+        x[b, L:] = 0
+        spk[b, L:] = 0
+        mask[b, :L] = 1
+    y = torch.randint(0, n_classes, (sum(lengths),), generator=g)
+    return dict(input_tensor=x, speaker_tensor=F.one_hot(spk, 2).float(), text_length=torch.tensor(lengths),
+                attention_mask=mask, label=y)
+
+
+def dagerc_fixture(ref):
+    """Real DAGERCModule (dagerc.py:73-198: 4 layers, hidden 300).  Weights by seeded.fill_by_name."""
+    emb, C, lengths = 20, 6, [7, 2, 11, 1]
+    torch.manual_seed(0)
+    m = ref.dagerc.DAGERCModule(emb_dim=emb, dropout=0.0, n_classes=C, gnn_layers=4)
+    seeded.fill_by_name(m, DAGERC_SEED)
+    m.train()
+    b = dagerc_inputs(lengths, emb, C, seed=42)
+    mx = max(lengths)
+    adj = m.get_adj_v1(b["speaker_tensor"].tolist(), mx)
+    s_mask, _ = m.get_s_mask(b["speaker_tensor"].tolist(), mx)
+    logits, _ = m(input_tensor=b["input_tensor"], text_length=b["text_length"], speaker_tensor=b["speaker_tensor"])
+    sel = logits[b["attention_mask"].bool()]
+    loss = F.cross_entropy(sel, b["label"])          # dagerc.py:223-226
+    loss.backward()
+    grads = _grads(m)
+    out = {k: _np(v) for k, v in b.items()}
+    out.update(logits=_np(logits), loss=_np(loss), adj=_np(adj), s_mask=_np(s_mask), live=np.array(sorted(grads)))
+    _store_grads(out, grads)
+    np.savez_compressed(os.path.join(OUT, "dagerc_small.npz"), **out)
+    print("dagerc_small.npz loss", float(loss), "live grads", len(grads), "max grad",
+          max(float(np.abs(v).max()) for v in grads.values()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["graph", "cogmen", "dgcn"]
+    which = sys.argv[1:] or ["graph", "cogmen", "dgcn", "mmgcn", "dagerc"]
     if "graph" in which:
         graph_fixtures(ref)
     if "cogmen" in which:
         cogmen_fixture(ref)
     if "dgcn" in which:
         dgcn_fixture(ref)
+    if "mmgcn" in which:
+        mmgcn_fixture(ref)
+    if "dagerc" in which:
+        dagerc_fixture(ref)
 
 
 if __name__ == "__main__":
