@@ -68,6 +68,17 @@ SIGNATURES = {
     "ercg_ce_workspace_bytes": (SZ, [L]),
     "ercg_ce_fwd": (I, [P, L, P, P, P, P, L, L, I, P, SZ, P]),
     "ercg_scale_by_ratio": (I, [P, L, P, P, P]),
+    # K7 / K8 (MMGCN)
+    "ercg_mmgcn_block_offsets": (I, [P, I, P, P]),
+    "ercg_mmgcn_adj_fwd": (I, [P, L, P, P, P, L, L, I, I, P, L, P, P, P, P, P]),
+    "ercg_mmgcn_adj_bwd": (I, [P, P, P, P, L, P, P, P, P, L, L, I, I, P, P, L, P]),
+    "ercg_mmgcn_spmm": (I, [P, I, P, L, P, L, P, P, P, L, L, I, I, P, L, P, L, P]),
+    "ercg_mmgcn_sddmm": (I, [P, L, P, L, P, P, P, L, L, I, I, P, I, P]),
+    "ercg_gcnii_layer_fwd": (I, [P, L, P, L, P, L, P, L, L, I, F, F, I, F, U64, P]),
+    "ercg_gcnii_layer_bwd_input": (I, [P, L, P, L, P, L, L, I, F, F, P]),
+    "ercg_node_rows": (I, [P, P, L, I, I, I, P, P]),
+    "ercg_speaker_embed_add": (I, [P, L, P, I, P, P, L, P, L, P, P, L, I, P]),
+    "ercg_relu_dropout": (I, [P, P, L, F, U64, P]),
 }
 
 _lib = None

@@ -19,7 +19,11 @@ constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
 
 struct Epilogue {
   const float* bias; int act; const float* aux; long long ldaux; float aux_scale; float drop_p; unsigned long long seed;
+  // GCNII epilogues (internal act codes, see ercg_gcnii_layer_fwd / ercg_gcnii_layer_bwd_input below)
+  const float* aux2; long long ldaux2; float c_acc, c1, c2; int half;
 };
+constexpr int ACT_GCNII_FWD = 16;   // x = [relu if half](c_acc*acc + c1*aux[m,n] + c2*aux2[m,n]) (+ inverted dropout)
+constexpr int ACT_GCNII_BWD = 17;   // x = c_acc*acc + (n < half ? c1*aux[m,n] : c2*aux[m,n-half])
 
 __device__ __forceinline__ void mma_slab(const float (*As)[BM + 4], const float (*Bs)[BN + 4], float acc[8][8], int ty, int tx) {
 #pragma unroll
@@ -73,7 +77,8 @@ template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(GT, 2)
 gemm_nn_kernel(const float* __restrict__ A, long long lda, const int* __restrict__ a_rows,
                const float* __restrict__ B, long long ldb, float* __restrict__ C, long long ldc,
-               long long M, int N, int K, Epilogue ep) {
+               long long M, int N, int K, Epilogue ep,
+               const float* __restrict__ A2 = nullptr, long long lda2 = 0, int ksplit = 0x7fffffff) {
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -85,6 +90,9 @@ gemm_nn_kernel(const float* __restrict__ A, long long lda, const int* __restrict
   const bool a_ok = am < M;
   const float* arow = A;
   if (a_ok) arow = A + (a_rows ? (long long)a_rows[am] : am) * lda;
+  // optional second source for the columns k >= ksplit of the A operand ([A | A2] without materialising the concat;
+  // ksplit % 8 == 0 so every 8-wide thread chunk lies on one side)
+  const float* arow2 = a_ok && A2 ? A2 + am * lda2 - ksplit : arow;
   const int bk = t >> 5, bn = (t & 31) * 4;
 
   float acc[8][8];
@@ -94,7 +102,7 @@ gemm_nn_kernel(const float* __restrict__ A, long long lda, const int* __restrict
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   float ra[8], rb0[4], rb1[4];
-  load_a_nn<VEC_A>(arow, a_ok, ak, K, ra);
+  load_a_nn<VEC_A>(ak >= ksplit ? arow2 : arow, a_ok, ak, K, ra);
   load_b_nn<VEC_B>(B, ldb, bk, K, n0 + bn, N, rb0);
   load_b_nn<VEC_B>(B, ldb, bk + 8, K, n0 + bn, N, rb1);
   const int nslab = (K + BK - 1) / BK;
@@ -107,7 +115,7 @@ gemm_nn_kernel(const float* __restrict__ A, long long lda, const int* __restrict
   for (int s = 0; s < nslab; ++s) {
     const int kn = (s + 1) * BK;
     if (s + 1 < nslab) {
-      load_a_nn<VEC_A>(arow, a_ok, kn + ak, K, ra);
+      load_a_nn<VEC_A>(kn + ak >= ksplit ? arow2 : arow, a_ok, kn + ak, K, ra);
       load_b_nn<VEC_B>(B, ldb, kn + bk, K, n0 + bn, N, rb0);
       load_b_nn<VEC_B>(B, ldb, kn + bk + 8, K, n0 + bn, N, rb1);
     }
@@ -150,6 +158,16 @@ gemm_nn_kernel(const float* __restrict__ A, long long lda, const int* __restrict
               x = u < ep.drop_p ? 0.f : x * (1.0f / (1.0f - ep.drop_p));
             } else if (ep.act == ERCG_ACT_MASK_POS) {
               x = __ldg(ep.aux + m * ep.ldaux + nn) > 0.f ? x * ep.aux_scale : 0.f;
+            } else if (ep.act == ACT_GCNII_FWD) {
+              x = ep.c_acc * x + (ep.c1 * __ldg(ep.aux + m * ep.ldaux + nn) + ep.c2 * __ldg(ep.aux2 + m * ep.ldaux2 + nn));
+              if (ep.half) x = fmaxf(x, 0.f);
+              if (ep.drop_p > 0.f) {
+                const float u = hash_uniform(ep.seed, (unsigned long long)m * (unsigned long long)N + nn);
+                x = u < ep.drop_p ? 0.f : x * (1.0f / (1.0f - ep.drop_p));
+              }
+            } else if (ep.act == ACT_GCNII_BWD) {
+              x = ep.c_acc * x + (nn < ep.half ? ep.c1 * __ldg(ep.aux + m * ep.ldaux + nn)
+                                               : ep.c2 * __ldg(ep.aux + m * ep.ldaux + nn - ep.half));
             }
           }
           v[j] = x;
@@ -338,7 +356,7 @@ extern "C" int ercg_gemm_nn(const float* A, int64_t lda, const int32_t* a_rows, 
   if (!A || !B || !C || lda < K || ldb < N || ldc < N) return ERCG_EINVAL;
   if (act < 0 || act > 3 || (act == ERCG_ACT_MASK_POS && !aux)) return ERCG_EINVAL;
   if (act == ERCG_ACT_RELU_DROPOUT && !(drop_p >= 0.f && drop_p < 1.f)) return ERCG_EINVAL;
-  Epilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed};
+  Epilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, nullptr, 0, 1.f, 0.f, 0.f, 0};
   const bool va = ((lda & 3) == 0) && aligned16(A);
   const bool vb = ((ldb & 3) == 0) && aligned16(B);
   long long gm = (M + BM - 1) / BM;
@@ -415,5 +433,46 @@ extern "C" int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float*
   int rc = finish_launch();
   if (rc != ERCG_OK) return rc;
   colsum_final_kernel<<<(N + 31) / 32, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), nb, N, out);
+  return finish_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// GCNII layer (GraphConvolution.forward with variant=True, residual=False; track_mm/mmgcn_models.py:27-39)
+//   out = dropout(relu(theta * [hi | h0] @ W + (1 - theta) * ((1 - alpha) * hi + alpha * h0)))
+// [hi | h0] is never materialised: the A operand is read from two sources split at k = H.
+// The ReLU and the NEXT layer's input dropout (GCNII_lyc.forward :388-392) are the epilogue.
+// ---------------------------------------------------------------------------------------------
+extern "C" int ercg_gcnii_layer_fwd(const float* hi, int64_t ldhi, const float* h0, int64_t ldh0, const float* W,
+                                    int64_t ldw, float* out, int64_t ldo, int64_t M, int H, float theta, float alpha,
+                                    int relu, float drop_p, uint64_t seed, void* stream) {
+  if (M < 0 || H <= 0 || (H & 7)) return ERCG_EINVAL;
+  if (M == 0) return ERCG_OK;
+  if (!hi || !h0 || !W || !out || ldhi < H || ldh0 < H || ldw < H || ldo < H) return ERCG_EINVAL;
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return ERCG_EINVAL;
+  if (!aligned16(hi) || !aligned16(h0) || !aligned16(W) || (ldhi & 3) || (ldh0 & 3) || (ldw & 3)) return ERCG_EALIGN;
+  Epilogue ep{nullptr, ACT_GCNII_FWD, hi, (long long)ldhi, 1.f, drop_p, (unsigned long long)seed,
+              h0, (long long)ldh0, theta, (1.f - theta) * (1.f - alpha), (1.f - theta) * alpha, relu ? 1 : 0};
+  long long gm = (M + BM - 1) / BM;
+  if (gm > 2147483647LL) return ERCG_ERANGE;
+  dim3 grid((unsigned)gm, (unsigned)((H + BN - 1) / BN));
+  gemm_nn_kernel<true, true><<<grid, GT, 0, (cudaStream_t)stream>>>(hi, ldhi, nullptr, W, ldw, out, ldo, M, H, 2 * H, ep,
+                                                                   h0, ldh0, H);
+  return finish_launch();
+}
+
+// dS[M, 2H] = theta * dZ @ Wt + [ (1-theta)(1-alpha) dZ | (1-theta) alpha dZ ],  Wt = W^T [H, 2H]
+// (left half = gradient w.r.t. hi, right half = this layer's contribution to the gradient w.r.t. h0)
+extern "C" int ercg_gcnii_layer_bwd_input(const float* dZ, int64_t lddz, const float* Wt, int64_t ldwt, float* dS,
+                                          int64_t ldds, int64_t M, int H, float theta, float alpha, void* stream) {
+  if (M < 0 || H <= 0 || (H & 7)) return ERCG_EINVAL;
+  if (M == 0) return ERCG_OK;
+  if (!dZ || !Wt || !dS || lddz < H || ldwt < 2 * H || ldds < 2 * H) return ERCG_EINVAL;
+  if (!aligned16(dZ) || !aligned16(Wt) || (lddz & 3) || (ldwt & 3)) return ERCG_EALIGN;
+  Epilogue ep{nullptr, ACT_GCNII_BWD, dZ, (long long)lddz, 1.f, 0.f, 0ull,
+              nullptr, 0, theta, (1.f - theta) * (1.f - alpha), (1.f - theta) * alpha, H};
+  long long gm = (M + BM - 1) / BM;
+  if (gm > 2147483647LL) return ERCG_ERANGE;
+  dim3 grid((unsigned)gm, (unsigned)((2 * H + BN - 1) / BN));
+  gemm_nn_kernel<true, true><<<grid, GT, 0, (cudaStream_t)stream>>>(dZ, lddz, nullptr, Wt, ldwt, dS, ldds, M, 2 * H, H, ep);
   return finish_launch();
 }

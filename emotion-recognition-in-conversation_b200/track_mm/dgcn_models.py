@@ -22,6 +22,23 @@ def _fresh_seed():
     return int(torch.empty((), dtype=torch.int64).random_().item())
 
 
+def bilstm_forward(rnn, x2d, graph, a_rows, training):
+    """Multi-layer bidirectional nn.LSTM over the dialogues of ``graph`` (packed-sequence semantics): per layer one
+    hoisted input GEMM for all utterances and both directions (K2) + the recurrence kernel (K6)."""
+    h = x2d
+    for layer in range(rnn.num_layers):
+        sfx = "_l%d" % layer
+        w_ih = torch.cat([getattr(rnn, "weight_ih" + sfx), getattr(rnn, "weight_ih" + sfx + "_reverse")], 0)
+        b = torch.cat([getattr(rnn, "bias_ih" + sfx) + getattr(rnn, "bias_hh" + sfx),
+                       getattr(rnn, "bias_ih" + sfx + "_reverse") + getattr(rnn, "bias_hh" + sfx + "_reverse")], 0)
+        w_hh = torch.stack([getattr(rnn, "weight_hh" + sfx), getattr(rnn, "weight_hh" + sfx + "_reverse")], 0)
+        gx = ops.linear(h, w_ih, b, a_rows=a_rows if layer == 0 else None)
+        h = ops.lstm_layer(gx, w_hh, graph)
+        if training and rnn.dropout > 0 and layer + 1 < rnn.num_layers:
+            h = ops.dropout(h, rnn.dropout, _fresh_seed())
+    return h
+
+
 class SeqContext(nn.Module):
     def __init__(self, u_dim, g_dim, dropout=0.4, rnn_type="lstm"):
         super().__init__()
@@ -32,18 +49,7 @@ class SeqContext(nn.Module):
 
     def packed_forward(self, x2d, graph, a_rows=None):
         """x2d: [rows, u_dim]; a_rows maps packed node -> row of x2d (None = already packed). -> [N, g_dim]"""
-        rnn, h = self.rnn, x2d
-        for layer in range(rnn.num_layers):
-            sfx = "_l%d" % layer
-            w_ih = torch.cat([getattr(rnn, "weight_ih" + sfx), getattr(rnn, "weight_ih" + sfx + "_reverse")], 0)
-            b = torch.cat([getattr(rnn, "bias_ih" + sfx) + getattr(rnn, "bias_hh" + sfx),
-                           getattr(rnn, "bias_ih" + sfx + "_reverse") + getattr(rnn, "bias_hh" + sfx + "_reverse")], 0)
-            w_hh = torch.stack([getattr(rnn, "weight_hh" + sfx), getattr(rnn, "weight_hh" + sfx + "_reverse")], 0)
-            gx = ops.linear(h, w_ih, b, a_rows=a_rows if layer == 0 else None)
-            h = ops.lstm_layer(gx, w_hh, graph)
-            if self.training and rnn.dropout > 0 and layer + 1 < rnn.num_layers:
-                h = ops.dropout(h, rnn.dropout, _fresh_seed())
-        return h
+        return bilstm_forward(self.rnn, x2d, graph, a_rows, self.training)
 
     def forward(self, text_len_tensor, text_tensor):
         """Reference signature: -> zero-padded [B, max(L), g_dim] like pad_packed_sequence."""

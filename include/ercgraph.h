@@ -258,6 +258,64 @@ int ercg_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, const fl
                 void* workspace, size_t workspace_bytes, void* stream);
 int ercg_scale_by_ratio(float* x, int64_t n, const float* num, const float* den, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K7  MMGCN cross-modal utterance graph as a block adjacency (MMGCN.create_big_adj,
+ * track_mm/mmgcn_models.py:582-646).  M modalities, N utterances, node (m,i) = row m*N + i
+ * (modality-major then dialogue-major, :616).  Non-zeros of the reference's dense [M*N, M*N] matrix:
+ *   blocks: flat[m*SB + blk_off[d] + i*L + j]            L x L similarity block of dialogue d, modality m
+ *   cross : flat[M*SB + (m*(M-1) + (n<m ? n : n-1))*N + node]   entry ((m,node),(n,node)), m != n
+ * with SB = sum_d L_d^2 (ercg_mmgcn_block_offsets writes the prefix blk_off[B+1]); the flat array has
+ * M*SB + M*(M-1)*N floats.
+ *   adj_fwd: xhat = x/|x| (:606-607), cs = 0.99999 <xhat_i,xhat_j> (:608-609), A = 1 - acos(cs)/pi (:610),
+ *            dinv = rowsum(A)^-1/2, ahat = (dinv_i A_ij) dinv_j  (D.mm(adj).mm(D), :638-644)
+ *   adj_bwd: gradient G w.r.t. ahat (same flat layout) -> dx (create_big_adj is differentiable in the features)
+ * D, H <= 256, multiples of 4; all feature rows 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int ercg_mmgcn_block_offsets(const int32_t* node_off, int B, int64_t* blk_off, void* stream);
+int ercg_mmgcn_adj_fwd(const float* x, int64_t ldx, const int32_t* node_off, const int32_t* node_dlg,
+                       const int64_t* blk_off, int64_t N, int64_t SB, int M, int D, float* xhat, int64_t ldh,
+                       float* rinv /*[M*N]*/, float* cs /*flat*/, float* ahat /*flat*/, float* dinv /*[M*N]*/, void* stream);
+int ercg_mmgcn_adj_bwd(const float* G, const float* cs, const float* dinv, const float* xhat, int64_t ldh,
+                       const float* rinv, const int32_t* node_off, const int32_t* node_dlg, const int64_t* blk_off,
+                       int64_t N, int64_t SB, int M, int D, float* ddeg /*[M*N] scratch*/, float* dx, int64_t ldx,
+                       void* stream);
+/* out = Ahat @ h over the block pattern (torch.spmm(adj, input), mmgcn_models.py:29); transpose != 0 uses Ahat^T
+ * (input gradient).  Optional side job for the backward: acc_dst[row,:] += acc_src[row,:]. */
+int ercg_mmgcn_spmm(const float* ahat, int transpose, const float* h, int64_t ldh, float* out, int64_t ldo,
+                    const int32_t* node_off, const int32_t* node_dlg, const int64_t* blk_off, int64_t N, int64_t SB,
+                    int M, int H, const float* acc_src, int64_t lds, float* acc_dst, int64_t ldd, void* stream);
+/* G[(i,j)] (+)= <dhi_i, h_j> on the block pattern: gradient w.r.t. ahat of out = Ahat @ h */
+int ercg_mmgcn_sddmm(const float* dhi, int64_t ldd, const float* h, int64_t ldh, const int32_t* node_off,
+                     const int32_t* node_dlg, const int64_t* blk_off, int64_t N, int64_t SB, int M, int H, float* G,
+                     int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K8  GCNII layer (GraphConvolution.forward, variant=True, residual=False; mmgcn_models.py:27-39) with the ReLU and
+ * the next layer's input dropout of GCNII_lyc.forward (:388-392) as the epilogue:
+ *   out = dropout(relu(theta * [hi | h0] @ W + (1-theta) * ((1-alpha) * hi + alpha * h0))),  W [2H, H]
+ * (relu == 0: the bare GraphConvolution output, drop_p == 0: no dropout).  [hi | h0] is read from its two sources, never concatenated.  Backward w.r.t. the inputs:
+ *   dS[M, 2H] = theta * dZ @ Wt + [(1-theta)(1-alpha) dZ | (1-theta) alpha dZ],  Wt = W^T [H, 2H], dZ = relu/dropout-masked dout
+ * (weight gradient = theta * [hi | h0]^T dZ through ercg_gemm_tn).  H % 8 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int ercg_gcnii_layer_fwd(const float* hi, int64_t ldhi, const float* h0, int64_t ldh0, const float* W, int64_t ldw,
+                         float* out, int64_t ldo, int64_t M, int H, float theta, float alpha, int relu, float drop_p,
+                         uint64_t seed, void* stream);
+int ercg_gcnii_layer_bwd_input(const float* dZ, int64_t lddz, const float* Wt, int64_t ldwt, float* dS, int64_t ldds,
+                               int64_t M, int H, float theta, float alpha, void* stream);
+
+/* helpers of the MMGCN path */
+/* rows[i] = row of packed node i in a padded tensor: seq-first [Lmax,B,*] -> k*B + d, batch-first -> d*Lmax + k
+ * (simple_batch_graphify, track_mm/mmgcn_utils.py:5-21, fused into the consumer GEMM as its row gather) */
+int ercg_node_rows(const int32_t* node_off, const int32_t* node_dlg, int64_t N, int B, int Lmax, int seq_first,
+                   int32_t* rows, void* stream);
+/* out[i,:] = x[i,:] + emb[argmax(qmask[rows[i], :]), :]; ids[i] = that argmax, onehot[N, n_speakers] for the
+ * embedding gradient (onehot^T @ dout through ercg_gemm_tn).  MMGCN.forward, mmgcn_models.py:540-545. */
+int ercg_speaker_embed_add(const float* x, int64_t ldx, const float* qmask, int n_speakers, const int32_t* rows,
+                           const float* emb, int64_t lde, float* out, int64_t ldo, int32_t* ids, float* onehot, int64_t N,
+                           int D, void* stream);
+/* out = dropout(relu(x)) with the counter-hash mask (relu(dropout(x)) of mmgcn.py:117-118 is the same function) */
+int ercg_relu_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
