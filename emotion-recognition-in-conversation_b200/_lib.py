@@ -24,6 +24,14 @@ class GraphOut(Structure):
         "node_dlg", "inv_cnt", "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row")]
 
 
+class DagLayer(Structure):
+    """ercg_dag_layer (include/ercgraph.h)."""
+    _fields_ = ([(n, c_int) for n in ("B", "D", "Tmax", "reserved")] +
+                [(n, c_void_p) for n in ("node_off", "order", "spk", "lo", "eoff", "wk", "Wr0", "Wr1", "Whh_c", "bhh_c",
+                                         "Wih_p", "bih_p", "Hin", "pre", "H1", "a", "S", "M", "alpha", "gc", "hnc", "gp",
+                                         "dH1", "dpre", "dGseq", "dM", "dS", "dHdir", "ga")])
+
+
 P, I, L, F, D, U64, SZ = c_void_p, c_int, c_int64, c_float, c_double, c_uint64, c_size_t
 
 # name -> (restype, argtypes); mirrors include/ercgraph.h one to one
@@ -79,6 +87,12 @@ SIGNATURES = {
     "ercg_node_rows": (I, [P, P, L, I, I, I, P, P]),
     "ercg_speaker_embed_add": (I, [P, L, P, I, P, P, L, P, L, P, P, L, I, P]),
     "ercg_relu_dropout": (I, [P, P, L, F, U64, P]),
+    # K9 / K10 (DAG-ERC)
+    "ercg_dag_build_workspace_bytes": (SZ, [L]),
+    "ercg_dag_build": (I, [P, P, P, L, I, P, P, P, P, P, SZ, P]),
+    "ercg_dag_dense_masks": (I, [P, I, I, I, P, P, P]),
+    "ercg_dag_layer_fwd": (I, [POINTER(DagLayer), P]),
+    "ercg_dag_layer_bwd": (I, [POINTER(DagLayer), P]),
 }
 
 _lib = None

@@ -316,6 +316,54 @@ int ercg_speaker_embed_add(const float* x, int64_t ldx, const float* qmask, int 
 /* out = dropout(relu(x)) with the counter-hash mask (relu(dropout(x)) of mmgcn.py:117-118 is the same function) */
 int ercg_relu_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K9  DAG-ERC predecessor structure (DAGERCModule.get_adj_v1 / get_s_mask, track_mm/dagerc.py:109-154) on packed
+ * dialogues: the direct predecessors of utterance i are the contiguous local range [lo_i, i-1], lo_i = the
+ * windowp-th latest j < i with spk_j == spk_i (0 if there are fewer); s_mask[i,j] = (spk_i == spk_j).
+ *   lo[N], cnt[N] = i - lo_i, eoff[N] = exclusive scan of cnt (where node i's attention weights are stored),
+ *   total[1] = sum cnt (device).  ercg_dag_dense_masks emits the reference's dense layout from PADDED speaker ids:
+ *   adj [B,Lmax,Lmax] fp32, s_mask [B,Lmax,Lmax] int64 (computed over all Lmax positions, like the reference).
+ * ------------------------------------------------------------------------------------------- */
+size_t ercg_dag_build_workspace_bytes(int64_t N);
+int ercg_dag_build(const int32_t* node_off, const int32_t* node_dlg, const int32_t* spk, int64_t N, int windowp,
+                   int32_t* lo, int32_t* cnt, int64_t* eoff, int64_t* total, void* workspace, size_t workspace_bytes,
+                   void* stream);
+int ercg_dag_dense_masks(const int32_t* spk_padded, int B, int Lmax, int windowp, float* adj, int64_t* s_mask,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K10  one DAG-ERC GNN layer over all dialogues (the i-loop of DAGERCModule.forward, dagerc.py:167-185, with
+ * GAT_dialoggcn_v1.forward, dagerc_models.py:326-365, and the two nn.GRUCell of :89-90) as ONE persistent
+ * cooperative kernel; backward = the same in reverse time.  D = hidden size (300 in the reference), D % 4 == 0.
+ *   pre[N,6D] = Hin @ [W_ih^c ; W_hh^p]^T + [b_ih^c ; b_hh^p]   (hoisted, by ercg_gemm_nn)
+ *   per step i: alpha = softmax_{j in [lo_i, i-1]} (wk . H1_j)      (the w_q.Q + b part of linear() is constant in j)
+ *               S0/S1 = alpha-weighted sums of H1_j over same-/other-speaker j;  M = Wr0 S0 + Wr1 S1
+ *               C = GRUCell_c(H_i, M), P = GRUCell_p(M, H_i), H1_i = C + P
+ * order[B] = dialogues by decreasing length; Tmax = the longest.  Saved for the backward: a[N], S[N,2D], M[N,D],
+ * alpha[total], gc[N,3D] (r,z,n of cell c), hnc[N,D] (W_hn^c M + b_hn^c), gp[N,3D].
+ * Backward: dH1 [N,D] holds the incoming gradient and is used as the accumulator; outputs dpre[N,6D] (w.r.t. pre),
+ * dGseq[N,6D] (w.r.t. [W_hh^c M + b ; W_ih^p M + b]), dM[N,D], dHdir[N,D] (direct z'*dP term of H_i), ga[N] (zero-
+ * initialised; sum of the attention-logit gradients per utterance), dS[N,2D] scratch.  Weight gradients are TN GEMMs
+ * of these against Hin / M / S / H1.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ercg_dag_layer {
+  int32_t B, D, Tmax, reserved;
+  const int32_t* node_off; const int32_t* order; const int32_t* spk; const int32_t* lo; const int64_t* eoff;
+  const float* wk;      /* [D]     gather.linear.weight[0, D:2D] */
+  const float* Wr0;     /* [D,D]   row-major (out, in) like nn.Linear.weight */
+  const float* Wr1;
+  const float* Whh_c;   /* [3D,D]  grus_c.weight_hh */
+  const float* bhh_c;   /* [3D] */
+  const float* Wih_p;   /* [3D,D]  grus_p.weight_ih */
+  const float* bih_p;
+  const float* Hin;     /* [N,D]   H[l] */
+  const float* pre;     /* [N,6D] */
+  float *H1, *a, *S, *M, *alpha, *gc, *hnc, *gp;
+  float *dH1, *dpre, *dGseq, *dM, *dS, *dHdir, *ga;   /* backward only */
+} ercg_dag_layer;
+int ercg_dag_layer_fwd(const ercg_dag_layer* args, void* stream);
+int ercg_dag_layer_bwd(const ercg_dag_layer* args, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
