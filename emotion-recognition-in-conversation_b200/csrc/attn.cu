@@ -37,6 +37,48 @@ __device__ __forceinline__ float row_dot(const float4 a[NC], const float* p, int
   return warp_sum(s);
 }
 
+// <a, row_q> for 4 rows at once: the 4 row loads are issued back to back, the 4 reductions interleave.
+// Rows with live[q] == false are not read (warp-uniform) and yield 0.
+template <int NC>
+__device__ __forceinline__ void row_dot4(const float4 a[NC], const float* const p[4], const bool live[4], int nch, int lane,
+                                         float out[4]) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      float4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = live[q] ? ld4(p[q] + 4 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += dot4(a[c], v[q]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[q] = s[q];
+}
+// acc += sum_q w[q] * row_q (4 rows in flight)
+template <int NC>
+__device__ __forceinline__ void row_axpy4(float4 acc[NC], const float w[4], const float* const p[4], const bool live[4],
+                                          int nch, int lane) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      float4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = live[q] ? ld4(p[q] + 4 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) fma4(acc[c], w[q], v[q]);
+    }
+  }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(AW * 32)
 attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
@@ -56,9 +98,20 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
   for (int cb = beg; cb < end; cb += 32) {
     const int cn = min(32, end - cb);
     float my = -INFINITY;                       // score of edge cb + lane
-    for (int u = 0; u < cn; ++u) {
-      const float d = row_dot<NC>(qi, k + (long long)col[cb + u] * ld, nch, lane) * scale;
-      if (lane == u) my = d;
+    const int mc = lane < cn ? col[cb + lane] : 0;      // sources of this batch, one coalesced load
+    for (int u = 0; u < cn; u += 4) {
+      const float* p[4];
+      bool live[4];
+      float d[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        live[qq] = u + qq < cn;
+        p[qq] = k + (long long)__shfl_sync(0xffffffffu, mc, min(u + qq, cn - 1)) * ld;
+      }
+      row_dot4<NC>(qi, p, live, nch, lane, d);
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+        if (lane == u + qq) my = d[qq] * scale;
     }
     const float cmax = warp_max(my);
     const float new_max = fmaxf(run_max, cmax);
@@ -71,14 +124,18 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
     if (alpha && cb > beg && resc != 1.f) {               // rescale earlier chunks (rare: deg > 32)
       for (int e2 = beg + lane; e2 < cb; e2 += 32) alpha[e2] *= resc;
     }
-    for (int u = 0; u < cn; ++u) {
-      const float a = __shfl_sync(0xffffffffu, ex, u);
-      const float* pv = v + (long long)col[cb + u] * ld;
+    for (int u = 0; u < cn; u += 4) {
+      const float* p[4];
+      bool live[4];
+      float a[4];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int ch = lane + 32 * c;
-        if (ch < nch) fma4(acc[c], a, ld4(pv + 4 * ch));
+      for (int qq = 0; qq < 4; ++qq) {
+        const int l = min(u + qq, cn - 1);
+        live[qq] = u + qq < cn;
+        a[qq] = __shfl_sync(0xffffffffu, ex, l);
+        p[qq] = v + (long long)__shfl_sync(0xffffffffu, mc, l) * ld;
       }
+      row_axpy4<NC>(acc, a, p, live, nch, lane);
     }
     run_max = new_max;
   }
@@ -118,6 +175,54 @@ attn_bwd_dst_kernel(const float* __restrict__ dout, long long ldo, const float* 
   float4 go[NC], acc[NC];
   load_row<NC>(dout + node * ldo, nch, lane, go);
   const int beg = rowptr[node], end = rowptr[node + 1];
+  if (end - beg <= 32) {
+    // common case: every per-edge scalar of the row lives in one lane; no round trip through the dsig buffer
+    const int cn = end - beg;
+    const int mc = lane < cn ? col[beg + lane] : 0;
+    const float al = lane < cn ? alpha[beg + lane] : 0.f;
+    float my = 0.f;
+    for (int u = 0; u < cn; u += 4) {
+      const float* p[4];
+      bool live[4];
+      float d[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        live[qq] = u + qq < cn;
+        p[qq] = v + (long long)__shfl_sync(0xffffffffu, mc, min(u + qq, cn - 1)) * ld;
+      }
+      row_dot4<NC>(go, p, live, nch, lane, d);
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+        if (lane == u + qq) my = d[qq];
+    }
+    const float D = warp_sum(al * my);
+    const float g = al * (my - D);
+    if (lane < cn) dsig[beg + lane] = g;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < cn; u += 4) {
+      const float* p[4];
+      bool live[4];
+      float gw[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int l = min(u + qq, cn - 1);
+        live[qq] = u + qq < cn;
+        gw[qq] = __shfl_sync(0xffffffffu, g, l) * scale;
+        p[qq] = k + (long long)__shfl_sync(0xffffffffu, mc, l) * ld;
+      }
+      row_axpy4<NC>(acc, gw, p, live, nch, lane);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        st4(dq + node * ldd + 4 * ch, acc[c]);
+        if (ds) st4(ds + node * ldd + 4 * ch, go[c]);
+      }
+    }
+    return;
+  }
   // pass 1: dalpha per edge -> dsig buffer (temporarily), D
   float D = 0.f;
   for (int cb = beg; cb < end; cb += 32) {

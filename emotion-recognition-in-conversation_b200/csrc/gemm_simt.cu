@@ -12,6 +12,8 @@
 // dimension so the shared-memory reads are conflict-free float4 / broadcasts), double-buffered
 // shared memory with register prefetch of the next K-slab.
 #include "common.cuh"
+#include "gemm_skinny.cuh"
+#include <algorithm>
 
 namespace ercg {
 
@@ -330,6 +332,19 @@ colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float
   }
 }
 
+// skinny weight gradient (N1 <= 16, K1 <= 256, no row gather): slabs of rows, one block each
+static bool tn_skinny(int64_t M, int K1, int N1, bool gather) { return !gather && N1 <= SK_MAXN && K1 <= 256 && M >= 1024; }
+static void tn_skinny_plan(int64_t M, int K1, int& S, long long& rps, int& groups, int& KP) {
+  KP = (K1 + 31) / 32 * 32;
+  groups = 512 / KP;
+  long long want = (long long)kNumSMs * 4;
+  long long maxs = (M + 255) / 256;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  rps = (M + want - 1) / want;
+  S = (int)((M + rps - 1) / rps);
+}
+
 static void tn_plan(int64_t M, int K1, int N1, int& S, long long& rows_per_split) {
   const long long tiles = (long long)((K1 + BM - 1) / BM) * ((N1 + BN - 1) / BN);
   long long want = (2LL * kNumSMs + tiles - 1) / tiles;      // ~2 CTAs per SM in flight
@@ -356,13 +371,30 @@ extern "C" int ercg_gemm_nn(const float* A, int64_t lda, const int32_t* a_rows, 
   if (!A || !B || !C || lda < K || ldb < N || ldc < N) return ERCG_EINVAL;
   if (act < 0 || act > 3 || (act == ERCG_ACT_MASK_POS && !aux)) return ERCG_EINVAL;
   if (act == ERCG_ACT_RELU_DROPOUT && !(drop_p >= 0.f && drop_p < 1.f)) return ERCG_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!a_rows && act == ERCG_ACT_NONE && M >= 1024 && K > 0) {          // skinny shapes: see gemm_skinny.cuh
+    if (N <= SK_MAXN && K <= 2048) {
+      const int NN = N <= 8 ? 8 : 16;
+      const unsigned grid = (unsigned)std::min<long long>((long long)kNumSMs * 16, (long long)((M + 7) / 8));
+      const size_t sm = (size_t)((K + 3) & ~3) * NN * sizeof(float);
+      if (NN == 8) skinny_nn_small_n_kernel<8><<<grid, 256, sm, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+      else skinny_nn_small_n_kernel<16><<<grid, 256, sm, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+      return finish_launch();
+    }
+    if (K <= SK_MAXN && N <= 1024) {
+      const int NP = (N + 3) / 4 * 4;
+      const long long total = M * (NP / 4);
+      const unsigned grid = (unsigned)std::min<long long>((long long)kNumSMs * 16, (total + 255) / 256);
+      skinny_nn_small_k_kernel<<<grid, 256, (size_t)(K + 1) * NP * sizeof(float), st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+      return finish_launch();
+    }
+  }
   Epilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, nullptr, 0, 1.f, 0.f, 0.f, 0};
   const bool va = ((lda & 3) == 0) && aligned16(A);
   const bool vb = ((ldb & 3) == 0) && aligned16(B);
   long long gm = (M + BM - 1) / BM;
   if (gm > 2147483647LL) return ERCG_ERANGE;
   dim3 grid((unsigned)gm, (unsigned)((N + BN - 1) / BN));
-  cudaStream_t st = (cudaStream_t)stream;
   if (va && vb) gemm_nn_kernel<true, true><<<grid, GT, 0, st>>>(A, lda, a_rows, B, ldb, C, ldc, M, N, K, ep);
   else if (va) gemm_nn_kernel<true, false><<<grid, GT, 0, st>>>(A, lda, a_rows, B, ldb, C, ldc, M, N, K, ep);
   else if (vb) gemm_nn_kernel<false, true><<<grid, GT, 0, st>>>(A, lda, a_rows, B, ldb, C, ldc, M, N, K, ep);
@@ -374,7 +406,14 @@ extern "C" size_t ercg_gemm_tn_workspace_bytes(int64_t M, int K1, int N1) {
   if (M <= 0 || K1 <= 0 || N1 <= 0) return 0;
   int S; long long rps;
   tn_plan(M, K1, N1, S, rps);
-  return S > 1 ? (size_t)S * K1 * N1 * sizeof(float) : 0;
+  size_t need = S > 1 ? (size_t)S * K1 * N1 * sizeof(float) : 0;
+  if (tn_skinny(M, K1, N1, false)) {
+    int g, kp;
+    tn_skinny_plan(M, K1, S, rps, g, kp);
+    const size_t n2 = (size_t)S * K1 * N1 * sizeof(float);
+    if (n2 > need) need = n2;
+  }
+  return need;
 }
 
 extern "C" int ercg_gemm_tn(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb,
@@ -390,6 +429,23 @@ extern "C" int ercg_gemm_tn(const float* A, int64_t lda, const int32_t* a_rows, 
   }
   if (!A || !B || lda < K1 || ldb < N1) return ERCG_EINVAL;
   int S; long long rps;
+  if (tn_skinny(M, K1, N1, a_rows != nullptr)) {
+    int groups, KP;
+    tn_skinny_plan(M, K1, S, rps, groups, KP);
+    const size_t need2 = (size_t)S * K1 * N1 * sizeof(float);
+    if (need2 <= workspace_bytes && workspace) {
+      float* Pw = reinterpret_cast<float*>(workspace);
+      const int NN = N1 <= 8 ? 8 : 16;
+      const size_t sm = (size_t)groups * KP * NN * sizeof(float);
+      if (NN == 8) skinny_tn_small_n_kernel<8><<<S, 512, sm, st>>>(A, lda, B, ldb, Pw, M, K1, N1, rps, groups, KP);
+      else skinny_tn_small_n_kernel<16><<<S, 512, sm, st>>>(A, lda, B, ldb, Pw, M, K1, N1, rps, groups, KP);
+      int rc2 = finish_launch();
+      if (rc2 != ERCG_OK) return rc2;
+      const long long tot = (long long)K1 * N1;
+      reduce_splits_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Pw, tot, S, C, ldc, K1, N1);
+      return finish_launch();
+    }
+  }
   tn_plan(M, K1, N1, S, rps);
   const size_t need = S > 1 ? (size_t)S * K1 * N1 * sizeof(float) : 0;
   if (need > workspace_bytes || (need && !workspace)) return ERCG_EWORKSPACE;

@@ -109,26 +109,62 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-// Shared-memory plan (1 CTA / SM):
-//   raw ring  : TC_R stages x 16 KB   A tile as TMA wrote it; the splitter rewrites it in place as A_hi
-//   oper ring : TC_Q stages x 48 KB   A_lo (16 KB) + B_hi (16 KB) + B_lo (16 KB)
-// The raw ring is deeper than the operand ring so that enough HBM bytes are in flight per SM to cover the loaded
-// DRAM latency; B comes from L2.  Chunk i uses raw stage i % TC_R and operand stage i % TC_Q.
-constexpr int TC_R = 5;
-constexpr int TC_Q = 3;
-constexpr uint32_t TC_OPER_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;
-constexpr uint32_t TC_SMEM_BYTES = TC_R * TC_A_BYTES + TC_Q * TC_OPER_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+// NN kernel, A operand through TENSOR MEMORY (tcgen05.mma "TS" form).
+//
+// Measured on the first version (A_hi/A_lo/B_hi/B_lo all in shared memory, profiles/r01_ncu_full_262k.csv): the kernel was
+// bound by shared-memory bandwidth, not by HBM or the tensor pipe -- per 32-k chunk the splitter read 16 KB and wrote
+// 32 KB, TMA wrote 44 KB and the twelve SS-form MMAs read 92 KB of operands (~184 KB per 16 KB of HBM data at
+// 128 B/clk/SM).  Here the splitter threads (one per row of the 128-row tile = one per TMEM lane) read the raw TMA tile
+// once and write A_hi / A_lo straight into TMEM columns with tcgen05.st; the MMAs take A from TMEM and only B from
+// shared memory.  Shared-memory traffic per chunk drops to ~100 KB.
+//
+//   shared memory: raw A ring TC_R x 16 KB (as TMA wrote it, 128-byte swizzle) | B ring TC_Q x (B_hi 16 KB + B_lo 16 KB)
+//                  | epilogue staging 4 warps x 32 rows x 36 floats
+//   tensor memory (512 columns): accumulator stages 2 x 128 | A stages TC_TA x (hi 32 + lo 32 columns)
+//
+// Loop nest: M tile -> N tile -> k chunk.  When the whole K extent fits the TMEM A stages (K <= 32*TC_TA = 128) and there
+// are several N tiles ("resident" mode: the K = 100 transforms of COGMEN with N = 900 / 400), A is loaded and split ONCE
+// per M tile and stays in TMEM while the N tiles stream B only; otherwise A is re-streamed per N tile (n_tiles is 1 for
+// every long-K transform of the reference models).
+constexpr int TC_R = 4;           // raw A stages
+constexpr int TC_Q = 4;           // B stages
+constexpr int TC_TA = 4;          // TMEM A stages
+constexpr uint32_t TC_TMEM_A0 = 2 * TC_BN;                       // first A column
+constexpr uint32_t TC_STAGE_FLOATS = 36;                         // padded row pitch of the epilogue staging tile
+constexpr uint32_t TC_STAGE_BYTES = 4 * 32 * TC_STAGE_FLOATS * 4;
+constexpr uint32_t TC_SMEM_BYTES = TC_R * TC_A_BYTES + TC_Q * 2 * TC_B_BYTES + TC_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int TC_THREADS = 352;   // 4 splitter + 4 epilogue warps, A producer, MMA, B producer
 
 // barrier indices
-constexpr int BAR_A_FULL = 0;                    // [TC_R] TMA bytes of the raw A tile landed
-constexpr int BAR_R_FREE = BAR_A_FULL + TC_R;    // [TC_R] MMAs that read A_hi of this raw stage retired
-constexpr int BAR_B_FULL = BAR_R_FREE + TC_R;    // [TC_Q] TMA bytes of B_hi/B_lo landed
-constexpr int BAR_SPLIT = BAR_B_FULL + TC_Q;     // [TC_Q] A_hi / A_lo written (128 arrivals)
-constexpr int BAR_Q_FREE = BAR_SPLIT + TC_Q;     // [TC_Q] MMAs that read this operand stage retired
+constexpr int BAR_A_FULL = 0;                    // [TC_R]  TMA bytes of the raw A tile landed
+constexpr int BAR_R_FREE = BAR_A_FULL + TC_R;    // [TC_R]  splitter has read the raw tile (128 arrivals)
+constexpr int BAR_TA_FULL = BAR_R_FREE + TC_R;   // [TC_TA] A_hi / A_lo written to TMEM (128 arrivals)
+constexpr int BAR_TA_FREE = BAR_TA_FULL + TC_TA; // [TC_TA] MMAs that read this TMEM A stage retired
+constexpr int BAR_B_FULL = BAR_TA_FREE + TC_TA;  // [TC_Q]  TMA bytes of B_hi/B_lo landed
+constexpr int BAR_Q_FREE = BAR_B_FULL + TC_Q;    // [TC_Q]  MMAs that read this B stage retired
 constexpr int BAR_ACC_FULL = BAR_Q_FREE + TC_Q;  // [2]
-constexpr int BAR_ACC_EMPTY = BAR_ACC_FULL + 2;  // [2]   (128 arrivals)
+constexpr int BAR_ACC_EMPTY = BAR_ACC_FULL + 2;  // [2]     (128 arrivals)
 constexpr int BAR_COUNT = BAR_ACC_EMPTY + 2;
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int ACT>
 __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, long long m, int nn0, int N) {
@@ -170,25 +206,23 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, TcEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* oper = smem + TC_R * TC_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(oper + TC_Q * TC_OPER_BYTES);
+  uint8_t* bring = smem + TC_R * TC_A_BYTES;
+  float* stage_all = reinterpret_cast<float*>(bring + TC_Q * 2 * TC_B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_all) + TC_STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_R; ++i) { mbar_init(BAR(BAR_A_FULL + i), 1); mbar_init(BAR(BAR_R_FREE + i), 1); }
-    for (int i = 0; i < TC_Q; ++i) {
-      mbar_init(BAR(BAR_B_FULL + i), 1);
-      mbar_init(BAR(BAR_SPLIT + i), 128);
-      mbar_init(BAR(BAR_Q_FREE + i), 1);
-    }
+    for (int i = 0; i < TC_R; ++i) { mbar_init(BAR(BAR_A_FULL + i), 1); mbar_init(BAR(BAR_R_FREE + i), 128); }
+    for (int i = 0; i < TC_TA; ++i) { mbar_init(BAR(BAR_TA_FULL + i), 128); mbar_init(BAR(BAR_TA_FREE + i), 1); }
+    for (int i = 0; i < TC_Q; ++i) { mbar_init(BAR(BAR_B_FULL + i), 1); mbar_init(BAR(BAR_Q_FREE + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_ACC_FULL + i), 1); mbar_init(BAR(BAR_ACC_EMPTY + i), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {   // TMEM: 2 accumulator stages x 128 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+  if (warp == 9) {   // all 512 TMEM columns: 2 accumulator stages x 128 + TC_TA A stages x 64
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -198,155 +232,179 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const long long m_tiles = (M + TC_BM - 1) / TC_BM;
   const int n_tiles = (N + bn - 1) / bn;
-  const long long tiles = m_tiles * n_tiles;
   const int k_chunks = (K + TC_BK - 1) / TC_BK;
-  const uint32_t raw_base = smem_u32(smem), oper_base = smem_u32(oper);
-  auto A_HI = [&](int r) { return raw_base + r * TC_A_BYTES; };
-  auto A_LO = [&](int q) { return oper_base + q * TC_OPER_BYTES; };
-  auto B_HI = [&](int q) { return oper_base + q * TC_OPER_BYTES + TC_A_BYTES; };
-  auto B_LO = [&](int q) { return oper_base + q * TC_OPER_BYTES + TC_A_BYTES + TC_B_BYTES; };
+  const bool resident = n_tiles > 1 && k_chunks <= TC_TA;     // A stays in TMEM across the N tiles of an M tile
+  const int a_reps = resident ? 1 : n_tiles;                  // A chunk loads per M tile = a_reps * k_chunks
+  const uint32_t raw_base = smem_u32(smem), b_base = smem_u32(bring);
+  auto B_HI = [&](int q) { return b_base + q * 2 * TC_B_BYTES; };
+  auto B_LO = [&](int q) { return b_base + q * 2 * TC_B_BYTES + TC_B_BYTES; };
+  auto TA_HI = [&](int s) { return tmem_base + TC_TMEM_A0 + (uint32_t)s * 64u; };
 
   if (warp == 8) {
-    // ------------------------------------------------------------------ A producer (HBM stream, deep ring)
+    // ------------------------------------------------------------------ A producer (HBM stream)
     if (lane == 0) {
-      int r = 0;
-      uint32_t rph = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int m0 = (int)(t / n_tiles) * TC_BM;
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          mbar_wait(BAR(BAR_R_FREE + r), rph ^ 1);
-          mbar_expect_tx(BAR(BAR_A_FULL + r), TC_A_BYTES);
-          tma_load_2d(A_HI(r), &tmA, kc * TC_BK, m0, BAR(BAR_A_FULL + r));
-          if (++r == TC_R) { r = 0; rph ^= 1; }
-        }
+      uint32_t n = 0;
+      for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+        const int m0 = (int)t * TC_BM;
+        for (int rep = 0; rep < a_reps; ++rep)
+          for (int kc = 0; kc < k_chunks; ++kc, ++n) {
+            const int r = n % TC_R;
+            mbar_wait(BAR(BAR_R_FREE + r), ((n / TC_R) & 1) ^ 1);
+            mbar_expect_tx(BAR(BAR_A_FULL + r), TC_A_BYTES);
+            tma_load_2d(raw_base + r * TC_A_BYTES, &tmA, kc * TC_BK, m0, BAR(BAR_A_FULL + r));
+          }
       }
     }
   } else if (warp == 10) {
     // ------------------------------------------------------------------ B producer (L2-resident weights)
     if (lane == 0) {
-      int q = 0;
-      uint32_t qph = 0;
+      uint32_t n = 0;
       const uint32_t tx = 2u * (uint32_t)bn * TC_BK * 4u;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int n0 = (int)(t % n_tiles) * bn;
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          mbar_wait(BAR(BAR_Q_FREE + q), qph ^ 1);
-          mbar_expect_tx(BAR(BAR_B_FULL + q), tx);
-          tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, n0, BAR(BAR_B_FULL + q));
-          tma_load_2d(B_LO(q), &tmBl, kc * TC_BK, n0, BAR(BAR_B_FULL + q));
-          if (++q == TC_Q) { q = 0; qph ^= 1; }
-        }
-      }
+      for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x)
+        for (int nt = 0; nt < n_tiles; ++nt)
+          for (int kc = 0; kc < k_chunks; ++kc, ++n) {
+            const int q = n % TC_Q;
+            mbar_wait(BAR(BAR_Q_FREE + q), ((n / TC_Q) & 1) ^ 1);
+            mbar_expect_tx(BAR(BAR_B_FULL + q), tx);
+            tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
+            tma_load_2d(B_LO(q), &tmBl, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
+          }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int r = 0, q = 0, a = 0;
-      uint32_t rph = 0, qph = 0, aph = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          const int in_group = kc % TC_GROUP;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
-          if (in_group == 0) {
-            mbar_wait(BAR(BAR_ACC_EMPTY + a), aph ^ 1);           // epilogue has drained this accumulator stage
+      uint32_t a_base = 0, nb_ = 0;     // A chunk loads before this M tile; B chunk loads so far
+      int a = 0;
+      uint32_t aph = 0;
+      for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+        for (int nt = 0; nt < n_tiles; ++nt) {
+          for (int kc = 0; kc < k_chunks; ++kc, ++nb_) {
+            const int in_group = kc % TC_GROUP;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
+            if (in_group == 0) {
+              mbar_wait(BAR(BAR_ACC_EMPTY + a), aph ^ 1);           // epilogue has drained this accumulator stage
+              tc_fence_after();
+            }
+            const uint32_t an = a_base + (resident ? 0 : nt * k_chunks) + kc;
+            const int s = an % TC_TA, q = nb_ % TC_Q;
+            mbar_wait(BAR(BAR_TA_FULL + s), (an / TC_TA) & 1);      // A_hi / A_lo of this chunk are in TMEM
+            mbar_wait(BAR(BAR_B_FULL + q), (nb_ / TC_Q) & 1);       // B tiles landed
             tc_fence_after();
-          }
-          mbar_wait(BAR(BAR_B_FULL + q), qph);                    // B tiles landed
-          mbar_wait(BAR(BAR_SPLIT + q), qph);                     // A split into hi (raw stage r) / lo (operand stage q)
-          tc_fence_after();
+            // k-steps of 8 that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 steps, not 16)
+            const int ks_n = min(TC_BK / 8, (K - kc * TC_BK + 7) >> 3);
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const uint64_t ah = make_desc_k_sw128(A_HI(r) + ks * 32), al = make_desc_k_sw128(A_LO(q) + ks * 32);
-            const uint64_t bh = make_desc_k_sw128(B_HI(q) + ks * 32), bl = make_desc_k_sw128(B_LO(q) + ks * 32);
-            tc_mma_tf32(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
-            tc_mma_tf32(d_tmem, ah, bl, idesc, 1u);
-            tc_mma_tf32(d_tmem, ah, bh, idesc, 1u);
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              if (ks >= ks_n) break;
+              const uint32_t ah = TA_HI(s) + ks * 8, al = ah + 32;
+              const uint64_t bh = make_desc_k_sw128(B_HI(q) + ks * 32), bl = make_desc_k_sw128(B_LO(q) + ks * 32);
+              tc_mma_tf32_ts(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
+              tc_mma_tf32_ts(d_tmem, ah, bl, idesc, 1u);
+              tc_mma_tf32_ts(d_tmem, ah, bh, idesc, 1u);
+            }
+            tc_commit(BAR(BAR_Q_FREE + q));
+            if (!resident || nt == n_tiles - 1) tc_commit(BAR(BAR_TA_FREE + s));
+            if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) {   // partial sum complete -> epilogue
+              tc_commit(BAR(BAR_ACC_FULL + a));
+              if (++a == 2) { a = 0; aph ^= 1; }
+            }
           }
-          tc_commit(BAR(BAR_R_FREE + r));                         // both smem stages are free once these MMAs retire
-          tc_commit(BAR(BAR_Q_FREE + q));
-          if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) {   // partial sum complete -> epilogue
-            tc_commit(BAR(BAR_ACC_FULL + a));
-            if (++a == 2) { a = 0; aph ^= 1; }
-          }
-          if (++r == TC_R) { r = 0; rph ^= 1; }
-          if (++q == TC_Q) { q = 0; qph ^= 1; }
         }
+        a_base += (uint32_t)a_reps * k_chunks;
       }
-      (void)rph;
     }
   } else if (warp < 4) {
-    // ------------------------------------------------------------------ splitter (128 threads)
-    int r = 0, q = 0;
-    uint32_t rph = 0, qph = 0;
-    const int tid = threadIdx.x;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-      for (int kc = 0; kc < k_chunks; ++kc) {
-        mbar_wait(BAR(BAR_Q_FREE + q), qph ^ 1);       // A_lo slot of the operand stage is reusable
-        mbar_wait(BAR(BAR_A_FULL + r), rph);           // raw tile landed
-        float4* hi = reinterpret_cast<float4*>(smem + r * TC_A_BYTES);
-        float4* lo = reinterpret_cast<float4*>(oper + q * TC_OPER_BYTES);
+    // ------------------------------------------------------------------ splitter: thread = row of the tile = TMEM lane
+    const int row = threadIdx.x;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    uint32_t n = 0;
+    for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+      for (int rep = 0; rep < a_reps; ++rep)
+        for (int kc = 0; kc < k_chunks; ++kc, ++n) {
+          const int r = n % TC_R, s = n % TC_TA;
+          mbar_wait(BAR(BAR_A_FULL + r), (n / TC_R) & 1);          // raw tile landed
+          const float4* src = reinterpret_cast<const float4*>(smem + r * TC_A_BYTES + row * 128);
+          uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int i = 0; i < (int)(TC_A_BYTES / 16 / 128); ++i) {
-          const int idx = tid + 128 * i;
-          const float4 x = hi[idx];
-          float4 h, l;
-          h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
-          l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
-          hi[idx] = h;
-          lo[idx] = l;
+          for (int c = 0; c < 8; ++c) {                            // logical 16-byte chunk c sits at position c ^ (row & 7)
+            const float4 x = src[c ^ (row & 7)];
+            const float h0 = rn_tf32(x.x), h1 = rn_tf32(x.y), h2 = rn_tf32(x.z), h3 = rn_tf32(x.w);
+            hi[4 * c + 0] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+            hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+            lo[4 * c + 0] = __float_as_uint(rn_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(rn_tf32(x.y - h1));
+            lo[4 * c + 2] = __float_as_uint(rn_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(rn_tf32(x.w - h3));
+          }
+          mbar_arrive(BAR(BAR_R_FREE + r));                        // raw stage can be refilled
+          mbar_wait(BAR(BAR_TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
+          tc_fence_after();
+          tc_st32(TA_HI(s) + lane_addr, hi);
+          tc_st32(TA_HI(s) + 32 + lane_addr, lo);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(BAR(BAR_TA_FULL + s));
         }
-        fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(BAR(BAR_SPLIT + q));
-        if (++r == TC_R) { r = 0; rph ^= 1; }
-        if (++q == TC_Q) { q = 0; qph ^= 1; }
-      }
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue (warps 4-7 -> TMEM lanes 32*(warp%4))
     int a = 0;
     uint32_t aph = 0;
     const int ew = warp & 3;
+    float* stg = stage_all + ew * 32 * TC_STAGE_FLOATS;          // this warp's 32 x 32 staging tile (pitch 36)
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     const int n_groups = (k_chunks + TC_GROUP - 1) / TC_GROUP;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const long long m0 = (t / n_tiles) * TC_BM;
-      const int n0 = (int)(t % n_tiles) * bn;
-      const long long m = m0 + ew * 32 + lane;
-      float acc[TC_BN];
+    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;          // write-out mapping: 8 lanes cover 32 columns of one row
+    for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+      const long long m0 = t * TC_BM + ew * 32;
+      for (int nt = 0; nt < n_tiles; ++nt) {
+        const int n0 = nt * bn;
+        float acc[TC_BN];
 #pragma unroll
-      for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
-      for (int g = 0; g < n_groups; ++g) {
-        mbar_wait(BAR(BAR_ACC_FULL + a), aph);
-        tc_fence_after();
+        for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
+        for (int g = 0; g < n_groups; ++g) {
+          mbar_wait(BAR(BAR_ACC_FULL + a), aph);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < TC_BN; c += 32) {
+            if (c < bn) {
+              uint32_t rr[32];
+              tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN + c), rr);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(rr[j]);     // round-to-nearest accumulation
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(BAR(BAR_ACC_EMPTY + a));
+          if (++a == 2) { a = 0; aph ^= 1; }
+        }
+        // write-out: 32-column slabs go through the staging tile so that a warp stores four full 128-byte row
+        // segments per instruction (thread-per-row stores touch 32 different lines per instruction)
 #pragma unroll
         for (int c = 0; c < TC_BN; c += 32) {
-          if (c < bn) {
-            uint32_t rr[32];
-            tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN + c), rr);
-            tc_wait_ld();
+          if (c < bn && n0 + c < N) {
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(rr[j]);     // round-to-nearest accumulation
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(BAR(BAR_ACC_EMPTY + a));
-        if (++a == 2) { a = 0; aph ^= 1; }
-      }
-      if (m < M) {
-        float* crow = C + m * ldc + n0;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(stg + lane * TC_STAGE_FLOATS + j) = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
+            __syncwarp();
+            const int nn0 = n0 + c + sub_c;
 #pragma unroll
-        for (int j = 0; j < TC_BN; j += 4) {
-          const int nn0 = n0 + j;
-          if (j < bn && nn0 < N) {
-            const float4 v = tc_finish4<ACT>(make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), ep, m, nn0, N);
-            if (vec_ok && nn0 + 4 <= N) {
-              st4(crow + j, v);
-            } else {
-              if (nn0 + 0 < N) crow[j + 0] = v.x;
-              if (nn0 + 1 < N) crow[j + 1] = v.y;
-              if (nn0 + 2 < N) crow[j + 2] = v.z;
-              if (nn0 + 3 < N) crow[j + 3] = v.w;
+            for (int i = 0; i < 8; ++i) {
+              const int rr_ = sub_r + 4 * i;
+              const long long m = m0 + rr_;
+              if (m < M && nn0 < N) {
+                const float4 x = *reinterpret_cast<const float4*>(stg + rr_ * TC_STAGE_FLOATS + sub_c);
+                const float4 v = tc_finish4<ACT>(x, ep, m, nn0, N);
+                float* cp = C + m * ldc + nn0;
+                if (vec_ok && nn0 + 4 <= N) {
+                  st4(cp, v);
+                } else {
+                  if (nn0 + 0 < N) cp[0] = v.x;
+                  if (nn0 + 1 < N) cp[1] = v.y;
+                  if (nn0 + 2 < N) cp[2] = v.z;
+                  if (nn0 + 3 < N) cp[3] = v.w;
+                }
+              }
             }
           }
         }
@@ -357,7 +415,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -702,7 +760,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms < 1) num_sms = kNumSMs;
   }
-  const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  const long long tiles = (M + TC_BM - 1) / TC_BM;          // a CTA owns whole M tiles (all their N tiles)
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed};
   switch (act) {

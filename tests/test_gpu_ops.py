@@ -23,7 +23,10 @@ def _graph(lengths, n=2, wp=5, wf=5, seed=0):
 
 
 @pytest.mark.parametrize("M,K,N", [(1, 1, 1), (37, 100, 100), (300, 1380, 100), (257, 1443, 100), (130, 100, 900),
-                                   (64, 900, 100), (129, 100, 6), (200, 6, 100), (513, 200, 131)])
+                                   (64, 900, 100), (129, 100, 6), (200, 6, 100), (513, 200, 131),
+                                   # skinny kernels (narrow side <= 16, >= 1024 rows): gemm_skinny.cuh
+                                   (5000, 100, 6), (3000, 6, 100), (4097, 100, 7), (2048, 300, 16), (1500, 13, 10),
+                                   (1025, 101, 3), (70001, 100, 6)])
 def test_gemm_nn_tn_colsum(M, K, N):
     import erc_b200
     from erc_b200 import ops
