@@ -28,6 +28,7 @@
 // hanging the GPU.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace ercg {
 
@@ -40,6 +41,7 @@ constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;      // 16 KB
 
 struct TcEpilogue {
   const float* bias; int act; const float* aux; long long ldaux; float aux_scale; float drop_p; unsigned long long seed;
+  int dbg;   // ERCG_TC_DBG: performance experiments only (1 no MMA, 2 no TMEM store, 4 no accumulator drain, 8 no B loads)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -119,7 +121,7 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
 // shared memory.  Shared-memory traffic per chunk drops to ~100 KB.
 //
 //   shared memory: raw A ring TC_R x 16 KB (as TMA wrote it, 128-byte swizzle) | B ring TC_Q x (B_hi 16 KB + B_lo 16 KB)
-//                  | epilogue staging 4 warps x 32 rows x 36 floats
+//                  | epilogue staging 4 warps x 2 slabs x 4 KB (written out by TMA bulk stores)
 //   tensor memory (512 columns): accumulator stages 2 x 128 | A stages TC_TA x (hi 32 + lo 32 columns)
 //
 // Loop nest: M tile -> N tile -> k chunk.  When the whole K extent fits the TMEM A stages (K <= 32*TC_TA = 128) and there
@@ -127,11 +129,12 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
 // per M tile and stays in TMEM while the N tiles stream B only; otherwise A is re-streamed per N tile (n_tiles is 1 for
 // every long-K transform of the reference models).
 constexpr int TC_R = 4;           // raw A stages
-constexpr int TC_Q = 4;           // B stages
+constexpr int TC_Q = 3;           // B stages
 constexpr int TC_TA = 4;          // TMEM A stages
 constexpr uint32_t TC_TMEM_A0 = 2 * TC_BN;                       // first A column
-constexpr uint32_t TC_STAGE_FLOATS = 36;                         // padded row pitch of the epilogue staging tile
-constexpr uint32_t TC_STAGE_BYTES = 4 * 32 * TC_STAGE_FLOATS * 4;
+constexpr uint32_t TC_SLAB_BYTES = 32 * 128;                     // epilogue staging slab: 32 rows x 32 columns, 128-byte swizzle
+constexpr int TC_SLABS = 2;                                     // staging slabs per epilogue warp (two write-out rounds per tile)
+constexpr uint32_t TC_STAGE_BYTES = 4 * TC_SLABS * TC_SLAB_BYTES;   // 4 warps x 2 slabs = 32 KB
 constexpr uint32_t TC_SMEM_BYTES = TC_R * TC_A_BYTES + TC_Q * 2 * TC_B_BYTES + TC_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int TC_THREADS = 352;   // 4 splitter + 4 epilogue warps, A producer, MMA, B producer
 
@@ -146,6 +149,11 @@ constexpr int BAR_ACC_FULL = BAR_Q_FREE + TC_Q;  // [2]
 constexpr int BAR_ACC_EMPTY = BAR_ACC_FULL + 2;  // [2]     (128 arrivals)
 constexpr int BAR_COUNT = BAR_ACC_EMPTY + 2;
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -164,6 +172,13 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int ACT>
@@ -202,13 +217,14 @@ __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, lon
 template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-                  const __grid_constant__ CUtensorMap tmBl, float* __restrict__ C, long long ldc, long long M, int N,
+                  const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
+                  float* __restrict__ C, long long ldc, long long M, int N,
                   int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, TcEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bring = smem + TC_R * TC_A_BYTES;
-  float* stage_all = reinterpret_cast<float*>(bring + TC_Q * 2 * TC_B_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_all) + TC_STAGE_BYTES);
+  uint8_t* stage_all = bring + TC_Q * 2 * TC_B_BYTES;          // 1024-byte aligned (every ring is a multiple of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + TC_STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -265,6 +281,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int kc = 0; kc < k_chunks; ++kc, ++n) {
             const int q = n % TC_Q;
             mbar_wait(BAR(BAR_Q_FREE + q), ((n / TC_Q) & 1) ^ 1);
+            if (ep.dbg & 8) { mbar_arrive(BAR(BAR_B_FULL + q)); continue; }
             mbar_expect_tx(BAR(BAR_B_FULL + q), tx);
             tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
             tma_load_2d(B_LO(q), &tmBl, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
@@ -272,46 +289,51 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      uint32_t a_base = 0, nb_ = 0;     // A chunk loads before this M tile; B chunk loads so far
-      int a = 0;
-      uint32_t aph = 0;
-      for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-        for (int nt = 0; nt < n_tiles; ++nt) {
-          for (int kc = 0; kc < k_chunks; ++kc, ++nb_) {
-            const int in_group = kc % TC_GROUP;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
-            if (in_group == 0) {
-              mbar_wait(BAR(BAR_ACC_EMPTY + a), aph ^ 1);           // epilogue has drained this accumulator stage
-              tc_fence_after();
-            }
-            const uint32_t an = a_base + (resident ? 0 : nt * k_chunks) + kc;
-            const int s = an % TC_TA, q = nb_ % TC_Q;
-            mbar_wait(BAR(BAR_TA_FULL + s), (an / TC_TA) & 1);      // A_hi / A_lo of this chunk are in TMEM
-            mbar_wait(BAR(BAR_B_FULL + q), (nb_ / TC_Q) & 1);       // B tiles landed
-            tc_fence_after();
-            // k-steps of 8 that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 steps, not 16)
-            const int ks_n = min(TC_BK / 8, (K - kc * TC_BK + 7) >> 3);
+    // The whole warp runs this loop with warp-uniform control flow and one ELECTED lane issues the tcgen05 instructions
+    // (profiles/r01_*: inside an `if (lane == 0)` region every descriptor had to be moved vector -> uniform register
+    // per instruction and the issue loop itself, ~150 clk per UTCHMMA, was the bottleneck of the kernel).
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+    uint32_t a_base = 0, nb_ = 0;     // A chunk loads before this M tile; B chunk loads so far
+    int a = 0;
+    uint32_t aph = 0;
+    for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+      for (int nt = 0; nt < n_tiles; ++nt) {
+        for (int kc = 0; kc < k_chunks; ++kc, ++nb_) {
+          const int in_group = kc % TC_GROUP;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
+          if (in_group == 0) mbar_wait(BAR(BAR_ACC_EMPTY + a), aph ^ 1);   // epilogue has drained this accumulator stage
+          const uint32_t an = a_base + (resident ? 0 : nt * k_chunks) + kc;
+          const int s = an % TC_TA, q = nb_ % TC_Q;
+          mbar_wait(BAR(BAR_TA_FULL + s), (an / TC_TA) & 1);        // A_hi / A_lo of this chunk are in TMEM
+          mbar_wait(BAR(BAR_B_FULL + q), (nb_ / TC_Q) & 1);         // B tiles landed
+          tc_fence_after();
+          // k-steps of 8 that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 steps, not 16)
+          const int ks_n = (ep.dbg & 1) ? 0 : min(TC_BK / 8, (K - kc * TC_BK + 7) >> 3);
+          const uint32_t ah0 = TA_HI(s);
+          const uint64_t bh0 = desc_hi | (uint64_t)((B_HI(q) >> 4) & 0x3FFF), bl0 = desc_hi | (uint64_t)((B_LO(q) >> 4) & 0x3FFF);
+          if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < TC_BK / 8; ++ks) {
-              if (ks >= ks_n) break;
-              const uint32_t ah = TA_HI(s) + ks * 8, al = ah + 32;
-              const uint64_t bh = make_desc_k_sw128(B_HI(q) + ks * 32), bl = make_desc_k_sw128(B_LO(q) + ks * 32);
-              tc_mma_tf32_ts(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
-              tc_mma_tf32_ts(d_tmem, ah, bl, idesc, 1u);
-              tc_mma_tf32_ts(d_tmem, ah, bh, idesc, 1u);
+              if (ks < ks_n) {
+                const uint32_t ah = ah0 + ks * 8, al = ah + 32;
+                const uint64_t bh = bh0 + (uint64_t)(ks * 2), bl = bl0 + (uint64_t)(ks * 2);   // +32 bytes per k-step
+                tc_mma_tf32_ts(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
+                tc_mma_tf32_ts(d_tmem, ah, bl, idesc, 1u);
+                tc_mma_tf32_ts(d_tmem, ah, bh, idesc, 1u);
+              }
             }
             tc_commit(BAR(BAR_Q_FREE + q));
             if (!resident || nt == n_tiles - 1) tc_commit(BAR(BAR_TA_FREE + s));
-            if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) {   // partial sum complete -> epilogue
-              tc_commit(BAR(BAR_ACC_FULL + a));
-              if (++a == 2) { a = 0; aph ^= 1; }
-            }
+            if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) tc_commit(BAR(BAR_ACC_FULL + a));   // partial sum -> epilogue
+          }
+          __syncwarp();
+          if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) {
+            if (++a == 2) { a = 0; aph ^= 1; }
           }
         }
-        a_base += (uint32_t)a_reps * k_chunks;
       }
+      a_base += (uint32_t)a_reps * k_chunks;
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------------ splitter: thread = row of the tile = TMEM lane
@@ -334,12 +356,21 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             lo[4 * c + 0] = __float_as_uint(rn_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(rn_tf32(x.y - h1));
             lo[4 * c + 2] = __float_as_uint(rn_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(rn_tf32(x.w - h3));
           }
+          {   // the raw stage may be refilled only after every shared-memory load above has RETURNED its data: make the
+              // arrive depend on the loaded values (a load that is merely issued could still read the next TMA fill)
+            uint32_t dep = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dep |= hi[j] ^ lo[j];
+            asm volatile("" ::"r"(dep) : "memory");
+          }
           mbar_arrive(BAR(BAR_R_FREE + r));                        // raw stage can be refilled
           mbar_wait(BAR(BAR_TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
           tc_fence_after();
-          tc_st32(TA_HI(s) + lane_addr, hi);
-          tc_st32(TA_HI(s) + 32 + lane_addr, lo);
-          tc_wait_st();
+          if (!(ep.dbg & 2)) {
+            tc_st32(TA_HI(s) + lane_addr, hi);
+            tc_st32(TA_HI(s) + 32 + lane_addr, lo);
+            tc_wait_st();
+          }
           tc_fence_before();
           mbar_arrive(BAR(BAR_TA_FULL + s));
         }
@@ -349,67 +380,73 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int a = 0;
     uint32_t aph = 0;
     const int ew = warp & 3;
-    float* stg = stage_all + ew * 32 * TC_STAGE_FLOATS;          // this warp's 32 x 32 staging tile (pitch 36)
-    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    uint8_t* stg = stage_all + ew * TC_SLABS * TC_SLAB_BYTES;       // this warp's slabs of 32 rows x 32 columns
+    const uint32_t stg_u32 = smem_u32(stg);
     const int n_groups = (k_chunks + TC_GROUP - 1) / TC_GROUP;
-    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;          // write-out mapping: 8 lanes cover 32 columns of one row
     for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
       const long long m0 = t * TC_BM + ew * 32;
+      const long long m = m0 + lane;                               // this thread's row (TMEM lane)
       for (int nt = 0; nt < n_tiles; ++nt) {
         const int n0 = nt * bn;
         float acc[TC_BN];
-#pragma unroll
-        for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
         for (int g = 0; g < n_groups; ++g) {
           mbar_wait(BAR(BAR_ACC_FULL + a), aph);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < TC_BN; c += 32) {
-            if (c < bn) {
+            if (c < bn && !(ep.dbg & 4)) {
               uint32_t rr[32];
               tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN + c), rr);
               tc_wait_ld();
+              if (g == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(rr[j]);     // round-to-nearest accumulation
+                for (int j = 0; j < 32; ++j) acc[c + j] = __uint_as_float(rr[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(rr[j]);   // round-to-nearest accumulation
+              }
             }
           }
           tc_fence_before();
           mbar_arrive(BAR(BAR_ACC_EMPTY + a));
           if (++a == 2) { a = 0; aph ^= 1; }
         }
-        // write-out: 32-column slabs go through the staging tile so that a warp stores four full 128-byte row
-        // segments per instruction (thread-per-row stores touch 32 different lines per instruction)
+        // write-out: every 32-column slab is staged in shared memory (thread = row, 16-byte chunks XOR-swizzled like a
+        // 128-byte-swizzle TMA box, so the stores are bank-conflict free) and leaves as ONE bulk tensor store per
+        // slab; TMA clips the M and N tails.  No per-element address arithmetic or bounds checks on the SM.
 #pragma unroll
-        for (int c = 0; c < TC_BN; c += 32) {
-          if (c < bn && n0 + c < N) {
+        for (int c0 = 0; c0 < TC_BN; c0 += 32 * TC_SLABS) {         // rounds of TC_SLABS slabs
+          if (c0 < bn && n0 + c0 < N && !(ep.dbg & 64)) {
+            if (lane == 0) tma_store_wait_read();                  // earlier bulk stores have read the staging slabs
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(stg + lane * TC_STAGE_FLOATS + j) = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
-            __syncwarp();
-            const int nn0 = n0 + c + sub_c;
+            for (int sl = 0; sl < TC_SLABS; ++sl) {
+              const int c = c0 + 32 * sl;
+              if (c < bn && n0 + c < N) {
+                uint8_t* slab = stg + sl * TC_SLAB_BYTES + lane * 128;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr_ = sub_r + 4 * i;
-              const long long m = m0 + rr_;
-              if (m < M && nn0 < N) {
-                const float4 x = *reinterpret_cast<const float4*>(stg + rr_ * TC_STAGE_FLOATS + sub_c);
-                const float4 v = tc_finish4<ACT>(x, ep, m, nn0, N);
-                float* cp = C + m * ldc + nn0;
-                if (vec_ok && nn0 + 4 <= N) {
-                  st4(cp, v);
-                } else {
-                  if (nn0 + 0 < N) cp[0] = v.x;
-                  if (nn0 + 1 < N) cp[1] = v.y;
-                  if (nn0 + 2 < N) cp[2] = v.z;
-                  if (nn0 + 3 < N) cp[3] = v.w;
+                for (int j = 0; j < 32; j += 4) {
+                  float4 v = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
+                  if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, m < M ? m : M - 1, n0 + c + j, N);
+                  *reinterpret_cast<float4*>(slab + (((j >> 2) ^ (lane & 7)) << 4)) = v;
                 }
               }
+            }
+            fence_proxy_async();                                   // generic-proxy stores -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0 && !(ep.dbg & 32)) {
+#pragma unroll
+              for (int sl = 0; sl < TC_SLABS; ++sl) {
+                const int c = c0 + 32 * sl;
+                if (c < bn && n0 + c < N) tma_store_2d(&tmC, stg_u32 + sl * TC_SLAB_BYTES, n0 + c, (int)m0);
+              }
+              tma_store_commit();
             }
           }
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();                           // global writes complete before the kernel exits
   }
   tc_fence_before();
   __syncthreads();
@@ -741,8 +778,9 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   // UMMA N: multiple of 16, <= 128, chosen to waste the fewest columns
   int bn = 128;
   if (N <= 128) bn = (N + 15) / 16 * 16;
-  CUtensorMap tmA, tmBh, tmBl;
-  if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, bn) || !make_map(&tmBl, blo, N, K, Kp, bn))
+  CUtensorMap tmA, tmBh, tmBl, tmC;
+  if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, bn) || !make_map(&tmBl, blo, N, K, Kp, bn) ||
+      !make_map(&tmC, C, M, N, ldc, 32))                     // output: boxes of 32 rows x 32 columns (TMA bulk stores)
     return ERCG_ECUDA;
   static bool attr_set = false;
   if (!attr_set) {
@@ -762,12 +800,14 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   }
   const long long tiles = (M + TC_BM - 1) / TC_BM;          // a CTA owns whole M tiles (all their N tiles)
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed};
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("ERCG_TC_DBG"); dbg = e ? atoi(e) : 0; }
+  TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg};
   switch (act) {
-    case 0: gemm_tc_nn_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
-    case 1: gemm_tc_nn_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
-    case 2: gemm_tc_nn_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
-    default: gemm_tc_nn_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, C, ldc, M, N, K, bn, ep); break;
+    case 0: gemm_tc_nn_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep); break;
+    case 1: gemm_tc_nn_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep); break;
+    case 2: gemm_tc_nn_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep); break;
+    default: gemm_tc_nn_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep); break;
   }
   return finish_launch();
 }

@@ -88,3 +88,25 @@ def test_tc_gemm_tn_matches_fp64(M, K1, N1):
     r1, r2 = _tc(run)
     assert torch.equal(r1, r2)
     assert rel_err(r1, want) < TOL
+
+
+@pytest.mark.parametrize("M,K,N", [(1376, 800, 200), (8192, 1443, 100), (4096, 100, 900), (3000, 256, 384)])
+def test_tc_gemm_race_stress(M, K, N):
+    """The same product 25 times with other work in between: bit-identical and correct every time.  (A shared-memory
+    stage that is released before its loads have returned shows up here as a rare, small mismatch.)"""
+    g = torch.Generator().manual_seed(M + N)
+    A, B = torch.randn(M, K, generator=g).cuda(), torch.randn(K, N, generator=g).cuda()
+    want = A.double() @ B.double()
+
+    def run(ops):
+        outs = []
+        for i in range(25):
+            outs.append(ops.gemm_nn(A, B))
+            ops.gemm_nn(A[: M // 2], B)                     # perturbs the timing of the next launch
+        torch.cuda.synchronize()
+        return outs
+
+    outs = _tc(run)
+    assert rel_err(outs[0], want) < TOL
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
