@@ -356,21 +356,16 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             lo[4 * c + 0] = __float_as_uint(rn_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(rn_tf32(x.y - h1));
             lo[4 * c + 2] = __float_as_uint(rn_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(rn_tf32(x.w - h3));
           }
-          {   // the raw stage may be refilled only after every shared-memory load above has RETURNED its data: make the
-              // arrive depend on the loaded values (a load that is merely issued could still read the next TMA fill)
-            uint32_t dep = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dep |= hi[j] ^ lo[j];
-            asm volatile("" ::"r"(dep) : "memory");
-          }
-          mbar_arrive(BAR(BAR_R_FREE + r));                        // raw stage can be refilled
           mbar_wait(BAR(BAR_TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
           tc_fence_after();
-          if (!(ep.dbg & 2)) {
-            tc_st32(TA_HI(s) + lane_addr, hi);
-            tc_st32(TA_HI(s) + 32 + lane_addr, lo);
-            tc_wait_st();
-          }
+          tc_st32(TA_HI(s) + lane_addr, hi);
+          tc_st32(TA_HI(s) + 32 + lane_addr, lo);
+          tc_wait_st();
+          // The raw stage is released only HERE: the TMEM stores above consume every loaded register, so the
+          // shared-memory loads have returned.  (An arrive placed right after the loads was scheduled by ptxas before
+          // their data came back -- SASS: LD.E.128 x8, SYNCS.ARRIVE, then the first use -- and a refill by TMA could
+          // overtake a slow warp: rare wrong 32-row x 128-column blocks, caught by test_tc_gemm_race_stress.)
+          mbar_arrive(BAR(BAR_R_FREE + r));
           tc_fence_before();
           mbar_arrive(BAR(BAR_TA_FULL + s));
         }
@@ -457,49 +452,55 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------- TN (weight gradients)
-// C[K1,N1] = A[M,K1]^T @ B[M,N1]: the contraction runs over the M utterance rows, so both operands are "MN-major"
-// for the tensor core (the non-contracted index is the contiguous one).  Per chunk of 32 rows TMA brings
-//   A boxes {32 k1, 32 rows} x 4  -> [k1-block][row][32]   (LBO = 4096 B between k1 blocks, SBO = 1024 B per 8 rows)
-//   B boxes {32 n1, 32 rows} x nb -> [n1-block][row][32]
-// both are activations, so both are hi/lo-split in shared memory (in place + twin buffer).  Work unit = (k1 tile,
-// n1 tile, row slab); each unit writes its [128 x bn] partial to the workspace and a fixed-order reduction sums the
-// slabs (bit-reproducible).  Same grouped-TMEM / register accumulation as the NN kernel.
-constexpr int TN_R = 4;           // raw stages (A_hi | B_hi), 32 KB each
-constexpr int TN_Q = 3;           // lo stages  (A_lo | B_lo), 32 KB each
-constexpr uint32_t TN_STAGE = TC_A_BYTES + TC_B_BYTES;
-constexpr uint32_t TN_SMEM_BYTES = (TN_R + TN_Q) * TN_STAGE + 1024 + 512;
-constexpr int TN_FULL = 0, TN_RFREE = TN_FULL + TN_R, TN_SPLIT = TN_RFREE + TN_R, TN_QFREE = TN_SPLIT + TN_Q,
-              TN_ACC_FULL = TN_QFREE + TN_Q, TN_ACC_EMPTY = TN_ACC_FULL + 2, TN_BARS = TN_ACC_EMPTY + 2;
-constexpr int TN_THREADS = 320;
+// C[K1,N1] = A[M,K1]^T @ B[M,N1]: the contraction runs over the M utterance rows.  Same design as the NN kernel: the WIDE
+// operand W (the one with more columns; 128-column tiles = the MMA M side) streams from HBM through a raw shared-memory
+// ring, is split by one thread per column and goes to TENSOR MEMORY (lane = column, TMEM column = row of the 32-row
+// chunk, i.e. K-major by construction -- the transposition costs nothing); the NARROW operand (<= 128 columns, the
+// MMA N side) stays in shared memory as an MN-major tile ("128-byte swizzle with 32-byte atoms", UMMA layout type 1,
+// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; the plain 128-byte swizzle silently produces zeros for MN-major tf32) and
+// is hi/lo-split in place.  When N1 > K1 the roles of A and B are swapped and the transposed result is written back by
+// the reduction kernel.  Work unit = (128-column tile of W, row slab); each unit writes its [128 x n] partial to the
+// workspace and a fixed-order reduction sums the slabs (bit-reproducible).  Same grouped-TMEM / register accumulation.
+constexpr int TN_R = 4;           // raw W stages, 16 KB each ([32 rows][128 columns], no swizzle)
+constexpr int TN_Q = 3;           // narrow-operand stages: hi (raw, split in place) 16 KB + lo 16 KB
+constexpr int TN_TA = 4;          // TMEM stages of W: hi 32 + lo 32 columns
+constexpr uint32_t TN_SMEM_BYTES = TN_R * TC_A_BYTES + TN_Q * 2 * TC_B_BYTES + 1024 + 512;
+constexpr int TN_W_FULL = 0, TN_W_FREE = TN_W_FULL + TN_R, TN_TA_FULL = TN_W_FREE + TN_R, TN_TA_FREE = TN_TA_FULL + TN_TA,
+              TN_B_FULL = TN_TA_FREE + TN_TA, TN_B_SPLIT = TN_B_FULL + TN_Q, TN_B_FREE = TN_B_SPLIT + TN_Q,
+              TN_ACC_FULL = TN_B_FREE + TN_Q, TN_ACC_EMPTY = TN_ACC_FULL + 2, TN_BARS = TN_ACC_EMPTY + 2;
+constexpr int TN_THREADS = 352;   // 4 splitter + 4 epilogue warps, W producer, MMA, narrow-operand producer
 
-// MN-major tf32 operands only exist in the "128-byte swizzle, 32-byte atom" layout (UMMA layout type 1; TMA
-// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B (32 MN elements), the four 32-byte chunks of a row XOR-ed with
-// (row & 3), atoms of 4 K-rows = 512 B.  SBO = 512 B between 4-row K groups, LBO = 4096 B between 32-wide MN blocks.
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 
 __global__ void __launch_bounds__(TN_THREADS, 1)
-gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  float* __restrict__ P /* [S][K1][N1] */, long long M, int K1, int N1, int bn, int k1_tiles, int n1_tiles,
-                  int S, long long rows_per_slab) {
+gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
+                  float* __restrict__ P /* [S][Wc][Nc] */, long long M, int Wc /* columns of the wide operand */,
+                  int Nc /* columns of the narrow operand */, int bn /* narrow columns per unit: multiple of 32, <= 128 */,
+                  int w_tiles, int n_tiles, int S, long long rows_per_slab) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* lo_ring = smem + TN_R * TN_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + TN_Q * TN_STAGE);
+  uint8_t* nring = smem + TN_R * TC_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nring + TN_Q * 2 * TC_B_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TN_BARS);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TN_R; ++i) { mbar_init(BAR(TN_FULL + i), 1); mbar_init(BAR(TN_RFREE + i), 1); }
-    for (int i = 0; i < TN_Q; ++i) { mbar_init(BAR(TN_SPLIT + i), 128); mbar_init(BAR(TN_QFREE + i), 1); }
+    for (int i = 0; i < TN_R; ++i) { mbar_init(BAR(TN_W_FULL + i), 1); mbar_init(BAR(TN_W_FREE + i), 128); }
+    for (int i = 0; i < TN_TA; ++i) { mbar_init(BAR(TN_TA_FULL + i), 128); mbar_init(BAR(TN_TA_FREE + i), 1); }
+    for (int i = 0; i < TN_Q; ++i) {
+      mbar_init(BAR(TN_B_FULL + i), 1);
+      mbar_init(BAR(TN_B_SPLIT + i), 128);
+      mbar_init(BAR(TN_B_FREE + i), 1);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(TN_ACC_FULL + i), 1); mbar_init(BAR(TN_ACC_EMPTY + i), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -507,120 +508,150 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long units = (long long)k1_tiles * n1_tiles * S;
-  const int nb = (bn + 31) / 32;                       // 32-wide n1 boxes per B tile
-  const uint32_t raw_base = smem_u32(smem), lo_base = smem_u32(lo_ring);
-  auto A_HI = [&](int r) { return raw_base + r * TN_STAGE; };
-  auto B_HI = [&](int r) { return raw_base + r * TN_STAGE + TC_A_BYTES; };
-  auto A_LO = [&](int q) { return lo_base + q * TN_STAGE; };
-  auto B_LO = [&](int q) { return lo_base + q * TN_STAGE + TC_A_BYTES; };
-  // unit -> (k1 tile, n1 tile, slab); slab fastest so that concurrently running CTAs stream different rows
-  auto decode = [&](long long u, int& k1_0, int& n1_0, long long& mbeg, long long& mend, int& slab) {
+  const long long units = (long long)w_tiles * n_tiles * S;
+  const int nb = bn / 32;                              // 32-wide boxes of the narrow operand per unit
+  const int mma_n = n_tiles == 1 ? (Nc + 15) / 16 * 16 : bn;   // UMMA N
+  const uint32_t raw_base = smem_u32(smem), n_base = smem_u32(nring);
+  auto N_HI = [&](int q) { return n_base + q * 2 * TC_B_BYTES; };
+  auto N_LO = [&](int q) { return n_base + q * 2 * TC_B_BYTES + TC_B_BYTES; };
+  auto TA_HI = [&](int s) { return tmem_base + 2 * TC_BN + (uint32_t)s * 64u; };
+  // unit -> (W tile, narrow tile, slab); slab fastest so that concurrently running CTAs stream different rows
+  auto decode = [&](long long u, int& w0, int& n0, long long& mbeg, long long& mend, int& slab) {
     slab = (int)(u % S);
     const long long kn = u / S;
-    k1_0 = (int)(kn / n1_tiles) * TC_BM;
-    n1_0 = (int)(kn % n1_tiles) * bn;
+    w0 = (int)(kn / n_tiles) * TC_BM;
+    n0 = (int)(kn % n_tiles) * bn;
     mbeg = (long long)slab * rows_per_slab;
     mend = mbeg + rows_per_slab < M ? mbeg + rows_per_slab : M;
     if (mbeg > M) mbeg = M;
   };
 
   if (warp == 8) {
-    if (lane == 0) {   // ---------------------------------------------------- TMA producer
-      int r = 0;
-      uint32_t rph = 0;
-      const uint32_t tx = TC_A_BYTES + (uint32_t)nb * 4096u;
+    if (lane == 0) {   // ---------------------------------------------------- wide-operand producer (HBM stream)
+      uint32_t n = 0;
       for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-        int k1_0, n1_0, slab; long long mbeg, mend;
-        decode(u, k1_0, n1_0, mbeg, mend, slab);
-        for (long long m = mbeg; m < mend; m += TC_BK) {
-          mbar_wait(BAR(TN_RFREE + r), rph ^ 1);
-          mbar_expect_tx(BAR(TN_FULL + r), tx);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) tma_load_2d(A_HI(r) + i * 4096, &tmA, k1_0 + 32 * i, (int)m, BAR(TN_FULL + r));
-          for (int i = 0; i < nb; ++i) tma_load_2d(B_HI(r) + i * 4096, &tmB, n1_0 + 32 * i, (int)m, BAR(TN_FULL + r));
-          if (++r == TN_R) { r = 0; rph ^= 1; }
+        int w0, n0, slab; long long mbeg, mend;
+        decode(u, w0, n0, mbeg, mend, slab);
+        for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
+          const int r = n % TN_R;
+          mbar_wait(BAR(TN_W_FREE + r), ((n / TN_R) & 1) ^ 1);
+          mbar_expect_tx(BAR(TN_W_FULL + r), TC_A_BYTES);
+          tma_load_2d(raw_base + r * TC_A_BYTES, &tmW, w0, (int)m, BAR(TN_W_FULL + r));
+        }
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {   // ---------------------------------------------------- narrow-operand producer (mostly L2)
+      uint32_t n = 0;
+      const uint32_t tx = (uint32_t)nb * 4096u;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        int w0, n0, slab; long long mbeg, mend;
+        decode(u, w0, n0, mbeg, mend, slab);
+        for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
+          const int q = n % TN_Q;
+          mbar_wait(BAR(TN_B_FREE + q), ((n / TN_Q) & 1) ^ 1);
+          mbar_expect_tx(BAR(TN_B_FULL + q), tx);
+          for (int i = 0; i < nb; ++i) tma_load_2d(N_HI(q) + i * 4096, &tmN, n0 + 32 * i, (int)m, BAR(TN_B_FULL + q));
         }
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {   // ---------------------------------------------------- MMA issuer
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
-                             ((uint32_t)(TC_BM >> 4) << 24);
-      int r = 0, q = 0, a = 0;
-      uint32_t qph = 0, aph = 0;
-      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-        int k1_0, n1_0, slab; long long mbeg, mend;
-        decode(u, k1_0, n1_0, mbeg, mend, slab);
-        const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
-        for (long long kc = 0; kc < chunks; ++kc) {
-          const int in_group = (int)(kc % TC_GROUP);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
-          if (in_group == 0) {
-            mbar_wait(BAR(TN_ACC_EMPTY + a), aph ^ 1);
-            tc_fence_after();
-          }
-          mbar_wait(BAR(TN_SPLIT + q), qph);
-          tc_fence_after();
+    // ------------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) /* B is MN-major */ |
+                           ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    uint32_t n = 0;
+    int a = 0;
+    uint32_t aph = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      int w0, n0, slab; long long mbeg, mend;
+      decode(u, w0, n0, mbeg, mend, slab);
+      const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
+      for (long long kc = 0; kc < chunks; ++kc, ++n) {
+        const int in_group = (int)(kc % TC_GROUP);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
+        if (in_group == 0) mbar_wait(BAR(TN_ACC_EMPTY + a), aph ^ 1);
+        const int s = n % TN_TA, q = n % TN_Q;
+        mbar_wait(BAR(TN_TA_FULL + s), (n / TN_TA) & 1);
+        mbar_wait(BAR(TN_B_SPLIT + q), (n / TN_Q) & 1);
+        tc_fence_after();
+        const uint32_t ah0 = TA_HI(s);
+        const uint64_t bh0 = make_desc_mn_sw128(N_HI(q)), bl0 = make_desc_mn_sw128(N_LO(q));
+        const bool last = in_group == TC_GROUP - 1 || kc == chunks - 1;
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const uint64_t ah = make_desc_mn_sw128(A_HI(r) + ks * 1024), al = make_desc_mn_sw128(A_LO(q) + ks * 1024);
-            const uint64_t bh = make_desc_mn_sw128(B_HI(r) + ks * 1024), bl = make_desc_mn_sw128(B_LO(q) + ks * 1024);
-            tc_mma_tf32(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
-            tc_mma_tf32(d_tmem, ah, bl, idesc, 1u);
-            tc_mma_tf32(d_tmem, ah, bh, idesc, 1u);
+            const uint32_t ah = ah0 + ks * 8, al = ah + 32;
+            const uint64_t bh = bh0 + (uint64_t)(ks * 64), bl = bl0 + (uint64_t)(ks * 64);   // 8 rows = 1024 bytes per k-step
+            tc_mma_tf32_ts(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
+            tc_mma_tf32_ts(d_tmem, ah, bl, idesc, 1u);
+            tc_mma_tf32_ts(d_tmem, ah, bh, idesc, 1u);
           }
-          tc_commit(BAR(TN_RFREE + r));
-          tc_commit(BAR(TN_QFREE + q));
-          if (in_group == TC_GROUP - 1 || kc == chunks - 1) {
-            tc_commit(BAR(TN_ACC_FULL + a));
-            if (++a == 2) { a = 0; aph ^= 1; }
-          }
-          if (++r == TN_R) r = 0;
-          if (++q == TN_Q) { q = 0; qph ^= 1; }
+          tc_commit(BAR(TN_TA_FREE + s));
+          tc_commit(BAR(TN_B_FREE + q));
+          if (last) tc_commit(BAR(TN_ACC_FULL + a));
         }
+        __syncwarp();
+        if (last) { if (++a == 2) { a = 0; aph ^= 1; } }
       }
     }
   } else if (warp < 4) {
-    // ------------------------------------------------------------------------ splitter: A tile and B tile
-    int r = 0, q = 0;
-    uint32_t rph = 0, qph = 0;
+    // ------------------------------------------------------------------------ splitter: thread = column of W = TMEM lane
     const int tid = threadIdx.x;
-    const int b_vec = nb * 256;                        // float4s in the B tile
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const int b_vec = nb * 256;                        // float4s in the narrow tile
+    uint32_t n = 0;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-      int k1_0, n1_0, slab; long long mbeg, mend;
-      decode(u, k1_0, n1_0, mbeg, mend, slab);
-      for (long long m = mbeg; m < mend; m += TC_BK) {
-        mbar_wait(BAR(TN_QFREE + q), qph ^ 1);
-        mbar_wait(BAR(TN_FULL + r), rph);
-        float4* hi = reinterpret_cast<float4*>(smem + r * TN_STAGE);
-        float4* lo = reinterpret_cast<float4*>(lo_ring + q * TN_STAGE);
+      int w0, n0, slab; long long mbeg, mend;
+      decode(u, w0, n0, mbeg, mend, slab);
+      for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
+        const int r = n % TN_R, s = n % TN_TA, q = n % TN_Q;
+        // --- W chunk: raw [32 rows][128 columns] -> this thread's column, rows along the TMEM columns
+        mbar_wait(BAR(TN_W_FULL + r), (n / TN_R) & 1);
+        const float* src = reinterpret_cast<const float*>(smem + r * TC_A_BYTES) + tid;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {                 // 2048 float4 slots: A (1024) then B (up to 1024)
+        for (int j = 0; j < 32; ++j) {
+          const float x = src[j * 128];
+          const float h = rn_tf32(x);
+          hi[j] = __float_as_uint(h);
+          lo[j] = __float_as_uint(rn_tf32(x - h));
+        }
+        mbar_wait(BAR(TN_TA_FREE + s), ((n / TN_TA) & 1) ^ 1);
+        tc_fence_after();
+        tc_st32(TA_HI(s) + lane_addr, hi);
+        tc_st32(TA_HI(s) + 32 + lane_addr, lo);
+        tc_wait_st();
+        mbar_arrive(BAR(TN_W_FREE + r));                 // after the TMEM stores: every loaded register has been consumed
+        tc_fence_before();
+        mbar_arrive(BAR(TN_TA_FULL + s));
+        // --- narrow chunk: split in place (hi) + twin buffer (lo); elementwise, so the swizzled layout is preserved
+        mbar_wait(BAR(TN_B_FULL + q), (n / TN_Q) & 1);
+        float4* bhi = reinterpret_cast<float4*>(nring + q * 2 * TC_B_BYTES);
+        float4* blo = reinterpret_cast<float4*>(nring + q * 2 * TC_B_BYTES + TC_B_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
           const int idx = tid + 128 * i;
-          if (i < 8 || idx - 1024 < b_vec) {
-            const float4 x = hi[idx];
+          if (idx < b_vec) {
+            const float4 x = bhi[idx];
             float4 h, l;
             h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
             l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
-            hi[idx] = h;
-            lo[idx] = l;
+            bhi[idx] = h;
+            blo[idx] = l;
           }
         }
         fence_proxy_async();
-        mbar_arrive(BAR(TN_SPLIT + q));
-        if (++r == TN_R) { r = 0; rph ^= 1; }
-        if (++q == TN_Q) { q = 0; qph ^= 1; }
+        mbar_arrive(BAR(TN_B_SPLIT + q));
       }
     }
   } else if (warp < 8) {
-    // ------------------------------------------------------------------------ epilogue: partial [128 x bn] per unit
+    // ------------------------------------------------------------------------ epilogue: partial [128 x Nc] per unit
     int a = 0;
     uint32_t aph = 0;
     const int ew = warp & 3;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-      int k1_0, n1_0, slab; long long mbeg, mend;
-      decode(u, k1_0, n1_0, mbeg, mend, slab);
+      int w0, n0, slab; long long mbeg, mend;
+      decode(u, w0, n0, mbeg, mend, slab);
       const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
       const long long n_groups = (chunks + TC_GROUP - 1) / TC_GROUP;
       float acc[TC_BN];
@@ -631,7 +662,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < TC_BN; c += 32) {
-          if (c < bn) {
+          if (c < mma_n) {
             uint32_t rr[32];
             tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN + c), rr);
             tc_wait_ld();
@@ -643,12 +674,12 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_arrive(BAR(TN_ACC_EMPTY + a));
         if (++a == 2) { a = 0; aph ^= 1; }
       }
-      const int k1 = k1_0 + ew * 32 + lane;
-      if (k1 < K1) {
-        float* prow = P + ((long long)slab * K1 + k1) * N1 + n1_0;
+      const int wc = w0 + ew * 32 + lane;
+      if (wc < Wc) {
+        float* prow = P + ((long long)slab * Wc + wc) * Nc + n0;
 #pragma unroll
         for (int j = 0; j < TC_BN; ++j)
-          if (j < bn && n1_0 + j < N1) prow[j] = acc[j];
+          if (j < bn && n0 + j < Nc) prow[j] = acc[j];
       }
     }
   }
@@ -656,27 +687,31 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
+// C = sum over slabs of P[s]; P[s] is [rows, cols] or, when the operand roles were swapped, [cols, rows] (transposed)
 __global__ void tn_reduce_kernel(const float* __restrict__ P, long long stride, int S, float* __restrict__ C, long long ldc,
-                                 int rows, int cols) {
+                                 int rows, int cols, int transposed) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)rows * cols) return;
+  const int r = (int)(idx / cols), c = (int)(idx % cols);
+  const long long src = transposed ? (long long)c * rows + r : idx;
   float s = 0.f;
-  for (int z = 0; z < S; ++z) s += P[(long long)z * stride + idx];
-  C[(idx / cols) * ldc + (idx % cols)] = s;
+  for (int z = 0; z < S; ++z) s += P[(long long)z * stride + src];
+  C[(long long)r * ldc + c] = s;
 }
 
-static void tn_tc_plan(int64_t M, int K1, int N1, int& bn, int& k1_tiles, int& n1_tiles, int& S, long long& rps) {
-  n1_tiles = (N1 + 127) / 128;
-  bn = ((N1 + n1_tiles - 1) / n1_tiles + 31) / 32 * 32;      // whole 32-wide boxes
-  if (bn > 128) bn = 128;
-  n1_tiles = (N1 + bn - 1) / bn;
-  k1_tiles = (K1 + TC_BM - 1) / TC_BM;
-  const int kn = k1_tiles * n1_tiles;
-  S = kNumSMs / kn;
+// wide operand = the one with more columns; its 128-column tiles x row slabs are the work units
+static void tn_tc_plan(int64_t M, int K1, int N1, bool& swap, int& w_tiles, int& n_tiles, int& bn, int& S, long long& rps) {
+  swap = N1 > K1;
+  const int Wc = swap ? N1 : K1, Nc = swap ? K1 : N1;
+  w_tiles = (Wc + TC_BM - 1) / TC_BM;
+  n_tiles = (Nc + 127) / 128;
+  bn = ((Nc + n_tiles - 1) / n_tiles + 31) / 32 * 32;
+  n_tiles = (Nc + bn - 1) / bn;
+  S = kNumSMs / (w_tiles * n_tiles);
   if (S < 1) S = 1;
   const long long quantum = (long long)TC_BK * TC_GROUP;
   long long maxS = (M + quantum - 1) / quantum;
@@ -814,8 +849,8 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
 
 extern "C" size_t ercg_gemm_tn_tc_workspace_bytes(int64_t M, int K1, int N1) {
   if (M <= 0 || K1 <= 0 || N1 <= 0) return 0;
-  int bn, kt, nt, S; long long rps;
-  tn_tc_plan(M, K1, N1, bn, kt, nt, S, rps);
+  bool swap; int wt, nt, bn, S; long long rps;
+  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps);
   return (size_t)S * K1 * N1 * sizeof(float) + 256;
 }
 
@@ -826,17 +861,34 @@ extern "C" int ercg_gemm_tn_tc_supported(const float* A, int64_t lda, const floa
   return 1;
 }
 
+// 2-D fp32 row-major [rows, cols]; box {128 cols, 32 rows}, no swizzle (the raw W tile is only read by the splitter)
+static bool make_map_plain(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BM, (cuuint32_t)TC_BK};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                                int K1, int N1, void* workspace, size_t workspace_bytes, void* stream) {
   if (M < 1 || K1 < 1 || N1 < 1 || !A || !B || !C || lda < K1 || ldb < N1 || ldc < N1) return ERCG_EINVAL;
   if (!ercg_gemm_tn_tc_supported(A, lda, B, ldb, M, K1, N1)) return ERCG_EALIGN;
   if (workspace_bytes < ercg_gemm_tn_tc_workspace_bytes(M, K1, N1) || !workspace) return ERCG_EWORKSPACE;
-  int bn, kt, nt, S; long long rps;
-  tn_tc_plan(M, K1, N1, bn, kt, nt, S, rps);
+  bool swap; int wt, nt, bn, S; long long rps;
+  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps);
   float* P = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-  CUtensorMap tmA, tmB;
-  if (!make_map(&tmA, A, M, K1, lda, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
-      !make_map(&tmB, B, M, N1, ldb, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ERCG_ECUDA;
+  const float* W = swap ? B : A;
+  const float* Nw = swap ? A : B;
+  const long long ldw = swap ? ldb : lda, ldn = swap ? lda : ldb;
+  const int Wc = swap ? N1 : K1, Nc = swap ? K1 : N1;
+  CUtensorMap tmW, tmN;
+  if (!make_map_plain(&tmW, W, M, Wc, ldw) ||
+      !make_map(&tmN, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ERCG_ECUDA;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
@@ -844,12 +896,12 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const long long units = (long long)kt * nt * S;
+  const long long units = (long long)wt * nt * S;
   const int grid = (int)(units < kNumSMs ? units : kNumSMs);
-  gemm_tc_tn_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmA, tmB, P, M, K1, N1, bn, kt, nt, S, rps);
+  gemm_tc_tn_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps);
   int rc = finish_launch();
   if (rc) return rc;
   const long long tot = (long long)K1 * N1;
-  tn_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tot, S, C, ldc, K1, N1);
+  tn_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tot, S, C, ldc, K1, N1, swap ? 1 : 0);
   return finish_launch();
 }
