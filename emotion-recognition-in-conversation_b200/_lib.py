@@ -9,7 +9,7 @@ import os
 from ctypes import c_int, c_int64, c_uint64, c_float, c_double, c_void_p, c_size_t, c_char_p, POINTER, Structure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libercgraph.so")
+LIB_PATH = os.environ.get("ERCG_LIB_PATH") or os.path.join(_HERE, "libercgraph.so")   # override: A/B kernel experiments only
 
 ACT_NONE, ACT_RELU, ACT_RELU_DROPOUT, ACT_MASK_POS = 0, 1, 2, 3
 

@@ -67,6 +67,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 24)) __trap();            // ~seconds: a broken pipeline must fail, not hang the GPU
   }
 }
+// same wait for warps that are NOT on the latency-critical path (TMA producers): back off between polls so that the spin
+// loop does not eat the issue slots of the splitter / epilogue warps that share the SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) __nanosleep(96);
+    if (spin > (1u << 22)) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -98,6 +112,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// hi/lo split for 3xTF32.  The tensor core reads only the upper 19 bits of a tf32 operand, so hi = x with the low 13
+// mantissa bits cleared is what it would see anyway, lo = x - hi is exact, and lo is passed unrounded (the hardware
+// truncates it to 11 significant bits: error <= 2^-20 |x| worst case, ~2^-22 on average).  2 instructions per element
+// instead of ~10 for two cvt.rna.tf32 -- the splitter warps were issue-bound (profiles/r01_tn_v2_hot.txt).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
 __device__ __forceinline__ float rn_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -149,6 +171,19 @@ constexpr int BAR_ACC_FULL = BAR_Q_FREE + TC_Q;  // [2]
 constexpr int BAR_ACC_EMPTY = BAR_ACC_FULL + 2;  // [2]     (128 arrivals)
 constexpr int BAR_COUNT = BAR_ACC_EMPTY + 2;
 
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds1(uint32_t saddr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(saddr) : "memory");
+  return r;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -265,7 +300,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int rep = 0; rep < a_reps; ++rep)
           for (int kc = 0; kc < k_chunks; ++kc, ++n) {
             const int r = n % TC_R;
-            mbar_wait(BAR(BAR_R_FREE + r), ((n / TC_R) & 1) ^ 1);
+            mbar_wait_relaxed(BAR(BAR_R_FREE + r), ((n / TC_R) & 1) ^ 1);
             mbar_expect_tx(BAR(BAR_A_FULL + r), TC_A_BYTES);
             tma_load_2d(raw_base + r * TC_A_BYTES, &tmA, kc * TC_BK, m0, BAR(BAR_A_FULL + r));
           }
@@ -280,7 +315,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int nt = 0; nt < n_tiles; ++nt)
           for (int kc = 0; kc < k_chunks; ++kc, ++n) {
             const int q = n % TC_Q;
-            mbar_wait(BAR(BAR_Q_FREE + q), ((n / TC_Q) & 1) ^ 1);
+            mbar_wait_relaxed(BAR(BAR_Q_FREE + q), ((n / TC_Q) & 1) ^ 1);
             if (ep.dbg & 8) { mbar_arrive(BAR(BAR_B_FULL + q)); continue; }
             mbar_expect_tx(BAR(BAR_B_FULL + q), tx);
             tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
@@ -345,16 +380,15 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kc = 0; kc < k_chunks; ++kc, ++n) {
           const int r = n % TC_R, s = n % TC_TA;
           mbar_wait(BAR(BAR_A_FULL + r), (n / TC_R) & 1);          // raw tile landed
-          const float4* src = reinterpret_cast<const float4*>(smem + r * TC_A_BYTES + row * 128);
+          const uint32_t src = raw_base + r * TC_A_BYTES + row * 128;
           uint32_t hi[32], lo[32];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                            // logical 16-byte chunk c sits at position c ^ (row & 7)
-            const float4 x = src[c ^ (row & 7)];
-            const float h0 = rn_tf32(x.x), h1 = rn_tf32(x.y), h2 = rn_tf32(x.z), h3 = rn_tf32(x.w);
-            hi[4 * c + 0] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
-            hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
-            lo[4 * c + 0] = __float_as_uint(rn_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(rn_tf32(x.y - h1));
-            lo[4 * c + 2] = __float_as_uint(rn_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(rn_tf32(x.w - h3));
+            const float4 x = lds4(src + ((c ^ (row & 7)) << 4));
+            split_tf32(x.x, hi[4 * c + 0], lo[4 * c + 0]);
+            split_tf32(x.y, hi[4 * c + 1], lo[4 * c + 1]);
+            split_tf32(x.z, hi[4 * c + 2], lo[4 * c + 2]);
+            split_tf32(x.w, hi[4 * c + 3], lo[4 * c + 3]);
           }
           mbar_wait(BAR(BAR_TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
           tc_fence_after();
@@ -461,8 +495,14 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // is hi/lo-split in place.  When N1 > K1 the roles of A and B are swapped and the transposed result is written back by
 // the reduction kernel.  Work unit = (128-column tile of W, row slab); each unit writes its [128 x n] partial to the
 // workspace and a fixed-order reduction sums the slabs (bit-reproducible).  Same grouped-TMEM / register accumulation.
-constexpr int TN_R = 4;           // raw W stages, 16 KB each ([32 rows][128 columns], no swizzle)
-constexpr int TN_Q = 3;           // narrow-operand stages: hi (raw, split in place) 16 KB + lo 16 KB
+#ifndef TN_R_
+#define TN_R_ 4
+#endif
+#ifndef TN_Q_
+#define TN_Q_ 3
+#endif
+constexpr int TN_R = TN_R_;       // raw W stages, 16 KB each ([32 rows][128 columns], no swizzle)
+constexpr int TN_Q = TN_Q_;       // narrow-operand stages: hi (raw, split in place) 16 KB + lo 16 KB
 constexpr int TN_TA = 4;          // TMEM stages of W: hi 32 + lo 32 columns
 constexpr uint32_t TN_SMEM_BYTES = TN_R * TC_A_BYTES + TN_Q * 2 * TC_B_BYTES + 1024 + 512;
 constexpr int TN_W_FULL = 0, TN_W_FREE = TN_W_FULL + TN_R, TN_TA_FULL = TN_W_FREE + TN_R, TN_TA_FREE = TN_TA_FULL + TN_TA,
@@ -534,7 +574,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         decode(u, w0, n0, mbeg, mend, slab);
         for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
           const int r = n % TN_R;
-          mbar_wait(BAR(TN_W_FREE + r), ((n / TN_R) & 1) ^ 1);
+          mbar_wait_relaxed(BAR(TN_W_FREE + r), ((n / TN_R) & 1) ^ 1);
           mbar_expect_tx(BAR(TN_W_FULL + r), TC_A_BYTES);
           tma_load_2d(raw_base + r * TC_A_BYTES, &tmW, w0, (int)m, BAR(TN_W_FULL + r));
         }
@@ -549,7 +589,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         decode(u, w0, n0, mbeg, mend, slab);
         for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
           const int q = n % TN_Q;
-          mbar_wait(BAR(TN_B_FREE + q), ((n / TN_Q) & 1) ^ 1);
+          mbar_wait_relaxed(BAR(TN_B_FREE + q), ((n / TN_Q) & 1) ^ 1);
           mbar_expect_tx(BAR(TN_B_FULL + q), tx);
           for (int i = 0; i < nb; ++i) tma_load_2d(N_HI(q) + i * 4096, &tmN, n0 + 32 * i, (int)m, BAR(TN_B_FULL + q));
         }
@@ -598,23 +638,19 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // ------------------------------------------------------------------------ splitter: thread = column of W = TMEM lane
     const int tid = threadIdx.x;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const int b_vec = nb * 256;                        // float4s in the narrow tile
     uint32_t n = 0;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
       int w0, n0, slab; long long mbeg, mend;
       decode(u, w0, n0, mbeg, mend, slab);
       for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
-        const int r = n % TN_R, s = n % TN_TA, q = n % TN_Q;
-        // --- W chunk: raw [32 rows][128 columns] -> this thread's column, rows along the TMEM columns
+        const int r = n % TN_R, s = n % TN_TA;
+        // raw [32 rows][128 columns] -> this thread's column, rows along the TMEM columns
         mbar_wait(BAR(TN_W_FULL + r), (n / TN_R) & 1);
-        const float* src = reinterpret_cast<const float*>(smem + r * TC_A_BYTES) + tid;
+        const uint32_t src = raw_base + r * TC_A_BYTES + tid * 4;
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float x = src[j * 128];
-          const float h = rn_tf32(x);
-          hi[j] = __float_as_uint(h);
-          lo[j] = __float_as_uint(rn_tf32(x - h));
+          split_tf32(lds1(src + j * 512), hi[j], lo[j]);
         }
         mbar_wait(BAR(TN_TA_FREE + s), ((n / TN_TA) & 1) ^ 1);
         tc_fence_after();
@@ -624,31 +660,18 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         mbar_arrive(BAR(TN_W_FREE + r));                 // after the TMEM stores: every loaded register has been consumed
         tc_fence_before();
         mbar_arrive(BAR(TN_TA_FULL + s));
-        // --- narrow chunk: split in place (hi) + twin buffer (lo); elementwise, so the swizzled layout is preserved
-        mbar_wait(BAR(TN_B_FULL + q), (n / TN_Q) & 1);
-        float4* bhi = reinterpret_cast<float4*>(nring + q * 2 * TC_B_BYTES);
-        float4* blo = reinterpret_cast<float4*>(nring + q * 2 * TC_B_BYTES + TC_B_BYTES);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = tid + 128 * i;
-          if (idx < b_vec) {
-            const float4 x = bhi[idx];
-            float4 h, l;
-            h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
-            l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
-            bhi[idx] = h;
-            blo[idx] = l;
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(BAR(TN_B_SPLIT + q));
       }
     }
   } else if (warp < 8) {
-    // ------------------------------------------------------------------------ epilogue: partial [128 x Nc] per unit
+    // ------------------------------------------------------------------------ epilogue warps: (1) hi/lo split of the narrow
+    // operand, chunk by chunk (these warps are idle ~90 % of the time otherwise; on the splitter warps the split sat on
+    // the critical path: profiles/r01_tn_v2_hot.txt), (2) accumulator drain, one group behind the split.
     int a = 0;
     uint32_t aph = 0;
     const int ew = warp & 3;
+    const int te = threadIdx.x - 128;                  // 0..127
+    const int b_vec = nb * 256;                        // float4s in the narrow tile
+    uint32_t n = 0;                                    // chunk counter (narrow-operand ring)
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
       int w0, n0, slab; long long mbeg, mend;
       decode(u, w0, n0, mbeg, mend, slab);
@@ -657,7 +680,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       float acc[TC_BN];
 #pragma unroll
       for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
-      for (long long g = 0; g < n_groups; ++g) {
+      auto drain = [&]() {
         mbar_wait(BAR(TN_ACC_FULL + a), aph);
         tc_fence_after();
 #pragma unroll
@@ -673,7 +696,34 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         tc_fence_before();
         mbar_arrive(BAR(TN_ACC_EMPTY + a));
         if (++a == 2) { a = 0; aph ^= 1; }
+      };
+      for (long long g = 0; g < n_groups; ++g) {
+        const long long kc_end = (g + 1) * TC_GROUP < chunks ? (g + 1) * TC_GROUP : chunks;
+        for (long long kc = g * TC_GROUP; kc < kc_end; ++kc, ++n) {
+          const int q = n % TN_Q;
+          mbar_wait(BAR(TN_B_FULL + q), (n / TN_Q) & 1);
+          const uint32_t bhi = N_HI(q), blo = N_LO(q);
+          float4 x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (te + 128 * i < b_vec) x[i] = lds4(bhi + (te + 128 * i) * 16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (te + 128 * i < b_vec) {
+              uint32_t h[4], l[4];
+              split_tf32(x[i].x, h[0], l[0]); split_tf32(x[i].y, h[1], l[1]);
+              split_tf32(x[i].z, h[2], l[2]); split_tf32(x[i].w, h[3], l[3]);
+              // elementwise, so the swizzled layout is preserved; the hi tile needs no rewrite (same upper 19 bits)
+              sts4(blo + (te + 128 * i) * 16, make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]),
+                                                         __uint_as_float(l[3])));
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(BAR(TN_B_SPLIT + q));
+        }
+        if (g > 0) drain();                            // group g-1, while the MMAs of group g run
       }
+      drain();
       const int wc = w0 + ew * 32 + lane;
       if (wc < Wc) {
         float* prow = P + ((long long)slab * Wc + wc) * Nc + n0;
