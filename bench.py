@@ -6,8 +6,9 @@
 
 Workload ("config.workload"): COGMEN train step (graphify + forward + cross entropy + backward + gradient
 all-reduce + Adam) on ~2^20 synthetic MOSEI-shaped utterances (hidden_all = 768+640+35 = 1443, one speaker id,
-dialogue lengths 1+Geometric(1/7) clipped to 40, 6 classes), whole dialogues sharded across the N GPUs
-(strong scaling: the total is fixed).  One "step" = one pass over all ~2^20 utterances as ONE batch per GPU.
+dialogue lengths 1+Geometric(1/7) clipped to 40, 6 classes) PER GPU, whole dialogues per GPU, no data-path collective
+(weak scaling, the default; ``--scaling strong`` splits one ~2^20-utterance set over the GPUs instead -- measured
+numbers for both are in DESIGN.md).  One "step" = one pass over a GPU's utterances as ONE batch.
 ``value`` = utterances / second with inputs resident in HBM; ``e2e`` = the same step fed from pinned HOST
 buffers (H2D of the inputs and D2H of the loss inside the timed region).
 """
@@ -29,7 +30,7 @@ METRIC = "COGMEN fwd+bwd utterances/sec"
 UNIT = "utterances/s"
 HIDDEN = 1443
 N_CLASSES = 6
-WORKLOAD = "cogmen-train-step mosei-emo-sbert-fbank-6 shape (hidden_all=1443, 1 speaker id, window 5/5), ~2^20 utterances/step sharded by dialogue"
+WORKLOAD = "cogmen-train-step mosei-emo-sbert-fbank-6 shape (hidden_all=1443, 1 speaker id, window 5/5), ~2^20 utterances per GPU per step, whole dialogues sharded over the GPUs"
 
 
 def peaks():
@@ -50,12 +51,12 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.samples, self.stop_flag, self.proc, self.mark = index, [], False, None, 0
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -70,7 +71,7 @@ class ClockSampler(threading.Thread):
             self.proc.terminate()
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.samples[self.mark:]:
             try:
                 sm.append(float(s[1]))
                 mx = max(mx, float(s[2]))
@@ -152,13 +153,13 @@ def run_reference(args):
     sample = "%d steps x %d batches x 32 dialogues (%d utterances) of the MOSEI-shaped workload; throughput is per-batch, linear in dialogues" % (
         args.steps, bps, utts)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "reference_batch": "32 dialogues/batch (cogmen.py:43-45)", "device": "cpu"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -197,7 +198,10 @@ def run_ours(args):
     _lib.lib()                                            # fail loudly now if the .so is missing
 
     # ---- workload
-    lengths_all = synth.config5_lengths(args.total_utts, seed=0)
+    # weak scaling (default): every GPU gets its own ~args.total_utts utterances -- whole dialogues, no data-path collective
+    # (SURVEY.md 8e); strong scaling: the same ~args.total_utts utterances are split over the GPUs
+    weak = args.scaling == "weak"
+    lengths_all = synth.config5_lengths(args.total_utts * (world if weak else 1), seed=0)
     total_utts = int(lengths_all.sum())
     mine = shard_dialogues(lengths_all, world)[rank]
     lengths = lengths_all[mine].contiguous()
@@ -237,12 +241,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step(x, spk, labels)
-    barrier()
+    # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up: spawning it inside the timed region stalls
+    # rank 0's launch thread for tens of ms, which the other ranks then wait out in the first all-reduce
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(x, spk, labels)
+    barrier()
+    if sampler:
+        t_wait = time.perf_counter()
+        while not sampler.samples and time.perf_counter() - t_wait < 2.0:
+            time.sleep(0.01)
+        sampler.mark = len(sampler.samples)          # only samples taken from here on are reported
+    barrier()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     timer = _lib.KernelTimer(labeler=kernel_label)      # GEMM records are split by shape
@@ -337,10 +349,11 @@ def run_ours(args):
         graph_kernels = {k: kernels[k] for k in ("gather_fwd", "gather_bwd", "attn_fwd", "attn_bwd_dst", "attn_bwd_src",
                                                  "graphify_csr") if k in kernels}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "utterances_per_step": total_utts, "dialogues": int(lengths_all.numel()),
-                           "edges_per_step_rank0": E, "parallelism": "dp%d (whole dialogues per GPU)" % world,
+                           "edges_per_step_rank0": E, "parallelism": "dp%d (whole dialogues per GPU, %s scaling: %d utterances %s)" % (
+                               world, args.scaling, args.total_utts, "per GPU" if weak else "in total"),
                            "l2": "inputs (%.1f GB/step/GPU) are larger than the 126 MB L2" % (x_store.numel() * 4 / 1e9),
                            "dropout": "on (train mode)", "optimizer": "Adam inside the step", "dead_encoder": "not executed (cogmen.py:146-147 discards its output)"},
                 "roofline": roof, "graph_kernels": graph_kernels,
@@ -354,9 +367,27 @@ def run_ours(args):
             v2, sample2, _ = cpu_reference_rate(args.cpu_budget_s / 2, skip_dead_encoder=True)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample,
                                     "value_dead_encoder_skipped": v2}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner to stdout) must not pollute the ONE JSON line: route fd 1 to stderr for
+    the whole run and keep a private duplicate of the real stdout for the result."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -369,7 +400,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-budget-s", type=float, default=16.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --total-utts utterances PER GPU (default); strong: --total-utts in total, sharded over the GPUs")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

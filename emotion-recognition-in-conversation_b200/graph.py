@@ -17,8 +17,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+from .ops import _stream  # noqa: E402  (raw handle of torch's current stream)
 
 
 class PackedGraph:
