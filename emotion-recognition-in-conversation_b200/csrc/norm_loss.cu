@@ -54,6 +54,81 @@ col_partials_kernel(const float* __restrict__ x, long long ldx, const float* __r
   }
 }
 
+// float4 version of the above for 16-byte aligned rows: one pass over the columns (H <= 128 per pass), each warp load
+// covers a whole 400-byte row instead of one 128-byte line, rows unrolled x4 -> 4x the bytes in flight per warp.
+// Same row-to-warp assignment and the same fixed summation order inside a lane; only the partial sums differ in rounding.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+col_partials_v4_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dout, long long ldo,
+                       const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                       long long N, int H, float* __restrict__ partial) {
+  __shared__ float4 sm0[8][33], sm1[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long rbeg = (long long)blockIdx.x * RPB;
+  long long rend = rbeg + RPB;
+  if (rend > N) rend = N;
+  for (int c0 = 0; c0 < H; c0 += 128) {
+    const int c = c0 + 4 * tx;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (c < H) {
+      float4 mu = s0, istd = s0, g = s0, b = s0, shift = s0;
+      if (MODE == 1) {
+        mu = ld4(mean + c); g = ld4(gamma + c); b = ld4(beta + c);
+        const float4 vv = ld4(var + c);
+        istd = make_float4(1.0f / sqrtf(vv.x + eps), 1.0f / sqrtf(vv.y + eps), 1.0f / sqrtf(vv.z + eps), 1.0f / sqrtf(vv.w + eps));
+      } else {
+        shift = ld4(x + c);                       // row 0 as a per-column shift
+      }
+      auto acc = [&](const float4& xv, const float4& dv) {
+        if (MODE == 0) {
+          const float4 xs = make_float4(xv.x - shift.x, xv.y - shift.y, xv.z - shift.z, xv.w - shift.w);
+          s0.x += xs.x; s0.y += xs.y; s0.z += xs.z; s0.w += xs.w;
+          s1.x = fmaf(xs.x, xs.x, s1.x); s1.y = fmaf(xs.y, xs.y, s1.y); s1.z = fmaf(xs.z, xs.z, s1.z); s1.w = fmaf(xs.w, xs.w, s1.w);
+        } else {
+          const float4 xh = make_float4((xv.x - mu.x) * istd.x, (xv.y - mu.y) * istd.y, (xv.z - mu.z) * istd.z, (xv.w - mu.w) * istd.w);
+          const float4 dy = make_float4(dv.x * (fmaf(g.x, xh.x, b.x) > 0.f ? 1.f : slope), dv.y * (fmaf(g.y, xh.y, b.y) > 0.f ? 1.f : slope),
+                                        dv.z * (fmaf(g.z, xh.z, b.z) > 0.f ? 1.f : slope), dv.w * (fmaf(g.w, xh.w, b.w) > 0.f ? 1.f : slope));
+          s0.x += dy.x; s0.y += dy.y; s0.z += dy.z; s0.w += dy.w;
+          s1.x = fmaf(dy.x, xh.x, s1.x); s1.y = fmaf(dy.y, xh.y, s1.y); s1.z = fmaf(dy.z, xh.z, s1.z); s1.w = fmaf(dy.w, xh.w, s1.w);
+        }
+      };
+      long long r = rbeg + ty;
+      for (; r + 24 < rend; r += 32) {
+        float4 xv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          xv[u] = ld4_stream(x + (r + 8 * u) * ldx + c);
+          dv[u] = MODE == 1 ? ld4_stream(dout + (r + 8 * u) * ldo + c) : xv[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc(xv[u], dv[u]);
+      }
+      for (; r < rend; r += 8) {
+        const float4 xv = ld4_stream(x + r * ldx + c);
+        acc(xv, MODE == 1 ? ld4_stream(dout + r * ldo + c) : xv);
+      }
+    }
+    sm0[ty][tx] = s0; sm1[ty][tx] = s1;
+    __syncthreads();
+    if (ty == 0 && c < H) {
+      float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        const float4 a = sm0[y][tx], bq = sm1[y][tx];
+        t0.x += a.x; t0.y += a.y; t0.z += a.z; t0.w += a.w;
+        t1.x += bq.x; t1.y += bq.y; t1.z += bq.z; t1.w += bq.w;
+      }
+      float* p0 = partial + (long long)blockIdx.x * 2 * H + c;
+      p0[0] = t0.x; p0[H] = t1.x;
+      if (c + 1 < H) { p0[1] = t0.y; p0[H + 1] = t1.y; }
+      if (c + 2 < H) { p0[2] = t0.z; p0[H + 2] = t1.z; }
+      if (c + 3 < H) { p0[3] = t0.w; p0[H + 3] = t1.w; }
+    }
+    __syncthreads();
+  }
+}
+
 // fixed-order fp64 reduction of partial[nb][2H] column c: 8 row-lanes per column, then a fixed 8-term sum
 __device__ __forceinline__ double reduce_partials(const float* __restrict__ partial, int nb, int width, int c, bool ok,
                                                   double (*sm)[33]) {
@@ -134,6 +209,33 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, long long ldo, const flo
   dx[r * lddx + c] = g * istd * v;
 }
 
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_v4_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ x, long long ldx,
+                           const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                           const float* __restrict__ sums, float inv_count, int use_batch_stats,
+                           float* __restrict__ dx, long long lddx, long long N, int H) {
+  const int nch = H >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nch) return;
+  const long long r = idx / nch;
+  const int c = (int)(idx % nch) * 4;
+  const float4 xv = ld4_stream(x + r * ldx + c), dv = ld4_stream(dout + r * ldo + c);
+  const float4 mu = ld4(mean + c), vv = ld4(var + c), g = ld4(gamma + c), b = ld4(beta + c);
+  float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+  if (use_batch_stats) { sa = ld4(sums + c); sb = ld4(sums + H + c); }
+  auto one = [&](float xe, float de, float m, float v, float ge, float be, float s0, float s1) {
+    const float istd = 1.0f / sqrtf(v + eps);
+    const float xh = (xe - m) * istd;
+    const float dy = de * (fmaf(ge, xh, be) > 0.f ? 1.f : slope);
+    float t = dy;
+    if (use_batch_stats) t = dy - s0 * inv_count - xh * (s1 * inv_count);
+    return ge * istd * t;
+  };
+  st4_stream(dx + r * lddx + c, make_float4(one(xv.x, dv.x, mu.x, vv.x, g.x, b.x, sa.x, sb.x), one(xv.y, dv.y, mu.y, vv.y, g.y, b.y, sa.y, sb.y),
+                                            one(xv.z, dv.z, mu.z, vv.z, g.z, b.z, sa.z, sb.z), one(xv.w, dv.w, mu.w, vv.w, g.w, b.w, sa.w, sb.w)));
+}
+
 // ------------------------------------------------------------------------------------------- CE
 __global__ void __launch_bounds__(256)
 ce_fwd_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
@@ -194,6 +296,21 @@ __global__ void mask_pos_kernel(const float* __restrict__ x, long long ldx, cons
   out[r * ldo + c] = ref[r * ldr + c] > 0.f ? x[r * ldx + c] * scale : 0.f;
 }
 
+__global__ void __launch_bounds__(256)
+mask_pos_v4_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ ref, long long ldr, float scale,
+                   float* __restrict__ out, long long ldo, long long M, int N) {
+  const int nch = N >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * nch) return;
+  const long long r = idx / nch;
+  const int c = (int)(idx % nch) * 4;
+  const float4 xv = ld4_stream(x + r * ldx + c), rv = ld4_stream(ref + r * ldr + c);
+  st4_stream(out + r * ldo + c, make_float4(rv.x > 0.f ? xv.x * scale : 0.f, rv.y > 0.f ? xv.y * scale : 0.f,
+                                            rv.z > 0.f ? xv.z * scale : 0.f, rv.w > 0.f ? xv.w * scale : 0.f));
+}
+
+static inline bool v4_ok(const void* p, long long ld) { return aligned16(p) && (ld & 3) == 0; }
+
 }  // namespace ercg
 
 using namespace ercg;
@@ -204,6 +321,10 @@ extern "C" int ercg_mask_pos(const float* x, int64_t ldx, const float* ref, int6
   if (M == 0 || N == 0) return ERCG_OK;
   if (!x || !ref || !out) return ERCG_EINVAL;
   const long long tot = M * N;
+  if ((N & 3) == 0 && v4_ok(x, ldx) && v4_ok(ref, ldr) && v4_ok(out, ldo)) {
+    mask_pos_v4_kernel<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, ref, ldr, scale, out, ldo, M, N);
+    return finish_launch();
+  }
   mask_pos_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, ref, ldr, scale, out, ldo, M, N);
   return finish_launch();
 }
@@ -220,7 +341,10 @@ extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, floa
   const int nb = (int)((N + RPB - 1) / RPB);
   cudaStream_t st = (cudaStream_t)stream;
   float* part = reinterpret_cast<float*>(workspace);
-  col_partials_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
+  if (v4_ok(x, ldx))
+    col_partials_v4_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
+  else
+    col_partials_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
   int rc = finish_launch();
   if (rc) return rc;
   bn_stats_final_kernel<<<(H + 31) / 32, 256, 0, st>>>(part, nb, H, N, x, mean, var);
@@ -250,6 +374,7 @@ extern "C" int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const floa
   const int nb = (int)((N + RPB - 1) / RPB);
   cudaStream_t st = (cudaStream_t)stream;
   float* part = reinterpret_cast<float*>(workspace);
+  // (the float4 variant measured slower for this two-input mode: 0.33 vs 0.29 ms at 2^20 x 100)
   col_partials_kernel<1><<<nb, 256, 0, st>>>(x, ldx, dout, ldo, mean, var, eps, gamma, beta, slope, N, H, part);
   int rc = finish_launch();
   if (rc) return rc;
@@ -266,6 +391,13 @@ extern "C" int ercg_bn_act_bwd_apply(const float* dout, int64_t ldo, const float
   if (N == 0) return ERCG_OK;
   if (!dout || !x || !mean || !var || !gamma || !beta || !dx || (use_batch_stats && (!sums || count <= 0))) return ERCG_EINVAL;
   const long long tot = N * H;
+  if ((H & 3) == 0 && v4_ok(dout, ldo) && v4_ok(x, ldx) && v4_ok(dx, lddx) && aligned16(mean) && aligned16(var) &&
+      aligned16(gamma) && aligned16(beta) && (!use_batch_stats || aligned16(sums))) {
+    bn_act_bwd_apply_v4_kernel<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        dout, ldo, x, ldx, mean, var, eps, gamma, beta, slope, sums, use_batch_stats ? (float)(1.0 / count) : 0.f,
+        use_batch_stats, dx, lddx, N, H);
+    return finish_launch();
+  }
   bn_act_bwd_apply_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       dout, ldo, x, ldx, mean, var, eps, gamma, beta, slope, sums, use_batch_stats ? (float)(1.0 / count) : 0.f,
       use_batch_stats, dx, lddx, N, H);
