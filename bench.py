@@ -175,6 +175,7 @@ def kernel_label(name, args):
             return "gemm_tn[K1=%d,N1=%d]" % (args[8], args[9])
     except Exception:
         pass
+    name = name.replace("attn_window_", "attn_")        # CTA-tiled window-graph variants of the same three kernels
     return name[5:] if name.startswith("ercg_") else name
 
 

@@ -62,6 +62,10 @@ SIGNATURES = {
     "ercg_attn_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, L, I, P]),
     "ercg_attn_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, L, I, P]),
     "ercg_attn_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, L, I, P]),
+    "ercg_attn_window_supported": (I, [I, I, I]),
+    "ercg_attn_window_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, L, I, I, I, P]),
+    "ercg_attn_window_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, L, I, I, I, P]),
+    "ercg_attn_window_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, L, I, I, I, P]),
     "ercg_edgeatt_fwd": (I, [P, L, P, L, P, P, P, P, L, I, P]),
     "ercg_edgeatt_bwd_src": (I, [P, P, P, L, P, P, P, P, P, L, L, I, P]),
     "ercg_edgeatt_bwd_dst": (I, [P, P, L, P, P, P, L, L, I, P]),

@@ -305,6 +305,228 @@ attn_bwd_src_kernel(const float* __restrict__ dout, long long ldo, const float* 
   }
 }
 
+// ---------------------------------------------------------------------------------- K4 on WINDOW graphs: CTA tiles
+// ncu on the warp-per-node kernels above (profiles/r01b_ncu_full_262k.csv): attn_fwd executes ~790 warp instructions
+// per node at 63 % issue utilisation and 55 % occupancy -- issue- and latency-bound, DRAM at 20-30 %.  For the graphs
+// K1 builds, the neighbours of node i are the contiguous rows [i - wlo, i + whi] of its dialogue, so a CTA that owns 32
+// consecutive nodes needs only the 32 + wlo + whi rows around them.  These kernels stage those rows of k / v (and q or
+// dout) in shared memory with plain coalesced loads (all global latency is paid once, in parallel), then
+//   * scores / dalpha: ONE LANE PER EDGE walks the 25 float4 chunks of "its" neighbour row in shared memory -- no
+//     shuffle reduction at all; two nodes share a warp (16 lanes each) when wlo + whi + 1 <= 16,
+//   * aggregation: one lane per float4 chunk, per-edge scalars broadcast by shuffle.
+// ~210 instead of ~790 instructions per node.  Same arithmetic per edge; the summation order over edges is unchanged
+// (ascending CSR order), so results stay bit-reproducible.  A source outside the promised window traps.
+constexpr int WT = 32;        // nodes per CTA tile
+
+__device__ __forceinline__ void stage_rows(float4* dst, const float* __restrict__ src, long long ld, long long r0, int rows,
+                                           int nch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < nch)
+    for (int r = warp; r < rows; r += 8) dst[r * nch + lane] = ld4(src + (r0 + r) * ld + 4 * lane);
+}
+template <bool PAIR>
+__device__ __forceinline__ float half_max(float v) {
+  if (!PAIR) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+}
+template <bool PAIR>
+__device__ __forceinline__ float half_sum(float v) {
+  if (!PAIR) v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v + __shfl_xor_sync(0xffffffffu, v, 1);
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(256)
+attn_fwd_tile_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                     const float* __restrict__ s, long long ld, const int* __restrict__ rowptr,
+                     const int* __restrict__ col, float scale, float* __restrict__ out, long long ldo,
+                     float* __restrict__ alpha, long long N, int H, int wlo, int whi) {
+  extern __shared__ float4 attn_sm[];
+  const int nch = H >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t0 = (long long)blockIdx.x * WT;
+  const int tn = (int)min((long long)WT, N - t0);
+  const long long r0 = max(0LL, t0 - wlo), r1 = min(N, t0 + tn + whi);
+  const int R = (int)(r1 - r0), Rmax = WT + wlo + whi;
+  float4* sq = attn_sm;
+  float4* sk = sq + WT * nch;
+  float4* sv = sk + Rmax * nch;
+  stage_rows(sq, q, ld, t0, tn, nch);
+  stage_rows(sk, k, ld, r0, R, nch);
+  stage_rows(sv, v, ld, r0, R, nch);
+  __syncthreads();
+  constexpr int NPW = WT / 8;                 // nodes per warp
+  constexpr int G = PAIR ? 2 : 1;             // nodes handled together in the score phase
+  const int half = PAIR ? lane >> 4 : 0, e = PAIR ? lane & 15 : lane;
+  for (int p = 0; p < NPW; p += G) {
+    const int nl = warp * NPW + p + half;     // node of this lane's half
+    const bool nok = nl < tn;
+    const long long node = t0 + nl;
+    const int beg = nok ? rowptr[node] : 0, deg = nok ? rowptr[node + 1] - beg : 0;
+    const bool live = e < deg;
+    int row = 0;
+    if (live) {
+      const long long src = col[beg + e];
+      if (src < r0 || src >= r1) __trap();    // the caller promised a window graph
+      row = (int)(src - r0);
+    }
+    float d = 0.f;
+    const float4* qi = sq + nl * nch;
+    const float4* kr = sk + row * nch;
+    if (live) {
+#pragma unroll 5
+      for (int c = 0; c < nch; ++c) d += dot4(qi[c], kr[c]);
+    }
+    d *= scale;
+    const float mx = half_max<PAIR>(live ? d : -INFINITY);
+    const float ex = live ? expf(d - mx) : 0.f;
+    const float inv = 1.f / (half_sum<PAIR>(ex) + 1e-16f);
+    const float al = ex * inv;
+    if (live && alpha) alpha[beg + e] = al;
+    // aggregation: lanes = float4 chunks, one node after the other
+#pragma unroll
+    for (int h = 0; h < G; ++h) {
+      const int base = PAIR ? h * 16 : 0;
+      const int hdeg = __shfl_sync(0xffffffffu, deg, base);
+      const int hnl = warp * NPW + p + h;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < hdeg; ++u) {
+        const float a = __shfl_sync(0xffffffffu, al, base + u);
+        const int rw = __shfl_sync(0xffffffffu, row, base + u);
+        if (lane < nch) fma4(acc, a, sv[rw * nch + lane]);
+      }
+      if (hnl < tn && lane < nch) {
+        if (s) {
+          const float4 sk4 = ld4(s + (t0 + hnl) * ld + 4 * lane);
+          acc.x += sk4.x; acc.y += sk4.y; acc.z += sk4.z; acc.w += sk4.w;
+        }
+        st4(out + (t0 + hnl) * ldo + 4 * lane, acc);
+      }
+    }
+  }
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(256)
+attn_bwd_dst_tile_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ k,
+                         const float* __restrict__ v, long long ld, const int* __restrict__ rowptr,
+                         const int* __restrict__ col, const float* __restrict__ alpha, float scale,
+                         float* __restrict__ dq, float* __restrict__ ds, long long ldd, float* __restrict__ dsig,
+                         long long N, int H, int wlo, int whi) {
+  extern __shared__ float4 attn_sm[];
+  const int nch = H >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t0 = (long long)blockIdx.x * WT;
+  const int tn = (int)min((long long)WT, N - t0);
+  const long long r0 = max(0LL, t0 - wlo), r1 = min(N, t0 + tn + whi);
+  const int R = (int)(r1 - r0), Rmax = WT + wlo + whi;
+  float4* sd = attn_sm;
+  float4* sk = sd + WT * nch;
+  float4* sv = sk + Rmax * nch;
+  stage_rows(sd, dout, ldo, t0, tn, nch);
+  stage_rows(sk, k, ld, r0, R, nch);
+  stage_rows(sv, v, ld, r0, R, nch);
+  __syncthreads();
+  constexpr int NPW = WT / 8;
+  constexpr int G = PAIR ? 2 : 1;
+  const int half = PAIR ? lane >> 4 : 0, e = PAIR ? lane & 15 : lane;
+  for (int p = 0; p < NPW; p += G) {
+    const int nl = warp * NPW + p + half;
+    const bool nok = nl < tn;
+    const long long node = t0 + nl;
+    const int beg = nok ? rowptr[node] : 0, deg = nok ? rowptr[node + 1] - beg : 0;
+    const bool live = e < deg;
+    int row = 0;
+    float al = 0.f;
+    if (live) {
+      const long long src = col[beg + e];
+      if (src < r0 || src >= r1) __trap();
+      row = (int)(src - r0);
+      al = alpha[beg + e];
+    }
+    float da = 0.f;
+    const float4* gi = sd + nl * nch;
+    const float4* vr = sv + row * nch;
+    if (live) {
+#pragma unroll 5
+      for (int c = 0; c < nch; ++c) da += dot4(gi[c], vr[c]);
+    }
+    const float D = half_sum<PAIR>(al * da);
+    const float g = al * (da - D);
+    if (live) dsig[beg + e] = g;
+    const float gs = g * scale;
+#pragma unroll
+    for (int h = 0; h < G; ++h) {
+      const int base = PAIR ? h * 16 : 0;
+      const int hdeg = __shfl_sync(0xffffffffu, deg, base);
+      const int hnl = warp * NPW + p + h;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < hdeg; ++u) {
+        const float a = __shfl_sync(0xffffffffu, gs, base + u);
+        const int rw = __shfl_sync(0xffffffffu, row, base + u);
+        if (lane < nch) fma4(acc, a, sk[rw * nch + lane]);
+      }
+      if (hnl < tn && lane < nch) {
+        st4(dq + (t0 + hnl) * ldd + 4 * lane, acc);
+        if (ds) st4(ds + (t0 + hnl) * ldd + 4 * lane, sd[hnl * nch + lane]);
+      }
+    }
+  }
+}
+
+// by-source half on window graphs: the destinations of node j are rows [j - wlo, j + whi]
+__global__ void __launch_bounds__(256)
+attn_bwd_src_tile_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ q, long long ld,
+                         const int* __restrict__ t_rowptr, const int* __restrict__ t_col, const int* __restrict__ t_eid,
+                         const float* __restrict__ alpha, const float* __restrict__ dsig, float scale,
+                         float* __restrict__ dk, float* __restrict__ dv, long long ldd, long long N, int H, int wlo, int whi) {
+  extern __shared__ float4 attn_sm[];
+  const int nch = H >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t0 = (long long)blockIdx.x * WT;
+  const int tn = (int)min((long long)WT, N - t0);
+  const long long r0 = max(0LL, t0 - wlo), r1 = min(N, t0 + tn + whi);
+  const int R = (int)(r1 - r0), Rmax = WT + wlo + whi;
+  float4* sq = attn_sm;
+  float4* sd = sq + Rmax * nch;
+  stage_rows(sq, q, ld, r0, R, nch);
+  stage_rows(sd, dout, ldo, r0, R, nch);
+  __syncthreads();
+  constexpr int NPW = WT / 8;
+  for (int p = 0; p < NPW; ++p) {
+    const int nl = warp * NPW + p;
+    if (nl >= tn) break;                       // warp-uniform
+    const long long node = t0 + nl;
+    const int beg = t_rowptr[node], deg = t_rowptr[node + 1] - beg;
+    int row = 0;
+    float a = 0.f, g = 0.f;
+    if (lane < deg) {
+      const long long dst = t_col[beg + lane];
+      if (dst < r0 || dst >= r1) __trap();
+      row = (int)(dst - r0);
+      const int id = t_eid[beg + lane];
+      a = alpha[id];
+      g = dsig[id] * scale;
+    }
+    float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), av = ak;
+    for (int u = 0; u < deg; ++u) {
+      const float au = __shfl_sync(0xffffffffu, a, u), gu = __shfl_sync(0xffffffffu, g, u);
+      const int rw = __shfl_sync(0xffffffffu, row, u);
+      if (lane < nch) {
+        fma4(ak, gu, sq[rw * nch + lane]);
+        fma4(av, au, sd[rw * nch + lane]);
+      }
+    }
+    if (lane < nch) {
+      st4(dk + node * ldd + 4 * lane, ak);
+      st4(dv + node * ldd + 4 * lane, av);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------- K5 EdgeAtt
 // by-source softmax of <x_j, u_k> over k in out(j); result stored at the by-destination edge id.
 template <int NC>
@@ -464,6 +686,78 @@ extern "C" int ercg_attn_bwd_src(const float* dout, int64_t ldo, const float* q,
   if (!t_rowptr || !t_col || !t_eid || !alpha || !dsig) return ERCG_EINVAL;
   ERCG_CHK(dout, ldo); ERCG_CHK(q, ld); ERCG_CHK(dk, ldd); ERCG_CHK(dv, ldd);
   ERCG_LAUNCH_NC(attn_bwd_src_kernel, dout, ldo, q, ld, t_rowptr, t_col, t_eid, alpha, dsig, scale, dk, dv, ldd, N, H);
+}
+
+// ---- window-graph variants (contract: the in-neighbours of node i lie in [i - wlo, i + whi]; violated -> trap)
+static size_t attn_tile_smem(int H, int wlo, int whi, int full_tiles /* tile-only matrices */, int halo_tiles) {
+  return (size_t)(H >> 2) * 16 * ((size_t)full_tiles * WT + (size_t)halo_tiles * (WT + wlo + whi));
+}
+static bool attn_tile_ok(int H, int wlo, int whi) { return H <= 128 && (H & 3) == 0 && wlo >= 0 && whi >= 0 && wlo + whi + 1 <= 32; }
+
+extern "C" int ercg_attn_window_supported(int H, int wlo, int whi) { return attn_tile_ok(H, wlo, whi) ? 1 : 0; }
+
+extern "C" int ercg_attn_window_fwd(const float* q, const float* k, const float* v, const float* s, int64_t ld,
+                                    const int32_t* rowptr, const int32_t* col, float scale, float* out, int64_t ldo,
+                                    float* alpha, int64_t N, int H, int wlo, int whi, void* stream) {
+  if (N < 0 || !attn_tile_ok(H, wlo, whi)) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!rowptr || !col) return ERCG_EINVAL;
+  ERCG_CHK(q, ld); ERCG_CHK(k, ld); ERCG_CHK(v, ld); ERCG_CHK(out, ldo);
+  if (s) ERCG_CHK(s, ld);
+  const size_t sm = attn_tile_smem(H, wlo, whi, 1, 2);
+  const unsigned blocks = (unsigned)((N + WT - 1) / WT);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_fwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(attn_fwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  if (wlo + whi + 1 <= 16) attn_fwd_tile_kernel<true><<<blocks, 256, sm, st>>>(q, k, v, s, ld, rowptr, col, scale, out, ldo, alpha, N, H, wlo, whi);
+  else attn_fwd_tile_kernel<false><<<blocks, 256, sm, st>>>(q, k, v, s, ld, rowptr, col, scale, out, ldo, alpha, N, H, wlo, whi);
+  return finish_launch();
+}
+
+extern "C" int ercg_attn_window_bwd_dst(const float* dout, int64_t ldo, const float* k, const float* v, int64_t ld,
+                                        const int32_t* rowptr, const int32_t* col, const float* alpha, float scale,
+                                        float* dq, float* ds, int64_t ldd, float* dsig, int64_t N, int H, int wlo, int whi,
+                                        void* stream) {
+  if (N < 0 || !attn_tile_ok(H, wlo, whi)) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!rowptr || !col || !alpha || !dsig) return ERCG_EINVAL;
+  ERCG_CHK(dout, ldo); ERCG_CHK(k, ld); ERCG_CHK(v, ld); ERCG_CHK(dq, ldd);
+  if (ds) ERCG_CHK(ds, ldd);
+  const size_t sm = attn_tile_smem(H, wlo, whi, 1, 2);
+  const unsigned blocks = (unsigned)((N + WT - 1) / WT);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_bwd_dst_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(attn_bwd_dst_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  if (wlo + whi + 1 <= 16) attn_bwd_dst_tile_kernel<true><<<blocks, 256, sm, st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, N, H, wlo, whi);
+  else attn_bwd_dst_tile_kernel<false><<<blocks, 256, sm, st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, N, H, wlo, whi);
+  return finish_launch();
+}
+
+extern "C" int ercg_attn_window_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld,
+                                        const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
+                                        const float* alpha, const float* dsig, float scale, float* dk, float* dv,
+                                        int64_t ldd, int64_t N, int H, int wlo, int whi, void* stream) {
+  if (N < 0 || !attn_tile_ok(H, wlo, whi)) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!t_rowptr || !t_col || !t_eid || !alpha || !dsig) return ERCG_EINVAL;
+  ERCG_CHK(dout, ldo); ERCG_CHK(q, ld); ERCG_CHK(dk, ldd); ERCG_CHK(dv, ldd);
+  const size_t sm = attn_tile_smem(H, wlo, whi, 0, 2);
+  const unsigned blocks = (unsigned)((N + WT - 1) / WT);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_bwd_src_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  attn_bwd_src_tile_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(dout, ldo, q, ld, t_rowptr, t_col, t_eid, alpha, dsig, scale, dk, dv, ldd, N, H, wlo, whi);
+  return finish_launch();
 }
 
 extern "C" int ercg_edgeatt_fwd(const float* x, int64_t ldx, const float* u, int64_t ldu,

@@ -195,6 +195,16 @@ def gather(Y, graph, H, R, w=None, bias=None, root_off=-1, use_types=True):
 
 
 # ------------------------------------------------------------------------------------------- K4 attention
+def _window(graph, H):
+    """(wf, wp) when ``graph`` is a K1 window graph the tiled attention kernels support, else None."""
+    wp, wf = getattr(graph, "wp", None), getattr(graph, "wf", None)
+    if wp is None or wf is None or getattr(graph, "perm", None) is not None:
+        return None
+    if wp < 0 or wf < 0 or not lib().ercg_attn_window_supported(H, wf, wp):
+        return None
+    return wf, wp
+
+
 class _Attn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkvs, graph, H, scale):
@@ -203,21 +213,35 @@ class _Attn(torch.autograd.Function):
         out = torch.empty((N, H), dtype=torch.float32, device=qkvs.device)
         alpha = torch.empty(graph.E, dtype=torch.float32, device=qkvs.device)
         b = qkvs.data_ptr()
-        check(lib().ercg_attn_fwd(b, b + 4 * H, b + 8 * H, b + 12 * H, ld, _p(graph.rowptr), _p(graph.col), scale,
-                                  _p(out), H, _p(alpha), N, H, _stream()), "ercg_attn_fwd")
-        ctx.graph, ctx.H, ctx.scale = graph, H, scale
+        win = _window(graph, H)
+        if win is not None:      # in-neighbours of node k: [k - wf, k + wp]
+            check(lib().ercg_attn_window_fwd(b, b + 4 * H, b + 8 * H, b + 12 * H, ld, _p(graph.rowptr), _p(graph.col), scale,
+                                             _p(out), H, _p(alpha), N, H, win[0], win[1], _stream()), "ercg_attn_window_fwd")
+        else:
+            check(lib().ercg_attn_fwd(b, b + 4 * H, b + 8 * H, b + 12 * H, ld, _p(graph.rowptr), _p(graph.col), scale,
+                                      _p(out), H, _p(alpha), N, H, _stream()), "ercg_attn_fwd")
+        ctx.graph, ctx.H, ctx.scale, ctx.win = graph, H, scale, win
         ctx.save_for_backward(qkvs, alpha)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkvs, alpha = ctx.saved_tensors
-        g, H, scale = ctx.graph, ctx.H, ctx.scale
+        g, H, scale, win = ctx.graph, ctx.H, ctx.scale, ctx.win
         dout, ldo = _rows(dout)
         N, ld = qkvs.size(0), qkvs.stride(0)
         d = torch.empty((N, 4 * H), dtype=torch.float32, device=dout.device)
         dsig = torch.empty(g.E, dtype=torch.float32, device=dout.device)
         b, db = qkvs.data_ptr(), d.data_ptr()
+        if win is not None:
+            check(lib().ercg_attn_window_bwd_dst(_p(dout), ldo, b + 4 * H, b + 8 * H, ld, _p(g.rowptr), _p(g.col), _p(alpha),
+                                                 scale, db, db + 12 * H, 4 * H, _p(dsig), N, H, win[0], win[1], _stream()),
+                  "ercg_attn_window_bwd_dst")
+            # out-neighbours of node j: [j - wp, j + wf]
+            check(lib().ercg_attn_window_bwd_src(_p(dout), ldo, b, ld, _p(g.t_rowptr), _p(g.t_col), _p(g.t_eid), _p(alpha),
+                                                 _p(dsig), scale, db + 4 * H, db + 8 * H, 4 * H, N, H, win[1], win[0],
+                                                 _stream()), "ercg_attn_window_bwd_src")
+            return d, None, None, None
         check(lib().ercg_attn_bwd_dst(_p(dout), ldo, b + 4 * H, b + 8 * H, ld, _p(g.rowptr), _p(g.col), _p(alpha), scale,
                                       db, db + 12 * H, 4 * H, _p(dsig), N, H, _stream()), "ercg_attn_bwd_dst")
         check(lib().ercg_attn_bwd_src(_p(dout), ldo, b, ld, _p(g.t_rowptr), _p(g.t_col), _p(g.t_eid), _p(alpha), _p(dsig),

@@ -187,6 +187,22 @@ int ercg_attn_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld
                       const float* alpha, const float* dsig, float scale,
                       float* dk, float* dv, int64_t ldd, int64_t N, int H, void* stream);
 
+/* Window-graph variants of K4: same results, for graphs whose neighbourhoods are contiguous row ranges -- every graph
+ * ercg_graphify_csr builds: the in-neighbours of node i lie in [i - wlo, i + whi] (wlo = wf, whi = wp of batch_graphify),
+ * its out-neighbours in [i - wp, i + wf].  A CTA stages the rows around its 32 nodes in shared memory; a neighbour outside
+ * the promised range traps.  Supported: H <= 128, H % 4 == 0, 0 <= wlo, whi, wlo + whi + 1 <= 32. */
+int ercg_attn_window_supported(int H, int wlo, int whi);
+int ercg_attn_window_fwd(const float* q, const float* k, const float* v, const float* s, int64_t ld,
+                         const int32_t* rowptr, const int32_t* col, float scale, float* out, int64_t ldo, float* alpha,
+                         int64_t N, int H, int wlo, int whi, void* stream);
+int ercg_attn_window_bwd_dst(const float* dout, int64_t ldo, const float* k, const float* v, int64_t ld,
+                             const int32_t* rowptr, const int32_t* col, const float* alpha, float scale, float* dq,
+                             float* ds, int64_t ldd, float* dsig, int64_t N, int H, int wlo, int whi, void* stream);
+int ercg_attn_window_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld, const int32_t* t_rowptr,
+                             const int32_t* t_col, const int32_t* t_eid, const float* alpha, const float* dsig,
+                             float scale, float* dk, float* dv, int64_t ldd, int64_t N, int H, int wlo, int whi,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K5  EdgeAtt of DialogueGCN (dgcn_models.py:121-152): per-SOURCE window softmax
  *   nu[j->k] = softmax_{k in out(j)} <x_j, u_k>,  u = x @ W^T  (u computed by ercg_gemm_nn)

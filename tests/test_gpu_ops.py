@@ -116,7 +116,7 @@ def test_gather_fwd_bwd(H, R, wp, wf):
     assert rel_err(bc.grad, dout.double().sum(0)) < TOL
 
 
-@pytest.mark.parametrize("wp,wf", [(5, 5), (-1, -1), (2, 40)])
+@pytest.mark.parametrize("wp,wf", [(5, 5), (-1, -1), (2, 40), (10, 10), (16, 15), (0, 3), (0, 0)])
 def test_edge_attention_fwd_bwd(wp, wf):
     import erc_b200
     from erc_b200 import ops
