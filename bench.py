@@ -276,27 +276,34 @@ def run_ours(args):
     value = total_utts * args.steps / (ms / 1e3)
     ksum = timer.summary()
 
-    # ---- e2e: same step fed from pinned host memory, loss read back
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    # ---- e2e: the same step through the public API with HOST buffers: every step's inputs (6 GB of features, speakers,
+    # labels) are copied from pinned host memory inside the timed region and the loss is read back.  The copies go through
+    # the package's DeviceFeeder (loader.py): double-buffered, on a copy stream, so the H2D of step i+1 overlaps the kernels
+    # of step i -- what a training loop with a pinned-memory DataLoader does.  PCIe (~55 GB/s) is the bound.
+    from erc_b200.loader import DeviceFeeder
+    e2e_steps = max(1, args.e2e_steps)
     hx = torch.empty((N, ld), dtype=torch.float32, pin_memory=True)
     hx.copy_(x_store)
-    hspk = torch.zeros(N, dtype=torch.int64).pin_memory()
-    hlab = labels.cpu().pin_memory()
-    dx = torch.empty_like(x_store)
-    dspk, dlab = torch.empty_like(spk), torch.empty_like(labels)
+    host = {"x": hx, "spk": torch.zeros(N, dtype=torch.int64).pin_memory(), "label": labels.cpu().pin_memory()}
+    feeder = DeviceFeeder(dev, depth=2)
 
-    def e2e_step():
-        dx.copy_(hx, non_blocking=True)
-        dspk.copy_(hspk, non_blocking=True)
-        dlab.copy_(hlab, non_blocking=True)
-        return float(step(dx[:, :HIDDEN], dspk, dlab).item())
+    def e2e_run(n):
+        losses = []
+        feeder.submit(host)
+        for i in range(n):
+            if i + 1 < n:
+                feeder.submit(host)                      # prefetch the next step's inputs
+            d = feeder.get()
+            loss_i = step(d["x"][:, :HIDDEN], d["spk"], d["label"])
+            feeder.release()
+            losses.append(float(loss_i.item()))          # D2H of the step's result
+        return losses
 
-    e2e_step()
+    e2e_run(2)
     barrier()
-    t0 = time.perf_counter()
+    b0 = feeder.h2d_bytes
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -304,7 +311,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     e2e_value = total_utts * e2e_steps / (e2e_ms / 1e3)
-    h2d = hx.numel() * 4 + hspk.numel() * 8 + hlab.numel() * 8
+    h2d = (feeder.h2d_bytes - b0) // e2e_steps
     if world > 1:
         b = torch.tensor([h2d], dtype=torch.float64, device=dev)
         dist.all_reduce(b)
@@ -361,7 +368,8 @@ def run_ours(args):
                 "kernels": kernels,
                 "kernel_time_share_of_step": round(step_kernel_ms / (ms / args.steps), 4),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
-                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                        "how": "pinned host buffers -> DeviceFeeder (double-buffered copy stream) -> step -> loss.item(); all copies inside the timed region"},
                 "gpu_launches": launches, "clocks": clocks, "loss": float(loss.item())}
         if world == 1 and not args.no_cpu_baseline:
             v, sample, _ = cpu_reference_rate(args.cpu_budget_s)
@@ -398,7 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--total-utts", type=int, default=1 << 20)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-budget-s", type=float, default=16.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

@@ -21,7 +21,7 @@ class ErcgError(RuntimeError):
 class GraphOut(Structure):
     _fields_ = [(n, c_void_p) for n in (
         "node_off", "edge_off", "rowptr", "col", "etype", "t_rowptr", "t_col", "t_etype", "t_eid", "spk",
-        "node_dlg", "inv_cnt", "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row")]
+        "node_dlg", "inv_cnt", "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row", "rel_info")]
 
 
 class DagLayer(Structure):
@@ -57,8 +57,8 @@ SIGNATURES = {
     "ercg_mask_pos": (I, [P, L, P, L, F, P, L, L, I, P]),
     "ercg_colsum_workspace_bytes": (SZ, [L, I]),
     "ercg_colsum": (I, [P, L, L, I, P, P, SZ, P]),
-    "ercg_gather_fwd": (I, [P, L, P, P, P, P, I, P, P, L, L, I, P]),
-    "ercg_gather_bwd": (I, [P, L, P, L, P, P, P, P, P, I, I, P, L, P, L, I, P]),
+    "ercg_gather_fwd": (I, [P, L, P, P, P, P, P, I, P, P, L, L, I, P]),
+    "ercg_gather_bwd": (I, [P, L, P, L, P, P, P, P, P, P, I, I, P, L, P, L, I, P]),
     "ercg_attn_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, L, I, P]),
     "ercg_attn_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, L, I, P]),
     "ercg_attn_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, L, I, P]),

@@ -23,8 +23,8 @@ constexpr int MAXC = 2;    // float4 chunks per lane => H <= 256
 template <int NC>
 __global__ void __launch_bounds__(GW * 32)
 gather_fwd_kernel(const float* __restrict__ Y, long long ldy, const int* __restrict__ rowptr,
-                  const int* __restrict__ col, const uint8_t* __restrict__ etype, const float* __restrict__ w,
-                  int root_off, const float* __restrict__ bias, float* __restrict__ out, long long ldo,
+                  const int* __restrict__ col, const uint8_t* __restrict__ etype, const int* __restrict__ rel_slot,
+                  const float* __restrict__ w, int root_off, const float* __restrict__ bias, float* __restrict__ out, long long ldo,
                   long long N, int H) {
   const int lane = threadIdx.x & 31;
   const long long node = (long long)blockIdx.x * GW + (threadIdx.x >> 5);
@@ -41,7 +41,8 @@ gather_fwd_kernel(const float* __restrict__ Y, long long ldy, const int* __restr
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int s = col[e + u];
-      const int t = etype ? (int)etype[e + u] : 0;
+      int t = etype ? (int)etype[e + u] : 0;
+      if (rel_slot) t = __ldg(rel_slot + t);
       ww[u] = w ? w[e + u] : 1.f;
       p[u] = Y + (long long)s * ldy + (long long)t * H;
     }
@@ -59,7 +60,8 @@ gather_fwd_kernel(const float* __restrict__ Y, long long ldy, const int* __restr
   }
   for (; e < end; ++e) {
     const int s = col[e];
-    const int t = etype ? (int)etype[e] : 0;
+    int t = etype ? (int)etype[e] : 0;
+    if (rel_slot) t = __ldg(rel_slot + t);
     const float ww = w ? w[e] : 1.f;
     const float* p = Y + (long long)s * ldy + (long long)t * H;
 #pragma unroll
@@ -92,8 +94,8 @@ template <int NC>
 __global__ void __launch_bounds__(GW * 32)
 gather_bwd_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ Y, long long ldy,
                   const int* __restrict__ t_rowptr, const int* __restrict__ t_col,
-                  const uint8_t* __restrict__ t_etype, const int* __restrict__ t_eid, const float* __restrict__ w,
-                  int R, int root_off, float* __restrict__ dY, long long lddy, float* __restrict__ dw,
+                  const uint8_t* __restrict__ t_etype, const int* __restrict__ t_eid, const int* __restrict__ rel_slot,
+                  const float* __restrict__ w, int R, int root_off, float* __restrict__ dY, long long lddy, float* __restrict__ dw,
                   long long N, int H) {
   const int lane = threadIdx.x & 31;
   const long long node = (long long)blockIdx.x * GW + (threadIdx.x >> 5);
@@ -112,6 +114,8 @@ gather_bwd_kernel(const float* __restrict__ dout, long long ldo, const float* __
       mw = w ? w[t_eid[beg + lane]] : 1.f;
     }
     for (int r = 0; r < R; ++r) {
+      const int slot = rel_slot ? __ldg(rel_slot + r) : r;       // relation ids without a slot occur on no edge
+      if (slot < 0) continue;
       unsigned m = __ballot_sync(0xffffffffu, mt == r);
       float4 acc[NC];
 #pragma unroll
@@ -143,11 +147,13 @@ gather_bwd_kernel(const float* __restrict__ dout, long long ldo, const float* __
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int ch = lane + 32 * c;
-        if (ch < nch) st4_stream(dY + node * lddy + (long long)r * H + 4 * ch, acc[c]);
+        if (ch < nch) st4_stream(dY + node * lddy + (long long)slot * H + 4 * ch, acc[c]);
       }
     }
   } else {
     for (int r = 0; r < R; ++r) {
+      const int slot = rel_slot ? __ldg(rel_slot + r) : r;
+      if (slot < 0) continue;
       float4 acc[NC];
 #pragma unroll
       for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -166,7 +172,7 @@ gather_bwd_kernel(const float* __restrict__ dout, long long ldo, const float* __
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int ch = lane + 32 * c;
-        if (ch < nch) st4_stream(dY + node * lddy + (long long)r * H + 4 * ch, acc[c]);
+        if (ch < nch) st4_stream(dY + node * lddy + (long long)slot * H + 4 * ch, acc[c]);
       }
     }
   }
@@ -179,7 +185,8 @@ gather_bwd_kernel(const float* __restrict__ dout, long long ldo, const float* __
   }
   if (dw) {
     for (int e = beg; e < end; ++e) {
-      const int t = t_etype ? (int)t_etype[e] : 0;
+      int t = t_etype ? (int)t_etype[e] : 0;
+      if (rel_slot) t = __ldg(rel_slot + t);
       const int d = t_col[e];
       const float* pd = dout + (long long)d * ldo;
       const float* py = Y + node * ldy + (long long)t * H;
@@ -206,8 +213,8 @@ static int check_rows(const void* p, long long ld, int H) {
 using namespace ercg;
 
 extern "C" int ercg_gather_fwd(const float* Y, int64_t ldy, const int32_t* rowptr, const int32_t* col,
-                               const uint8_t* etype, const float* w, int root_off, const float* bias,
-                               float* out, int64_t ldo, int64_t N, int H, void* stream) {
+                               const uint8_t* etype, const int32_t* rel_slot, const float* w, int root_off,
+                               const float* bias, float* out, int64_t ldo, int64_t N, int H, void* stream) {
   if (N < 0) return ERCG_EINVAL;
   if (N == 0) return ERCG_OK;
   if (!Y || !rowptr || !col || !out) return ERCG_EINVAL;
@@ -218,14 +225,14 @@ extern "C" int ercg_gather_fwd(const float* Y, int64_t ldy, const int32_t* rowpt
   if ((root_off >= 0 && (root_off & 3)) || (bias && !aligned16(bias))) return ERCG_EALIGN;
   const unsigned blocks = (unsigned)((N + GW - 1) / GW);
   cudaStream_t st = (cudaStream_t)stream;
-  if (H <= 128) gather_fwd_kernel<1><<<blocks, GW * 32, 0, st>>>(Y, ldy, rowptr, col, etype, w, root_off, bias, out, ldo, N, H);
-  else gather_fwd_kernel<2><<<blocks, GW * 32, 0, st>>>(Y, ldy, rowptr, col, etype, w, root_off, bias, out, ldo, N, H);
+  if (H <= 128) gather_fwd_kernel<1><<<blocks, GW * 32, 0, st>>>(Y, ldy, rowptr, col, etype, etype ? rel_slot : nullptr, w, root_off, bias, out, ldo, N, H);
+  else gather_fwd_kernel<2><<<blocks, GW * 32, 0, st>>>(Y, ldy, rowptr, col, etype, etype ? rel_slot : nullptr, w, root_off, bias, out, ldo, N, H);
   return finish_launch();
 }
 
 extern "C" int ercg_gather_bwd(const float* dout, int64_t ldo, const float* Y, int64_t ldy,
                                const int32_t* t_rowptr, const int32_t* t_col, const uint8_t* t_etype,
-                               const int32_t* t_eid, const float* w, int R, int root_off,
+                               const int32_t* t_eid, const int32_t* rel_slot, const float* w, int R, int root_off,
                                float* dY, int64_t lddy, float* dw, int64_t N, int H, void* stream) {
   if (N < 0 || R < 1) return ERCG_EINVAL;
   if (N == 0) return ERCG_OK;
@@ -240,7 +247,7 @@ extern "C" int ercg_gather_bwd(const float* dout, int64_t ldo, const float* Y, i
   if (root_off >= 0 && (root_off & 3)) return ERCG_EALIGN;
   const unsigned blocks = (unsigned)((N + GW - 1) / GW);
   cudaStream_t st = (cudaStream_t)stream;
-  if (H <= 128) gather_bwd_kernel<1><<<blocks, GW * 32, 0, st>>>(dout, ldo, Y, ldy, t_rowptr, t_col, t_etype, t_eid, w, R, root_off, dY, lddy, dw, N, H);
-  else gather_bwd_kernel<2><<<blocks, GW * 32, 0, st>>>(dout, ldo, Y, ldy, t_rowptr, t_col, t_etype, t_eid, w, R, root_off, dY, lddy, dw, N, H);
+  if (H <= 128) gather_bwd_kernel<1><<<blocks, GW * 32, 0, st>>>(dout, ldo, Y, ldy, t_rowptr, t_col, t_etype, t_eid, t_etype ? rel_slot : nullptr, w, R, root_off, dY, lddy, dw, N, H);
+  else gather_bwd_kernel<2><<<blocks, GW * 32, 0, st>>>(dout, ldo, Y, ldy, t_rowptr, t_col, t_etype, t_eid, t_etype ? rel_slot : nullptr, w, R, root_off, dY, lddy, dw, N, H);
   return finish_launch();
 }

@@ -417,6 +417,12 @@ extern "C" int ercg_gemm_nn(const float* A, int64_t lda, const int32_t* a_rows, 
       const int NN = N <= 8 ? 8 : 16;
       const unsigned grid = (unsigned)std::min<long long>((long long)kNumSMs * 16, (long long)((M + 7) / 8));
       const size_t sm = (size_t)((K + 3) & ~3) * NN * sizeof(float);
+      if (((lda & 3) == 0) && aligned16(A) && (K & 3) == 0 && K <= 128) {
+        const unsigned g8 = (unsigned)std::min<long long>((long long)kNumSMs * 16, (long long)((M + 31) / 32));
+        if (NN == 8) skinny_nn_small_n_q8_kernel<8><<<g8, 256, sm, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+        else skinny_nn_small_n_q8_kernel<16><<<g8, 256, sm, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+        return finish_launch();
+      }
       if (NN == 8) skinny_nn_small_n_kernel<8><<<grid, 256, sm, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
       else skinny_nn_small_n_kernel<16><<<grid, 256, sm, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
       return finish_launch();
@@ -476,6 +482,21 @@ extern "C" int ercg_gemm_tn(const float* A, int64_t lda, const int32_t* a_rows, 
     if (need2 <= workspace_bytes && workspace) {
       float* Pw = reinterpret_cast<float*>(workspace);
       const int NN = N1 <= 8 ? 8 : 16;
+      if (((lda & 3) == 0) && aligned16(A) && (K1 & 3) == 0 && NN == 8) {
+        const int KQ = K1 / 4;
+        int g4 = 512 / KQ;
+        const int cap = (int)(48 * 1024 / ((size_t)K1 * N1 * sizeof(float)));
+        if (g4 > cap) g4 = cap;
+        if (g4 >= 1) {
+          const size_t sm4 = (size_t)g4 * K1 * N1 * sizeof(float);
+          skinny_tn_small_n_v4_kernel<8><<<S, 512, sm4, st>>>(A, lda, B, ldb, Pw, M, K1, N1, rps, g4);
+          int rc4 = finish_launch();
+          if (rc4 != ERCG_OK) return rc4;
+          const long long tot4 = (long long)K1 * N1;
+          reduce_splits_kernel<<<(unsigned)((tot4 + 255) / 256), 256, 0, st>>>(Pw, tot4, S, C, ldc, K1, N1);
+          return finish_launch();
+        }
+      }
       const size_t sm = (size_t)groups * KP * NN * sizeof(float);
       if (NN == 8) skinny_tn_small_n_kernel<8><<<S, 512, sm, st>>>(A, lda, B, ldb, Pw, M, K1, N1, rps, groups, KP);
       else skinny_tn_small_n_kernel<16><<<S, 512, sm, st>>>(A, lda, B, ldb, Pw, M, K1, N1, rps, groups, KP);

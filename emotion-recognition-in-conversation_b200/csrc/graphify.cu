@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(256) graphify_kernel(GraphifyParams p) {
   __shared__ long long sm[66];
   const int T = blockDim.x;
   const int numTiles = (p.B + T - 1) / T;
+  if (p.o.rel_info && blockIdx.x == 0)       // [0] count, [1..256] id -> slot, [257..512] slot -> id: see rel_census_kernel
+    for (int i = threadIdx.x; i < 513; i += T) p.o.rel_info[i] = i == 0 ? 0 : -1;
 
   // ---- phase 1: tile aggregates
   for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
@@ -222,6 +224,51 @@ __global__ void __launch_bounds__(256) graphify_kernel(GraphifyParams p) {
   }
 }
 
+// ---- relation census: which relation ids occur on at least one edge, and their compact numbering.  Consumers (RGCNConv)
+// transform and gather only the relation slots that exist (one-speaker data such as MOSEI uses 2 of the 8 ids).
+// Pass 1 streams etype[E] (16 ids per load) and marks the ids it sees: rel_info[1 + id] = 0 (every writer stores the same
+// value -> no atomics on global memory); pass 2 (one block) turns the marks into slots.  Kept out of graphify_kernel: the
+// extra live state there cost 0.12 ms per launch (spills in the edge loop), these two launches cost ~5 us.
+__global__ void __launch_bounds__(256) rel_census_kernel(const uint8_t* __restrict__ etype, long long E, int* __restrict__ rel_info) {
+  __shared__ unsigned bits[8];
+  if (threadIdx.x < 8) bits[threadIdx.x] = 0u;
+  __syncthreads();
+  unsigned lo = 0u;
+  auto see = [&](unsigned t) {
+    if (t < 32u) lo |= 1u << t;
+    else atomicOr(&bits[t >> 5], 1u << (t & 31u));
+  };
+  const long long nvec = aligned16(etype) ? E >> 4 : 0;       // (an unaligned caller buffer takes the scalar tail loop)
+  const uint4* v = reinterpret_cast<const uint4*>(etype);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 x = __ldg(v + i);
+    const unsigned w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) see((w[a] >> (8 * b)) & 0xffu);
+  }
+  if (blockIdx.x == 0)
+    for (long long e = (nvec << 4) + threadIdx.x; e < E; e += blockDim.x) see(etype[e]);
+  lo = __reduce_or_sync(0xffffffffu, lo);
+  if ((threadIdx.x & 31) == 0 && lo) atomicOr(&bits[0], lo);
+  __syncthreads();
+  if ((bits[threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u) rel_info[1 + threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(256) rel_slots_kernel(int* __restrict__ rel_info) {
+  __shared__ int wcnt[8];
+  const int t = threadIdx.x, lane = t & 31;
+  const bool here = rel_info[1 + t] >= 0;
+  const unsigned m = __ballot_sync(0xffffffffu, here);
+  if (lane == 0) wcnt[t >> 5] = __popc(m);
+  __syncthreads();
+  int slot = __popc(m & ((1u << lane) - 1u));
+  for (int w = 0; w < (t >> 5); ++w) slot += wcnt[w];
+  if (here) { rel_info[1 + t] = slot; rel_info[257 + slot] = t; }
+  if (t == 0) { int c = 0; for (int w = 0; w < 8; ++w) c += wcnt[w]; rel_info[0] = c; }
+}
+
 __global__ void graphify_count_kernel(const void* lengths, int len64, int B, int wp, int wf, long long* totals) {
   __shared__ long long sm[66];
   long long n = 0, e = 0;
@@ -315,7 +362,19 @@ extern "C" int ercg_graphify_csr(const void* lengths_dev, int lengths_is_i64, in
   cudaError_t err = cudaLaunchCooperativeKernel((const void*)graphify_kernel, dim3(grid), dim3(256), args, 0,
                                                 (cudaStream_t)stream);
   ++g_launches;
-  return err == cudaSuccess ? ERCG_OK : ERCG_ECUDA;
+  if (err != cudaSuccess) return ERCG_ECUDA;
+  if (out->rel_info) {
+    if (E > 0) {
+      const long long want_c = (E / 16 + 255) / 256;
+      const unsigned gc = (unsigned)(want_c < 1 ? 1 : (want_c > 4LL * num_sms ? 4LL * num_sms : want_c));
+      rel_census_kernel<<<gc, 256, 0, (cudaStream_t)stream>>>(out->etype, E, out->rel_info);
+      int rc = finish_launch();
+      if (rc) return rc;
+    }
+    rel_slots_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(out->rel_info);
+    return finish_launch();
+  }
+  return ERCG_OK;
 }
 
 static int pack_launch(const float* padded, int64_t ld, int64_t Lmax, int B, int seq_first,

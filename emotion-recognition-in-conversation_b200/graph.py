@@ -25,7 +25,8 @@ class PackedGraph:
 
     __slots__ = ("B", "N", "E", "wp", "wf", "n_speakers", "num_relations", "device", "node_off", "edge_off",
                  "rowptr", "col", "etype", "t_rowptr", "t_col", "t_etype", "t_eid", "spk", "node_dlg", "inv_cnt",
-                 "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row", "perm", "Lpad")
+                 "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row", "perm", "Lpad", "rel_info",
+                 "_rel_host", "_rel_event", "_rel_cache")
 
     def __init__(self):
         for s in self.__slots__:
@@ -36,6 +37,19 @@ class PackedGraph:
         if self.inv_cnt is None:
             self.inv_cnt = _inv_count_from_csr(self)
         return self.inv_cnt
+
+    def relation_slots(self):
+        """K1's relation census: (ids, rel_slot) -- the sorted relation ids that occur on at least one edge (python list)
+        and the device int32 table id -> compact slot (-1 = absent) -- or None for graphs that did not come from K1.
+        The census left the GPU with an async copy right behind K1; waiting for it here does not drain the stream."""
+        if self.rel_info is None:
+            return None
+        if self._rel_cache is None:
+            self._rel_event.synchronize()
+            P = int(self._rel_host[0])
+            ids = [int(v) for v in self._rel_host[257:257 + P]]
+            self._rel_cache = (ids, self.rel_info[1:1 + self.num_relations])
+        return self._rel_cache
 
 
 def graph_sizes(lengths_cpu, wp, wf):
@@ -106,12 +120,17 @@ def build_graph(lengths, speakers, wp, wf, n_speakers, device=None, reference_la
         g.edge_index = torch.empty((2, E), dtype=torch.int64, device=device)
         g.edge_type = torch.empty(E, dtype=torch.int64, device=device)
         g.edge_index_lengths = torch.empty(B, dtype=torch.int64, device=device)
+    g.rel_info = torch.empty(513, **i32)
     out = GraphOut(*[_p(getattr(g, n)) for n, _ in GraphOut._fields_])
     ws_bytes = lib().ercg_graphify_workspace_bytes(B)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
     check(lib().ercg_graphify_csr(_p(ldev), 1 if ldev.dtype == torch.int64 else 0, B, _p(sdev),
                                   1 if sdev.dtype == torch.int64 else 0, spk_ld, wp, wf, n_speakers, N, E,
                                   ctypes.byref(out), _p(ws), ws.numel(), _stream()), "ercg_graphify_csr")
+    g._rel_host = torch.empty(513, dtype=torch.int32, pin_memory=True)
+    g._rel_host.copy_(g.rel_info, non_blocking=True)
+    g._rel_event = torch.cuda.Event()
+    g._rel_event.record()
     return g
 
 

@@ -1,0 +1,73 @@
+"""Host -> device feeder for packed dialogue batches (the step right before the hot path).
+
+The reference collates on the CPU (``ERCCollate``, track_mm/mmbase.py:344-455), and its DataLoader hands the trainer
+pageable tensors that ``accelerate`` moves to the GPU synchronously at the top of every step
+(lumo/trainer/trainer.py:315-327).  At the scale of BASELINE config 5 one step's inputs are 6 GB, i.e. ~110 ms of
+PCIe time against ~17 ms of kernels, so the copy has to overlap the previous step's compute:
+
+  * ``DeviceFeeder`` owns ``depth`` sets of device buffers and a dedicated copy stream;
+  * ``submit(batch)`` enqueues the H2D copies of a dict of (pinned) host tensors on the copy stream as soon as the
+    buffer set is free (an event recorded by ``release``), and returns immediately;
+  * ``get()`` makes the CURRENT stream wait for the oldest submitted batch and returns its device tensors;
+  * ``release()`` marks that batch's buffers reusable once the work queued so far on the current stream is done.
+
+Nothing here computes; it is stream/event plumbing around ``Tensor.copy_(non_blocking=True)``.
+"""
+from collections import deque
+
+import torch
+
+
+def pin(batch):
+    """Pinned copies of a dict of CPU tensors (what a DataLoader with ``pin_memory=True`` hands out)."""
+    return {k: (v if v.is_pinned() else v.pin_memory()) for k, v in batch.items()}
+
+
+class DeviceFeeder:
+    def __init__(self, device, depth=2):
+        assert depth >= 1
+        self.device = torch.device(device)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._bufs = [dict() for _ in range(depth)]          # slot -> {key: device tensor}
+        self._free = [None] * depth                          # slot -> event after which the slot may be overwritten
+        self._ready = deque()                                # (slot, event, keys) in submission order
+        self._in_use = deque()                               # slots handed out by get() and not yet released
+        self._next = 0
+        self.h2d_bytes = 0
+
+    def submit(self, batch):
+        """Start copying ``batch`` (dict of host tensors; pinned memory makes the copies asynchronous)."""
+        if len(self._ready) + len(self._in_use) >= self.depth:
+            raise RuntimeError("DeviceFeeder: all %d buffer sets are in flight; call get()/release() first" % self.depth)
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        bufs = self._bufs[slot]
+        for k, h in batch.items():                           # buffers live as long as the feeder (allocated on the
+            d = bufs.get(k)                                  # caller's stream, never returned to the allocator)
+            if d is None or d.shape != h.shape or d.dtype != h.dtype:
+                bufs[k] = torch.empty(h.shape, dtype=h.dtype, device=self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self._free[slot] is not None:
+                self.copy_stream.wait_event(self._free[slot])
+            for k, h in batch.items():
+                bufs[k].copy_(h, non_blocking=True)
+                self.h2d_bytes += h.numel() * h.element_size()
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._ready.append((slot, ev, tuple(batch.keys())))
+        return slot
+
+    def get(self):
+        """Device tensors of the oldest submitted batch; the current stream waits for its copies."""
+        slot, ev, keys = self._ready.popleft()
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        self._in_use.append(slot)
+        return {k: self._bufs[slot][k] for k in keys}
+
+    def release(self):
+        """The oldest batch handed out by get() may be overwritten once the current stream reaches this point."""
+        slot = self._in_use.popleft()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._free[slot] = ev

@@ -159,13 +159,13 @@ def matmul_kn(x, w_kn, bias=None, act=ACT_NONE, a_rows=None):
 # ------------------------------------------------------------------------------------------- K3 gather
 class _Gather(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, Y, w, bias, graph, H, R, root_off, use_types):
+    def forward(ctx, Y, w, bias, graph, H, R, root_off, use_types, rel_slot):
         Y, ldy = _rows(Y)
         N = Y.size(0)
         out = torch.empty((N, H), dtype=torch.float32, device=Y.device)
         check(lib().ercg_gather_fwd(_p(Y), ldy, _p(graph.rowptr), _p(graph.col), _p(graph.etype) if use_types else None,
-                                    _p(w), root_off, _p(bias), _p(out), H, N, H, _stream()), "ercg_gather_fwd")
-        ctx.graph, ctx.H, ctx.R, ctx.root_off, ctx.use_types = graph, H, R, root_off, use_types
+                                    _p(rel_slot), _p(w), root_off, _p(bias), _p(out), H, N, H, _stream()), "ercg_gather_fwd")
+        ctx.graph, ctx.H, ctx.R, ctx.root_off, ctx.use_types, ctx.rel_slot = graph, H, R, root_off, use_types, rel_slot
         ctx.has_bias = bias is not None
         ctx.w_grad = w is not None and w.requires_grad
         ctx.save_for_backward(Y if ctx.w_grad else None, w)
@@ -182,16 +182,18 @@ class _Gather(torch.autograd.Function):
         dw = torch.empty(g.E, dtype=torch.float32, device=dout.device) if ctx.w_grad else None
         ldy = Y.stride(0) if Y is not None else 0
         check(lib().ercg_gather_bwd(_p(dout), ldo, _p(Y), ldy, _p(g.t_rowptr), _p(g.t_col),
-                                    _p(g.t_etype) if ctx.use_types else None, _p(g.t_eid), _p(w), R, ctx.root_off,
-                                    _p(dY), ctx.ycols, _p(dw), N, H, _stream()), "ercg_gather_bwd")
+                                    _p(g.t_etype) if ctx.use_types else None, _p(g.t_eid), _p(ctx.rel_slot), _p(w), R,
+                                    ctx.root_off, _p(dY), ctx.ycols, _p(dw), N, H, _stream()), "ercg_gather_bwd")
         dbias = colsum(dout) if ctx.has_bias else None
-        return dY, dw, dbias, None, None, None, None, None
+        return dY, dw, dbias, None, None, None, None, None, None
 
 
-def gather(Y, graph, H, R, w=None, bias=None, root_off=-1, use_types=True):
-    """out[k] = sum_e w[e] * Y[col[e], etype[e]*H:+H] (+ Y[k, root_off:+H]) (+ bias)."""
-    assert Y.size(1) == (R * H + (H if root_off >= 0 else 0)), (Y.shape, R, H, root_off)
-    return _Gather.apply(Y, w, bias, graph, H, R, root_off, use_types)
+def gather(Y, graph, H, R, w=None, bias=None, root_off=-1, use_types=True, rel_slot=None, n_slots=None):
+    """out[k] = sum_e w[e] * Y[col[e], slot(e)*H:+H] (+ Y[k, root_off:+H]) (+ bias), slot(e) = etype[e], or
+    rel_slot[etype[e]] when Y only holds the ``n_slots`` relation ids that occur in the graph (K1's relation census)."""
+    slots = R if rel_slot is None else n_slots
+    assert Y.size(1) == (slots * H + (H if root_off >= 0 else 0)), (Y.shape, R, slots, H, root_off)
+    return _Gather.apply(Y, w, bias, graph, H, R, root_off, use_types, rel_slot)
 
 
 # ------------------------------------------------------------------------------------------- K4 attention

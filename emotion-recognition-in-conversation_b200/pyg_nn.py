@@ -41,6 +41,17 @@ class RGCNConv(nn.Module):
     def forward(self, x, edge_index, edge_type):
         R, H = self.num_relations, self.out_channels
         g = graph_from_edge_index(edge_index, edge_type, x.size(0), R)
+        census = g.relation_slots()
+        if census is not None and g.num_relations == R and len(census[0]) < R:
+            # only the relation ids that occur in this batch are transformed and gathered (one-speaker MOSEI batches use
+            # 2 of the 8 ids): Y is [N, (P+1)*H]; the other weights get an exactly-zero gradient, as in the reference
+            ids, rel_slot = census
+            P = len(ids)
+            sel = g.rel_info[257:257 + P].long()
+            wrel = self.weight.index_select(0, sel)
+            wcat = torch.cat([wrel.permute(1, 0, 2).reshape(self.in_channels, P * H), self.root], dim=1)
+            y = ops.matmul_kn(x, wcat)
+            return ops.gather(y, g, H, R, w=g.mean_weight(), bias=self.bias, root_off=P * H, rel_slot=rel_slot, n_slots=P)
         wcat = torch.cat([self.weight.permute(1, 0, 2).reshape(self.in_channels, R * H), self.root], dim=1)
         y = ops.matmul_kn(x, wcat)
         return ops.gather(y, g, H, R, w=g.mean_weight(), bias=self.bias, root_off=R * H)

@@ -85,6 +85,9 @@ typedef struct ercg_graph_out {
   int64_t* edge_index_lengths; /* [B] cogmen_utils.py:142 */
   int64_t* totals;     /* [2]   N, E as computed on the device (for validation) */
   int32_t* pad_row;    /* [N]   d*spk_ld + k: row of the node in a padded [B,spk_ld,*] tensor (node id if spk_ld=0) */
+  int32_t* rel_info;   /* [513] relation census: [0] = P = number of relation ids that occur on at least one edge,
+                          [1 + r] = compact slot of relation id r (-1 if no edge has it), [257 + s] = id of slot s (s < P).
+                          One-speaker data (MOSEI, mosei_feature.py:211) uses 2 of the 2n^2 = 8 ids of cogmen.py:64. */
 } ercg_graph_out;
 
 /* speakers: padded [B, spk_ld] when spk_ld > 0 (reference layout), packed [N] when spk_ld == 0. */
@@ -159,13 +162,16 @@ int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float* out,
  *   dY[j, r*H:+H] = sum_{e in out(j), type r} w[e] * dout[dst e]   for r in [0,R)   (all slots written)
  *   dY[j, root_off:+H] = dout[j]                                     (if root_off >= 0)
  *   dw[eid] = <dout[dst e], Y[src e, type e]>                        (if dw != NULL; needs Y)
+ * rel_slot (optional, device int32 [R]): relation id -> column slot of Y / dY (K1's rel_info + 1), so that Y only holds
+ * the P <= R relation ids that occur in the graph: Y is [N, P*H (+H root)], slot(e) = rel_slot[etype[e]]; ids with
+ * rel_slot < 0 occur on no edge and are skipped by the backward.  NULL = identity (Y holds all R slots).
  * ------------------------------------------------------------------------------------------- */
 int ercg_gather_fwd(const float* Y, int64_t ldy, const int32_t* rowptr, const int32_t* col,
-                    const uint8_t* etype, const float* w, int root_off, const float* bias,
+                    const uint8_t* etype, const int32_t* rel_slot, const float* w, int root_off, const float* bias,
                     float* out, int64_t ldo, int64_t N, int H, void* stream);
 int ercg_gather_bwd(const float* dout, int64_t ldo, const float* Y, int64_t ldy,
                     const int32_t* t_rowptr, const int32_t* t_col, const uint8_t* t_etype,
-                    const int32_t* t_eid, const float* w, int R, int root_off,
+                    const int32_t* t_eid, const int32_t* rel_slot, const float* w, int R, int root_off,
                     float* dY, int64_t lddy, float* dw, int64_t N, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

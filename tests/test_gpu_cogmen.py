@@ -75,6 +75,37 @@ def test_cogmen_config1_shape_vs_oracle():
     check_grads(grads, {k: p.grad.numpy() for k, p in o.named_parameters()}, 5 * TOL)
 
 
+@pytest.mark.parametrize("speaker", [0, 1])
+def test_cogmen_one_speaker_batch_relation_census_vs_oracle(speaker):
+    """MOSEI-shaped batches carry ONE speaker id (mosei_feature.py:211): only 2 of the 8 relation ids occur and RGCNConv
+    transforms / gathers only those slots.  Logits, loss and every gradient (absent relations: exactly zero) must match
+    the oracle, which evaluates all 8 relations."""
+    import erc_b200
+    from erc_b200.track_mm.cogmen import COGMENModule
+    from erc_b200 import synth
+    batch = synth.config1(seed=5, B=8)
+    batch["speaker_tensor"] = torch.full_like(batch["speaker_tensor"], speaker)
+    torch.manual_seed(0)
+    o = om.CogmenOracle(1380, n_classes=4, dropout=0.0)
+    o.train()
+    ol, of = o(batch["input_tensor"], batch["speaker_tensor"], batch["text_length"])
+    oloss = F.cross_entropy(ol, batch["label"])
+    oloss.backward()
+    m = COGMENModule(1380, 100, 17, 2, 4, build_dead_encoder=False).cuda()
+    m.load_state_dict(o.state_dict(), strict=False)
+    m.cls[2].p = 0.0
+    m.train()
+    logits, feats, loss, grads = _run_ours(m, batch["input_tensor"], batch["speaker_tensor"], batch["text_length"],
+                                           batch["label"])
+    assert rel_err(logits, ol.detach()) < TOL
+    assert abs(loss - float(oloss)) < TOL * float(oloss)
+    check_grads(grads, {k: p.grad.numpy() for k, p in o.named_parameters()}, 5 * TOL)
+    gw = grads["gcn.conv1.weight"]
+    live = [speaker * 6, speaker * 6 + 1]                      # ((s*2 + s)*2 + dir)
+    assert all(np.abs(gw[r]).max() > 0 for r in live)
+    assert all(np.abs(gw[r]).max() == 0 for r in range(8) if r not in live)
+
+
 def test_cogmen_packed_entry_point_equals_padded():
     import erc_b200
     from erc_b200.track_mm.cogmen import COGMENModule

@@ -33,6 +33,16 @@ def _check(g, b):
     assert np.array_equal(c(g.edge_type), b["edge_type"])
     assert np.array_equal(c(g.edge_index_lengths), b["edge_index_lengths"])
     assert np.array_equal(c(g.inv_cnt), b["inv_cnt"])          # 1/c is exact in both
+    # relation census: ids that occur on at least one edge, compact numbering in ascending id order
+    ids = np.unique(b["edge_type"]).astype(np.int64)
+    info = c(g.rel_info)
+    assert info[0] == len(ids)
+    assert np.array_equal(info[257:257 + len(ids)], ids)
+    want_slot = np.full(256, -1, dtype=np.int64)
+    want_slot[ids] = np.arange(len(ids))
+    assert np.array_equal(info[1:257], want_slot)
+    got_ids, slot_dev = g.relation_slots()
+    assert got_ids == ids.tolist() and np.array_equal(c(slot_dev), want_slot[:g.num_relations])
 
 
 def test_reference_fixture_cases(golden):

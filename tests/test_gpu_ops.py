@@ -116,6 +116,38 @@ def test_gather_fwd_bwd(H, R, wp, wf):
     assert rel_err(bc.grad, dout.double().sum(0)) < TOL
 
 
+def test_gather_compact_relation_slots_equals_full_layout():
+    """One speaker id out of n=2 (relation ids {6,7} only): Y restricted to the slots K1's census reports, addressed
+    through rel_slot, gives the same output, dY (per present slot) and dw as the full 8-slot layout."""
+    import erc_b200
+    from erc_b200 import ops
+    from erc_b200.graph import build_graph
+    H, R = 100, 8
+    lens = torch.tensor([7, 1, 23, 60, 4])
+    spk = torch.ones(5, 60, dtype=torch.int64)
+    g = build_graph(lens, spk.cuda(), 5, 5, 2)
+    ids, rel_slot = g.relation_slots()
+    assert ids == [6, 7]
+    P = len(ids)
+    gen = torch.Generator().manual_seed(11)
+    Yfull = torch.randn(g.N, (R + 1) * H, generator=gen)
+    w = torch.rand(g.E, generator=gen) + 0.1
+    dout = torch.randn(g.N, H, generator=gen).cuda()
+    cols = torch.cat([torch.arange(r * H, (r + 1) * H) for r in ids] + [torch.arange(R * H, (R + 1) * H)])
+    Yf, wf_ = Yfull.cuda().requires_grad_(), w.cuda().requires_grad_()
+    a = ops.gather(Yf, g, H, R, w=wf_, root_off=R * H)
+    a.backward(dout)
+    Yc, wc = Yfull[:, cols].contiguous().cuda().requires_grad_(), w.cuda().requires_grad_()
+    b = ops.gather(Yc, g, H, R, w=wc, root_off=P * H, rel_slot=rel_slot, n_slots=P)
+    b.backward(dout)
+    assert torch.equal(a, b)
+    assert torch.equal(Yf.grad[:, cols.cuda()], Yc.grad)
+    mask = torch.ones((R + 1) * H, dtype=torch.bool)
+    mask[cols] = False
+    assert float(Yf.grad[:, mask.cuda()].abs().max()) == 0.0
+    assert torch.equal(wf_.grad, wc.grad)
+
+
 @pytest.mark.parametrize("wp,wf", [(5, 5), (-1, -1), (2, 40), (10, 10), (16, 15), (0, 3), (0, 0)])
 def test_edge_attention_fwd_bwd(wp, wf):
     import erc_b200
@@ -238,3 +270,29 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libercgraph.so")
     with pytest.raises(_lib.ErcgError):
         _lib.lib()
+
+
+def test_device_feeder_double_buffering():
+    """loader.DeviceFeeder: batches come out in submission order with the right contents while later copies are in
+    flight; a third un-consumed submit is refused (depth 2)."""
+    import erc_b200
+    from erc_b200.loader import DeviceFeeder, pin
+    dev = torch.device("cuda")
+    feeder = DeviceFeeder(dev, depth=2)
+    gen = torch.Generator().manual_seed(0)
+    batches = [pin({"x": torch.randn(4096, 257, generator=gen), "spk": torch.randint(0, 2, (4096,), generator=gen)})
+               for _ in range(5)]
+    feeder.submit(batches[0])
+    for i in range(5):
+        if i + 1 < 5:
+            feeder.submit(batches[i + 1])
+        d = feeder.get()
+        y = d["x"] * 2.0 + d["spk"][:, None].float()           # work on the current stream that reads the buffers
+        feeder.release()
+        want = batches[i]["x"] * 2.0 + batches[i]["spk"][:, None].float()
+        assert torch.equal(y.cpu(), want)
+    feeder.submit(batches[0])
+    feeder.submit(batches[1])
+    with pytest.raises(RuntimeError):
+        feeder.submit(batches[2])
+    assert feeder.h2d_bytes == 7 * (4096 * 257 * 4 + 4096 * 8)
