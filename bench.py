@@ -43,46 +43,55 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock / throttle reasons sampled WHILE the timed region runs, through NVML in this process (nvidia_ml_py).
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    An `nvidia-smi -lms 100` child was measured to perturb the run it observes: single steps of the 16 ms loop took
+    100-290 ms whenever a poll landed in them (gpurun_out/bench_c4_1.json: step_ms).  Two NVML calls per 50 ms do not."""
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.05):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag, self.proc, self.mark = index, [], False, None, 0
+        self.index, self.period_s, self.samples, self.stop_flag, self.mark = index, period_s, [], False, 0
+        self.sm_max = None
+        self.err = None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.samples.append([c.strip() for c in line.split(",")])
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except ValueError:
+                    idx = self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+            while not self.stop_flag:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((sm, [n for n, b in names if bits & b]))
+                time.sleep(self.period_s)
+        except Exception as e:          # no NVML: report that, never fail the bench
+            self.err = repr(e)
 
     def finish(self):
         self.stop_flag = True
-        if self.proc is not None:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples[self.mark:]:
-            try:
-                sm.append(float(s[1]))
-                mx = max(mx, float(s[2]))
-                for n, v in zip(names, s[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except (ValueError, IndexError):
-                continue
+        self.join(timeout=1.0)
+        sm, reasons = [], set()
+        for clk, rs in self.samples[self.mark:]:
+            sm.append(clk)
+            reasons.update(rs)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
+               "samples": len(sm), "how": "NVML (nvidia_ml_py) polled every %d ms during the timed region" % int(self.period_s * 1e3)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # --------------------------------------------------------------------------------------------- reference arm
@@ -226,15 +235,32 @@ def run_ours(args):
         loss_sync = LossSync()
         grad_sync = GradSync(model)
 
+    trace = [] if os.environ.get("ERCG_BENCH_TRACE") else None      # diagnostics: host timestamps of the step's phases
+
     def step(xi, spki, labi):
+        t = [time.perf_counter()] if trace is not None else None
         g = build_graph(lengths, spki, 5, 5, 2, device=dev, sizes=sizes)
+        if t is not None:
+            t.append(time.perf_counter())
+            g.relation_slots()
+            t.append(time.perf_counter())
         logits, _ = model.forward_packed(xi, spki, lengths, graph=g)
         loss = ops.cross_entropy(logits, labi, reduce_sync=loss_sync)
+        if t is not None:
+            t.append(time.perf_counter())
         optim.zero_grad(set_to_none=True)
         loss.backward()
+        if t is not None:
+            t.append(time.perf_counter())
         if grad_sync is not None:
             grad_sync()
         optim.step()
+        if t is not None:
+            t.append(time.perf_counter())
+            ms_ = torch.cuda.memory_stats(dev)
+            trace.append([round((b - a) * 1e3, 3) for a, b in zip(t[:-1], t[1:])] +
+                         [ms_.get("num_device_alloc", 0), ms_.get("allocated_bytes.all.current", 0) >> 20,
+                          ms_.get("reserved_bytes.all.current", 0) >> 20])
         return loss
 
     def barrier():
@@ -247,26 +273,52 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    import gc
+    step(x, spk, labels)                                 # first step: lazy initialisation, allocator growth
+    gc.collect()
+    gc.freeze()                                         # a gen-2 collection inside a 15 ms step shows up as a 30 ms step;
+    gc.disable()                                        # frozen BEFORE the warm-up so the caching allocator settles after it
     for _ in range(max(args.warmup, 3)):
         step(x, spk, labels)
     barrier()
+    if args.profile_step:
+        # ncu --profile-from-start off: exactly ONE warm step between cudaProfilerStart/Stop, no timing, no JSON value
+        torch.cuda.profiler.start()
+        step(x, spk, labels)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            emit({"profile_step": True, "utterances_per_step": total_utts})
+        return
     if sampler:
         t_wait = time.perf_counter()
         while not sampler.samples and time.perf_counter() - t_wait < 2.0:
             time.sleep(0.01)
         sampler.mark = len(sampler.samples)          # only samples taken from here on are reported
     barrier()
-    launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with _lib.KernelTimer(labeler=kernel_label):        # one more warm step WITH the event bracketing active (event pool)
+        step(x, spk, labels)
+    barrier()
+    launches0 = _lib.launch_count()
+    mem_before = torch.cuda.memory_stats(dev)
+    if trace is not None:
+        del trace[:]
     timer = _lib.KernelTimer(labeler=kernel_label)      # GEMM records are split by shape
     with timer:
         barrier()
         e0.record()
+        marks = []
         for _ in range(args.steps):
             loss = step(x, spk, labels)
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         barrier()
+    gc.enable()
+    mem_after = torch.cuda.memory_stats(dev)
     ms = e0.elapsed_time(e1)
+    step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
     launches = _lib.launch_count() - launches0
     clocks = sampler.finish() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -366,11 +418,16 @@ def run_ours(args):
                            "dropout": "on (train mode)", "optimizer": "Adam inside the step", "dead_encoder": "not executed (cogmen.py:146-147 discards its output)"},
                 "roofline": roof, "graph_kernels": graph_kernels,
                 "kernels": kernels,
-                "kernel_time_share_of_step": round(step_kernel_ms / (ms / args.steps), 4),
+                "kernel_time_share_of_step": round(step_kernel_ms / (ms / args.steps), 4), "step_ms": step_ms,
+                "cuda_mallocs_in_timed_region": int(mem_after.get("num_device_alloc", 0) - mem_before.get("num_device_alloc", 0)),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                         "how": "pinned host buffers -> DeviceFeeder (double-buffered copy stream) -> step -> loss.item(); all copies inside the timed region"},
                 "gpu_launches": launches, "clocks": clocks, "loss": float(loss.item())}
+        if trace is not None:
+            line["host_trace_ms"] = {"phases": ["build_graph", "census_wait", "forward+loss", "backward", "optimizer",
+                                                "cudaMallocs so far", "allocated MiB", "reserved MiB"],
+                                     "steps": trace[:args.steps]}
         if world == 1 and not args.no_cpu_baseline:
             v, sample, _ = cpu_reference_rate(args.cpu_budget_s)
             v2, sample2, _ = cpu_reference_rate(args.cpu_budget_s / 2, skip_dead_encoder=True)
@@ -409,6 +466,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-budget-s", type=float, default=16.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, then run one step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --total-utts utterances PER GPU (default); strong: --total-utts in total, sharded over the GPUs")
     args = ap.parse_args()

@@ -48,7 +48,7 @@ SIGNATURES = {
     "ercg_gemm_nn": (I, [P, L, P, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P]),
     "ercg_gemm_nn_tc_workspace_bytes": (SZ, [I, I]),
     "ercg_gemm_nn_tc_supported": (I, [P, L, P, L, L, I, I]),
-    "ercg_gemm_nn_tc": (I, [P, L, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, SZ, P]),
+    "ercg_gemm_nn_tc": (I, [P, L, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, P, SZ, P]),
     "ercg_gemm_tn_workspace_bytes": (SZ, [L, I, I]),
     "ercg_gemm_tn": (I, [P, L, P, P, L, P, L, L, I, I, P, SZ, P]),
     "ercg_gemm_tn_tc_workspace_bytes": (SZ, [L, I, I]),
@@ -64,8 +64,9 @@ SIGNATURES = {
     "ercg_attn_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, L, I, P]),
     "ercg_attn_window_supported": (I, [I, I, I]),
     "ercg_attn_window_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, L, I, I, I, P]),
-    "ercg_attn_window_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, L, I, I, I, P]),
-    "ercg_attn_window_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, L, I, I, I, P]),
+    "ercg_attn_window_tiles": (L, [L]),
+    "ercg_attn_window_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, P, L, I, I, I, P]),
+    "ercg_attn_window_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, P, L, I, I, I, P]),
     "ercg_edgeatt_fwd": (I, [P, L, P, L, P, P, P, P, L, I, P]),
     "ercg_edgeatt_bwd_src": (I, [P, P, P, L, P, P, P, P, P, L, L, I, P]),
     "ercg_edgeatt_bwd_dst": (I, [P, P, L, P, P, P, L, L, I, P]),
@@ -140,7 +141,7 @@ class _Timed:
 
     def __getattr__(self, name):
         fn = getattr(self._h, name)
-        if name.endswith("_bytes") or name.endswith("_supported") or name in ("ercg_strerror", "ercg_version", "ercg_launch_count",
+        if name.endswith("_bytes") or name.endswith("_supported") or name.endswith("_tiles") or name in ("ercg_strerror", "ercg_version", "ercg_launch_count",
                                                "ercg_graphify_sizes_host"):
             setattr(self, name, fn)
             return fn

@@ -352,6 +352,25 @@ __device__ __forceinline__ float half_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 1);
 }
 
+// per-CTA column sums of two H-wide outputs: lane = float4 chunk, warps reduced in warp order through the staging buffer
+// (8 KB of it, reused once every warp is done with the staged rows -- no extra shared memory, so occupancy is unchanged)
+__device__ __forceinline__ void tile_colsum(float4* red /* [8][2][32] */, float4 a, float4 b, float* __restrict__ partial, int H) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nch = H >> 2;
+  __syncthreads();
+  red[(warp * 2 + 0) * 32 + lane] = a;
+  red[(warp * 2 + 1) * 32 + lane] = b;
+  __syncthreads();
+  if (warp < 2 && lane < nch) {
+    float4 t = red[warp * 32 + lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 v = red[(w * 2 + warp) * 32 + lane];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    st4(partial + (long long)blockIdx.x * 2 * H + warp * H + 4 * lane, t);
+  }
+}
+
 template <bool PAIR>
 __global__ void __launch_bounds__(256)
 attn_fwd_tile_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
@@ -370,22 +389,43 @@ attn_fwd_tile_kernel(const float* __restrict__ q, const float* __restrict__ k, c
   stage_rows(sq, q, ld, t0, tn, nch);
   stage_rows(sk, k, ld, r0, R, nch);
   stage_rows(sv, v, ld, r0, R, nch);
-  stage_wait();
   constexpr int NPW = WT / 8;                 // nodes per warp
   constexpr int G = PAIR ? 2 : 1;             // nodes handled together in the score phase
+  constexpr int IT = NPW / G;
   const int half = PAIR ? lane >> 4 : 0, e = PAIR ? lane & 15 : lane;
-  for (int p = 0; p < NPW; p += G) {
-    const int nl = warp * NPW + p + half;     // node of this lane's half
+  // Everything this warp needs from global memory besides the staged rows is requested NOW, while the cp.async traffic is
+  // in flight: CSR metadata of its nodes and their skip rows.  (ncu, first tiled version: a third of the stall samples
+  // were these small dependent loads issued one node at a time after the barrier.)
+  int begs[IT], degs[IT], rows[IT];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int nl = warp * NPW + it * G + half;
     const bool nok = nl < tn;
-    const long long node = t0 + nl;
-    const int beg = nok ? rowptr[node] : 0, deg = nok ? rowptr[node + 1] - beg : 0;
-    const bool live = e < deg;
-    int row = 0;
-    if (live) {
-      const long long src = col[beg + e];
+    begs[it] = nok ? rowptr[t0 + nl] : 0;
+    degs[it] = nok ? rowptr[t0 + nl + 1] - begs[it] : 0;
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    rows[it] = 0;
+    if (e < degs[it]) {
+      const long long src = col[begs[it] + e];
       if (src < r0 || src >= r1) __trap();    // the caller promised a window graph
-      row = (int)(src - r0);
+      rows[it] = (int)(src - r0);
     }
+  }
+  float4 skip[NPW];
+#pragma unroll
+  for (int h = 0; h < NPW; ++h) {
+    const int nl = warp * NPW + h;
+    skip[h] = (s && nl < tn && lane < nch) ? ld4(s + (t0 + nl) * ld + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  stage_wait();
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int p = it * G;
+    const int nl = warp * NPW + p + half;     // node of this lane's half
+    const int beg = begs[it], deg = degs[it], row = rows[it];
+    const bool live = e < deg;
     float d = 0.f;
     const float4* qi = sq + nl * nch;
     const float4* kr = sk + row * nch;
@@ -405,17 +445,15 @@ attn_fwd_tile_kernel(const float* __restrict__ q, const float* __restrict__ k, c
       const int base = PAIR ? h * 16 : 0;
       const int hdeg = __shfl_sync(0xffffffffu, deg, base);
       const int hnl = warp * NPW + p + h;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);                 // out = (sum_j alpha v_j) + skip, in that order
       for (int u = 0; u < hdeg; ++u) {
         const float a = __shfl_sync(0xffffffffu, al, base + u);
         const int rw = __shfl_sync(0xffffffffu, row, base + u);
         if (lane < nch) fma4(acc, a, sv[rw * nch + lane]);
       }
       if (hnl < tn && lane < nch) {
-        if (s) {
-          const float4 sk4 = ld4(s + (t0 + hnl) * ld + 4 * lane);
-          acc.x += sk4.x; acc.y += sk4.y; acc.z += sk4.z; acc.w += sk4.w;
-        }
+        const float4 sk4 = skip[p + h];
+        acc.x += sk4.x; acc.y += sk4.y; acc.z += sk4.z; acc.w += sk4.w;
         st4(out + (t0 + hnl) * ldo + 4 * lane, acc);
       }
     }
@@ -428,8 +466,10 @@ attn_bwd_dst_tile_kernel(const float* __restrict__ dout, long long ldo, const fl
                          const float* __restrict__ v, long long ld, const int* __restrict__ rowptr,
                          const int* __restrict__ col, const float* __restrict__ alpha, float scale,
                          float* __restrict__ dq, float* __restrict__ ds, long long ldd, float* __restrict__ dsig,
+                         float* __restrict__ colsum_partial /* [gridDim.x][2H]: column sums of dq | ds, or NULL */,
                          long long N, int H, int wlo, int whi) {
   extern __shared__ float4 attn_sm[];
+  float4 cs_q = make_float4(0.f, 0.f, 0.f, 0.f), cs_s = cs_q;
   const int nch = H >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long t0 = (long long)blockIdx.x * WT;
   const int tn = (int)min((long long)WT, N - t0);
@@ -441,24 +481,38 @@ attn_bwd_dst_tile_kernel(const float* __restrict__ dout, long long ldo, const fl
   stage_rows(sd, dout, ldo, t0, tn, nch);
   stage_rows(sk, k, ld, r0, R, nch);
   stage_rows(sv, v, ld, r0, R, nch);
-  stage_wait();
   constexpr int NPW = WT / 8;
   constexpr int G = PAIR ? 2 : 1;
+  constexpr int IT = NPW / G;
   const int half = PAIR ? lane >> 4 : 0, e = PAIR ? lane & 15 : lane;
-  for (int p = 0; p < NPW; p += G) {
-    const int nl = warp * NPW + p + half;
+  int begs[IT], degs[IT], rows[IT];            // CSR metadata and alpha of this warp's nodes, requested before the wait
+  float als[IT];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int nl = warp * NPW + it * G + half;
     const bool nok = nl < tn;
-    const long long node = t0 + nl;
-    const int beg = nok ? rowptr[node] : 0, deg = nok ? rowptr[node + 1] - beg : 0;
-    const bool live = e < deg;
-    int row = 0;
-    float al = 0.f;
-    if (live) {
-      const long long src = col[beg + e];
+    begs[it] = nok ? rowptr[t0 + nl] : 0;
+    degs[it] = nok ? rowptr[t0 + nl + 1] - begs[it] : 0;
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    rows[it] = 0;
+    als[it] = 0.f;
+    if (e < degs[it]) {
+      const long long src = col[begs[it] + e];
       if (src < r0 || src >= r1) __trap();
-      row = (int)(src - r0);
-      al = alpha[beg + e];
+      rows[it] = (int)(src - r0);
+      als[it] = alpha[begs[it] + e];
     }
+  }
+  stage_wait();
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int p = it * G;
+    const int nl = warp * NPW + p + half;
+    const int beg = begs[it], deg = degs[it], row = rows[it];
+    const bool live = e < deg;
+    const float al = als[it];
     float da = 0.f;
     const float4* gi = sd + nl * nch;
     const float4* vr = sv + row * nch;
@@ -483,19 +537,28 @@ attn_bwd_dst_tile_kernel(const float* __restrict__ dout, long long ldo, const fl
       }
       if (hnl < tn && lane < nch) {
         st4(dq + (t0 + hnl) * ldd + 4 * lane, acc);
-        if (ds) st4(ds + (t0 + hnl) * ldd + 4 * lane, sd[hnl * nch + lane]);
+        const float4 dsv = sd[hnl * nch + lane];
+        if (ds) st4(ds + (t0 + hnl) * ldd + 4 * lane, dsv);
+        cs_q.x += acc.x; cs_q.y += acc.y; cs_q.z += acc.z; cs_q.w += acc.w;
+        cs_s.x += dsv.x; cs_s.y += dsv.y; cs_s.z += dsv.z; cs_s.w += dsv.w;
       }
     }
   }
+  // bias gradient of the q/k/v/skip Linears = column sums of these outputs: reduced per CTA here (fixed order: nodes of a
+  // warp ascending, then warps ascending) so that no kernel has to re-read the [N, 4H] gradient
+  if (colsum_partial) tile_colsum(attn_sm, cs_q, cs_s, colsum_partial, H);
 }
 
 // by-source half on window graphs: the destinations of node j are rows [j - wlo, j + whi]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)      // <= 48 registers: 5 CTAs per SM (the 33.6 KB of staged rows allow 6)
 attn_bwd_src_tile_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ q, long long ld,
                          const int* __restrict__ t_rowptr, const int* __restrict__ t_col, const int* __restrict__ t_eid,
                          const float* __restrict__ alpha, const float* __restrict__ dsig, float scale,
-                         float* __restrict__ dk, float* __restrict__ dv, long long ldd, long long N, int H, int wlo, int whi) {
+                         float* __restrict__ dk, float* __restrict__ dv, long long ldd,
+                         float* __restrict__ colsum_partial /* [gridDim.x][2H]: column sums of dk | dv, or NULL */,
+                         long long N, int H, int wlo, int whi) {
   extern __shared__ float4 attn_sm[];
+  float4 cs_k = make_float4(0.f, 0.f, 0.f, 0.f), cs_v = cs_k;
   const int nch = H >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long t0 = (long long)blockIdx.x * WT;
   const int tn = (int)min((long long)WT, N - t0);
@@ -505,23 +568,35 @@ attn_bwd_src_tile_kernel(const float* __restrict__ dout, long long ldo, const fl
   float4* sd = sq + Rmax * nch;
   stage_rows(sq, q, ld, r0, R, nch);
   stage_rows(sd, dout, ldo, r0, R, nch);
-  stage_wait();
   constexpr int NPW = WT / 8;
+  int degs[NPW], rows[NPW];                    // per-edge metadata of this warp's nodes, requested before the wait
+  float as_[NPW], gs_[NPW];
+#pragma unroll
+  for (int p = 0; p < NPW; ++p) {
+    const int nl = warp * NPW + p;
+    const bool nok = nl < tn;
+    const int beg = nok ? t_rowptr[t0 + nl] : 0;
+    degs[p] = nok ? t_rowptr[t0 + nl + 1] - beg : 0;
+    rows[p] = 0;
+    as_[p] = 0.f;
+    gs_[p] = 0.f;
+    if (lane < degs[p]) {
+      const long long dst = t_col[beg + lane];
+      if (dst < r0 || dst >= r1) __trap();
+      rows[p] = (int)(dst - r0);
+      const int id = t_eid[beg + lane];
+      as_[p] = alpha[id];
+      gs_[p] = dsig[id] * scale;
+    }
+  }
+  stage_wait();
+#pragma unroll
   for (int p = 0; p < NPW; ++p) {
     const int nl = warp * NPW + p;
     if (nl >= tn) break;                       // warp-uniform
     const long long node = t0 + nl;
-    const int beg = t_rowptr[node], deg = t_rowptr[node + 1] - beg;
-    int row = 0;
-    float a = 0.f, g = 0.f;
-    if (lane < deg) {
-      const long long dst = t_col[beg + lane];
-      if (dst < r0 || dst >= r1) __trap();
-      row = (int)(dst - r0);
-      const int id = t_eid[beg + lane];
-      a = alpha[id];
-      g = dsig[id] * scale;
-    }
+    const int deg = degs[p], row = rows[p];
+    const float a = as_[p], g = gs_[p];
     float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), av = ak;
     for (int u = 0; u < deg; ++u) {
       const float au = __shfl_sync(0xffffffffu, a, u), gu = __shfl_sync(0xffffffffu, g, u);
@@ -534,8 +609,11 @@ attn_bwd_src_tile_kernel(const float* __restrict__ dout, long long ldo, const fl
     if (lane < nch) {
       st4(dk + node * ldd + 4 * lane, ak);
       st4(dv + node * ldd + 4 * lane, av);
+      cs_k.x += ak.x; cs_k.y += ak.y; cs_k.z += ak.z; cs_k.w += ak.w;
+      cs_v.x += av.x; cs_v.y += av.y; cs_v.z += av.z; cs_v.w += av.w;
     }
   }
+  if (colsum_partial) tile_colsum(attn_sm, cs_k, cs_v, colsum_partial, H);
 }
 
 // ---------------------------------------------------------------------------------- K5 EdgeAtt
@@ -706,6 +784,7 @@ static size_t attn_tile_smem(int H, int wlo, int whi, int full_tiles /* tile-onl
 static bool attn_tile_ok(int H, int wlo, int whi) { return H <= 128 && (H & 3) == 0 && wlo >= 0 && whi >= 0 && wlo + whi + 1 <= 32; }
 
 extern "C" int ercg_attn_window_supported(int H, int wlo, int whi) { return attn_tile_ok(H, wlo, whi) ? 1 : 0; }
+extern "C" int64_t ercg_attn_window_tiles(int64_t N) { return N <= 0 ? 0 : (N + WT - 1) / WT; }
 
 extern "C" int ercg_attn_window_fwd(const float* q, const float* k, const float* v, const float* s, int64_t ld,
                                     const int32_t* rowptr, const int32_t* col, float scale, float* out, int64_t ldo,
@@ -731,8 +810,8 @@ extern "C" int ercg_attn_window_fwd(const float* q, const float* k, const float*
 
 extern "C" int ercg_attn_window_bwd_dst(const float* dout, int64_t ldo, const float* k, const float* v, int64_t ld,
                                         const int32_t* rowptr, const int32_t* col, const float* alpha, float scale,
-                                        float* dq, float* ds, int64_t ldd, float* dsig, int64_t N, int H, int wlo, int whi,
-                                        void* stream) {
+                                        float* dq, float* ds, int64_t ldd, float* dsig, float* colsum_partial,
+                                        int64_t N, int H, int wlo, int whi, void* stream) {
   if (N < 0 || !attn_tile_ok(H, wlo, whi)) return ERCG_EINVAL;
   if (N == 0) return ERCG_OK;
   if (!rowptr || !col || !alpha || !dsig) return ERCG_EINVAL;
@@ -747,15 +826,16 @@ extern "C" int ercg_attn_window_bwd_dst(const float* dout, int64_t ldo, const fl
     cudaFuncSetAttribute(attn_bwd_dst_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr = true;
   }
-  if (wlo + whi + 1 <= 16) attn_bwd_dst_tile_kernel<true><<<blocks, 256, sm, st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, N, H, wlo, whi);
-  else attn_bwd_dst_tile_kernel<false><<<blocks, 256, sm, st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, N, H, wlo, whi);
+  if (wlo + whi + 1 <= 16) attn_bwd_dst_tile_kernel<true><<<blocks, 256, sm, st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, colsum_partial, N, H, wlo, whi);
+  else attn_bwd_dst_tile_kernel<false><<<blocks, 256, sm, st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, colsum_partial, N, H, wlo, whi);
   return finish_launch();
 }
 
 extern "C" int ercg_attn_window_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld,
                                         const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
                                         const float* alpha, const float* dsig, float scale, float* dk, float* dv,
-                                        int64_t ldd, int64_t N, int H, int wlo, int whi, void* stream) {
+                                        int64_t ldd, float* colsum_partial, int64_t N, int H, int wlo, int whi,
+                                        void* stream) {
   if (N < 0 || !attn_tile_ok(H, wlo, whi)) return ERCG_EINVAL;
   if (N == 0) return ERCG_OK;
   if (!t_rowptr || !t_col || !t_eid || !alpha || !dsig) return ERCG_EINVAL;
@@ -767,7 +847,7 @@ extern "C" int ercg_attn_window_bwd_src(const float* dout, int64_t ldo, const fl
     cudaFuncSetAttribute(attn_bwd_src_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr = true;
   }
-  attn_bwd_src_tile_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(dout, ldo, q, ld, t_rowptr, t_col, t_eid, alpha, dsig, scale, dk, dv, ldd, N, H, wlo, whi);
+  attn_bwd_src_tile_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(dout, ldo, q, ld, t_rowptr, t_col, t_eid, alpha, dsig, scale, dk, dv, ldd, colsum_partial, N, H, wlo, whi);
   return finish_launch();
 }
 

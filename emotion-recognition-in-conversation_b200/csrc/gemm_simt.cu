@@ -156,8 +156,8 @@ gemm_nn_kernel(const float* __restrict__ A, long long lda, const int* __restrict
               x = fmaxf(x, 0.f);
             } else if (ep.act == ERCG_ACT_RELU_DROPOUT) {
               x = fmaxf(x, 0.f);
-              const float u = hash_uniform(ep.seed, (unsigned long long)m * (unsigned long long)N + nn);
-              x = u < ep.drop_p ? 0.f : x * (1.0f / (1.0f - ep.drop_p));
+              const bool drop = dropout_drop(dropout_group_hash(ep.seed, m, nn, N), nn & 3, dropout_thr16(ep.drop_p));
+              x = drop ? 0.f : x * (1.0f / (1.0f - ep.drop_p));
             } else if (ep.act == ERCG_ACT_MASK_POS) {
               x = __ldg(ep.aux + m * ep.ldaux + nn) > 0.f ? x * ep.aux_scale : 0.f;
             } else if (ep.act == ACT_GCNII_FWD) {

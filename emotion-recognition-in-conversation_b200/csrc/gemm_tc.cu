@@ -41,7 +41,7 @@ constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;      // 16 KB
 
 struct TcEpilogue {
   const float* bias; int act; const float* aux; long long ldaux; float aux_scale; float drop_p; unsigned long long seed;
-  int dbg;   // ERCG_TC_DBG: performance experiments only (1 no MMA, 2 no TMEM store, 4 no accumulator drain, 8 no B loads)
+  int dbg;   // ERCG_TC_DBG: performance experiments only (1 no MMA, 8 no B loads)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -150,13 +150,19 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
 // are several N tiles ("resident" mode: the K = 100 transforms of COGMEN with N = 900 / 400), A is loaded and split ONCE
 // per M tile and stays in TMEM while the N tiles stream B only; otherwise A is re-streamed per N tile (n_tiles is 1 for
 // every long-K transform of the reference models).
-constexpr int TC_R = 4;           // raw A stages
-constexpr int TC_Q = 3;           // B stages
+#ifndef TC_R_
+#define TC_R_ 4
+#endif
+#ifndef TC_Q_
+#define TC_Q_ 3
+#endif
+constexpr int TC_R = TC_R_;       // raw A stages
+constexpr int TC_Q = TC_Q_;       // B stages
 constexpr int TC_TA = 4;          // TMEM A stages
 constexpr uint32_t TC_TMEM_A0 = 2 * TC_BN;                       // first A column
 constexpr uint32_t TC_SLAB_BYTES = 32 * 128;                     // epilogue staging slab: 32 rows x 32 columns, 128-byte swizzle
-constexpr int TC_SLABS = 2;                                     // staging slabs per epilogue warp (two write-out rounds per tile)
-constexpr uint32_t TC_STAGE_BYTES = 4 * TC_SLABS * TC_SLAB_BYTES;   // 4 warps x 2 slabs = 32 KB
+constexpr int TC_SLABS = 4;                                     // staging slabs per epilogue warp: the whole 128-column tile
+constexpr uint32_t TC_STAGE_BYTES = 4 * TC_SLABS * TC_SLAB_BYTES;   // 4 warps x 4 slabs = 64 KB
 constexpr uint32_t TC_SMEM_BYTES = TC_R * TC_A_BYTES + TC_Q * 2 * TC_B_BYTES + TC_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int TC_THREADS = 352;   // 4 splitter + 4 epilogue warps, A producer, MMA, B producer
 
@@ -233,11 +239,12 @@ __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, lon
   }
   if (ACT == ERCG_ACT_RELU_DROPOUT) {
     const float sc = 1.0f / (1.0f - ep.drop_p);
-    const unsigned long long base = (unsigned long long)m * (unsigned long long)N + (unsigned long long)nn0;
-    x.x = hash_uniform(ep.seed, base + 0) < ep.drop_p ? 0.f : x.x * sc;
-    x.y = hash_uniform(ep.seed, base + 1) < ep.drop_p ? 0.f : x.y * sc;
-    x.z = hash_uniform(ep.seed, base + 2) < ep.drop_p ? 0.f : x.z * sc;
-    x.w = hash_uniform(ep.seed, base + 3) < ep.drop_p ? 0.f : x.w * sc;
+    const unsigned thr = dropout_thr16(ep.drop_p);
+    const uint64_t h = dropout_group_hash(ep.seed, m, nn0, N);          // nn0 is a multiple of 4: one hash per float4
+    x.x = dropout_drop(h, 0, thr) ? 0.f : x.x * sc;
+    x.y = dropout_drop(h, 1, thr) ? 0.f : x.y * sc;
+    x.z = dropout_drop(h, 2, thr) ? 0.f : x.z * sc;
+    x.w = dropout_drop(h, 3, thr) ? 0.f : x.w * sc;
   }
   if (ACT == ERCG_ACT_MASK_POS) {
     const float* a = ep.aux + m * ep.ldaux + nn0;
@@ -249,12 +256,13 @@ __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, lon
   return x;
 }
 
-template <int ACT>
+template <int ACT, bool SMALLK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                   const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
                   float* __restrict__ C, long long ldc, long long M, int N,
-                  int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, TcEpilogue ep) {
+                  int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, TcEpilogue ep,
+                  float* __restrict__ colsum_partial /* [gridDim.x][4][128] column sums of C (N <= 128 only), or NULL */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bring = smem + TC_R * TC_A_BYTES;
@@ -406,74 +414,124 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue (warps 4-7 -> TMEM lanes 32*(warp%4))
+    // Every 32-column slab of the tile is staged in shared memory (thread = row, 16-byte chunks XOR-swizzled like a
+    // 128-byte-swizzle TMA box, so the st.shared are bank-conflict free) and leaves as ONE bulk tensor store per slab; TMA
+    // clips the M and N tails.  All (up to four) slabs of a tile are staged before the stores are issued, so there is one
+    // wait for the previous tile's stores per tile, not one per pair of slabs.
+    //   SMALLK (the whole K extent is one accumulation group: the K = 100 transforms): accumulator columns stream
+    //   TMEM -> registers -> staging 32 at a time.  (ncu on the first version, which kept a float acc[128] per thread for
+    //   every shape: the epilogue warps were busy ~97 % of the kernel -- local-memory spills of acc[], generic-address
+    //   stores into the staging buffer -- and the MMA warp waited on ACC_EMPTY; K = 100, N = 100 ran at 27 % of HBM.)
+    //   otherwise: partial sums of TC_GROUP k-chunks are added into fp32 registers with round-to-nearest (see top of file).
     int a = 0;
     uint32_t aph = 0;
     const int ew = warp & 3;
-    uint8_t* stg = stage_all + ew * TC_SLABS * TC_SLAB_BYTES;       // this warp's slabs of 32 rows x 32 columns
-    const uint32_t stg_u32 = smem_u32(stg);
+    const uint32_t stg_u32 = smem_u32(stage_all + ew * TC_SLABS * TC_SLAB_BYTES);     // this warp's 4 slabs of 32 x 32
+    const uint32_t my_row = stg_u32 + lane * 128;
     const int n_groups = (k_chunks + TC_GROUP - 1) / TC_GROUP;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
+    float colacc[TC_SLABS];                                        // lane = column of a slab: sums over this warp's rows
+#pragma unroll
+    for (int sl = 0; sl < TC_SLABS; ++sl) colacc[sl] = 0.f;
     for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
       const long long m0 = t * TC_BM + ew * 32;
       const long long m = m0 + lane;                               // this thread's row (TMEM lane)
+      const long long mrow = m < M ? m : M - 1;
       for (int nt = 0; nt < n_tiles; ++nt) {
         const int n0 = nt * bn;
-        float acc[TC_BN];
-        for (int g = 0; g < n_groups; ++g) {
+        if (SMALLK) {
           mbar_wait(BAR(BAR_ACC_FULL + a), aph);
           tc_fence_after();
+          if (lane == 0) tma_store_wait_read();                    // the previous tile's bulk stores have read the slabs
+          __syncwarp();
 #pragma unroll
-          for (int c = 0; c < TC_BN; c += 32) {
-            if (c < bn && !(ep.dbg & 4)) {
+          for (int sl = 0; sl < TC_SLABS; ++sl) {
+            const int c = 32 * sl;
+            if (c < bn && n0 + c < N) {
               uint32_t rr[32];
-              tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN + c), rr);
+              tc_ld32(tmem_lane + (uint32_t)(a * TC_BN + c), rr);
               tc_wait_ld();
-              if (g == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c + j] = __uint_as_float(rr[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(rr[j]);   // round-to-nearest accumulation
+              for (int j = 0; j < 32; j += 4) {
+                float4 v = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
+                                       __uint_as_float(rr[j + 3]));
+                if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N);
+                sts4(my_row + sl * TC_SLAB_BYTES + (((j >> 2) ^ (lane & 7)) << 4), v);
               }
             }
           }
           tc_fence_before();
           mbar_arrive(BAR(BAR_ACC_EMPTY + a));
           if (++a == 2) { a = 0; aph ^= 1; }
-        }
-        // write-out: every 32-column slab is staged in shared memory (thread = row, 16-byte chunks XOR-swizzled like a
-        // 128-byte-swizzle TMA box, so the stores are bank-conflict free) and leaves as ONE bulk tensor store per
-        // slab; TMA clips the M and N tails.  No per-element address arithmetic or bounds checks on the SM.
+        } else {
+          float acc[TC_BN];
+          for (int g = 0; g < n_groups; ++g) {
+            mbar_wait(BAR(BAR_ACC_FULL + a), aph);
+            tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < TC_BN; c0 += 32 * TC_SLABS) {         // rounds of TC_SLABS slabs
-          if (c0 < bn && n0 + c0 < N && !(ep.dbg & 64)) {
-            if (lane == 0) tma_store_wait_read();                  // earlier bulk stores have read the staging slabs
-            __syncwarp();
+            for (int c = 0; c < TC_BN; c += 32) {
+              if (c < bn) {
+                uint32_t rr[32];
+                tc_ld32(tmem_lane + (uint32_t)(a * TC_BN + c), rr);
+                tc_wait_ld();
+                if (g == 0) {
 #pragma unroll
-            for (int sl = 0; sl < TC_SLABS; ++sl) {
-              const int c = c0 + 32 * sl;
-              if (c < bn && n0 + c < N) {
-                uint8_t* slab = stg + sl * TC_SLAB_BYTES + lane * 128;
+                  for (int j = 0; j < 32; ++j) acc[c + j] = __uint_as_float(rr[j]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 v = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
-                  if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, m < M ? m : M - 1, n0 + c + j, N);
-                  *reinterpret_cast<float4*>(slab + (((j >> 2) ^ (lane & 7)) << 4)) = v;
+                  for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(rr[j]);   // round-to-nearest accumulation
                 }
               }
             }
-            fence_proxy_async();                                   // generic-proxy stores -> visible to the TMA engine
-            __syncwarp();
-            if (lane == 0 && !(ep.dbg & 32)) {
+            tc_fence_before();
+            mbar_arrive(BAR(BAR_ACC_EMPTY + a));
+            if (++a == 2) { a = 0; aph ^= 1; }
+          }
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
 #pragma unroll
-              for (int sl = 0; sl < TC_SLABS; ++sl) {
-                const int c = c0 + 32 * sl;
-                if (c < bn && n0 + c < N) tma_store_2d(&tmC, stg_u32 + sl * TC_SLAB_BYTES, n0 + c, (int)m0);
+          for (int sl = 0; sl < TC_SLABS; ++sl) {
+            const int c = 32 * sl;
+            if (c < bn && n0 + c < N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 v = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
+                if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N);
+                sts4(my_row + sl * TC_SLAB_BYTES + (((j >> 2) ^ (lane & 7)) << 4), v);
               }
-              tma_store_commit();
+            }
+          }
+        }
+        fence_proxy_async();                                       // generic-proxy stores -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int sl = 0; sl < TC_SLABS; ++sl) {
+            const int c = 32 * sl;
+            if (c < bn && n0 + c < N) tma_store_2d(&tmC, stg_u32 + sl * TC_SLAB_BYTES, n0 + c, (int)m0);
+          }
+          tma_store_commit();
+        }
+        // bias gradient of the upstream layer = column sums of this product: taken from the staged slabs while TMA reads
+        // them (lane = column, 32 conflict-free 4-byte reads per slab; rows past M are zero), so nobody re-reads C from HBM
+        if (colsum_partial) {
+#pragma unroll
+          for (int sl = 0; sl < TC_SLABS; ++sl) {
+            if (32 * sl < bn && n0 + 32 * sl < N) {
+              float sum = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r)
+                sum += lds1(stg_u32 + sl * TC_SLAB_BYTES + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+              colacc[sl] += sum;
             }
           }
         }
       }
+    }
+    if (colsum_partial) {
+#pragma unroll
+      for (int sl = 0; sl < TC_SLABS; ++sl)
+        colsum_partial[((long long)blockIdx.x * 4 + ew) * 128 + sl * 32 + lane] = colacc[sl];
     }
     if (lane == 0) tma_store_wait_all();                           // global writes complete before the kernel exits
   }
@@ -792,6 +850,25 @@ __global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int 
   }
 }
 
+// out[c] = sum_b partial[b * ldp + c], fixed order, fp64 accumulation
+__global__ void __launch_bounds__(256)
+tc_colsum_final_kernel(const float* __restrict__ partial, int nblocks, int ldp, int N, float* __restrict__ out) {
+  __shared__ double sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (c < N)
+    for (int b = ty; b < nblocks; b += 8) s += (double)partial[(long long)b * ldp + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    double tot = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += sm[y][tx];
+    out[c] = (float)tot;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -831,7 +908,7 @@ using namespace ercg;
 extern "C" size_t ercg_gemm_nn_tc_workspace_bytes(int N, int K) {
   if (N <= 0 || K <= 0) return 0;
   const size_t Kp = (size_t)(K + 3) / 4 * 4;
-  return 2 * (size_t)N * Kp * sizeof(float) + 256;
+  return 2 * (size_t)N * Kp * sizeof(float) + 256 + (size_t)kNumSMs * 2 * 4 * 128 * sizeof(float) /* column-sum partials */;
 }
 
 // returns 1 when this shape/alignment can run on the tensor-core path
@@ -844,9 +921,11 @@ extern "C" int ercg_gemm_nn_tc_supported(const float* A, int64_t lda, const floa
 
 extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                                int64_t ldc, int64_t M, int N, int K, int act, const float* aux, int64_t ldaux,
-                               float aux_scale, float drop_p, uint64_t seed, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+                               float aux_scale, float drop_p, uint64_t seed, float* colsum_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   if (M < 0 || N < 0 || K < 0) return ERCG_EINVAL;
+  if (colsum_out && (N > TC_BN || bias || act != ERCG_ACT_NONE)) return ERCG_EINVAL;
+  if (M == 0 && colsum_out && N > 0) cudaMemsetAsync(colsum_out, 0, (size_t)N * sizeof(float), (cudaStream_t)stream);
   if (M == 0 || N == 0) return ERCG_OK;
   if (!A || !B || !C || lda < K || ldb < N || ldc < N || K == 0) return ERCG_EINVAL;
   if (act < 0 || act > 3 || (act == ERCG_ACT_MASK_POS && !aux)) return ERCG_EINVAL;
@@ -867,13 +946,17 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, bn) || !make_map(&tmBl, blo, N, K, Kp, bn) ||
       !make_map(&tmC, C, M, N, ldc, 32))                     // output: boxes of 32 rows x 32 columns (TMA bulk stores)
     return ERCG_ECUDA;
+  typedef void (*NnKernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, float*, long long, long long, int, int, int,
+                           TcEpilogue, float*);
+  static const NnKernel kernels[4][2] = {
+      {gemm_tc_nn_kernel<0, false>, gemm_tc_nn_kernel<0, true>}, {gemm_tc_nn_kernel<1, false>, gemm_tc_nn_kernel<1, true>},
+      {gemm_tc_nn_kernel<2, false>, gemm_tc_nn_kernel<2, true>}, {gemm_tc_nn_kernel<3, false>, gemm_tc_nn_kernel<3, true>}};
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_nn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_nn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_nn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_nn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
-      return ERCG_ECUDA;
+    for (int i = 0; i < 4; ++i)
+      for (int k = 0; k < 2; ++k)
+        if (cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+          return ERCG_ECUDA;
     attr_set = true;
   }
   static int num_sms = 0;
@@ -888,11 +971,13 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("ERCG_TC_DBG"); dbg = e ? atoi(e) : 0; }
   TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg};
-  switch (act) {
-    case 0: gemm_tc_nn_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep); break;
-    case 1: gemm_tc_nn_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep); break;
-    case 2: gemm_tc_nn_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep); break;
-    default: gemm_tc_nn_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep); break;
+  const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;       // the whole K extent is one TMEM accumulation group
+  float* partial = colsum_out ? blo + (size_t)N * Kp : nullptr;     // [grid][4][128], after the two B copies
+  kernels[act][smallk]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep, partial);
+  if (colsum_out) {
+    rc = finish_launch();
+    if (rc) return rc;
+    tc_colsum_final_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial, grid * 4, 128, N, colsum_out);
   }
   return finish_launch();
 }

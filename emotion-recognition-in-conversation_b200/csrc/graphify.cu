@@ -82,6 +82,136 @@ __device__ inline void block_scan_pair(long long& a, long long& b, long long* sm
   if (wid > 0) { a += sm[2 * (wid - 1)]; b += sm[2 * (wid - 1) + 1]; }
 }
 
+// sum_{k' < k} [ min(L-1, k'+A) - max(0, k'-Bk) + 1 ] in the index type I (int when L <= 46340: every product below is
+// < 2^31 there; unsigned halves keep a*(a-1) exact)
+template <typename I>
+__device__ __forceinline__ I deg_prefix_t(I L, I A, I Bk, I k) {
+  const I t1 = L - A;
+  const I a = k < t1 ? k : t1;
+  const I sum1 = a * A + (I)(((unsigned long long)(unsigned)a * (unsigned)(a - 1)) >> 1) + (k - a) * (L - 1);
+  I b = k - 1 - Bk;
+  if (b < 0) b = 0;
+  return sum1 + k - (I)(((unsigned long long)(unsigned)b * (unsigned)(b + 1)) >> 1);
+}
+template <>
+__device__ __forceinline__ long long deg_prefix_t<long long>(long long L, long long A, long long Bk, long long k) {
+  return deg_prefix(L, A, Bk, k);
+}
+
+// One warp fills one dialogue: (a) node arrays lane-per-node, (b) by-destination edges, (c) by-source edges, lane-per-edge.
+// Edge chunks are ROW-ALIGNED (a chunk holds whole rows whenever the row degree is <= 32), so the PyG mean weight
+// 1/|{e' : dst = dst(e), type = type(e)}| is one __match_any_sync over (row, speaker, direction) instead of a loop over the
+// window per edge (that loop was ~1/3 of this kernel's instructions); rows longer than a warp keep the loop.
+template <typename I>
+__device__ __forceinline__ void fill_dialogue(const GraphifyParams& p, int d, I L, I o, I eo) {
+  const int lane = threadIdx.x & 31;
+  const int n_spk = p.n_speakers;
+  const I m = L - 1;
+  const I P = (p.wp < 0 || (long long)p.wp > (long long)m) ? m : (I)p.wp;
+  const I F = (p.wf < 0 || (long long)p.wf > (long long)m) ? m : (I)p.wf;
+  for (I k = lane; k < L; k += 32) {
+    long long s;
+    if (p.spk_ld > 0) {
+      const long long idx = (long long)d * p.spk_ld + (long long)k;
+      s = p.spk64 ? reinterpret_cast<const long long*>(p.speakers)[idx]
+                  : (long long)reinterpret_cast<const int*>(p.speakers)[idx];
+    } else {
+      s = p.spk64 ? reinterpret_cast<const long long*>(p.speakers)[(long long)o + k]
+                  : (long long)reinterpret_cast<const int*>(p.speakers)[(long long)o + k];
+    }
+    p.o.spk[o + k] = (int)s;
+    p.o.node_dlg[o + k] = d;
+    if (p.o.pad_row) p.o.pad_row[o + k] = (int)(p.spk_ld > 0 ? (long long)d * p.spk_ld + (long long)k : (long long)(o + k));
+    p.o.rowptr[o + k] = (int)(eo + deg_prefix_t<I>(L, P, F, k));
+    p.o.t_rowptr[o + k] = (int)(eo + deg_prefix_t<I>(L, F, P, k));
+  }
+  __syncwarp();
+  const int* spk = p.o.spk + o;
+  for (int pass = 0; pass < 2; ++pass) {
+    const I A = pass == 0 ? P : F;      // high-side reach of the row node
+    const I Bk = pass == 0 ? F : P;     // low-side reach
+    for (I k0 = 0; k0 < L; k0 += 32) {
+      I kmine = k0 + lane;
+      if (kmine > L) kmine = L;
+      const I myS = deg_prefix_t<I>(L, A, Bk, kmine);          // first edge of row k0 + lane (clamped to the end)
+      const I kend = k0 + 32 < L ? k0 + 32 : L;
+      const I end = deg_prefix_t<I>(L, A, Bk, kend);
+      I xb = __shfl_sync(0xffffffffu, myS, 0);
+      while (xb < end) {
+        // chunk = [xb, xe): as many WHOLE rows as fit in 32 lanes when a row starts at xb and fits; otherwise (row longer
+        // than a warp, or xb in the middle of such a row) up to 32 edges of that one row
+        const I nextS = __shfl_down_sync(0xffffffffu, myS, 1);
+        const I rowEnd = lane == 31 ? end : nextS;              // lane l's row ends where row l + 1 starts
+        const bool rowok = k0 + lane < kend;
+        unsigned fits = 0u;
+        if (__ballot_sync(0xffffffffu, rowok && myS == xb))
+          fits = __ballot_sync(0xffffffffu, rowok && myS >= xb && rowEnd <= xb + 32);
+        I xe;
+        bool whole;
+        if (fits) {
+          xe = __shfl_sync(0xffffffffu, rowEnd, 31 - __clz(fits));
+          whole = true;
+        } else {
+          const unsigned cont = __ballot_sync(0xffffffffu, rowok && myS <= xb && xb < rowEnd);
+          const I re = __shfl_sync(0xffffffffu, rowEnd, cont ? __ffs(cont) - 1 : 31);
+          xe = xb + 32 < re ? xb + 32 : re;
+          whole = false;
+        }
+        const I x = xb + lane;
+        const bool valid = x < xe;
+        const I xs = valid ? x : xb;
+        int lo = 0, hi = 31;
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+          const int mid = (lo + hi + 1) >> 1;
+          const I v = __shfl_sync(0xffffffffu, myS, mid);
+          if (v <= xs) lo = mid; else hi = mid - 1;
+        }
+        const I Srow = __shfl_sync(0xffffffffu, myS, lo);
+        const I row = k0 + lo;                                  // k (pass 0) or j (pass 1)
+        const I rlo = row - Bk > 0 ? row - Bk : 0;
+        const I other = rlo + (xs - Srow);                      // j (pass 0) or k (pass 1)
+        const I j = pass == 0 ? other : row;
+        const I k = pass == 0 ? row : other;
+        const int sj = spk[j], sk = spk[k];
+        const int ty = (sj * n_spk + sk) * 2 + (j >= k ? 1 : 0);
+        const long long e = (long long)eo + (long long)x;
+        if (pass == 0) {
+          unsigned same = 0u;
+          if (p.o.inv_cnt && whole) {
+            const unsigned key = valid ? (((unsigned)lo << 16) | ((unsigned)sj << 1) | (j >= k ? 1u : 0u)) : (0x80000000u | lane);
+            same = __match_any_sync(0xffffffffu, key);
+          }
+          if (valid) {
+            p.o.col[e] = (int)(o + j);
+            p.o.etype[e] = (uint8_t)ty;
+            if (p.o.edge_index) { p.o.edge_index[e] = (long long)(o + j); p.o.edge_index[p.E + e] = (long long)(o + k); }
+            if (p.o.edge_type) p.o.edge_type[e] = ty;
+            if (p.o.inv_cnt) {
+              int c;
+              if (whole) {
+                c = __popc(same);
+              } else {
+                const I rhi = k + P < L - 1 ? k + P : L - 1;
+                const bool dirj = j >= k;
+                c = 0;
+                for (I jj = rlo; jj <= rhi; ++jj) c += (spk[jj] == sj && ((jj >= k) == dirj)) ? 1 : 0;
+              }
+              p.o.inv_cnt[e] = 1.0f / (float)c;
+            }
+          }
+        } else if (valid) {
+          p.o.t_col[e] = (int)(o + k);
+          p.o.t_etype[e] = (uint8_t)ty;
+          const I klo = k - F > 0 ? k - F : 0;
+          p.o.t_eid[e] = (int)(eo + deg_prefix_t<I>(L, P, F, k) + (j - klo));
+        }
+        xb = xe;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) graphify_kernel(GraphifyParams p) {
   cg::grid_group grid = cg::this_grid();
   __shared__ long long sm[66];
@@ -136,91 +266,18 @@ __global__ void __launch_bounds__(256) graphify_kernel(GraphifyParams p) {
   grid.sync();
 
   // ---- phase 3: one warp per dialogue
-  const int lane = threadIdx.x & 31;
   const int warps_per_block = T >> 5;
   const long long gwarp = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * warps_per_block;
-  const int n_spk = p.n_speakers;
   for (long long d = gwarp; d < p.B; d += nwarps) {
     const long long L = load_len(p, (int)d);
     if (L == 0) continue;
     const long long o = p.o.node_off[d], eo = p.o.edge_off[d];
     if (o + L > p.N) continue;                  // caller passed a too-small N: never write out of bounds
-    long long P, F;
-    eff_window(L, p.wp, p.wf, P, F);
     if (eo + dialog_edges(L, p.wp, p.wf) > p.E) continue;
-    // (a) node arrays
-    for (long long k = lane; k < L; k += 32) {
-      long long s;
-      if (p.spk_ld > 0) {
-        long long idx = d * p.spk_ld + k;
-        s = p.spk64 ? reinterpret_cast<const long long*>(p.speakers)[idx]
-                    : (long long)reinterpret_cast<const int*>(p.speakers)[idx];
-      } else {
-        s = p.spk64 ? reinterpret_cast<const long long*>(p.speakers)[o + k]
-                    : (long long)reinterpret_cast<const int*>(p.speakers)[o + k];
-      }
-      p.o.spk[o + k] = (int)s;
-      p.o.node_dlg[o + k] = (int)d;
-      if (p.o.pad_row) p.o.pad_row[o + k] = (int)(p.spk_ld > 0 ? d * p.spk_ld + k : o + k);
-      p.o.rowptr[o + k] = (int)(eo + deg_prefix(L, P, F, k));
-      p.o.t_rowptr[o + k] = (int)(eo + deg_prefix(L, F, P, k));
-    }
-    __syncwarp();
-    const int* spk = p.o.spk + o;
-    // (b) by-destination edges, (c) by-source edges
-    for (int pass = 0; pass < 2; ++pass) {
-      const long long A = pass == 0 ? P : F;      // high-side reach of the row node
-      const long long Bk = pass == 0 ? F : P;     // low-side reach
-      for (long long k0 = 0; k0 < L; k0 += 32) {
-        long long kmine = k0 + lane;
-        if (kmine > L) kmine = L;
-        const long long myS = deg_prefix(L, A, Bk, kmine);
-        const long long base = __shfl_sync(0xffffffffu, myS, 0);
-        long long kend = k0 + 32 < L ? k0 + 32 : L;
-        const long long end = deg_prefix(L, A, Bk, kend);
-        for (long long xb = base; xb < end; xb += 32) {
-          const long long x = xb + lane;
-          const bool valid = x < end;
-          const long long xs = valid ? x : base;
-          int lo = 0, hi = 31;
-#pragma unroll
-          for (int it = 0; it < 5; ++it) {
-            int mid = (lo + hi + 1) >> 1;
-            long long v = __shfl_sync(0xffffffffu, myS, mid);
-            if (v <= xs) lo = mid; else hi = mid - 1;
-          }
-          const long long Srow = __shfl_sync(0xffffffffu, myS, lo);
-          if (!valid) continue;
-          const long long row = k0 + lo;                 // k (pass 0) or j (pass 1)
-          const long long rlo = row - Bk > 0 ? row - Bk : 0;
-          const long long other = rlo + (x - Srow);      // j (pass 0) or k (pass 1)
-          const long long j = pass == 0 ? other : row;
-          const long long k = pass == 0 ? row : other;
-          const int sj = spk[j], sk = spk[k];
-          const int ty = (sj * n_spk + sk) * 2 + (j >= k ? 1 : 0);
-          const long long e = eo + x;
-          if (pass == 0) {
-            p.o.col[e] = (int)(o + j);
-            p.o.etype[e] = (uint8_t)ty;
-            if (p.o.edge_index) { p.o.edge_index[e] = o + j; p.o.edge_index[p.E + e] = o + k; }
-            if (p.o.edge_type) p.o.edge_type[e] = ty;
-            if (p.o.inv_cnt) {
-              const long long rhi = k + P < L - 1 ? k + P : L - 1;
-              int c = 0;
-              const bool dirj = j >= k;
-              for (long long jj = rlo; jj <= rhi; ++jj) c += (spk[jj] == sj && ((jj >= k) == dirj)) ? 1 : 0;
-              p.o.inv_cnt[e] = 1.0f / (float)c;
-            }
-          } else {
-            p.o.t_col[e] = (int)(o + k);
-            p.o.t_etype[e] = (uint8_t)ty;
-            const long long klo = k - F > 0 ? k - F : 0;
-            p.o.t_eid[e] = (int)(eo + deg_prefix(L, P, F, k) + (j - klo));
-          }
-        }
-      }
-    }
+    // every in-dialogue quantity fits 32 bits when L <= 46340 (L^2 < 2^31): the integer pipe is the bound of this kernel
+    if (L <= 46340) fill_dialogue<int>(p, (int)d, (int)L, (int)o, (int)eo);
+    else fill_dialogue<long long>(p, (int)d, L, o, eo);
   }
 }
 

@@ -20,13 +20,17 @@ def _p(t):
 from .ops import _stream  # noqa: E402  (raw handle of torch's current stream)
 
 
+import os as _os
+_NO_CENSUS = bool(int(_os.environ.get("ERCG_NO_CENSUS", "0")))     # diagnostics: RGCNConv keeps all R relation slots
+
+
 class PackedGraph:
     """All arrays live on the GPU.  Canonical edge order: dialogue, then destination, then source."""
 
     __slots__ = ("B", "N", "E", "wp", "wf", "n_speakers", "num_relations", "device", "node_off", "edge_off",
                  "rowptr", "col", "etype", "t_rowptr", "t_col", "t_etype", "t_eid", "spk", "node_dlg", "inv_cnt",
                  "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row", "perm", "Lpad", "rel_info",
-                 "_rel_host", "_rel_event", "_rel_cache")
+                 "_rel_host", "_rel_event", "_rel_cache", "_rel_gen", "_core")
 
     def __init__(self):
         for s in self.__slots__:
@@ -38,16 +42,37 @@ class PackedGraph:
             self.inv_cnt = _inv_count_from_csr(self)
         return self.inv_cnt
 
+    def attach(self):
+        """Hang the packed CSR on the reference-layout ``edge_index`` tensor (``edge_index._ercg_graph``) so that the conv
+        layers find it when they are handed that tensor (graph_from_edge_index), and return ``edge_index``.
+
+        What is attached is a shallow copy WITHOUT the reference-layout tensors: ``edge_index -> core -> arrays`` has no
+        cycle, so a step's graph (a few hundred MB of index arrays) is released by reference counting the moment the step
+        drops it.  (Attaching ``self`` made a cycle that only the cyclic garbage collector could free; the resulting
+        irregular frees sent the caching allocator back to cudaMalloc inside steady-state steps -- 50-110 ms stalls.)"""
+        core = self._core
+        if core is None:
+            core = PackedGraph()
+            for name in self.__slots__:
+                if name not in ("edge_index", "edge_type", "edge_index_lengths", "_core"):
+                    setattr(core, name, getattr(self, name))
+            self._core = core
+        self.edge_index._ercg_graph = core
+        return self.edge_index
+
     def relation_slots(self):
         """K1's relation census: (ids, rel_slot) -- the sorted relation ids that occur on at least one edge (python list)
         and the device int32 table id -> compact slot (-1 = absent) -- or None for graphs that did not come from K1.
         The census left the GPU with an async copy right behind K1; waiting for it here does not drain the stream."""
-        if self.rel_info is None:
+        if self.rel_info is None or _NO_CENSUS:
             return None
         if self._rel_cache is None:
             self._rel_event.synchronize()
-            P = int(self._rel_host[0])
-            ids = [int(v) for v in self._rel_host[257:257 + P]]
+            info = self._rel_host.tolist()          # read NOW: the ring buffer is reused by later graphs
+            if _CENSUS_GEN.get(id(self._rel_host)) != self._rel_gen:
+                info = self.rel_info.cpu().tolist()  # the landing buffer was recycled before anyone asked: read the device copy
+            P = info[0]
+            ids = info[257:257 + P]
             self._rel_cache = (ids, self.rel_info[1:1 + self.num_relations])
         return self._rel_cache
 
@@ -127,11 +152,31 @@ def build_graph(lengths, speakers, wp, wf, n_speakers, device=None, reference_la
     check(lib().ercg_graphify_csr(_p(ldev), 1 if ldev.dtype == torch.int64 else 0, B, _p(sdev),
                                   1 if sdev.dtype == torch.int64 else 0, spk_ld, wp, wf, n_speakers, N, E,
                                   ctypes.byref(out), _p(ws), ws.numel(), _stream()), "ercg_graphify_csr")
-    g._rel_host = torch.empty(513, dtype=torch.int32, pin_memory=True)
+    g._rel_host, g._rel_event, g._rel_gen = _census_slot()
     g._rel_host.copy_(g.rel_info, non_blocking=True)
-    g._rel_event = torch.cuda.Event()
     g._rel_event.record()
     return g
+
+
+# Pinned landing buffers for the relation census, allocated ONCE and reused round-robin: a fresh pinned allocation per
+# graph (cudaHostAlloc when the caching host allocator has no free block) can stall the device for tens of ms.
+_CENSUS_RING = []
+_CENSUS_GEN = {}                     # id(host buffer) -> generation of the graph that currently owns it
+_census_next = 0
+
+
+def _census_slot(depth=8):
+    global _census_next
+    if not _CENSUS_RING:
+        for _ in range(depth):
+            _CENSUS_RING.append((torch.empty(513, dtype=torch.int32, pin_memory=True), torch.cuda.Event()))
+        _census_next = 0
+    host, ev = _CENSUS_RING[_census_next]
+    _census_next = (_census_next + 1) % len(_CENSUS_RING)
+    ev.synchronize()                 # the copy that last used this buffer (depth graphs ago) has landed
+    gen = _CENSUS_GEN.get(id(host), 0) + 1
+    _CENSUS_GEN[id(host)] = gen
+    return host, ev, gen
 
 
 def _inv_count_from_csr(g):

@@ -48,7 +48,11 @@ GEMM_ENGINE = _os.environ.get("ERCG_GEMM", "tc")
 TC_MIN_ROWS = 256
 
 
-def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_scale=1.0, drop_p=0.0, seed=0, out=None):
+def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_scale=1.0, drop_p=0.0, seed=0, out=None,
+            want_colsum=False):
+    """C = act(A[a_rows] @ Bm + bias).  ``want_colsum``: when the tensor-core kernel runs a plain product with N <= 128 it
+    also reduces the column sums of C (from the tiles in shared memory) and hangs them on the result (``C._ercg_colsum``)
+    for ops.colsum -- the bias gradient of the upstream layer costs no extra pass over C."""
     A, lda = _rows(A)
     Bm, ldb = _rows(Bm)
     K, N = Bm.shape
@@ -63,9 +67,14 @@ def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_s
     if (GEMM_ENGINE == "tc" and a_rows is None and M >= TC_MIN_ROWS and K > 0
             and lib().ercg_gemm_nn_tc_supported(_p(A), lda, _p(C), ldc, M, N, K)):
         ws = _ws(lib().ercg_gemm_nn_tc_workspace_bytes(N, K), A.device)
+        cs = None
+        if want_colsum and N <= 128 and bias is None and act == ACT_NONE and out is None:
+            cs = torch.empty(N, dtype=torch.float32, device=A.device)
         check(lib().ercg_gemm_nn_tc(_p(A), lda, _p(Bm), ldb, _p(bias), _p(C), ldc, M, N, K, act, _p(aux), ldaux,
-                                    float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _p(ws), ws.numel(), _stream()),
-              "ercg_gemm_nn_tc")
+                                    float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _p(cs), _p(ws), ws.numel(),
+                                    _stream()), "ercg_gemm_nn_tc")
+        if cs is not None:
+            C._ercg_colsum = cs
         return C
     check(lib().ercg_gemm_nn(_p(A), lda, _p(a_rows), _p(Bm), ldb, _p(bias), _p(C), C.stride(0) if M > 1 else N, M, N, K,
                              act, _p(aux), ldaux, float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _stream()),
@@ -95,6 +104,9 @@ def gemm_tn(A, Bm, a_rows=None, M=None):
 
 
 def colsum(A):
+    pre = getattr(A, "_ercg_colsum", None)       # column sums emitted by the kernel that produced A (see _Attn.backward)
+    if pre is not None and pre.numel() == A.size(1):
+        return pre
     A, lda = _rows(A)
     M, N = A.shape
     out = torch.empty(N, dtype=torch.float32, device=A.device)
@@ -127,7 +139,7 @@ class _LinearAct(torch.autograd.Function):
         dA = dB = dbias = None
         if ctx.needs_input_grad[0]:
             assert ctx.a_rows is None, "input gradient through a row gather is not needed by any reference path"
-            dA = gemm_nn(dZ, Bm.t().contiguous())
+            dA = gemm_nn(dZ, Bm.t().contiguous(), want_colsum=True)
         if ctx.needs_input_grad[1]:
             dB = gemm_tn(A, dZ, a_rows=ctx.a_rows, M=dZ.size(0))
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -236,13 +248,19 @@ class _Attn(torch.autograd.Function):
         dsig = torch.empty(g.E, dtype=torch.float32, device=dout.device)
         b, db = qkvs.data_ptr(), d.data_ptr()
         if win is not None:
+            tiles = int(lib().ercg_attn_window_tiles(N))
+            part = torch.empty((2, tiles, 2 * H), dtype=torch.float32, device=dout.device)   # per-CTA column sums
             check(lib().ercg_attn_window_bwd_dst(_p(dout), ldo, b + 4 * H, b + 8 * H, ld, _p(g.rowptr), _p(g.col), _p(alpha),
-                                                 scale, db, db + 12 * H, 4 * H, _p(dsig), N, H, win[0], win[1], _stream()),
-                  "ercg_attn_window_bwd_dst")
+                                                 scale, db, db + 12 * H, 4 * H, _p(dsig), _p(part[0]), N, H, win[0], win[1],
+                                                 _stream()), "ercg_attn_window_bwd_dst")
             # out-neighbours of node j: [j - wp, j + wf]
             check(lib().ercg_attn_window_bwd_src(_p(dout), ldo, b, ld, _p(g.t_rowptr), _p(g.t_col), _p(g.t_eid), _p(alpha),
-                                                 _p(dsig), scale, db + 4 * H, db + 8 * H, 4 * H, N, H, win[1], win[0],
-                                                 _stream()), "ercg_attn_window_bwd_src")
+                                                 _p(dsig), scale, db + 4 * H, db + 8 * H, 4 * H, _p(part[1]), N, H, win[1],
+                                                 win[0], _stream()), "ercg_attn_window_bwd_src")
+            # bias gradient of the fused q|k|v|skip Linear = column sums of d: finished from the per-CTA partials and handed
+            # to the consumer (ops.colsum) on the tensor itself, so the 4H-wide gradient is not read a second time
+            cs_dst, cs_src = colsum(part[0]), colsum(part[1])                               # (dq | ds), (dk | dv)
+            d._ercg_colsum = torch.cat([cs_dst[:H], cs_src, cs_dst[H:]])
             return d, None, None, None
         check(lib().ercg_attn_bwd_dst(_p(dout), ldo, b + 4 * H, b + 8 * H, ld, _p(g.rowptr), _p(g.col), _p(alpha), scale,
                                       db, db + 12 * H, 4 * H, _p(dsig), N, H, _stream()), "ercg_attn_bwd_dst")

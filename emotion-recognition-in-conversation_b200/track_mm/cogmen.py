@@ -93,7 +93,7 @@ class COGMENModule(nn.Module):
         return ops.linear(h, lin3.weight, lin3.bias)
 
     def _graph_forward(self, features, g):
-        g.edge_index._ercg_graph = g
+        g.attach()
         graph_out = self.gcn(features, g.edge_index, g.edge_type)
         return self._classify(graph_out), features
 

@@ -29,5 +29,5 @@ def batch_graphify(features, lengths, speaker_tensor, wp, wf, edge_type_to_idx):
     n_speakers = speakers_from_edge_dict(edge_type_to_idx)
     g = build_graph(lengths, speaker_tensor, wp, wf, n_speakers, device=features.device)
     node_features = ops.pack_rows(features, g)
-    g.edge_index._ercg_graph = g
+    g.attach()
     return node_features, g.edge_index, g.edge_type, g.edge_index_lengths

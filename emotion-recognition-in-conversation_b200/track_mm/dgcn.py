@@ -30,7 +30,7 @@ class DGCNModule(nn.Module):
                         mean_weight=False)
         features = self.rnn.packed_forward(input_tensor.reshape(B * Lmax, D), g, a_rows=g.pad_row)
         edge_norm = self.edge_att.edge_weights(features, g)
-        g.edge_index._ercg_graph = g
+        g.attach()
         graph_out = self.gcn(features, g.edge_index, edge_norm, g.edge_type)
         logits = self.clf(torch.cat([features, graph_out], dim=-1), text_length)
         return logits, graph_out

@@ -107,7 +107,7 @@ def batch_graphify(features, lengths, speaker_tensor, wp, wf, edge_type_to_idx, 
     g = build_graph(lengths, speaker_tensor, wp, wf, n_speakers, device=features.device, mean_weight=False)
     node_features = ops.pack_rows(features, g)
     edge_norm = att_model.edge_weights(node_features, g)
-    g.edge_index._ercg_graph = g
+    g.attach()
     return node_features, g.edge_index, edge_norm, g.edge_type, g.edge_index_lengths
 
 

@@ -126,8 +126,11 @@ size_t ercg_gemm_nn_tc_workspace_bytes(int N, int K);
 int ercg_gemm_nn_tc_supported(const float* A, int64_t lda, const float* C, int64_t ldc, int64_t M, int N, int K);
 int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                     int64_t ldc, int64_t M, int N, int K, int act, const float* aux, int64_t ldaux,
-                    float aux_scale, float drop_p, uint64_t seed, void* workspace, size_t workspace_bytes,
-                    void* stream);
+                    float aux_scale, float drop_p, uint64_t seed, float* colsum_out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* colsum_out (optional, [N]; needs N <= 128, bias == NULL, act == ERCG_ACT_NONE): also returns the column sums of C,
+ * reduced from the tiles while they sit in shared memory -- the bias gradient of the layer that produced A's operand
+ * (the input gradient dX = dZ @ W^T of one Linear is the dZ whose column sums the previous Linear needs). */
 
 /* C[K1,N1] = A[M,K1]^T @ B[M,N1]  (weight gradients; contraction over the M utterance rows, split
  * across CTAs into fixed slabs and reduced in a fixed order => bit-reproducible). */
@@ -151,6 +154,7 @@ int ercg_mask_pos(const float* x, int64_t ldx, const float* ref, int64_t ldr, fl
 size_t ercg_colsum_workspace_bytes(int64_t M, int N);
 int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float* out,
                 void* workspace, size_t workspace_bytes, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * K3  deterministic warp-segmented gather-reduce over the CSR (no atomics).
@@ -196,18 +200,23 @@ int ercg_attn_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld
 /* Window-graph variants of K4: same results, for graphs whose neighbourhoods are contiguous row ranges -- every graph
  * ercg_graphify_csr builds: the in-neighbours of node i lie in [i - wlo, i + whi] (wlo = wf, whi = wp of batch_graphify),
  * its out-neighbours in [i - wp, i + wf].  A CTA stages the rows around its 32 nodes in shared memory; a neighbour outside
- * the promised range traps.  Supported: H <= 128, H % 4 == 0, 0 <= wlo, whi, wlo + whi + 1 <= 32. */
+ * the promised range traps.  Supported: H <= 128, H % 4 == 0, 0 <= wlo, whi, wlo + whi + 1 <= 32.
+ * colsum_partial (optional, [ercg_attn_window_tiles(N)][2H]): per-CTA column sums of the two outputs (dq | ds, resp.
+ * dk | dv), i.e. the bias gradients of the q/k/v/skip Linears (cogmen.py:66) once ercg_colsum has added the tiles up
+ * (the partials are a [tiles, 2H] matrix, 1/16 of the gradient) -- the [N,4H] gradient is never re-read for them. */
 int ercg_attn_window_supported(int H, int wlo, int whi);
+int64_t ercg_attn_window_tiles(int64_t N);
 int ercg_attn_window_fwd(const float* q, const float* k, const float* v, const float* s, int64_t ld,
                          const int32_t* rowptr, const int32_t* col, float scale, float* out, int64_t ldo, float* alpha,
                          int64_t N, int H, int wlo, int whi, void* stream);
 int ercg_attn_window_bwd_dst(const float* dout, int64_t ldo, const float* k, const float* v, int64_t ld,
                              const int32_t* rowptr, const int32_t* col, const float* alpha, float scale, float* dq,
-                             float* ds, int64_t ldd, float* dsig, int64_t N, int H, int wlo, int whi, void* stream);
+                             float* ds, int64_t ldd, float* dsig, float* colsum_partial, int64_t N, int H, int wlo,
+                             int whi, void* stream);
 int ercg_attn_window_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld, const int32_t* t_rowptr,
                              const int32_t* t_col, const int32_t* t_eid, const float* alpha, const float* dsig,
-                             float scale, float* dk, float* dv, int64_t ldd, int64_t N, int H, int wlo, int whi,
-                             void* stream);
+                             float scale, float* dk, float* dv, int64_t ldd, float* colsum_partial, int64_t N, int H,
+                             int wlo, int whi, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  EdgeAtt of DialogueGCN (dgcn_models.py:121-152): per-SOURCE window softmax

@@ -24,7 +24,7 @@ def timeit(fn, iters=10):
 
 
 print("NN: C[M,N] = A[M,K] @ B[K,N]")
-for K, N in [(1443, 100), (100, 900), (100, 400), (900, 100), (400, 100), (100, 100)]:
+for K, N in [(1443, 100), (100, 300), (100, 400), (300, 100), (400, 100), (100, 100)]:
     ld = (K + 3) // 4 * 4
     A = torch.randn(M, ld, device=dev)[:, :K]
     B = torch.randn(K, N, device=dev)
@@ -34,7 +34,7 @@ for K, N in [(1443, 100), (100, 900), (100, 400), (900, 100), (400, 100), (100, 
     print("  K=%4d N=%4d  %.3f ms  %.0f GB/s  %.1f%% of HBM peak" % (K, N, ms, gb / ms * 1e3, 100 * gb / ms * 1e3 / PEAK))
     del A, B, C
 print("TN: C[K1,N1] = A[M,K1]^T @ B[M,N1]")
-for K1, N1 in [(1443, 100), (100, 900), (100, 400), (100, 100)]:
+for K1, N1 in [(1443, 100), (100, 300), (100, 400), (100, 100)]:
     ld = (K1 + 3) // 4 * 4
     A = torch.randn(M, ld, device=dev)[:, :K1]
     B = torch.randn(M, N1, device=dev)

@@ -22,7 +22,7 @@ def _declared():
     src = re.sub(r"//[^\n]*", " ", src)
     src = re.sub(r"typedef\s+struct[^{]*\{.*?\}\s*\w+\s*;", " ", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|size_t|const\s+char\s*\*|unsigned\s+long\s+long)\s+(ercg_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(?:int|int64_t|size_t|const\s+char\s*\*|unsigned\s+long\s+long)\s+(ercg_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
     return out

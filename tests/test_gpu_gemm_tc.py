@@ -110,3 +110,29 @@ def test_tc_gemm_race_stress(M, K, N):
     assert rel_err(outs[0], want) < TOL
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 100, 100), (1000, 300, 100), (33000, 400, 100), (2049, 100, 36), (70000, 900, 128)])
+def test_tc_gemm_fused_column_sums(M, K, N):
+    """want_colsum: the epilogue reduces the column sums of the product from the staged tiles (bias gradient of the
+    upstream layer).  Must equal the fp64 column sums of the fp64 product at the same 1e-5 bound, and ops.colsum must
+    pick them up from the tensor instead of launching its own reduction."""
+    g = torch.Generator().manual_seed(M * 3 + K + N)
+    A, B = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g)
+    want = (A.double() @ B.double()).sum(0)
+
+    def run(ops):
+        from erc_b200 import _lib
+        C = ops.gemm_nn(A.cuda(), B.cuda(), want_colsum=True)
+        assert getattr(C, "_ercg_colsum", None) is not None
+        n0 = _lib.launch_count()
+        cs = ops.colsum(C)
+        assert _lib.launch_count() == n0            # served from the fused result, no kernel
+        plain = ops.gemm_nn(A.cuda(), B.cuda())
+        return C, plain, cs, ops.colsum(plain)
+
+    C, plain, cs, cs_plain = _tc(run)
+    assert torch.equal(C, plain)                    # the product itself is untouched
+    scale = float((A.double().abs() @ B.double().abs()).sum(0).max())
+    assert float((cs.cpu().double() - want).abs().max()) < TOL * scale
+    assert rel_err(cs, cs_plain) < 1e-6
