@@ -33,6 +33,16 @@ N_CLASSES = 6
 WORKLOAD = "cogmen-train-step mosei-emo-sbert-fbank-6 shape (hidden_all=1443, 1 speaker id, window 5/5), ~2^20 utterances per GPU per step, whole dialogues sharded over the GPUs"
 
 
+def measured_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of
+    this workload: profiles/traffic.json {kernel label: {"bytes": ..., "utterances": ...}}."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -274,13 +284,13 @@ def run_ours(args):
     if sampler:
         sampler.start()
     import gc
-    step(x, spk, labels)                                 # first step: lazy initialisation, allocator growth
+    loss = step(x, spk, labels)                          # first step: lazy initialisation, allocator growth
     gc.collect()
     gc.freeze()                                         # a gen-2 collection inside a 15 ms step shows up as a 30 ms step;
     gc.disable()                                        # frozen BEFORE the warm-up so the caching allocator settles after it
     for _ in range(max(args.warmup, 3)):
-        step(x, spk, labels)
-    barrier()
+        loss = step(x, spk, labels)                      # (keeps the previous step's loss alive exactly like the timed loop:
+    barrier()                                           #  same allocation pattern => no cudaMalloc inside the timed region)
     if args.profile_step:
         # ncu --profile-from-start off: exactly ONE warm step between cudaProfilerStart/Stop, no timing, no JSON value
         torch.cuda.profiler.start()
@@ -298,7 +308,7 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with _lib.KernelTimer(labeler=kernel_label):        # one more warm step WITH the event bracketing active (event pool)
-        step(x, spk, labels)
+        loss = step(x, spk, labels)
     barrier()
     launches0 = _lib.launch_count()
     mem_before = torch.cuda.memory_stats(dev)
@@ -374,7 +384,7 @@ def run_ours(args):
         E = sizes[1]
         per = {k: (c, tot / c) for k, (c, tot) in ksum.items()}          # kernel label -> (calls, avg ms)
         step_kernel_ms = sum(tot for _, tot in ksum.values()) / args.steps
-        H, P = 100, 2          # row width; distinct (source, relation) slots referenced per source (1 speaker id -> 2)
+        H, P = 100, 2          # row width; relation ids that occur (1 speaker id -> 2 of 8): Y / dY hold P + 1 slots
 
         def alg_bytes(label):
             """Algorithmic (unique) HBM bytes of ONE launch on this rank (weights ignored)."""
@@ -383,7 +393,7 @@ def run_ours(args):
                 return 4 * N * (a + b)
             return {
                 "gather_fwd": 4 * H * P * N + 4 * H * N + 4 * H * N + 4 * (N + 1) + 9 * E,
-                "gather_bwd": 4 * H * N + 4 * H * 9 * N + 4 * (N + 1) + 13 * E,
+                "gather_bwd": 4 * H * N + 4 * H * (P + 1) * N + 4 * (N + 1) + 13 * E,
                 "attn_fwd": 5 * 4 * H * N + 4 * (N + 1) + 8 * E,
                 "attn_bwd_dst": 5 * 4 * H * N + 4 * (N + 1) + 12 * E,
                 "attn_bwd_src": 4 * 4 * H * N + 4 * (N + 1) + 16 * E,
@@ -403,8 +413,13 @@ def run_ours(args):
         dom_label = max(ksum.items(), key=lambda kv: kv[1][1])[0]
         dom_calls, dom_ms = per[dom_label]
         dom_bytes = alg_bytes(dom_label) or 0
+        tr = measured_traffic().get(dom_label)
+        traffic = None
+        if tr and tr.get("utterances"):
+            traffic = int(tr["bytes"] * (N / float(tr["utterances"])))      # ncu capture, scaled to this rank's utterance count
         roof = {"bound": "hbm", "kernel": dom_label, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "traffic_source": (tr or {}).get("source"), "peak_source": peak_src,
                 "avg_launch_ms": dom_ms, "launches_timed": dom_calls, "algorithmic_bytes_per_launch": dom_bytes}
         graph_kernels = {k: kernels[k] for k in ("gather_fwd", "gather_bwd", "attn_fwd", "attn_bwd_dst", "attn_bwd_src",
                                                  "graphify_csr") if k in kernels}

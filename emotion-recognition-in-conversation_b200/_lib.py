@@ -49,6 +49,7 @@ SIGNATURES = {
     "ercg_gemm_nn_tc_workspace_bytes": (SZ, [I, I]),
     "ercg_gemm_nn_tc_supported": (I, [P, L, P, L, L, I, I]),
     "ercg_gemm_nn_tc": (I, [P, L, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, P, SZ, P]),
+    "ercg_gemm_nn_tc_trace": (I, [P]),
     "ercg_gemm_tn_workspace_bytes": (SZ, [L, I, I]),
     "ercg_gemm_tn": (I, [P, L, P, P, L, P, L, L, I, I, P, SZ, P]),
     "ercg_gemm_tn_tc_workspace_bytes": (SZ, [L, I, I]),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "ercg_colsum": (I, [P, L, L, I, P, P, SZ, P]),
     "ercg_gather_fwd": (I, [P, L, P, P, P, P, P, I, P, P, L, L, I, P]),
     "ercg_gather_bwd": (I, [P, L, P, L, P, P, P, P, P, P, I, I, P, L, P, L, I, P]),
+    "ercg_gather_window_bwd": (I, [P, L, P, P, P, P, P, P, I, I, P, L, L, I, I, I, P]),
     "ercg_attn_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, L, I, P]),
     "ercg_attn_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, L, I, P]),
     "ercg_attn_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, L, I, P]),

@@ -202,6 +202,75 @@ gather_bwd_kernel(const float* __restrict__ dout, long long ldo, const float* __
   }
 }
 
+// ---------------------------------------------------------------------------------- K3 backward on WINDOW graphs: CTA tiles
+// For the graphs K1 builds, the destinations of source j are the contiguous rows [j - wlo, j + whi] (wlo = wp, whi = wf of
+// batch_graphify).  A CTA owns 32 consecutive sources and stages the 32 + wlo + whi rows of dout around them in shared
+// memory with cp.async (every row is needed by up to wlo + whi + 1 sources); edge metadata is fetched lane-per-edge while
+// the copies are in flight.  Per relation slot a ballot selects the edges, rows come from shared memory.  Same summation
+// order as gather_bwd_kernel (ascending by-source edge order inside a slot) => bit-identical results.
+constexpr int GT_TILE = 32;
+
+__global__ void __launch_bounds__(256)
+gather_bwd_tile_kernel(const float* __restrict__ dout, long long ldo, const int* __restrict__ t_rowptr,
+                       const int* __restrict__ t_col, const uint8_t* __restrict__ t_etype, const int* __restrict__ t_eid,
+                       const int* __restrict__ rel_slot, const float* __restrict__ w, int n_slots, int root_off,
+                       float* __restrict__ dY, long long lddy, long long N, int H, int wlo, int whi) {
+  extern __shared__ float4 gt_sm[];
+  const int nch = H >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t0 = (long long)blockIdx.x * GT_TILE;
+  const int tn = (int)min((long long)GT_TILE, N - t0);
+  const long long r0 = max(0LL, t0 - wlo), r1 = min(N, t0 + tn + whi);
+  const int R = (int)(r1 - r0);
+  if (lane < nch)
+    for (int r = warp; r < R; r += 8) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(gt_sm + r * nch + lane);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(dout + (r0 + r) * ldo + 4 * lane) : "memory");
+    }
+  constexpr int NPW = GT_TILE / 8;
+  int degs[NPW], rows[NPW], slots[NPW];
+  float ws[NPW];
+#pragma unroll
+  for (int p = 0; p < NPW; ++p) {
+    const int nl = warp * NPW + p;
+    const bool nok = nl < tn;
+    const int beg = nok ? t_rowptr[t0 + nl] : 0;
+    degs[p] = nok ? t_rowptr[t0 + nl + 1] - beg : 0;
+    rows[p] = 0;
+    slots[p] = -1;
+    ws[p] = 0.f;
+    if (lane < degs[p]) {
+      const long long dst = t_col[beg + lane];
+      if (dst < r0 || dst >= r1) __trap();               // the caller promised a window graph
+      rows[p] = (int)(dst - r0);
+      int t = t_etype ? (int)t_etype[beg + lane] : 0;
+      if (rel_slot) t = __ldg(rel_slot + t);
+      slots[p] = t;
+      ws[p] = w ? w[t_eid[beg + lane]] : 1.f;
+    }
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < NPW; ++p) {
+    const int nl = warp * NPW + p;
+    if (nl >= tn) break;                                   // warp-uniform
+    const long long node = t0 + nl;
+    for (int sidx = 0; sidx < n_slots; ++sidx) {
+      unsigned m = __ballot_sync(0xffffffffu, slots[p] == sidx);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const float wu = __shfl_sync(0xffffffffu, ws[p], l);
+        const int rw = __shfl_sync(0xffffffffu, rows[p], l);
+        if (lane < nch) fma4(acc, wu, gt_sm[rw * nch + lane]);
+      }
+      if (lane < nch) st4_stream(dY + node * lddy + (long long)sidx * H + 4 * lane, acc);
+    }
+    if (root_off >= 0 && lane < nch) st4_stream(dY + node * lddy + root_off + 4 * lane, gt_sm[(int)(node - r0) * nch + lane]);
+  }
+}
+
 static int check_rows(const void* p, long long ld, int H) {
   if ((H & 3) || H <= 0 || H > 128 * MAXC) return ERCG_EINVAL;
   if ((ld & 3) || !aligned16(p)) return ERCG_EALIGN;
@@ -249,5 +318,26 @@ extern "C" int ercg_gather_bwd(const float* dout, int64_t ldo, const float* Y, i
   cudaStream_t st = (cudaStream_t)stream;
   if (H <= 128) gather_bwd_kernel<1><<<blocks, GW * 32, 0, st>>>(dout, ldo, Y, ldy, t_rowptr, t_col, t_etype, t_eid, t_etype ? rel_slot : nullptr, w, R, root_off, dY, lddy, dw, N, H);
   else gather_bwd_kernel<2><<<blocks, GW * 32, 0, st>>>(dout, ldo, Y, ldy, t_rowptr, t_col, t_etype, t_eid, t_etype ? rel_slot : nullptr, w, R, root_off, dY, lddy, dw, N, H);
+  return finish_launch();
+}
+
+// window-graph variant of ercg_gather_bwd without the per-edge weight gradient (contract as for ercg_attn_window_*)
+extern "C" int ercg_gather_window_bwd(const float* dout, int64_t ldo, const int32_t* t_rowptr, const int32_t* t_col,
+                                      const uint8_t* t_etype, const int32_t* t_eid, const int32_t* rel_slot,
+                                      const float* w, int n_slots, int root_off, float* dY, int64_t lddy, int64_t N,
+                                      int H, int wlo, int whi, void* stream) {
+  if (N < 0 || n_slots < 1 || H > 128 || wlo < 0 || whi < 0 || wlo + whi + 1 > 32) return ERCG_EINVAL;
+  if (N == 0) return ERCG_OK;
+  if (!dout || !t_rowptr || !t_col || !dY || (w && !t_eid)) return ERCG_EINVAL;
+  int rc = check_rows(dout, ldo, H);
+  if (rc) return rc;
+  rc = check_rows(dY, lddy, H);
+  if (rc) return rc;
+  if (root_off >= 0 && (root_off & 3)) return ERCG_EALIGN;
+  const size_t sm = (size_t)(H >> 2) * 16 * (GT_TILE + wlo + whi);
+  const unsigned blocks = (unsigned)((N + GT_TILE - 1) / GT_TILE);
+  gather_bwd_tile_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(dout, ldo, t_rowptr, t_col, t_etype, t_eid,
+                                                                     t_etype ? rel_slot : nullptr, w, n_slots, root_off, dY,
+                                                                     lddy, N, H, wlo, whi);
   return finish_launch();
 }

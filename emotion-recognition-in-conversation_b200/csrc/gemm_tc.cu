@@ -42,7 +42,14 @@ constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;      // 16 KB
 struct TcEpilogue {
   const float* bias; int act; const float* aux; long long ldaux; float aux_scale; float drop_p; unsigned long long seed;
   int dbg;   // ERCG_TC_DBG: performance experiments only (1 no MMA, 8 no B loads)
+  long long* trace;   // ERCG_TC_TRACE: CTA 0 records clock64() per role and k-chunk (pipeline timeline, diagnostics only)
 };
+constexpr int TR_N = 160;          // traced chunks
+constexpr int TR_ROLES = 5;        // 0 A producer, 1 splitter, 2 MMA, 3 epilogue (per group), 4 B producer
+#define TC_TRACE(role, idx, slot)                                                                   \
+  do {                                                                                              \
+    if (ep.trace && blockIdx.x == 0 && (idx) < TR_N) ep.trace[((role) * TR_N + (idx)) * 4 + (slot)] = clock64(); \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -308,7 +315,9 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int rep = 0; rep < a_reps; ++rep)
           for (int kc = 0; kc < k_chunks; ++kc, ++n) {
             const int r = n % TC_R;
+            TC_TRACE(0, n, 0);
             mbar_wait_relaxed(BAR(BAR_R_FREE + r), ((n / TC_R) & 1) ^ 1);
+            TC_TRACE(0, n, 1);
             mbar_expect_tx(BAR(BAR_A_FULL + r), TC_A_BYTES);
             tma_load_2d(raw_base + r * TC_A_BYTES, &tmA, kc * TC_BK, m0, BAR(BAR_A_FULL + r));
           }
@@ -323,7 +332,9 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int nt = 0; nt < n_tiles; ++nt)
           for (int kc = 0; kc < k_chunks; ++kc, ++n) {
             const int q = n % TC_Q;
+            TC_TRACE(4, n, 0);
             mbar_wait_relaxed(BAR(BAR_Q_FREE + q), ((n / TC_Q) & 1) ^ 1);
+            TC_TRACE(4, n, 1);
             if (ep.dbg & 8) { mbar_arrive(BAR(BAR_B_FULL + q)); continue; }
             mbar_expect_tx(BAR(BAR_B_FULL + q), tx);
             tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
@@ -345,11 +356,15 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kc = 0; kc < k_chunks; ++kc, ++nb_) {
           const int in_group = kc % TC_GROUP;
           const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
+          if (lane == 0) TC_TRACE(2, nb_, 0);
           if (in_group == 0) mbar_wait(BAR(BAR_ACC_EMPTY + a), aph ^ 1);   // epilogue has drained this accumulator stage
+          if (lane == 0) TC_TRACE(2, nb_, 1);
           const uint32_t an = a_base + (resident ? 0 : nt * k_chunks) + kc;
           const int s = an % TC_TA, q = nb_ % TC_Q;
           mbar_wait(BAR(BAR_TA_FULL + s), (an / TC_TA) & 1);        // A_hi / A_lo of this chunk are in TMEM
+          if (lane == 0) TC_TRACE(2, nb_, 2);
           mbar_wait(BAR(BAR_B_FULL + q), (nb_ / TC_Q) & 1);         // B tiles landed
+          if (lane == 0) TC_TRACE(2, nb_, 3);
           tc_fence_after();
           // k-steps of 8 that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 steps, not 16)
           const int ks_n = (ep.dbg & 1) ? 0 : min(TC_BK / 8, (K - kc * TC_BK + 7) >> 3);
@@ -387,7 +402,9 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int rep = 0; rep < a_reps; ++rep)
         for (int kc = 0; kc < k_chunks; ++kc, ++n) {
           const int r = n % TC_R, s = n % TC_TA;
+          if (threadIdx.x == 0) TC_TRACE(1, n, 0);
           mbar_wait(BAR(BAR_A_FULL + r), (n / TC_R) & 1);          // raw tile landed
+          if (threadIdx.x == 0) TC_TRACE(1, n, 1);
           const uint32_t src = raw_base + r * TC_A_BYTES + row * 128;
           uint32_t hi[32], lo[32];
 #pragma unroll
@@ -399,6 +416,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             split_tf32(x.w, hi[4 * c + 3], lo[4 * c + 3]);
           }
           mbar_wait(BAR(BAR_TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
+          if (threadIdx.x == 0) TC_TRACE(1, n, 2);
           tc_fence_after();
           tc_st32(TA_HI(s) + lane_addr, hi);
           tc_st32(TA_HI(s) + 32 + lane_addr, lo);
@@ -410,6 +428,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_arrive(BAR(BAR_R_FREE + r));
           tc_fence_before();
           mbar_arrive(BAR(BAR_TA_FULL + s));
+          if (threadIdx.x == 0) TC_TRACE(1, n, 3);
         }
     }
   } else if (warp < 8) {
@@ -466,7 +485,9 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         } else {
           float acc[TC_BN];
           for (int g = 0; g < n_groups; ++g) {
+            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - blockIdx.x) / gridDim.x) * n_groups + g, 0);
             mbar_wait(BAR(BAR_ACC_FULL + a), aph);
+            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - blockIdx.x) / gridDim.x) * n_groups + g, 1);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < TC_BN; c += 32) {
@@ -485,6 +506,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tc_fence_before();
             mbar_arrive(BAR(BAR_ACC_EMPTY + a));
+            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - blockIdx.x) / gridDim.x) * n_groups + g, 2);
             if (++a == 2) { a = 0; aph ^= 1; }
           }
           if (lane == 0) tma_store_wait_read();
@@ -905,6 +927,8 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
 
 using namespace ercg;
 
+static long long* trace_buf = nullptr;      // ERCG_TC_TRACE=1: device buffer of the pipeline timeline (diagnostics only)
+
 extern "C" size_t ercg_gemm_nn_tc_workspace_bytes(int N, int K) {
   if (N <= 0 || K <= 0) return 0;
   const size_t Kp = (size_t)(K + 3) / 4 * 4;
@@ -970,7 +994,14 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("ERCG_TC_DBG"); dbg = e ? atoi(e) : 0; }
-  TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg};
+  static int trace_on = -1;
+  if (trace_on < 0) {
+    const char* e = getenv("ERCG_TC_TRACE");
+    trace_on = e ? atoi(e) : 0;
+    if (trace_on && cudaMalloc(&trace_buf, sizeof(long long) * TR_ROLES * TR_N * 4) != cudaSuccess) trace_buf = nullptr;
+  }
+  if (trace_buf) cudaMemsetAsync(trace_buf, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
+  TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg, trace_buf};
   const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;       // the whole K extent is one TMEM accumulation group
   float* partial = colsum_out ? blo + (size_t)N * Kp : nullptr;     // [grid][4][128], after the two B copies
   kernels[act][smallk]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep, partial);
@@ -980,6 +1011,13 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
     tc_colsum_final_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial, grid * 4, 128, N, colsum_out);
   }
   return finish_launch();
+}
+
+// diagnostics: copy out the pipeline timeline CTA 0 recorded during the last ercg_gemm_nn_tc launch (ERCG_TC_TRACE=1)
+extern "C" int ercg_gemm_nn_tc_trace(long long* host_out /* [5][160][4] clock64 values, 0 = not recorded */) {
+  if (!host_out || !trace_buf) return ERCG_EINVAL;
+  return cudaMemcpy(host_out, trace_buf, sizeof(long long) * TR_ROLES * TR_N * 4, cudaMemcpyDeviceToHost) == cudaSuccess
+             ? ERCG_OK : ERCG_ECUDA;
 }
 
 extern "C" size_t ercg_gemm_tn_tc_workspace_bytes(int64_t M, int K1, int N1) {

@@ -175,6 +175,8 @@ class _Gather(torch.autograd.Function):
         Y, ldy = _rows(Y)
         N = Y.size(0)
         out = torch.empty((N, H), dtype=torch.float32, device=Y.device)
+        # (a CTA-tiled forward that stages all relation slots of the window in shared memory was measured SLOWER than this
+        # warp-per-node kernel -- 0.59 vs 0.55 ms at 2^20 nodes: 1200-byte rows make the tile 50 KB -- and was dropped)
         check(lib().ercg_gather_fwd(_p(Y), ldy, _p(graph.rowptr), _p(graph.col), _p(graph.etype) if use_types else None,
                                     _p(rel_slot), _p(w), root_off, _p(bias), _p(out), H, N, H, _stream()), "ercg_gather_fwd")
         ctx.graph, ctx.H, ctx.R, ctx.root_off, ctx.use_types, ctx.rel_slot = graph, H, R, root_off, use_types, rel_slot
@@ -193,6 +195,15 @@ class _Gather(torch.autograd.Function):
         dY = torch.empty((N, ctx.ycols), dtype=torch.float32, device=dout.device)
         dw = torch.empty(g.E, dtype=torch.float32, device=dout.device) if ctx.w_grad else None
         ldy = Y.stride(0) if Y is not None else 0
+        win = _window(g, H) if dw is None else None
+        if win is not None:          # K1 window graph, no edge-weight gradient: CTA-tiled kernel (out-neighbours [j-wp, j+wf])
+            n_slots = (ctx.ycols - (H if ctx.root_off >= 0 else 0)) // H
+            check(lib().ercg_gather_window_bwd(_p(dout), ldo, _p(g.t_rowptr), _p(g.t_col),
+                                               _p(g.t_etype) if ctx.use_types else None, _p(g.t_eid), _p(ctx.rel_slot), _p(w),
+                                               n_slots, ctx.root_off, _p(dY), ctx.ycols, N, H, win[1], win[0], _stream()),
+                  "ercg_gather_window_bwd")
+            dbias = colsum(dout) if ctx.has_bias else None
+            return dY, dw, dbias, None, None, None, None, None, None
         check(lib().ercg_gather_bwd(_p(dout), ldo, _p(Y), ldy, _p(g.t_rowptr), _p(g.t_col),
                                     _p(g.t_etype) if ctx.use_types else None, _p(g.t_eid), _p(ctx.rel_slot), _p(w), R,
                                     ctx.root_off, _p(dY), ctx.ycols, _p(dw), N, H, _stream()), "ercg_gather_bwd")

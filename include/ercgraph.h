@@ -132,6 +132,10 @@ int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, co
  * reduced from the tiles while they sit in shared memory -- the bias gradient of the layer that produced A's operand
  * (the input gradient dX = dZ @ W^T of one Linear is the dZ whose column sums the previous Linear needs). */
 
+/* Diagnostics (ERCG_TC_TRACE=1 in the environment): CTA 0 of ercg_gemm_nn_tc records clock64() per pipeline role and
+ * k-chunk; this copies the [5 roles][160 chunks][4 marks] table of the last launch to the host (synchronous). */
+int ercg_gemm_nn_tc_trace(long long* host_out);
+
 /* C[K1,N1] = A[M,K1]^T @ B[M,N1]  (weight gradients; contraction over the M utterance rows, split
  * across CTAs into fixed slabs and reduced in a fixed order => bit-reproducible). */
 size_t ercg_gemm_tn_workspace_bytes(int64_t M, int K1, int N1);
@@ -177,6 +181,14 @@ int ercg_gather_bwd(const float* dout, int64_t ldo, const float* Y, int64_t ldy,
                     const int32_t* t_rowptr, const int32_t* t_col, const uint8_t* t_etype,
                     const int32_t* t_eid, const int32_t* rel_slot, const float* w, int R, int root_off,
                     float* dY, int64_t lddy, float* dw, int64_t N, int H, void* stream);
+/* Backward on window graphs (every graph ercg_graphify_csr builds: the destinations of source j lie in [j - wlo, j + whi],
+ * wlo = wp, whi = wf of batch_graphify; same limits as ercg_attn_window_supported): a CTA stages the dout rows around its 32
+ * sources in shared memory.  n_slots = relation slots of dY (P with rel_slot, R without).  No dw (use ercg_gather_bwd when
+ * the edge weights need a gradient).  Bit-identical to ercg_gather_bwd. */
+int ercg_gather_window_bwd(const float* dout, int64_t ldo, const int32_t* t_rowptr, const int32_t* t_col,
+                           const uint8_t* t_etype, const int32_t* t_eid, const int32_t* rel_slot, const float* w,
+                           int n_slots, int root_off, float* dY, int64_t lddy, int64_t N, int H, int wlo, int whi,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  fused edge attention of PyG TransformerConv(heads=1) (cogmen.py:66,72): score, segment
