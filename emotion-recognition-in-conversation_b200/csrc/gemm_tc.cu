@@ -28,6 +28,7 @@
 // hanging the GPU.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace ercg {
@@ -209,6 +210,20 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
+// 16-bit operands (bf16): A from tensor memory (two k-elements per 32-bit column), B from shared memory, K = 16
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+// {hi16 = bf16(b), lo16 = bf16(a)} -> element a sits at the EVEN k position (low half), round-to-nearest
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -338,7 +353,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (ep.dbg & 8) { mbar_arrive(BAR(BAR_B_FULL + q)); continue; }
             mbar_expect_tx(BAR(BAR_B_FULL + q), tx);
             tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
-            tma_load_2d(B_LO(q), &tmBl, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
+            tma_load_2d(B_LO(q), &tmBl, kc * 64, nt * bn, BAR(BAR_B_FULL + q));      // bf16(B_hi) | bf16(B_lo) of this chunk
           }
     }
   } else if (warp == 9) {
@@ -347,6 +362,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // (profiles/r01_*: inside an `if (lane == 0)` region every descriptor had to be moved vector -> uniform register
     // per instruction and the issue loop itself, ~150 clk per UTCHMMA, was the bottleneck of the kernel).
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // bf16 x bf16 -> f32
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
     uint32_t a_base = 0, nb_ = 0;     // A chunk loads before this M tile; B chunk loads so far
     int a = 0;
@@ -366,19 +382,23 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(BAR(BAR_B_FULL + q), (nb_ / TC_Q) & 1);         // B tiles landed
           if (lane == 0) TC_TRACE(2, nb_, 3);
           tc_fence_after();
-          // k-steps of 8 that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 steps, not 16)
-          const int ks_n = (ep.dbg & 1) ? 0 : min(TC_BK / 8, (K - kc * TC_BK + 7) >> 3);
+          // k-steps that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 tf32 steps of 8, not 16)
+          const int krem = K - kc * TC_BK;
+          const int ks_n = (ep.dbg & 1) ? 0 : min(TC_BK / 8, (krem + 7) >> 3);
+          const int k16_n = (ep.dbg & 1) ? 0 : min(TC_BK / 16, (krem + 15) >> 4);
           const uint32_t ah0 = TA_HI(s);
-          const uint64_t bh0 = desc_hi | (uint64_t)((B_HI(q) >> 4) & 0x3FFF), bl0 = desc_hi | (uint64_t)((B_LO(q) >> 4) & 0x3FFF);
+          const uint64_t bh0 = desc_hi | (uint64_t)((B_HI(q) >> 4) & 0x3FFF), b16 = desc_hi | (uint64_t)((B_LO(q) >> 4) & 0x3FFF);
           if (elect_one()) {
+            // A_hi * B_hi in tf32 (exact products); the two 2^-11-sized correction terms A_lo * B_hi + A_hi * B_lo in bf16
+            // at twice the rate: 4 + 4 instructions per 32-k chunk instead of 12 tf32 ones (see top of file)
 #pragma unroll
-            for (int ks = 0; ks < TC_BK / 8; ++ks) {
-              if (ks < ks_n) {
-                const uint32_t ah = ah0 + ks * 8, al = ah + 32;
-                const uint64_t bh = bh0 + (uint64_t)(ks * 2), bl = bl0 + (uint64_t)(ks * 2);   // +32 bytes per k-step
-                tc_mma_tf32_ts(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
-                tc_mma_tf32_ts(d_tmem, ah, bl, idesc, 1u);
-                tc_mma_tf32_ts(d_tmem, ah, bh, idesc, 1u);
+            for (int ks = 0; ks < TC_BK / 8; ++ks)
+              if (ks < ks_n) tc_mma_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 2), idesc, (in_group | ks) ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < TC_BK / 16; ++j) {
+              if (j < k16_n) {
+                tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);        // bf16(A_lo) * bf16(B_hi)
+                tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);    // bf16(A_hi) * bf16(B_lo)
               }
             }
             tc_commit(BAR(BAR_Q_FREE + q));
@@ -406,20 +426,25 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(BAR(BAR_A_FULL + r), (n / TC_R) & 1);          // raw tile landed
           if (threadIdx.x == 0) TC_TRACE(1, n, 1);
           const uint32_t src = raw_base + r * TC_A_BYTES + row * 128;
-          uint32_t hi[32], lo[32];
+          uint32_t hi[32], p16[32];                                // tf32 A_hi | bf16 pairs: [0,16) A_hi, [16,32) A_lo
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                            // logical 16-byte chunk c sits at position c ^ (row & 7)
             const float4 x = lds4(src + ((c ^ (row & 7)) << 4));
-            split_tf32(x.x, hi[4 * c + 0], lo[4 * c + 0]);
-            split_tf32(x.y, hi[4 * c + 1], lo[4 * c + 1]);
-            split_tf32(x.z, hi[4 * c + 2], lo[4 * c + 2]);
-            split_tf32(x.w, hi[4 * c + 3], lo[4 * c + 3]);
+            uint32_t l0, l1, l2, l3;
+            split_tf32(x.x, hi[4 * c + 0], l0);
+            split_tf32(x.y, hi[4 * c + 1], l1);
+            split_tf32(x.z, hi[4 * c + 2], l2);
+            split_tf32(x.w, hi[4 * c + 3], l3);
+            p16[2 * c + 0] = pack_bf16x2(__uint_as_float(hi[4 * c + 0]), __uint_as_float(hi[4 * c + 1]));
+            p16[2 * c + 1] = pack_bf16x2(__uint_as_float(hi[4 * c + 2]), __uint_as_float(hi[4 * c + 3]));
+            p16[16 + 2 * c + 0] = pack_bf16x2(__uint_as_float(l0), __uint_as_float(l1));
+            p16[16 + 2 * c + 1] = pack_bf16x2(__uint_as_float(l2), __uint_as_float(l3));
           }
           mbar_wait(BAR(BAR_TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
           if (threadIdx.x == 0) TC_TRACE(1, n, 2);
           tc_fence_after();
           tc_st32(TA_HI(s) + lane_addr, hi);
-          tc_st32(TA_HI(s) + 32 + lane_addr, lo);
+          tc_st32(TA_HI(s) + 32 + lane_addr, p16);
           tc_wait_st();
           // The raw stage is released only HERE: the TMEM stores above consume every loaded register, so the
           // shared-memory loads have returned.  (An arrive placed right after the loads was scheduled by ptxas before
@@ -851,9 +876,11 @@ static void tn_tc_plan(int64_t M, int K1, int N1, bool& swap, int& w_tiles, int&
   S = (int)((M + rps - 1) / rps);
 }
 
-// B[K,N] (row-major, ldb) -> Bt_hi, Bt_lo [N, Kp] (K-major, pitch Kp floats), tf32 split
-__global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int K, int N, int Kp, float* __restrict__ hi,
-                                float* __restrict__ lo) {
+// B[K,N] (row-major, ldb) -> Bt_hi [N, Kp] fp32 (K-major, tf32-rounded) and B16 [N, Kc, 64] bf16 (Kc = chunks of 32 k):
+// per chunk the 32 values bf16(B_hi) followed by the 32 values bf16(B - B_hi), i.e. one 128-byte row per (n, chunk) so that
+// a {64 x bn} TMA box lands as a 128-byte-swizzled K-major tile with the two bf16 operands side by side
+__global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int K, int N, int Kp, int Kc, float* __restrict__ hi,
+                                __nv_bfloat16* __restrict__ b16) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -863,11 +890,13 @@ __global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int 
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int n = n0 + i, k = k0 + threadIdx.x;
-    if (n < N && k < Kp) {
-      const float x = tile[threadIdx.x][i];
+    if (n < N) {
+      const float x = tile[threadIdx.x][i];                 // zero beyond K
       const float h = rn_tf32(x);
-      hi[(long long)n * Kp + k] = h;
-      lo[(long long)n * Kp + k] = rn_tf32(x - h);
+      if (k < Kp) hi[(long long)n * Kp + k] = h;
+      __nv_bfloat16* row = b16 + ((long long)n * Kc + blockIdx.x) * 64;
+      row[threadIdx.x] = __float2bfloat16_rn(h);
+      row[32 + threadIdx.x] = __float2bfloat16_rn(x - h);
     }
   }
 }
@@ -923,6 +952,19 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// bf16 [rows, Kc*64] (row pitch Kc*128 bytes); box {64 elements = 128 bytes, box_rows}; 128-byte swizzle
+static bool make_map_b16(CUtensorMap* map, const __nv_bfloat16* base, long long rows, long long kc, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)kc * 64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kc * 128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace ercg
 
 using namespace ercg;
@@ -931,8 +973,9 @@ static long long* trace_buf = nullptr;      // ERCG_TC_TRACE=1: device buffer of
 
 extern "C" size_t ercg_gemm_nn_tc_workspace_bytes(int N, int K) {
   if (N <= 0 || K <= 0) return 0;
-  const size_t Kp = (size_t)(K + 3) / 4 * 4;
-  return 2 * (size_t)N * Kp * sizeof(float) + 256 + (size_t)kNumSMs * 2 * 4 * 128 * sizeof(float) /* column-sum partials */;
+  const size_t Kp = (size_t)(K + 3) / 4 * 4, Kc = (size_t)(K + TC_BK - 1) / TC_BK;
+  return (size_t)N * Kp * sizeof(float) + (size_t)N * Kc * 128 /* bf16 pairs */ + 512 +
+         (size_t)kNumSMs * 2 * 4 * 128 * sizeof(float) /* column-sum partials */;
 }
 
 // returns 1 when this shape/alignment can run on the tensor-core path
@@ -958,16 +1001,18 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   if (workspace_bytes < ercg_gemm_nn_tc_workspace_bytes(N, K) || !workspace) return ERCG_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int Kp = (K + 3) / 4 * 4;
+  const int Kc = (K + TC_BK - 1) / TC_BK;
   float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-  float* blo = bhi + (size_t)N * Kp;
-  split_bt_kernel<<<dim3((Kp + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Kp, bhi, blo);
+  __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(
+      (reinterpret_cast<uintptr_t>(bhi + (size_t)N * Kp) + 255) & ~uintptr_t(255));
+  split_bt_kernel<<<dim3(Kc, (N + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Kp, Kc, bhi, b16);
   int rc = finish_launch();
   if (rc) return rc;
   // UMMA N: multiple of 16, <= 128, chosen to waste the fewest columns
   int bn = 128;
   if (N <= 128) bn = (N + 15) / 16 * 16;
   CUtensorMap tmA, tmBh, tmBl, tmC;
-  if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, bn) || !make_map(&tmBl, blo, N, K, Kp, bn) ||
+  if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, bn) || !make_map_b16(&tmBl, b16, N, Kc, bn) ||
       !make_map(&tmC, C, M, N, ldc, 32))                     // output: boxes of 32 rows x 32 columns (TMA bulk stores)
     return ERCG_ECUDA;
   typedef void (*NnKernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, float*, long long, long long, int, int, int,
@@ -1003,7 +1048,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   if (trace_buf) cudaMemsetAsync(trace_buf, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
   TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg, trace_buf};
   const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;       // the whole K extent is one TMEM accumulation group
-  float* partial = colsum_out ? blo + (size_t)N * Kp : nullptr;     // [grid][4][128], after the two B copies
+  float* partial = colsum_out ? reinterpret_cast<float*>(b16 + (size_t)N * Kc * 64) : nullptr;   // [grid][4][128], after the B copies
   kernels[act][smallk]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep, partial);
   if (colsum_out) {
     rc = finish_launch();
