@@ -238,7 +238,8 @@ def run_ours(args):
     torch.manual_seed(0)
     model = COGMENModule(HIDDEN, 100, 17, 2, N_CLASSES).to(dev)
     model.train()
-    optim = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8)
+    # cogmen.py:50 (Adam, lr 1e-4, wd 1e-8); fused=True = ATen's single-kernel multi-tensor Adam, same arithmetic
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8, fused=True)
     loss_sync = grad_sync = None
     if world > 1:
         model.gcn.stat_sync = StatSync(global_count=total_utts)

@@ -13,6 +13,7 @@
 // shared memory with register prefetch of the next K-slab.
 #include "common.cuh"
 #include "gemm_skinny.cuh"
+#include "col_stream.cuh"
 #include <algorithm>
 
 namespace ercg {
@@ -281,6 +282,26 @@ __global__ void reduce_splits_kernel(const float* __restrict__ P, long long spli
   C[(long long)r * ldc + c] = s;
 }
 
+// Same sum for MANY splits and few outputs (the skinny weight gradients: S ~ 600 slabs, K1*N1 ~ 600 outputs): 8 lanes per
+// output take the splits round-robin, then a fixed 3-step shuffle tree => still bit-reproducible, 8x shorter serial chain.
+__global__ void __launch_bounds__(256)
+reduce_splits_wide_kernel(const float* __restrict__ P, long long split_stride, int S, float* __restrict__ C, long long ldc,
+                          int rows, int cols) {
+  const int sub = threadIdx.x & 7;
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool ok = idx < (long long)rows * cols;
+  float s = 0.f;
+  if (ok)
+    for (int z = sub; z < S; z += 8) s += P[(long long)z * split_stride + idx];
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (ok && sub == 0) {
+    const int r = (int)(idx / cols), c = (int)(idx % cols);
+    C[(long long)r * ldc + c] = s;
+  }
+}
+
 // column sums: block b sums rows [b*CS_RPB, (b+1)*CS_RPB) -> partial[b][N]; the final kernel reduces the partials with
 // the same (32 columns x 8 row-lanes) pattern in fp64.  Fixed order => bit-reproducible.
 constexpr int CS_RPB = 256;
@@ -493,7 +514,7 @@ extern "C" int ercg_gemm_tn(const float* A, int64_t lda, const int32_t* a_rows, 
           int rc4 = finish_launch();
           if (rc4 != ERCG_OK) return rc4;
           const long long tot4 = (long long)K1 * N1;
-          reduce_splits_kernel<<<(unsigned)((tot4 + 255) / 256), 256, 0, st>>>(Pw, tot4, S, C, ldc, K1, N1);
+          reduce_splits_wide_kernel<<<(unsigned)((tot4 * 8 + 255) / 256), 256, 0, st>>>(Pw, tot4, S, C, ldc, K1, N1);
           return finish_launch();
         }
       }
@@ -532,7 +553,8 @@ extern "C" int ercg_gemm_tn(const float* A, int64_t lda, const int32_t* a_rows, 
 
 extern "C" size_t ercg_colsum_workspace_bytes(int64_t M, int N) {
   if (M <= 0 || N <= 0) return 0;
-  return (size_t)((M + CS_RPB - 1) / CS_RPB) * N * sizeof(float);
+  const size_t a = (size_t)((M + CS_RPB - 1) / CS_RPB) * N * sizeof(float), b = (size_t)CS_MAX_BLOCKS * N * sizeof(float);
+  return a > b ? a : b;
 }
 
 extern "C" int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float* out,
@@ -545,8 +567,13 @@ extern "C" int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float*
   if (!A || lda < N) return ERCG_EINVAL;
   const size_t need = ercg_colsum_workspace_bytes(M, N);
   if (need > workspace_bytes || !workspace) return ERCG_EWORKSPACE;
-  const int nb = (int)((M + CS_RPB - 1) / CS_RPB);
-  if ((N & 3) == 0 && (lda & 3) == 0 && aligned16(A))
+  int nb = (int)((M + CS_RPB - 1) / CS_RPB);
+  if (col_stream_ok(A, lda, N, M)) {      // contiguous rows: flat float4 stream (col_stream.cuh)
+    const long long total4 = M * (long long)(N >> 2);
+    nb = col_stream_blocks(N >> 2, total4);
+    col_stream_kernel<2><<<nb, 256, 0, st>>>(A, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, total4, N >> 2,
+                                             reinterpret_cast<float*>(workspace));
+  } else if ((N & 3) == 0 && (lda & 3) == 0 && aligned16(A))
     colsum_partial_v4_kernel<<<nb, 256, 0, st>>>(A, lda, M, N, reinterpret_cast<float*>(workspace));
   else
     colsum_partial_kernel<<<nb, 256, 0, st>>>(A, lda, M, N, reinterpret_cast<float*>(workspace));

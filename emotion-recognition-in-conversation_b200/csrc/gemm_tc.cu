@@ -1,31 +1,31 @@
-// K2 (tensor-core path): C[M,N] = act(A[M,K] @ B[K,N] + bias) on tcgen05 with fp32-grade accuracy (3xTF32).
+// K2 (tensor-core path): C[M,N] = act(A[M,K] @ B[K,N] + bias) and C[K1,N1] = A^T @ B on tcgen05 with fp32-grade accuracy.
 //
 // Replaces the same reference code as gemm_simt.cu (nn.Linear of cogmen.py:103-105,116-122, the relation
 // weights of RGCNConv cogmen.py:65 / models/rgcn.py:329-343, the Linears of TransformerConv cogmen.py:66).
 //
-// The reference is fp32 and BASELINE.json asks for 1e-5 relative parity, which plain TF32 (10-bit mantissa)
-// cannot give.  Every operand is therefore split x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi) and the
-// product is accumulated in fp32 TMEM as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is 2^-22
-// relative).  Weights (B) are split once per call on the device into K-major [N,K] hi/lo copies; activations (A)
-// are split on the fly in shared memory: the split is elementwise, so it preserves whatever (swizzled) layout
-// TMA wrote -- hi overwrites the raw tile in place, lo goes to a twin buffer at the same offsets.
+// The reference is fp32 and BASELINE.json asks for 1e-5 relative parity, which plain TF32 (10-bit mantissa) cannot give.
+// Every operand is split x = hi + lo (hi = upper 19 bits = what a tf32 operand read sees, lo = x - hi exact) and the product
+// is accumulated in fp32 as  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (the dropped lo*lo term is 2^-22 relative):
+//   NN kernel: A_hi*B_hi as kind::tf32 MMAs (exact products); the two correction terms, 2^-11 of the result, as kind::f16
+//              (bf16) MMAs at twice the rate -- 8 instead of 12 instructions per 32-k chunk;
+//   TN kernel: three kind::tf32 MMAs (3xTF32).
 //
-// Persistent, warp-specialised CTA (320 threads, 1 CTA / SM):
-//   warps 0-3  splitter   : raw A tile -> hi (in place) + lo, fence.proxy.async, arrive split_done[s]
-//   warps 4-7  epilogue   : tcgen05.ld 32x32b accumulator rows -> bias/activation -> 16-byte global stores
-//   warp  8    TMA        : cp.async.bulk.tensor 2D boxes {32 k, 128 rows} (A) and {32 k, BN rows} (B hi, B lo),
-//                           128-byte swizzle, out-of-bounds rows/columns zero-filled (K and N tails for free)
-//   warp  9    MMA        : one elected lane issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per
-//                           stage, tcgen05.commit releases the smem stage / publishes the accumulator
-// 3 smem stages of (A_hi, A_lo, B_hi, B_lo) = 64 KB each; 2 TMEM accumulator stages of BN columns.
+// Both kernels are persistent, warp-specialised CTAs of 352 threads, 1 CTA / SM:
+//   warps 0-3  splitter : raw TMA tile of the streamed operand -> hi / lo (bf16 pairs in the NN kernel) written straight
+//                         into TENSOR MEMORY with tcgen05.st; the MMAs take that operand from TMEM (TS form)
+//   warps 4-7  epilogue : tcgen05.ld accumulator rows -> round-to-nearest register accumulation across k groups ->
+//                         bias / activation -> swizzled staging slabs -> TMA bulk stores (NN); partials to the workspace (TN)
+//   warp  8    TMA producer of the streamed operand (HBM), warp 10 TMA producer of the other operand (L2-resident)
+//   warp  9    MMA issuer: warp-uniform loop, one elected lane issues, tcgen05.commit releases stages
+// Tensor memory (512 columns): 2 accumulator stages x 128 + 4 operand stages x 64.
 //
 // Accumulation accuracy: the tensor core adds into TMEM with round-toward-zero, which on random-sign data shrinks
 // |D| by ~0.3 ulp per instruction (measured on B200: -8.8e-6 relative at K=1443 with one long chain -- see
 // DESIGN.md).  As in Ootomo & Yokota's error-corrected tensor-core GEMM, the long sum therefore lives OUTSIDE the
-// tensor core: the MMA warp accumulates only TC_GROUP k-chunks (128 k) into a TMEM stage, the epilogue warps add
-// each such partial into fp32 REGISTER accumulators with round-to-nearest, and the two TMEM stages ping-pong so
-// the drain of group g overlaps the MMAs of group g+1.  Every mbarrier wait is bounded: a protocol bug traps instead of
-// hanging the GPU.
+// tensor core: the MMA warp accumulates only a group of k-chunks (128 k in the NN kernel, 256 rows in the TN kernel) into a
+// TMEM stage, the epilogue warps add each such partial into fp32 REGISTER accumulators with round-to-nearest, and the two
+// TMEM stages ping-pong so the drain of group g overlaps the MMAs of group g+1.  Every mbarrier wait is bounded: a protocol
+// bug traps instead of hanging the GPU.  DESIGN.md section 5 has the measurements behind each of these choices.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -614,6 +614,18 @@ constexpr int TN_W_FULL = 0, TN_W_FREE = TN_W_FULL + TN_R, TN_TA_FULL = TN_W_FRE
               TN_B_FULL = TN_TA_FREE + TN_TA, TN_B_SPLIT = TN_B_FULL + TN_Q, TN_B_FREE = TN_B_SPLIT + TN_Q,
               TN_ACC_FULL = TN_B_FREE + TN_Q, TN_ACC_EMPTY = TN_ACC_FULL + 2, TN_BARS = TN_ACC_EMPTY + 2;
 constexpr int TN_THREADS = 352;   // 4 splitter + 4 epilogue warps, W producer, MMA, narrow-operand producer
+#ifndef TN_GROUP_
+#define TN_GROUP_ 8
+#endif
+#ifndef TN_DRAIN_AT_
+#define TN_DRAIN_AT_ 2
+#endif
+// k-chunks accumulated inside TMEM before the round-to-nearest flush to registers.  8 (256 rows) instead of the NN kernel's
+// 4: the epilogue warps of this kernel also split the narrow operand, and the pipeline trace (ERCG_TC_TRACE=2) showed the
+// MMA warp waiting ~2000 clk at every group boundary for "drain the previous group, then split the next chunk".  Fewer,
+// and mid-group, drains take that off the critical path; the truncation drift of a 256-row chain is ~1.6e-6 relative.
+constexpr int TN_GROUP = TN_GROUP_;
+constexpr int TN_DRAIN_AT = TN_DRAIN_AT_;     // the drain of group g-1 runs after this many chunks of group g were split
 
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
@@ -624,8 +636,12 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                   float* __restrict__ P /* [S][Wc][Nc] */, long long M, int Wc /* columns of the wide operand */,
                   int Nc /* columns of the narrow operand */, int bn /* narrow columns per unit: multiple of 32, <= 128 */,
-                  int w_tiles, int n_tiles, int S, long long rows_per_slab) {
+                  int w_tiles, int n_tiles, int S, long long rows_per_slab, long long* trace) {
   extern __shared__ uint8_t smem_raw[];
+#define TN_TRACE(role, idx, slot)                                                                                     \
+  do {                                                                                                                \
+    if (trace && blockIdx.x == 0 && (idx) < (unsigned)TR_N) trace[((role) * TR_N + (idx)) * 4 + (slot)] = clock64();   \
+  } while (0)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* nring = smem + TN_R * TC_A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(nring + TN_Q * 2 * TC_B_BYTES);
@@ -680,6 +696,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
           const int r = n % TN_R;
           mbar_wait_relaxed(BAR(TN_W_FREE + r), ((n / TN_R) & 1) ^ 1);
+          TN_TRACE(0, n, 1);
           mbar_expect_tx(BAR(TN_W_FULL + r), TC_A_BYTES);
           tma_load_2d(raw_base + r * TC_A_BYTES, &tmW, w0, (int)m, BAR(TN_W_FULL + r));
         }
@@ -695,6 +712,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
           const int q = n % TN_Q;
           mbar_wait_relaxed(BAR(TN_B_FREE + q), ((n / TN_Q) & 1) ^ 1);
+          TN_TRACE(4, n, 1);
           mbar_expect_tx(BAR(TN_B_FULL + q), tx);
           for (int i = 0; i < nb; ++i) tma_load_2d(N_HI(q) + i * 4096, &tmN, n0 + 32 * i, (int)m, BAR(TN_B_FULL + q));
         }
@@ -712,16 +730,19 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       decode(u, w0, n0, mbeg, mend, slab);
       const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
       for (long long kc = 0; kc < chunks; ++kc, ++n) {
-        const int in_group = (int)(kc % TC_GROUP);
+        const int in_group = (int)(kc % TN_GROUP);
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
+        if (lane == 0) TN_TRACE(2, n, 0);
         if (in_group == 0) mbar_wait(BAR(TN_ACC_EMPTY + a), aph ^ 1);
         const int s = n % TN_TA, q = n % TN_Q;
         mbar_wait(BAR(TN_TA_FULL + s), (n / TN_TA) & 1);
+        if (lane == 0) TN_TRACE(2, n, 2);
         mbar_wait(BAR(TN_B_SPLIT + q), (n / TN_Q) & 1);
+        if (lane == 0) TN_TRACE(2, n, 3);
         tc_fence_after();
         const uint32_t ah0 = TA_HI(s);
         const uint64_t bh0 = make_desc_mn_sw128(N_HI(q)), bl0 = make_desc_mn_sw128(N_LO(q));
-        const bool last = in_group == TC_GROUP - 1 || kc == chunks - 1;
+        const bool last = in_group == TN_GROUP - 1 || kc == chunks - 1;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 8; ++ks) {
@@ -751,6 +772,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int r = n % TN_R, s = n % TN_TA;
         // raw [32 rows][128 columns] -> this thread's column, rows along the TMEM columns
         mbar_wait(BAR(TN_W_FULL + r), (n / TN_R) & 1);
+        if (tid == 0) TN_TRACE(1, n, 1);
         const uint32_t src = raw_base + r * TC_A_BYTES + tid * 4;
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -758,6 +780,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           split_tf32(lds1(src + j * 512), hi[j], lo[j]);
         }
         mbar_wait(BAR(TN_TA_FREE + s), ((n / TN_TA) & 1) ^ 1);
+        if (tid == 0) TN_TRACE(1, n, 2);
         tc_fence_after();
         tc_st32(TA_HI(s) + lane_addr, hi);
         tc_st32(TA_HI(s) + 32 + lane_addr, lo);
@@ -765,6 +788,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         mbar_arrive(BAR(TN_W_FREE + r));                 // after the TMEM stores: every loaded register has been consumed
         tc_fence_before();
         mbar_arrive(BAR(TN_TA_FULL + s));
+        if (tid == 0) TN_TRACE(1, n, 3);
       }
     }
   } else if (warp < 8) {
@@ -781,7 +805,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       int w0, n0, slab; long long mbeg, mend;
       decode(u, w0, n0, mbeg, mend, slab);
       const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
-      const long long n_groups = (chunks + TC_GROUP - 1) / TC_GROUP;
+      const long long n_groups = (chunks + TN_GROUP - 1) / TN_GROUP;
       float acc[TC_BN];
 #pragma unroll
       for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
@@ -803,10 +827,13 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (++a == 2) { a = 0; aph ^= 1; }
       };
       for (long long g = 0; g < n_groups; ++g) {
-        const long long kc_end = (g + 1) * TC_GROUP < chunks ? (g + 1) * TC_GROUP : chunks;
-        for (long long kc = g * TC_GROUP; kc < kc_end; ++kc, ++n) {
+        const long long kc_end = (g + 1) * TN_GROUP < chunks ? (g + 1) * TN_GROUP : chunks;
+        bool pending = g > 0;                          // group g-1 still has to be drained (its MMAs retired long ago)
+        for (long long kc = g * TN_GROUP; kc < kc_end; ++kc, ++n) {
+          if (pending && kc - g * TN_GROUP == TN_DRAIN_AT) { drain(); pending = false; }
           const int q = n % TN_Q;
           mbar_wait(BAR(TN_B_FULL + q), (n / TN_Q) & 1);
+          if (te == 0) TN_TRACE(3, n, 1);
           const uint32_t bhi = N_HI(q), blo = N_LO(q);
           float4 x[8];
 #pragma unroll
@@ -825,8 +852,9 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           }
           fence_proxy_async();
           mbar_arrive(BAR(TN_B_SPLIT + q));
+          if (te == 0) TN_TRACE(3, n, 2);
         }
-        if (g > 0) drain();                            // group g-1, while the MMAs of group g run
+        if (pending) drain();                          // (group shorter than TN_DRAIN_AT chunks)
       }
       drain();
       const int wc = w0 + ew * 32 + lane;
@@ -868,7 +896,7 @@ static void tn_tc_plan(int64_t M, int K1, int N1, bool& swap, int& w_tiles, int&
   n_tiles = (Nc + bn - 1) / bn;
   S = kNumSMs / (w_tiles * n_tiles);
   if (S < 1) S = 1;
-  const long long quantum = (long long)TC_BK * TC_GROUP;
+  const long long quantum = (long long)TC_BK * TN_GROUP;
   long long maxS = (M + quantum - 1) / quantum;
   if (maxS < 1) maxS = 1;
   if (S > maxS) S = (int)maxS;
@@ -1045,8 +1073,9 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
     trace_on = e ? atoi(e) : 0;
     if (trace_on && cudaMalloc(&trace_buf, sizeof(long long) * TR_ROLES * TR_N * 4) != cudaSuccess) trace_buf = nullptr;
   }
-  if (trace_buf) cudaMemsetAsync(trace_buf, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
-  TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg, trace_buf};
+  long long* nn_trace = (trace_on & 1) ? trace_buf : nullptr;
+  if (nn_trace) cudaMemsetAsync(nn_trace, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
+  TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg, nn_trace};
   const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;       // the whole K extent is one TMEM accumulation group
   float* partial = colsum_out ? reinterpret_cast<float*>(b16 + (size_t)N * Kc * 64) : nullptr;   // [grid][4][128], after the B copies
   kernels[act][smallk]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep, partial);
@@ -1116,7 +1145,15 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
   cudaStream_t st = (cudaStream_t)stream;
   const long long units = (long long)wt * nt * S;
   const int grid = (int)(units < kNumSMs ? units : kNumSMs);
-  gemm_tc_tn_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps);
+  static int tn_trace_on = -1;
+  if (tn_trace_on < 0) {
+    const char* e = getenv("ERCG_TC_TRACE");
+    tn_trace_on = e ? atoi(e) : 0;
+    if (tn_trace_on && !trace_buf && cudaMalloc(&trace_buf, sizeof(long long) * TR_ROLES * TR_N * 4) != cudaSuccess) trace_buf = nullptr;
+  }
+  long long* tr = (tn_trace_on & 2) ? trace_buf : nullptr;          // ERCG_TC_TRACE=2: trace the TN kernel instead of the NN one
+  if (tr) cudaMemsetAsync(tr, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
+  gemm_tc_tn_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr);
   int rc = finish_launch();
   if (rc) return rc;
   const long long tot = (long long)K1 * N1;

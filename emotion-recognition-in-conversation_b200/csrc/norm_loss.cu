@@ -3,6 +3,7 @@
 // All reductions are two-level with a fixed order (per-block partials, then one thread per column
 // summing the partials in fp64) => bit-reproducible and independent of scheduling.
 #include "common.cuh"
+#include "col_stream.cuh"
 #include <math.h>
 
 namespace ercg {
@@ -331,17 +332,22 @@ extern "C" int ercg_mask_pos(const float* x, int64_t ldx, const float* ref, int6
 
 extern "C" size_t ercg_bn_workspace_bytes(int64_t N, int H) {
   if (N <= 0 || H <= 0) return 0;
-  return (size_t)((N + RPB - 1) / RPB) * 2 * H * sizeof(float);
+  const size_t a = (size_t)((N + RPB - 1) / RPB) * 2 * H * sizeof(float), b = (size_t)CS_MAX_BLOCKS * 2 * H * sizeof(float);
+  return a > b ? a : b;
 }
 
 extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, float* mean, float* var,
                              void* workspace, size_t workspace_bytes, void* stream) {
   if (N <= 0 || H <= 0 || !x || !mean || !var || ldx < H) return ERCG_EINVAL;
   if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
-  const int nb = (int)((N + RPB - 1) / RPB);
+  int nb = (int)((N + RPB - 1) / RPB);
   cudaStream_t st = (cudaStream_t)stream;
   float* part = reinterpret_cast<float*>(workspace);
-  if (v4_ok(x, ldx))
+  if (col_stream_ok(x, ldx, H, N)) {      // contiguous rows: flat float4 stream, every lane busy
+    const long long total4 = N * (long long)(H >> 2);
+    nb = col_stream_blocks(H >> 2, total4);
+    col_stream_kernel<0><<<nb, 256, 0, st>>>(x, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, total4, H >> 2, part);
+  } else if (v4_ok(x, ldx))
     col_partials_v4_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
   else
     col_partials_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
@@ -371,11 +377,18 @@ extern "C" int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const floa
                                       float* sums, int64_t N, int H, void* workspace, size_t workspace_bytes, void* stream) {
   if (N <= 0 || H <= 0 || !dout || !x || !mean || !var || !gamma || !beta || !sums) return ERCG_EINVAL;
   if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
-  const int nb = (int)((N + RPB - 1) / RPB);
+  int nb = (int)((N + RPB - 1) / RPB);
   cudaStream_t st = (cudaStream_t)stream;
   float* part = reinterpret_cast<float*>(workspace);
-  // (the float4 variant measured slower for this two-input mode: 0.33 vs 0.29 ms at 2^20 x 100)
-  col_partials_kernel<1><<<nb, 256, 0, st>>>(x, ldx, dout, ldo, mean, var, eps, gamma, beta, slope, N, H, part);
+  if (col_stream_ok(x, ldx, H, N) && col_stream_ok(dout, ldo, H, N) && aligned16(mean) && aligned16(var) && aligned16(gamma) &&
+      aligned16(beta)) {
+    const long long total4 = N * (long long)(H >> 2);
+    nb = col_stream_blocks(H >> 2, total4);
+    col_stream_kernel<1><<<nb, 256, 0, st>>>(x, dout, mean, var, eps, gamma, beta, slope, total4, H >> 2, part);
+  } else {
+    // (the row-per-warp float4 variant measured slower for this two-input mode: 0.33 vs 0.29 ms at 2^20 x 100)
+    col_partials_kernel<1><<<nb, 256, 0, st>>>(x, ldx, dout, ldo, mean, var, eps, gamma, beta, slope, N, H, part);
+  }
   int rc = finish_launch();
   if (rc) return rc;
   sums_final_kernel<<<(2 * H + 31) / 32, 256, 0, st>>>(part, nb, H, sums);
