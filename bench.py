@@ -348,7 +348,7 @@ def run_ours(args):
     hx = torch.empty((N, ld), dtype=torch.float32, pin_memory=True)
     hx.copy_(x_store)
     host = {"x": hx, "spk": torch.zeros(N, dtype=torch.int64).pin_memory(), "label": labels.cpu().pin_memory()}
-    feeder = DeviceFeeder(dev, depth=2)
+    feeder = DeviceFeeder(dev, depth=2, copy_streams=args.copy_streams)
 
     def e2e_run(n):
         losses = []
@@ -438,7 +438,7 @@ def run_ours(args):
                 "cuda_mallocs_in_timed_region": int(mem_after.get("num_device_alloc", 0) - mem_before.get("num_device_alloc", 0)),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                        "how": "pinned host buffers -> DeviceFeeder (double-buffered copy stream) -> step -> loss.item(); all copies inside the timed region"},
+                        "how": "pinned host buffers -> DeviceFeeder (double-buffered, %d copy streams) -> step -> loss.item(); all copies inside the timed region" % args.copy_streams},
                 "gpu_launches": launches, "clocks": clocks, "loss": float(loss.item())}
         if trace is not None:
             line["host_trace_ms"] = {"phases": ["build_graph", "census_wait", "forward+loss", "backward", "optimizer",
@@ -482,6 +482,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-budget-s", type=float, default=16.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--copy-streams", type=int, default=2, help="H2D copy streams of the e2e feeder (2: +3 % over one)")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run one step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

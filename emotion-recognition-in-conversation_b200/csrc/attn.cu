@@ -316,7 +316,10 @@ attn_bwd_src_kernel(const float* __restrict__ dout, long long ldo, const float* 
 //   * aggregation: one lane per float4 chunk, per-edge scalars broadcast by shuffle.
 // ~210 instead of ~790 instructions per node.  Same arithmetic per edge; the summation order over edges is unchanged
 // (ascending CSR order), so results stay bit-reproducible.  A source outside the promised window traps.
-constexpr int WT = 32;        // nodes per CTA tile
+#ifndef ATTN_WT_
+#define ATTN_WT_ 32
+#endif
+constexpr int WT = ATTN_WT_;  // nodes per CTA tile
 
 // Rows go global -> shared with 16-byte cp.async (LDGSTS): a lane issues all of its ~15 row chunks back to back and nobody
 // waits until stage_wait(), so the whole tile's HBM latency is paid once.  (The first version did a load + dependent

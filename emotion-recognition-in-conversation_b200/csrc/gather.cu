@@ -208,7 +208,10 @@ gather_bwd_kernel(const float* __restrict__ dout, long long ldo, const float* __
 // memory with cp.async (every row is needed by up to wlo + whi + 1 sources); edge metadata is fetched lane-per-edge while
 // the copies are in flight.  Per relation slot a ballot selects the edges, rows come from shared memory.  Same summation
 // order as gather_bwd_kernel (ascending by-source edge order inside a slot) => bit-identical results.
-constexpr int GT_TILE = 32;
+#ifndef GT_TILE_
+#define GT_TILE_ 32
+#endif
+constexpr int GT_TILE = GT_TILE_;
 
 __global__ void __launch_bounds__(256)
 gather_bwd_tile_kernel(const float* __restrict__ dout, long long ldo, const int* __restrict__ t_rowptr,

@@ -24,11 +24,15 @@ def pin(batch):
 
 
 class DeviceFeeder:
-    def __init__(self, device, depth=2):
-        assert depth >= 1
+    def __init__(self, device, depth=2, copy_streams=1, chunk_bytes=256 << 20):
+        """``copy_streams`` > 1 splits large tensors into ``chunk_bytes`` pieces issued round-robin on several streams
+        (more than one copy engine busy on the H2D direction); 1 = one stream, one copy per tensor."""
+        assert depth >= 1 and copy_streams >= 1
         self.device = torch.device(device)
         self.depth = depth
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.extra_streams = [torch.cuda.Stream(device=self.device) for _ in range(copy_streams - 1)]
+        self.chunk_bytes = chunk_bytes
         self._bufs = [dict() for _ in range(depth)]          # slot -> {key: device tensor}
         self._free = [None] * depth                          # slot -> event after which the slot may be overwritten
         self._ready = deque()                                # (slot, event, keys) in submission order
@@ -47,12 +51,29 @@ class DeviceFeeder:
             d = bufs.get(k)                                  # caller's stream, never returned to the allocator)
             if d is None or d.shape != h.shape or d.dtype != h.dtype:
                 bufs[k] = torch.empty(h.shape, dtype=h.dtype, device=self.device)
-        with torch.cuda.stream(self.copy_stream):
+        streams = [self.copy_stream] + self.extra_streams
+        for st in streams:
             if self._free[slot] is not None:
-                self.copy_stream.wait_event(self._free[slot])
-            for k, h in batch.items():
-                bufs[k].copy_(h, non_blocking=True)
-                self.h2d_bytes += h.numel() * h.element_size()
+                st.wait_event(self._free[slot])
+        turn = 0
+        for k, h in batch.items():
+            nbytes = h.numel() * h.element_size()
+            self.h2d_bytes += nbytes
+            if len(streams) == 1 or nbytes <= self.chunk_bytes or h.dim() == 0 or not h.is_contiguous():
+                with torch.cuda.stream(streams[0]):
+                    bufs[k].copy_(h, non_blocking=True)
+                continue
+            rows = h.size(0)
+            step = max(1, int(rows * self.chunk_bytes // nbytes))
+            for r0 in range(0, rows, step):
+                with torch.cuda.stream(streams[turn % len(streams)]):
+                    bufs[k][r0:r0 + step].copy_(h[r0:r0 + step], non_blocking=True)
+                turn += 1
+        for st in self.extra_streams:                       # the batch is ready when every stream is done
+            e = torch.cuda.Event()
+            e.record(st)
+            self.copy_stream.wait_event(e)
+        with torch.cuda.stream(self.copy_stream):
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         self._ready.append((slot, ev, tuple(batch.keys())))

@@ -272,13 +272,14 @@ def test_missing_library_fails_loudly(monkeypatch):
         _lib.lib()
 
 
-def test_device_feeder_double_buffering():
+@pytest.mark.parametrize("copy_streams,chunk_bytes", [(1, 256 << 20), (2, 1 << 20), (3, 300_000)])
+def test_device_feeder_double_buffering(copy_streams, chunk_bytes):
     """loader.DeviceFeeder: batches come out in submission order with the right contents while later copies are in
     flight; a third un-consumed submit is refused (depth 2)."""
     import erc_b200
     from erc_b200.loader import DeviceFeeder, pin
     dev = torch.device("cuda")
-    feeder = DeviceFeeder(dev, depth=2)
+    feeder = DeviceFeeder(dev, depth=2, copy_streams=copy_streams, chunk_bytes=chunk_bytes)
     gen = torch.Generator().manual_seed(0)
     batches = [pin({"x": torch.randn(4096, 257, generator=gen), "spk": torch.randint(0, 2, (4096,), generator=gen)})
                for _ in range(5)]
