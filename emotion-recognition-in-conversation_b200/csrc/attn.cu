@@ -321,10 +321,10 @@ attn_bwd_src_kernel(const float* __restrict__ dout, long long ldo, const float* 
 #endif
 constexpr int WT = ATTN_WT_;  // nodes per CTA tile
 
-// Rows go global -> shared with 16-byte cp.async (LDGSTS): a lane issues all of its ~15 row chunks back to back and nobody
-// waits until stage_wait(), so the whole tile's HBM latency is paid once.  (The first version did a load + dependent
-// shared-memory store per loop iteration -- ~15 serialised global round trips per CTA -- and ran at 35-40 % of the HBM
-// peak with the SMs mostly idle.)
+// Rows go global -> shared with 16-byte cp.async (LDGSTS): a lane issues all of its ~15 row chunks back to back, no
+// registers are tied up and nobody waits until stage_wait(), so the whole tile's HBM latency is paid once and the CSR
+// metadata loads issued right after overlap with it.  (The first version staged through registers -- ptxas kept only four
+// loads in flight per lane -- and ran at 35-40 % of the HBM peak.)
 __device__ __forceinline__ void stage_rows(float4* dst, const float* __restrict__ src, long long ld, long long r0, int rows,
                                            int nch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -107,4 +107,37 @@ col_stream_kernel(const float* __restrict__ x, const float* __restrict__ dout, c
   }
 }
 
+// Plain column sums for narrow contiguous matrices whose width is even but not a multiple of 4 (the classifier's [N, 6]
+// logit gradients): the same flat stream in float2 units.  partial layout [gridDim.x][H].
+static inline bool col_stream2_ok(const void* p, long long ld, int H, long long M) {
+  return (reinterpret_cast<uintptr_t>(p) & 7u) == 0 && ld == H && (H & 1) == 0 && H >= 2 && (H >> 1) <= 256 && M >= 1024 &&
+         col_stream_blocks(H >> 1, M * (long long)(H >> 1)) > 0;
+}
+static __global__ void __launch_bounds__(256)
+col_stream2_kernel(const float* __restrict__ x, long long total2, int nch, float* __restrict__ partial) {
+  __shared__ float2 red[256];
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long T = (long long)gridDim.x * 256;
+  const int c = (int)(t % nch) * 2;
+  float2 s = make_float2(0.f, 0.f);
+  const float2* x2 = reinterpret_cast<const float2*>(x);
+  long long i = t;
+  for (; i + 3 * T < total2; i += 4 * T) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(x2 + i + u * T);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; }
+  }
+  for (; i < total2; i += T) { const float2 v = __ldg(x2 + i); s.x += v.x; s.y += v.y; }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < nch) {
+    float2 a = red[threadIdx.x];
+    for (int k = threadIdx.x + nch; k < 256; k += nch) { a.x += red[k].x; a.y += red[k].y; }
+    partial[(long long)blockIdx.x * nch * 2 + c] = a.x;
+    partial[(long long)blockIdx.x * nch * 2 + c + 1] = a.y;
+  }
+}
+
 }  // namespace ercg

@@ -573,6 +573,10 @@ extern "C" int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float*
     nb = col_stream_blocks(N >> 2, total4);
     col_stream_kernel<2><<<nb, 256, 0, st>>>(A, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, total4, N >> 2,
                                              reinterpret_cast<float*>(workspace));
+  } else if (col_stream2_ok(A, lda, N, M)) {
+    const long long total2 = M * (long long)(N >> 1);
+    nb = col_stream_blocks(N >> 1, total2);
+    col_stream2_kernel<<<nb, 256, 0, st>>>(A, total2, N >> 1, reinterpret_cast<float*>(workspace));
   } else if ((N & 3) == 0 && (lda & 3) == 0 && aligned16(A))
     colsum_partial_v4_kernel<<<nb, 256, 0, st>>>(A, lda, M, N, reinterpret_cast<float*>(workspace));
   else

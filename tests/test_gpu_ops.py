@@ -44,6 +44,22 @@ def test_gemm_nn_tn_colsum(M, K, N):
     assert rel_err(ops.mask_pos(dC.cuda(), aux.cuda(), 2.0), torch.where(aux > 0, dC * 2.0, torch.zeros(()))) < 1e-7
 
 
+@pytest.mark.parametrize("M,N", [(1024, 100), (70001, 100), (33000, 200), (5000, 6), (40000, 6), (2049, 10), (3000, 7), (999, 100)])
+def test_column_sums_flat_stream_and_fallbacks(M, N):
+    """ercg_colsum: flat float4 / float2 streams for contiguous matrices (col_stream.cuh), row-block kernels otherwise;
+    bit-reproducible (two runs equal) and within 1e-5 of fp64."""
+    import erc_b200
+    from erc_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, N, generator=g) + 0.3
+    a, b = ops.colsum(A.cuda()), ops.colsum(A.cuda())
+    assert torch.equal(a, b)
+    scale = float(A.double().abs().sum(0).max())
+    assert float((a.cpu().double() - A.double().sum(0)).abs().max()) < TOL * scale
+    strided = torch.randn(M, N + 4, generator=g).cuda()[:, :N]          # row pitch != width: row-block path
+    assert float((ops.colsum(strided).cpu().double() - strided.cpu().double().sum(0)).abs().max()) < TOL * scale * 2
+
+
 def test_gemm_row_gather_and_unaligned_lda():
     import erc_b200
     from erc_b200 import ops
