@@ -195,6 +195,7 @@ def kernel_label(name, args):
     except Exception:
         pass
     name = name.replace("attn_window_", "attn_")        # CTA-tiled window-graph variants of the same three kernels
+    name = name.replace("gather_window_", "gather_")
     return name[5:] if name.startswith("ercg_") else name
 
 

@@ -6,12 +6,11 @@
 // The reference is fp32 and BASELINE.json asks for 1e-5 relative parity, which plain TF32 (10-bit mantissa) cannot give.
 // Every operand is split x = hi + lo (hi = upper 19 bits = what a tf32 operand read sees, lo = x - hi exact) and the product
 // is accumulated in fp32 as  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (the dropped lo*lo term is 2^-22 relative):
-//   NN kernel: A_hi*B_hi as kind::tf32 MMAs (exact products); the two correction terms, 2^-11 of the result, as kind::f16
-//              (bf16) MMAs at twice the rate -- 8 instead of 12 instructions per 32-k chunk;
-//   TN kernel: three kind::tf32 MMAs (3xTF32).
+// A_hi*B_hi runs as kind::tf32 MMAs (exact products); the two correction terms, 2^-11 of the result, as kind::f16 (bf16)
+// MMAs at twice the rate -- 8 instead of 12 instructions per 32-k chunk, in both kernels.
 //
 // Both kernels are persistent, warp-specialised CTAs of 352 threads, 1 CTA / SM:
-//   warps 0-3  splitter : raw TMA tile of the streamed operand -> hi / lo (bf16 pairs in the NN kernel) written straight
+//   warps 0-3  splitter : raw TMA tile of the streamed operand -> tf32 hi + bf16 pairs of hi and lo, written straight
 //                         into TENSOR MEMORY with tcgen05.st; the MMAs take that operand from TMEM (TS form)
 //   warps 4-7  epilogue : tcgen05.ld accumulator rows -> round-to-nearest register accumulation across k groups ->
 //                         bias / activation -> swizzled staging slabs -> TMA bulk stores (NN); partials to the workspace (TN)
@@ -596,8 +595,9 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ring, is split by one thread per column and goes to TENSOR MEMORY (lane = column, TMEM column = row of the 32-row
 // chunk, i.e. K-major by construction -- the transposition costs nothing); the NARROW operand (<= 128 columns, the
 // MMA N side) stays in shared memory as an MN-major tile ("128-byte swizzle with 32-byte atoms", UMMA layout type 1,
-// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; the plain 128-byte swizzle silently produces zeros for MN-major tf32) and
-// is hi/lo-split in place.  When N1 > K1 the roles of A and B are swapped and the transposed result is written back by
+// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; the plain 128-byte swizzle silently produces zeros for MN-major tf32) for the
+// tf32 hi*hi MMAs, is loaded a second time as plain boxes, and the epilogue warps turn that copy into a K-major bf16 tile
+// (bf16(hi) | bf16(lo), the NN kernel's B16 layout) for the two bf16 correction MMAs.  When N1 > K1 the roles of A and B are swapped and the transposed result is written back by
 // the reduction kernel.  Work unit = (128-column tile of W, row slab); each unit writes its [128 x n] partial to the
 // workspace and a fixed-order reduction sums the slabs (bit-reproducible).  Same grouped-TMEM / register accumulation.
 #ifndef TN_R_
@@ -607,9 +607,9 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #define TN_Q_ 3
 #endif
 constexpr int TN_R = TN_R_;       // raw W stages, 16 KB each ([32 rows][128 columns], no swizzle)
-constexpr int TN_Q = TN_Q_;       // narrow-operand stages: hi (raw, split in place) 16 KB + lo 16 KB
-constexpr int TN_TA = 4;          // TMEM stages of W: hi 32 + lo 32 columns
-constexpr uint32_t TN_SMEM_BYTES = TN_R * TC_A_BYTES + TN_Q * 2 * TC_B_BYTES + 1024 + 512;
+constexpr int TN_Q = TN_Q_;       // narrow-operand stages: swizzled fp32 tile 16 KB + plain fp32 tile 16 KB + bf16 tile 16 KB
+constexpr int TN_TA = 4;          // TMEM stages of W: tf32 hi 32 + bf16 pairs (hi 16, lo 16) columns
+constexpr uint32_t TN_SMEM_BYTES = TN_R * TC_A_BYTES + TN_Q * 3 * TC_B_BYTES + 1024 + 512;
 constexpr int TN_W_FULL = 0, TN_W_FREE = TN_W_FULL + TN_R, TN_TA_FULL = TN_W_FREE + TN_R, TN_TA_FREE = TN_TA_FULL + TN_TA,
               TN_B_FULL = TN_TA_FREE + TN_TA, TN_B_SPLIT = TN_B_FULL + TN_Q, TN_B_FREE = TN_B_SPLIT + TN_Q,
               TN_ACC_FULL = TN_B_FREE + TN_Q, TN_ACC_EMPTY = TN_ACC_FULL + 2, TN_BARS = TN_ACC_EMPTY + 2;
@@ -636,7 +636,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                   float* __restrict__ P /* [S][Wc][Nc] */, long long M, int Wc /* columns of the wide operand */,
                   int Nc /* columns of the narrow operand */, int bn /* narrow columns per unit: multiple of 32, <= 128 */,
-                  int w_tiles, int n_tiles, int S, long long rows_per_slab, long long* trace) {
+                  int w_tiles, int n_tiles, int S, long long rows_per_slab, long long* trace,
+                  const __grid_constant__ CUtensorMap tmNp /* the narrow operand again, unswizzled boxes */) {
   extern __shared__ uint8_t smem_raw[];
 #define TN_TRACE(role, idx, slot)                                                                                     \
   do {                                                                                                                \
@@ -644,7 +645,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   } while (0)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* nring = smem + TN_R * TC_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(nring + TN_Q * 2 * TC_B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nring + TN_Q * 3 * TC_B_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TN_BARS);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -673,8 +674,11 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const int nb = bn / 32;                              // 32-wide boxes of the narrow operand per unit
   const int mma_n = n_tiles == 1 ? (Nc + 15) / 16 * 16 : bn;   // UMMA N
   const uint32_t raw_base = smem_u32(smem), n_base = smem_u32(nring);
-  auto N_HI = [&](int q) { return n_base + q * 2 * TC_B_BYTES; };
-  auto N_LO = [&](int q) { return n_base + q * 2 * TC_B_BYTES + TC_B_BYTES; };
+  // per narrow stage: [fp32 tile, MN-major swizzled: B of the tf32 MMAs] [fp32 tile, plain boxes: source of the conversion]
+  //                   [bf16 tile, K-major 128-byte rows: bf16(hi) | bf16(lo) -- B of the bf16 MMAs, as in the NN kernel]
+  auto N_HI = [&](int q) { return n_base + q * 3 * TC_B_BYTES; };
+  auto N_PL = [&](int q) { return n_base + q * 3 * TC_B_BYTES + TC_B_BYTES; };
+  auto N_16 = [&](int q) { return n_base + q * 3 * TC_B_BYTES + 2 * TC_B_BYTES; };
   auto TA_HI = [&](int s) { return tmem_base + 2 * TC_BN + (uint32_t)s * 64u; };
   // unit -> (W tile, narrow tile, slab); slab fastest so that concurrently running CTAs stream different rows
   auto decode = [&](long long u, int& w0, int& n0, long long& mbeg, long long& mend, int& slab) {
@@ -705,7 +709,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   } else if (warp == 10) {
     if (lane == 0) {   // ---------------------------------------------------- narrow-operand producer (mostly L2)
       uint32_t n = 0;
-      const uint32_t tx = (uint32_t)nb * 4096u;
+      const uint32_t tx = 2u * (uint32_t)nb * 4096u;
       for (long long u = blockIdx.x; u < units; u += gridDim.x) {
         int w0, n0, slab; long long mbeg, mend;
         decode(u, w0, n0, mbeg, mend, slab);
@@ -714,7 +718,10 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           mbar_wait_relaxed(BAR(TN_B_FREE + q), ((n / TN_Q) & 1) ^ 1);
           TN_TRACE(4, n, 1);
           mbar_expect_tx(BAR(TN_B_FULL + q), tx);
-          for (int i = 0; i < nb; ++i) tma_load_2d(N_HI(q) + i * 4096, &tmN, n0 + 32 * i, (int)m, BAR(TN_B_FULL + q));
+          for (int i = 0; i < nb; ++i) {
+            tma_load_2d(N_HI(q) + i * 4096, &tmN, n0 + 32 * i, (int)m, BAR(TN_B_FULL + q));
+            tma_load_2d(N_PL(q) + i * 4096, &tmNp, n0 + 32 * i, (int)m, BAR(TN_B_FULL + q));
+          }
         }
       }
     }
@@ -722,6 +729,8 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // ------------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) /* B is MN-major */ |
                            ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint64_t desc_k = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
     uint32_t n = 0;
     int a = 0;
     uint32_t aph = 0;
@@ -741,16 +750,18 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (lane == 0) TN_TRACE(2, n, 3);
         tc_fence_after();
         const uint32_t ah0 = TA_HI(s);
-        const uint64_t bh0 = make_desc_mn_sw128(N_HI(q)), bl0 = make_desc_mn_sw128(N_LO(q));
+        const uint64_t bh0 = make_desc_mn_sw128(N_HI(q));
+        const uint64_t b16 = desc_k | (uint64_t)((N_16(q) >> 4) & 0x3FFF);
         const bool last = in_group == TN_GROUP - 1 || kc == chunks - 1;
         if (elect_one()) {
+          // W_hi * N_hi in tf32 (the fp32 tile is read with tf32 truncation = hi); the two correction terms in bf16
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const uint32_t ah = ah0 + ks * 8, al = ah + 32;
-            const uint64_t bh = bh0 + (uint64_t)(ks * 64), bl = bl0 + (uint64_t)(ks * 64);   // 8 rows = 1024 bytes per k-step
-            tc_mma_tf32_ts(d_tmem, al, bh, idesc, (in_group | ks) ? 1u : 0u);
-            tc_mma_tf32_ts(d_tmem, ah, bl, idesc, 1u);
-            tc_mma_tf32_ts(d_tmem, ah, bh, idesc, 1u);
+          for (int ks = 0; ks < TC_BK / 8; ++ks)
+            tc_mma_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 64), idesc, (in_group | ks) ? 1u : 0u);   // 8 rows = 1024 B
+#pragma unroll
+          for (int j = 0; j < TC_BK / 16; ++j) {
+            tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);        // bf16(W_lo) * bf16(N_hi)
+            tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);    // bf16(W_hi) * bf16(N_lo)
           }
           tc_commit(BAR(TN_TA_FREE + s));
           tc_commit(BAR(TN_B_FREE + q));
@@ -774,16 +785,20 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         mbar_wait(BAR(TN_W_FULL + r), (n / TN_R) & 1);
         if (tid == 0) TN_TRACE(1, n, 1);
         const uint32_t src = raw_base + r * TC_A_BYTES + tid * 4;
-        uint32_t hi[32], lo[32];
+        uint32_t hi[32], p16[32];                        // tf32 W_hi | bf16 pairs along the rows: [0,16) W_hi, [16,32) W_lo
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          split_tf32(lds1(src + j * 512), hi[j], lo[j]);
+        for (int j = 0; j < 32; j += 2) {
+          uint32_t l0, l1;
+          split_tf32(lds1(src + j * 512), hi[j], l0);
+          split_tf32(lds1(src + (j + 1) * 512), hi[j + 1], l1);
+          p16[j >> 1] = pack_bf16x2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1]));
+          p16[16 + (j >> 1)] = pack_bf16x2(__uint_as_float(l0), __uint_as_float(l1));
         }
         mbar_wait(BAR(TN_TA_FREE + s), ((n / TN_TA) & 1) ^ 1);
         if (tid == 0) TN_TRACE(1, n, 2);
         tc_fence_after();
         tc_st32(TA_HI(s) + lane_addr, hi);
-        tc_st32(TA_HI(s) + 32 + lane_addr, lo);
+        tc_st32(TA_HI(s) + 32 + lane_addr, p16);
         tc_wait_st();
         mbar_arrive(BAR(TN_W_FREE + r));                 // after the TMEM stores: every loaded register has been consumed
         tc_fence_before();
@@ -799,7 +814,6 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     uint32_t aph = 0;
     const int ew = warp & 3;
     const int te = threadIdx.x - 128;                  // 0..127
-    const int b_vec = nb * 256;                        // float4s in the narrow tile
     uint32_t n = 0;                                    // chunk counter (narrow-operand ring)
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
       int w0, n0, slab; long long mbeg, mend;
@@ -834,21 +848,26 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           const int q = n % TN_Q;
           mbar_wait(BAR(TN_B_FULL + q), (n / TN_Q) & 1);
           if (te == 0) TN_TRACE(3, n, 1);
-          const uint32_t bhi = N_HI(q), blo = N_LO(q);
-          float4 x[8];
+          // thread te = column te of the narrow tile: its 32 rows come from the plain boxes (conflict-free 4-byte reads),
+          // are split hi / lo and go, as bf16 pairs along k, into row te of the K-major bf16 tile (128-byte rows, 16-byte
+          // chunks XOR-swizzled with the row like a 128-byte-swizzle TMA box: chunks 0-3 = bf16(hi), 4-7 = bf16(lo))
+          if (te < nb * 32) {
+            const uint32_t src = N_PL(q) + (uint32_t)(te >> 5) * 4096u + (uint32_t)(te & 31) * 4u;
+            uint32_t p[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (te + 128 * i < b_vec) x[i] = lds4(bhi + (te + 128 * i) * 16);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (te + 128 * i < b_vec) {
-              uint32_t h[4], l[4];
-              split_tf32(x[i].x, h[0], l[0]); split_tf32(x[i].y, h[1], l[1]);
-              split_tf32(x[i].z, h[2], l[2]); split_tf32(x[i].w, h[3], l[3]);
-              // elementwise, so the swizzled layout is preserved; the hi tile needs no rewrite (same upper 19 bits)
-              sts4(blo + (te + 128 * i) * 16, make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]),
-                                                         __uint_as_float(l[3])));
+            for (int j = 0; j < 32; j += 2) {
+              uint32_t h0, h1, l0, l1;
+              split_tf32(lds1(src + j * 128), h0, l0);
+              split_tf32(lds1(src + (j + 1) * 128), h1, l1);
+              p[j >> 1] = pack_bf16x2(__uint_as_float(h0), __uint_as_float(h1));
+              p[16 + (j >> 1)] = pack_bf16x2(__uint_as_float(l0), __uint_as_float(l1));
             }
+            const uint32_t dst = N_16(q) + (uint32_t)te * 128u;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              sts4(dst + (uint32_t)((c ^ (te & 7)) << 4),
+                   make_float4(__uint_as_float(p[4 * c]), __uint_as_float(p[4 * c + 1]), __uint_as_float(p[4 * c + 2]),
+                               __uint_as_float(p[4 * c + 3])));
           }
           fence_proxy_async();
           mbar_arrive(BAR(TN_B_SPLIT + q));
@@ -1133,9 +1152,10 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
   const float* Nw = swap ? A : B;
   const long long ldw = swap ? ldb : lda, ldn = swap ? lda : ldb;
   const int Wc = swap ? N1 : K1, Nc = swap ? K1 : N1;
-  CUtensorMap tmW, tmN;
+  CUtensorMap tmW, tmN, tmNp;
   if (!make_map_plain(&tmW, W, M, Wc, ldw) ||
-      !make_map(&tmN, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ERCG_ECUDA;
+      !make_map(&tmN, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map(&tmNp, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return ERCG_ECUDA;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
@@ -1153,7 +1173,7 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
   }
   long long* tr = (tn_trace_on & 2) ? trace_buf : nullptr;          // ERCG_TC_TRACE=2: trace the TN kernel instead of the NN one
   if (tr) cudaMemsetAsync(tr, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
-  gemm_tc_tn_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr);
+  gemm_tc_tn_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr, tmNp);
   int rc = finish_launch();
   if (rc) return rc;
   const long long tot = (long long)K1 * N1;
