@@ -402,6 +402,7 @@ def run_ours(args):
                 "graphify_csr": 8 * lengths.numel() + 8 * N + 8 * (N + 1) + 12 * N + E * (4 + 1 + 4 + 1 + 4 + 4 + 24),
                 "bn_stats": 4 * H * N, "bn_act_fwd": 8 * H * N, "bn_act_bwd_reduce": 8 * H * N, "bn_act_bwd_apply": 12 * H * N,
                 "mask_pos": 12 * H * N, "colsum": None, "ce_fwd": (4 * N_CLASSES * 2 + 8) * N,
+                "cls_tail_bwd": (8 * H + 4 * N_CLASSES) * N,
             }.get(label)
 
         kernels = {}

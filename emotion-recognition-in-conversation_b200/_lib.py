@@ -55,6 +55,8 @@ SIGNATURES = {
     "ercg_gemm_tn_tc_workspace_bytes": (SZ, [L, I, I]),
     "ercg_gemm_tn_tc_supported": (I, [P, L, P, L, L, I, I]),
     "ercg_gemm_tn_tc": (I, [P, L, P, L, P, L, L, I, I, P, SZ, P]),
+    "ercg_cls_tail_bwd_workspace_bytes": (SZ, [I, I]),
+    "ercg_cls_tail_bwd": (I, [P, L, P, P, F, P, L, P, P, P, L, I, I, P, SZ, P]),
     "ercg_mask_pos": (I, [P, L, P, L, F, P, L, L, I, P]),
     "ercg_colsum_workspace_bytes": (SZ, [L, I]),
     "ercg_colsum": (I, [P, L, L, I, P, P, SZ, P]),

@@ -312,6 +312,108 @@ mask_pos_v4_kernel(const float* __restrict__ x, long long ldx, const float* __re
 
 static inline bool v4_ok(const void* p, long long ld) { return aligned16(p) && (ld & 3) == 0; }
 
+// ---------------------------------------------------------------------------------- classifier tail, backward
+// cls = Linear(100,100) -> ReLU -> Dropout -> Linear(100,C) (track_mm/cogmen.py:116-122; dgcn_models.py:158-167).  Given the
+// gradient of the logits, ONE pass over the hidden activations h [N,K] (post ReLU/dropout, K <= 128) produces everything
+// the last Linear and the activation need:
+//   dZ[m,:]  = (h[m,:] > 0 ? scale : 0) * (dl[m,:] @ W3)          gradient of the first Linear's pre-activation
+//   dW3[c,k] = sum_m dl[m,c] * h[m,k],   db3[c] = sum_m dl[m,c],   db0[k] = sum_m dZ[m,k]
+// instead of five launches (skinny TN, skinny NN, mask, two column sums) that read h or dZ again each time.
+// One warp per row, lane = float4 chunk of the row: every sum is column-parallel, so the inner loop has no shuffle at
+// all; rows are dealt to warps grid-stride and block partials are added in a fixed order => bit-reproducible.
+constexpr int CT_MAXC = 8;
+template <int C>
+__global__ void __launch_bounds__(256)
+cls_tail_bwd_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ dl /* [N,C] contiguous */,
+                    const float* __restrict__ W3 /* [C,K] row-major (nn.Linear weight) */, float scale,
+                    float* __restrict__ dZ, long long ldz, long long N, int K,
+                    float* __restrict__ partial /* [gridDim.x][C*K + K + CT_MAXC] */) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nch = K >> 2;
+  const bool on = lane < nch;
+  float4 w[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) w[c] = on ? ld4(W3 + (long long)c * K + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dw[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) dw[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 cz = make_float4(0.f, 0.f, 0.f, 0.f);
+  float cl = 0.f;                                            // lane c < C keeps sum_m dl[m,c]
+  const long long stride = (long long)gridDim.x * 8;
+  for (long long m0 = (long long)blockIdx.x * 8 + warp; m0 < N; m0 += 4 * stride) {
+    float4 hv[4];
+    float dv[4][C];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long m = m0 + u * stride;
+      ok[u] = m < N;
+      hv[u] = (ok[u] && on) ? ld4_stream(h + m * ldh + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) dv[u][c] = ok[u] ? __ldg(dl + m * C + c) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;                                  // warp-uniform
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        fma4(g, dv[u][c], w[c]);
+        fma4(dw[c], dv[u][c], hv[u]);
+      }
+      g.x = hv[u].x > 0.f ? g.x * scale : 0.f; g.y = hv[u].y > 0.f ? g.y * scale : 0.f;
+      g.z = hv[u].z > 0.f ? g.z * scale : 0.f; g.w = hv[u].w > 0.f ? g.w * scale : 0.f;
+      cz.x += g.x; cz.y += g.y; cz.z += g.z; cz.w += g.w;
+      if (on) st4_stream(dZ + (m0 + u * stride) * ldz + 4 * lane, g);
+      if (lane < C) {
+        float mine = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) if (lane == c) mine = dv[u][c];
+        cl += mine;
+      }
+    }
+  }
+  // block partial = warps added in warp order (through shared memory, one quantity at a time)
+  float* out = partial + (long long)blockIdx.x * (C * K + K + CT_MAXC);
+  auto reduce_store = [&](float4 v, float* dst) {
+    __syncthreads();
+    red[warp][lane] = v;
+    __syncthreads();
+    if (warp == 0 && on) {
+      float4 t = red[0][lane];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) { const float4 x = red[q][lane]; t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w; }
+      st4(dst + 4 * lane, t);
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < C; ++c) reduce_store(dw[c], out + c * K);
+  reduce_store(cz, out + C * K);
+  __syncthreads();
+  red[warp][lane] = make_float4(cl, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (warp == 0 && lane < CT_MAXC) {
+    float t = 0.f;
+    if (lane < C)
+      for (int q = 0; q < 8; ++q) t += red[q][lane].x;
+    out[C * K + K + lane] = t;
+  }
+}
+
+// fixed-order fp64 sum of the block partials [nb][width]; columns [0,CK) -> dW3, [CK,CK+K) -> db0, then C values -> db3
+__global__ void __launch_bounds__(256)
+cls_tail_final_kernel(const float* __restrict__ partial, int nb, int width, int CK, int K, int C, float* __restrict__ dW3,
+                      float* __restrict__ db0, float* __restrict__ db3) {
+  __shared__ double sm[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool ok = c < CK + K + C;
+  const double s = reduce_partials(partial, nb, width, c, ok, sm);
+  if (!ok || (threadIdx.x >> 5) != 0) return;
+  if (c < CK) dW3[c] = (float)s;
+  else if (c < CK + K) db0[c - CK] = (float)s;
+  else db3[c - CK - K] = (float)s;
+}
+
 }  // namespace ercg
 
 using namespace ercg;
@@ -443,5 +545,41 @@ extern "C" int ercg_scale_by_ratio(float* x, int64_t n, const float* num, const 
   if (n == 0) return ERCG_OK;
   if (!x || !num || !den) return ERCG_EINVAL;
   scale_by_ratio_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, num, den);
+  return finish_launch();
+}
+
+extern "C" size_t ercg_cls_tail_bwd_workspace_bytes(int K, int C) {
+  if (K <= 0 || C <= 0) return 0;
+  return (size_t)kNumSMs * 4 * ((size_t)C * K + K + CT_MAXC) * sizeof(float);
+}
+
+// see cls_tail_bwd_kernel.  dW3 [C,K], db3 [C], db0 [K] are written; dZ [N,K] (row pitch ldz).  K % 4 == 0, K <= 128, C <= 8.
+extern "C" int ercg_cls_tail_bwd(const float* h, int64_t ldh, const float* dlogits, const float* W3, float scale,
+                                 float* dZ, int64_t ldz, float* dW3, float* db3, float* db0, int64_t N, int K, int C,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (N < 0 || K <= 0 || (K & 3) || K > 128 || C < 1 || C > CT_MAXC) return ERCG_EINVAL;
+  if (!dW3 || !db3 || !db0) return ERCG_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {
+    cudaMemsetAsync(dW3, 0, (size_t)C * K * sizeof(float), st);
+    cudaMemsetAsync(db3, 0, (size_t)C * sizeof(float), st);
+    cudaMemsetAsync(db0, 0, (size_t)K * sizeof(float), st);
+    return ERCG_OK;
+  }
+  if (!h || !dlogits || !W3 || !dZ || ldh < K || ldz < K) return ERCG_EINVAL;
+  if (!v4_ok(h, ldh) || !v4_ok(dZ, ldz) || !aligned16(W3)) return ERCG_EALIGN;
+  if (workspace_bytes < ercg_cls_tail_bwd_workspace_bytes(K, C) || !workspace) return ERCG_EWORKSPACE;
+  long long want = (N + 31) / 32;
+  const int grid = (int)(want < 1 ? 1 : (want > 4LL * kNumSMs ? 4LL * kNumSMs : want));
+  float* part = reinterpret_cast<float*>(workspace);
+  const int width = C * K + K + CT_MAXC;
+  switch (C) {
+#define ERCG_CT_CASE(c) case c: cls_tail_bwd_kernel<c><<<grid, 256, 0, st>>>(h, ldh, dlogits, W3, scale, dZ, ldz, N, K, part); break;
+    ERCG_CT_CASE(1) ERCG_CT_CASE(2) ERCG_CT_CASE(3) ERCG_CT_CASE(4) ERCG_CT_CASE(5) ERCG_CT_CASE(6) ERCG_CT_CASE(7) ERCG_CT_CASE(8)
+#undef ERCG_CT_CASE
+  }
+  int rc = finish_launch();
+  if (rc) return rc;
+  cls_tail_final_kernel<<<(width + 31) / 32, 256, 0, st>>>(part, grid, width, C * K, K, C, dW3, db0, db3);
   return finish_launch();
 }

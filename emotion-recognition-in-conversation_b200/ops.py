@@ -133,7 +133,9 @@ class _LinearAct(torch.autograd.Function):
         dC = dC.contiguous()
         if ctx.act != ACT_NONE:
             scale = 1.0 / (1.0 - ctx.drop_p) if ctx.act == ACT_RELU_DROPOUT else 1.0
-            dZ = mask_pos(dC, C, scale)
+            # the fused classifier-tail backward hands over the gradient already masked and scaled (and its column sums)
+            masked = getattr(dC, "_ercg_masked", None)
+            dZ = dC if masked == (C.data_ptr(), scale) else mask_pos(dC, C, scale)
         else:
             dZ = dC
         dA = dB = dbias = None
@@ -156,6 +158,49 @@ def mask_pos(x, ref, scale=1.0):
     check(lib().ercg_mask_pos(_p(x), ldx, _p(ref), ldr, float(scale), _p(out), out.stride(0), x.size(0), x.size(1), _stream()),
           "ercg_mask_pos")
     return out
+
+
+class _ClassifierTail(torch.autograd.Function):
+    """logits = h @ W3^T + b3 where h is the output of a Linear+ReLU(+dropout) epilogue (ops.linear(..., act=ACT_RELU*)).
+
+    Backward is ONE kernel pass over h (ercg_cls_tail_bwd): it returns the gradient of that previous layer's PRE-activation
+    (mask and dropout scale applied) together with its column sums, tagged so that _LinearAct.backward skips its own mask
+    and bias-gradient passes, plus dW3 and db3."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, scale):
+        logits = gemm_nn(h, weight.t().contiguous(), bias)
+        ctx.scale = scale
+        ctx.save_for_backward(h, weight)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        h, weight = ctx.saved_tensors
+        h, ldh = _rows(h)
+        N, K = h.shape
+        C = weight.size(0)
+        dlogits = dlogits.contiguous()
+        dev = h.device
+        dZ = torch.empty((N, K), dtype=torch.float32, device=dev)
+        dW3 = torch.empty((C, K), dtype=torch.float32, device=dev)
+        db3 = torch.empty(C, dtype=torch.float32, device=dev)
+        db0 = torch.empty(K, dtype=torch.float32, device=dev)
+        ws = _ws(lib().ercg_cls_tail_bwd_workspace_bytes(K, C), dev)
+        check(lib().ercg_cls_tail_bwd(_p(h), ldh, _p(dlogits), _p(weight.contiguous()), float(ctx.scale), _p(dZ), K, _p(dW3),
+                                      _p(db3), _p(db0), N, K, C, _p(ws), ws.numel(), _stream()), "ercg_cls_tail_bwd")
+        dZ._ercg_masked = (h.data_ptr(), float(ctx.scale))
+        dZ._ercg_colsum = db0
+        return dZ, dW3, db3, None
+
+
+def classifier_tail(h, weight, bias, scale):
+    """Last Linear of  Linear -> ReLU -> Dropout -> Linear  (cogmen.py:116-122); ``h`` must be the tensor returned by
+    ops.linear(..., act=ACT_RELU or ACT_RELU_DROPOUT) and ``scale`` that layer's dropout scale (1/(1-p), or 1)."""
+    K, C = h.size(1), weight.size(0)
+    if bias is None or (K & 3) or K > 128 or C > 8 or not h.requires_grad:
+        return linear(h, weight, bias)
+    return _ClassifierTail.apply(h, weight, bias, float(scale))
 
 
 def linear(x, weight, bias=None, act=ACT_NONE, a_rows=None, drop_p=0.0, seed=0):

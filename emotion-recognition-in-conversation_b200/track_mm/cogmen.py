@@ -88,9 +88,11 @@ class COGMENModule(nn.Module):
         lin0, drop, lin3 = self.cls[0], self.cls[2], self.cls[3]
         if self.training and drop.p > 0:
             h = ops.linear(graph_out, lin0.weight, lin0.bias, act=ops.ACT_RELU_DROPOUT, drop_p=drop.p, seed=_fresh_seed())
+            scale = 1.0 / (1.0 - drop.p)
         else:
             h = ops.linear(graph_out, lin0.weight, lin0.bias, act=ops.ACT_RELU)
-        return ops.linear(h, lin3.weight, lin3.bias)
+            scale = 1.0
+        return ops.classifier_tail(h, lin3.weight, lin3.bias, scale)       # backward of both layers' tails in one kernel
 
     def _graph_forward(self, features, g):
         g.attach()

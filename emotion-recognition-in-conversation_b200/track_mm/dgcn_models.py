@@ -131,6 +131,8 @@ class Classifier(nn.Module):
         if self.training and self.drop.p > 0:
             hidden = ops.linear(h, self.lin1.weight, self.lin1.bias, act=ops.ACT_RELU_DROPOUT, drop_p=self.drop.p,
                                 seed=_fresh_seed())
+            scale = 1.0 / (1.0 - self.drop.p)
         else:
             hidden = ops.linear(h, self.lin1.weight, self.lin1.bias, act=ops.ACT_RELU)
-        return ops.linear(hidden, self.lin2.weight, self.lin2.bias)
+            scale = 1.0
+        return ops.classifier_tail(hidden, self.lin2.weight, self.lin2.bias, scale)   # fused backward of the tail

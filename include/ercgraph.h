@@ -301,6 +301,16 @@ int ercg_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, const fl
                 void* workspace, size_t workspace_bytes, void* stream);
 int ercg_scale_by_ratio(float* x, int64_t n, const float* num, const float* den, void* stream);
 
+/* Backward of the classifier tail  Linear(K,K) -> ReLU -> Dropout -> Linear(K,C)  (cogmen.py:116-122) in one pass over the
+ * hidden activations h [N,K] (post ReLU / dropout): dZ = (h > 0 ? scale : 0) * (dlogits @ W3)  (gradient of the first
+ * Linear's pre-activation; scale = 1/(1-p) with dropout, 1 without), dW3 [C,K] = dlogits^T @ h, db3 [C] = column sums of
+ * dlogits, db0 [K] = column sums of dZ.  dlogits is [N,C] contiguous, W3 the nn.Linear weight [C,K].  K % 4 == 0,
+ * K <= 128, C <= 8.  Replaces five launches (ercg_gemm_tn, ercg_gemm_nn, ercg_mask_pos, 2 x ercg_colsum). */
+size_t ercg_cls_tail_bwd_workspace_bytes(int K, int C);
+int ercg_cls_tail_bwd(const float* h, int64_t ldh, const float* dlogits, const float* W3, float scale,
+                      float* dZ, int64_t ldz, float* dW3, float* db3, float* db0, int64_t N, int K, int C,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K7  MMGCN cross-modal utterance graph as a block adjacency (MMGCN.create_big_adj,
  * track_mm/mmgcn_models.py:582-646).  M modalities, N utterances, node (m,i) = row m*N + i

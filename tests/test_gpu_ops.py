@@ -352,3 +352,43 @@ def test_gather_window_backward_is_bit_identical_to_generic(wp, wf, n, one_speak
         torch.cuda.synchronize()
         assert not torch.isnan(b).any()
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("N,C,p", [(37, 6, 0.0), (5000, 6, 0.5), (70001, 4, 0.5), (4096, 7, 0.0)])
+def test_classifier_tail_fused_backward(N, C, p):
+    """Linear -> ReLU -> Dropout -> Linear: the fused tail backward (one pass over the hidden activations) gives the same
+    gradients as the unfused chain (mask kernel, skinny GEMMs, column sums) and as fp64 autograd on the same dropout mask."""
+    import erc_b200
+    from erc_b200 import ops, _lib
+    K = 100
+    g = torch.Generator().manual_seed(N + C)
+    x = torch.randn(N, K, generator=g).cuda().requires_grad_()
+    W0, b0 = (torch.randn(K, K, generator=g) * 0.1).cuda().requires_grad_(), torch.randn(K, generator=g).cuda().requires_grad_()
+    W3, b3 = (torch.randn(C, K, generator=g) * 0.1).cuda().requires_grad_(), torch.randn(C, generator=g).cuda().requires_grad_()
+    dl = torch.randn(N, C, generator=g).cuda()
+    act = ops.ACT_RELU_DROPOUT if p > 0 else ops.ACT_RELU
+    scale = 1.0 / (1.0 - p) if p > 0 else 1.0
+
+    def run(fused):
+        for t in (x, W0, b0, W3, b3):
+            t.grad = None
+        h = ops.linear(x, W0, b0, act=act, drop_p=p, seed=77)
+        out = ops.classifier_tail(h, W3, b3, scale) if fused else ops.linear(h, W3, b3)
+        n0 = _lib.launch_count()
+        out.backward(dl)
+        launches = _lib.launch_count() - n0
+        return h.detach(), out.detach(), [t.grad.clone() for t in (x, W0, b0, W3, b3)], launches
+
+    h, out_f, gf, lf = run(True)
+    _, out_u, gu, lu = run(False)
+    assert torch.equal(out_f, out_u)
+    assert lf < lu                                   # fewer kernels, not just different ones
+    # fp64 autograd with the mask the kernel drew (h > 0 after relu+dropout)
+    mask = (h > 0).double() * scale
+    xd, W0d, b0d, W3d, b3d = (t.detach().double().cpu().requires_grad_() for t in (x, W0, b0, W3, b3))
+    hd = (xd @ W0d.t() + b0d) * mask.cpu()         # the mask IS relu' x dropout (no clamp: fp64 could flip a borderline sign)
+    (hd @ W3d.t() + b3d).backward(dl.double().cpu())
+    want = [t.grad for t in (xd, W0d, b0d, W3d, b3d)]
+    for a, b, w in zip(gf, gu, want):
+        assert rel_err(a, w) < 2e-5
+        assert rel_err(a, b) < 2e-5
