@@ -360,8 +360,11 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // The whole warp runs this loop with warp-uniform control flow and one ELECTED lane issues the tcgen05 instructions
     // (profiles/r01_*: inside an `if (lane == 0)` region every descriptor had to be moved vector -> uniform register
     // per instruction and the issue loop itself, ~150 clk per UTCHMMA, was the bottleneck of the kernel).
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // bf16 x bf16 -> f32
+    // UMMA N per N tile: bn, except the LAST tile of a row of tiles, which only computes the columns that exist (rounded up
+    // to 16) -- N = 400 is 3 x 128 + 16 and N = 300 is 2 x 128 + 44: the tail tile costs 1/8 resp. 3/8 of a full one
+    const int n_tail = (N - (n_tiles - 1) * bn + 15) & ~15;
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc16_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BM >> 4) << 24);   // bf16 x bf16 -> f32
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
     uint32_t a_base = 0, nb_ = 0;     // A chunk loads before this M tile; B chunk loads so far
     int a = 0;
@@ -382,6 +385,8 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane == 0) TC_TRACE(2, nb_, 3);
           tc_fence_after();
           // k-steps that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 tf32 steps of 8, not 16)
+          const uint32_t n_mma = (uint32_t)((nt == n_tiles - 1 ? n_tail : bn) >> 3) << 17;
+          const uint32_t idesc = idesc_base | n_mma, idesc16 = idesc16_base | n_mma;
           const int krem = K - kc * TC_BK;
           const int ks_n = (ep.dbg & 1) ? 0 : min(TC_BK / 8, (krem + 7) >> 3);
           const int k16_n = (ep.dbg & 1) ? 0 : min(TC_BK / 16, (krem + 15) >> 4);
@@ -515,7 +520,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < TC_BN; c += 32) {
-              if (c < bn) {
+              if (c < bn && n0 + c < N) {
                 uint32_t rr[32];
                 tc_ld32(tmem_lane + (uint32_t)(a * TC_BN + c), rr);
                 tc_wait_ld();
