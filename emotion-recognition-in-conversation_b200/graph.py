@@ -57,6 +57,11 @@ class PackedGraph:
                 if name not in ("edge_index", "edge_type", "edge_index_lengths", "_core"):
                     setattr(core, name, getattr(self, name))
             self._core = core
+        if self.edge_index is None:
+            # built without the reference-layout int64 arrays (24 bytes per edge nobody on the module path reads): the conv
+            # layers only need a handle that carries the packed graph, so an empty [2, 0] tensor stands in for edge_index
+            self.edge_index = torch.empty((2, 0), dtype=torch.int64, device=self.device)
+            self.edge_type = torch.empty(0, dtype=torch.int64, device=self.device)
         self.edge_index._ercg_graph = core
         return self.edge_index
 
