@@ -251,7 +251,7 @@ def run_ours(args):
 
     def step(xi, spki, labi):
         t = [time.perf_counter()] if trace is not None else None
-        g = build_graph(lengths, spki, 5, 5, 2, device=dev, sizes=sizes, reference_layout=False)   # packed CSR only
+        g = build_graph(lengths, spki, 5, 5, 2, device=dev, sizes=sizes)
         if t is not None:
             t.append(time.perf_counter())
             g.relation_slots()
@@ -399,7 +399,7 @@ def run_ours(args):
                 "attn_fwd": 5 * 4 * H * N + 4 * (N + 1) + 8 * E,
                 "attn_bwd_dst": 5 * 4 * H * N + 4 * (N + 1) + 12 * E,
                 "attn_bwd_src": 4 * 4 * H * N + 4 * (N + 1) + 16 * E,
-                "graphify_csr": 8 * lengths.numel() + 8 * N + 8 * (N + 1) + 12 * N + E * (4 + 1 + 4 + 1 + 4 + 4),
+                "graphify_csr": 8 * lengths.numel() + 8 * N + 8 * (N + 1) + 12 * N + E * (4 + 1 + 4 + 1 + 4 + 4 + 24),
                 "bn_stats": 4 * H * N, "bn_act_fwd": 8 * H * N, "bn_act_bwd_reduce": 8 * H * N, "bn_act_bwd_apply": 12 * H * N,
                 "mask_pos": 12 * H * N, "colsum": None, "ce_fwd": (4 * N_CLASSES * 2 + 8) * N,
                 "cls_tail_bwd": (8 * H + 4 * N_CLASSES) * N,

@@ -103,8 +103,7 @@ class COGMENModule(nn.Module):
         if self.run_dead_encoder:
             self.rnn[0](input_tensor)                # result discarded, exactly like cogmen.py:146-147
         B, Lmax, D = input_tensor.shape
-        g = build_graph(text_length, speaker_tensor, self.wp, self.wf, self.n_speakers, device=input_tensor.device,
-                        reference_layout=False)     # the int64 edge_index / edge_type are only materialised by batch_graphify
+        g = build_graph(text_length, speaker_tensor, self.wp, self.wf, self.n_speakers, device=input_tensor.device)
         lin = self.rnn[1]
         flat = input_tensor.reshape(B * Lmax, D)
         features = ops.linear(flat, lin.weight, lin.bias, a_rows=g.pad_row)   # Linear fused with the node packing
@@ -113,7 +112,7 @@ class COGMENModule(nn.Module):
     def forward_packed(self, x_packed, speaker_packed, text_length, graph=None):
         """Resident-data entry point: utterance rows already packed [N, hidden_all] (no padding)."""
         g = graph if graph is not None else build_graph(text_length, speaker_packed, self.wp, self.wf, self.n_speakers,
-                                                        device=x_packed.device, reference_layout=False)
+                                                        device=x_packed.device)
         lin = self.rnn[1]
         features = ops.linear(x_packed, lin.weight, lin.bias)
         return self._graph_forward(features, g)
