@@ -48,6 +48,20 @@ GEMM_ENGINE = _os.environ.get("ERCG_GEMM", "tc")
 TC_MIN_ROWS = 256
 
 
+def _tag_set(t, name, value):
+    """Attach a by-product of the kernel that produced ``t`` (its column sums, "already masked") to the tensor object.
+    The tag records the tensor's version counter: if anything writes into ``t`` afterwards (e.g. the autograd engine
+    accumulating a second gradient in place) the version moves on and the tag is ignored."""
+    setattr(t, name, (value, t._version))
+
+
+def _tag_get(t, name):
+    tag = getattr(t, name, None)
+    if tag is None or tag[1] != t._version:
+        return None
+    return tag[0]
+
+
 def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_scale=1.0, drop_p=0.0, seed=0, out=None,
             want_colsum=False):
     """C = act(A[a_rows] @ Bm + bias).  ``want_colsum``: when the tensor-core kernel runs a plain product with N <= 128 it
@@ -74,7 +88,7 @@ def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_s
                                     float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _p(cs), _p(ws), ws.numel(),
                                     _stream()), "ercg_gemm_nn_tc")
         if cs is not None:
-            C._ercg_colsum = cs
+            _tag_set(C, "_ercg_colsum", cs)
         return C
     check(lib().ercg_gemm_nn(_p(A), lda, _p(a_rows), _p(Bm), ldb, _p(bias), _p(C), C.stride(0) if M > 1 else N, M, N, K,
                              act, _p(aux), ldaux, float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _stream()),
@@ -104,7 +118,7 @@ def gemm_tn(A, Bm, a_rows=None, M=None):
 
 
 def colsum(A):
-    pre = getattr(A, "_ercg_colsum", None)       # column sums emitted by the kernel that produced A (see _Attn.backward)
+    pre = _tag_get(A, "_ercg_colsum")            # column sums emitted by the kernel that produced A (see _Attn.backward)
     if pre is not None and pre.numel() == A.size(1):
         return pre
     A, lda = _rows(A)
@@ -134,7 +148,7 @@ class _LinearAct(torch.autograd.Function):
         if ctx.act != ACT_NONE:
             scale = 1.0 / (1.0 - ctx.drop_p) if ctx.act == ACT_RELU_DROPOUT else 1.0
             # the fused classifier-tail backward hands over the gradient already masked and scaled (and its column sums)
-            masked = getattr(dC, "_ercg_masked", None)
+            masked = _tag_get(dC, "_ercg_masked")
             dZ = dC if masked == (C.data_ptr(), scale) else mask_pos(dC, C, scale)
         else:
             dZ = dC
@@ -189,18 +203,28 @@ class _ClassifierTail(torch.autograd.Function):
         ws = _ws(lib().ercg_cls_tail_bwd_workspace_bytes(K, C), dev)
         check(lib().ercg_cls_tail_bwd(_p(h), ldh, _p(dlogits), _p(weight.contiguous()), float(ctx.scale), _p(dZ), K, _p(dW3),
                                       _p(db3), _p(db0), N, K, C, _p(ws), ws.numel(), _stream()), "ercg_cls_tail_bwd")
-        dZ._ercg_masked = (h.data_ptr(), float(ctx.scale))
-        dZ._ercg_colsum = db0
+        _tag_set(dZ, "_ercg_masked", (h.data_ptr(), float(ctx.scale)))
+        _tag_set(dZ, "_ercg_colsum", db0)
         return dZ, dW3, db3, None
 
 
-def classifier_tail(h, weight, bias, scale):
-    """Last Linear of  Linear -> ReLU -> Dropout -> Linear  (cogmen.py:116-122); ``h`` must be the tensor returned by
-    ops.linear(..., act=ACT_RELU or ACT_RELU_DROPOUT) and ``scale`` that layer's dropout scale (1/(1-p), or 1)."""
+def classifier_tail(h, weight, bias, scale=None):
+    """Last Linear of  Linear -> ReLU -> Dropout -> Linear  (cogmen.py:116-122, dgcn_models.py:158-167).
+
+    The fused backward masks the gradient with ``h > 0`` and applies the dropout scale of the layer that PRODUCED ``h``, so
+    it is only taken when ``h`` is, verifiably, the contiguous output of ops.linear(..., act=ACT_RELU / ACT_RELU_DROPOUT)
+    (its autograd node says so and supplies the scale); anything else goes through the plain linear path."""
     K, C = h.size(1), weight.size(0)
-    if bias is None or (K & 3) or K > 128 or C > 8 or not h.requires_grad:
+    fn = h.grad_fn
+    fused = (bias is not None and (K & 3) == 0 and K <= 128 and C <= 8 and h.requires_grad and h.is_contiguous()
+             and fn is not None and type(fn).__name__ == "_LinearActBackward"
+             and getattr(fn, "act", ACT_NONE) in (ACT_RELU, ACT_RELU_DROPOUT))
+    if not fused:
         return linear(h, weight, bias)
-    return _ClassifierTail.apply(h, weight, bias, float(scale))
+    own = 1.0 / (1.0 - fn.drop_p) if fn.act == ACT_RELU_DROPOUT else 1.0
+    if scale is not None and abs(float(scale) - own) > 1e-12:
+        raise ValueError("classifier_tail: scale %r does not match the producing layer's dropout scale %r" % (scale, own))
+    return _ClassifierTail.apply(h, weight, bias, own)
 
 
 def linear(x, weight, bias=None, act=ACT_NONE, a_rows=None, drop_p=0.0, seed=0):
@@ -316,7 +340,7 @@ class _Attn(torch.autograd.Function):
             # bias gradient of the fused q|k|v|skip Linear = column sums of d: finished from the per-CTA partials and handed
             # to the consumer (ops.colsum) on the tensor itself, so the 4H-wide gradient is not read a second time
             cs_dst, cs_src = colsum(part[0]), colsum(part[1])                               # (dq | ds), (dk | dv)
-            d._ercg_colsum = torch.cat([cs_dst[:H], cs_src, cs_dst[H:]])
+            _tag_set(d, "_ercg_colsum", torch.cat([cs_dst[:H], cs_src, cs_dst[H:]]))
             return d, None, None, None
         check(lib().ercg_attn_bwd_dst(_p(dout), ldo, b + 4 * H, b + 8 * H, ld, _p(g.rowptr), _p(g.col), _p(alpha), scale,
                                       db, db + 12 * H, 4 * H, _p(dsig), N, H, _stream()), "ercg_attn_bwd_dst")

@@ -392,3 +392,62 @@ def test_classifier_tail_fused_backward(N, C, p):
     for a, b, w in zip(gf, gu, want):
         assert rel_err(a, w) < 2e-5
         assert rel_err(a, b) < 2e-5
+
+
+def test_classifier_tail_only_fuses_behind_a_relu_linear():
+    """The fused tail backward masks with h > 0: it must NOT be taken when h is not the output of a ReLU(+dropout) Linear
+    (plain Linear output, arbitrary tensor, non-contiguous view) -- those go through the ordinary linear path."""
+    import erc_b200
+    from erc_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    N, K, C = 4000, 100, 6
+    x = torch.randn(N, K, generator=g).cuda().requires_grad_()
+    W0, b0 = (torch.randn(K, K, generator=g) * 0.1).cuda(), torch.randn(K, generator=g).cuda()
+    W3, b3 = (torch.randn(C, K, generator=g) * 0.1).cuda().requires_grad_(), torch.randn(C, generator=g).cuda().requires_grad_()
+    dl = torch.randn(N, C, generator=g).cuda()
+    for make_h in (lambda: ops.linear(x, W0, b0),                          # no activation: gradient must NOT be masked
+                   lambda: (x * 1.0),                                       # not a Linear at all
+                   lambda: ops.linear(x, W0, b0, act=ops.ACT_RELU)[:, :]):  # a view of a ReLU Linear is still fine either way
+        for t in (x, W3, b3):
+            t.grad = None
+        h = make_h()
+        ops.classifier_tail(h, W3, b3).backward(dl)
+        got = [t.grad.clone() for t in (x, W3, b3)]
+        for t in (x, W3, b3):
+            t.grad = None
+        h2 = make_h()
+        ops.linear(h2, W3, b3).backward(dl)
+        for a, b in zip(got, (x.grad, W3.grad, b3.grad)):
+            assert rel_err(a, b) < 2e-5
+    h = ops.linear(x, W0, b0, act=ops.ACT_RELU_DROPOUT, drop_p=0.5, seed=1)
+    with pytest.raises(ValueError):
+        ops.classifier_tail(h, W3, b3, scale=1.0)
+
+
+def test_gradient_tags_do_not_survive_inplace_accumulation():
+    """The by-products hung on gradient tensors (fused column sums, "already masked") are tied to the tensor's version
+    counter.  A feature tensor with TWO consumers makes the autograd engine add a second gradient to the tagged one; the
+    bias gradient of the producing Linear must then be the column sums of the SUM, not the stale fused ones."""
+    import erc_b200
+    from erc_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    N, K = 3000, 100
+    x = torch.randn(N, K, generator=g).cuda()
+    W0, b0 = (torch.randn(K, K, generator=g) * 0.1).cuda().requires_grad_(), torch.randn(K, generator=g).cuda().requires_grad_()
+    W1 = (torch.randn(K, K, generator=g) * 0.1).cuda().requires_grad_()
+    extra = torch.randn(N, K, generator=g).cuda()
+    f = ops.linear(x, W0, b0)                       # feature tensor with two consumers
+    y = ops.linear(f, W1)                           # consumer 1: its input gradient carries fused column sums
+    loss = (y * y).sum() + (f * extra).sum()        # consumer 2: a plain ATen gradient added to it
+    loss.backward()
+    xd, W0d, b0d, W1d = x.double(), W0.detach().double().requires_grad_(), b0.detach().double().requires_grad_(), W1.detach().double()
+    fd = xd @ W0d.t() + b0d
+    ((fd @ W1d.t()) ** 2).sum().add((fd * extra.double()).sum()).backward()
+    assert rel_err(b0.grad, b0d.grad) < 2e-5
+    assert rel_err(W0.grad, W0d.grad) < 2e-5
+    # and the tag helpers themselves
+    t = torch.zeros(4, device="cuda")
+    ops._tag_set(t, "_ercg_colsum", "payload")
+    assert ops._tag_get(t, "_ercg_colsum") == "payload"
+    t.add_(1.0)
+    assert ops._tag_get(t, "_ercg_colsum") is None
