@@ -46,10 +46,15 @@ struct TcEpilogue {
 };
 constexpr int TR_N = 160;          // traced chunks
 constexpr int TR_ROLES = 5;        // 0 A producer, 1 splitter, 2 MMA, 3 epilogue (per group), 4 B producer
+// compiled in only with -DERCG_TRACE (make EXTRA=-DERCG_TRACE): the marks sit in the MMA issue loop, which paces the kernels
+#ifdef ERCG_TRACE
 #define TC_TRACE(role, idx, slot)                                                                   \
   do {                                                                                              \
     if (ep.trace && blockIdx.x == 0 && (idx) < TR_N) ep.trace[((role) * TR_N + (idx)) * 4 + (slot)] = clock64(); \
   } while (0)
+#else
+#define TC_TRACE(role, idx, slot) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -644,10 +649,14 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                   int w_tiles, int n_tiles, int S, long long rows_per_slab, long long* trace,
                   const __grid_constant__ CUtensorMap tmNp /* the narrow operand again, unswizzled boxes */) {
   extern __shared__ uint8_t smem_raw[];
+#ifdef ERCG_TRACE
 #define TN_TRACE(role, idx, slot)                                                                                     \
   do {                                                                                                                \
     if (trace && blockIdx.x == 0 && (idx) < (unsigned)TR_N) trace[((role) * TR_N + (idx)) * 4 + (slot)] = clock64();   \
   } while (0)
+#else
+#define TN_TRACE(role, idx, slot) do { } while (0)
+#endif
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* nring = smem + TN_R * TC_A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(nring + TN_Q * 3 * TC_B_BYTES);
@@ -1113,6 +1122,10 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
 
 // diagnostics: copy out the pipeline timeline CTA 0 recorded during the last ercg_gemm_nn_tc launch (ERCG_TC_TRACE=1)
 extern "C" int ercg_gemm_nn_tc_trace(long long* host_out /* [5][160][4] clock64 values, 0 = not recorded */) {
+#ifndef ERCG_TRACE
+  (void)host_out;
+  return ERCG_EINVAL;                       // library built without -DERCG_TRACE
+#endif
   if (!host_out || !trace_buf) return ERCG_EINVAL;
   return cudaMemcpy(host_out, trace_buf, sizeof(long long) * TR_ROLES * TR_N * 4, cudaMemcpyDeviceToHost) == cudaSuccess
              ? ERCG_OK : ERCG_ECUDA;

@@ -132,8 +132,9 @@ int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, co
  * reduced from the tiles while they sit in shared memory -- the bias gradient of the layer that produced A's operand
  * (the input gradient dX = dZ @ W^T of one Linear is the dZ whose column sums the previous Linear needs). */
 
-/* Diagnostics (ERCG_TC_TRACE=1 in the environment): CTA 0 of ercg_gemm_nn_tc records clock64() per pipeline role and
- * k-chunk; this copies the [5 roles][160 chunks][4 marks] table of the last launch to the host (synchronous). */
+/* Diagnostics (library built with -DERCG_TRACE and ERCG_TC_TRACE=1 / 2 in the environment): CTA 0 of ercg_gemm_nn_tc (1) or
+ * ercg_gemm_tn_tc (2) records clock64() per pipeline role and k-chunk; this copies the [5 roles][160 chunks][4 marks] table
+ * of the last launch to the host (synchronous).  Returns ERCG_EINVAL in a normal build. */
 int ercg_gemm_nn_tc_trace(long long* host_out);
 
 /* C[K1,N1] = A[M,K1]^T @ B[M,N1]  (weight gradients; contraction over the M utterance rows, split

@@ -1,4 +1,5 @@
-"""Pipeline timeline of the NN tensor-core GEMM (ERCG_TC_TRACE=1): per k-chunk clock deltas of CTA 0."""
+"""(needs a library built with `make -C emotion-recognition-in-conversation_b200/csrc EXTRA=-DERCG_TRACE`)
+Pipeline timeline of the NN tensor-core GEMM (ERCG_TC_TRACE=1): per k-chunk clock deltas of CTA 0."""
 import os, sys
 os.environ["ERCG_TC_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

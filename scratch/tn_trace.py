@@ -1,3 +1,4 @@
+# needs a library built with: make -C emotion-recognition-in-conversation_b200/csrc clean all EXTRA=-DERCG_TRACE
 import os, sys
 os.environ["ERCG_TC_TRACE"] = "2"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
