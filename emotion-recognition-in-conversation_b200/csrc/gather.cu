@@ -14,6 +14,7 @@
 // Algorithmic HBM bytes per node: 4H*P (distinct Y slots referenced) + 4H (root) +
 // 4H (out) + 4 (rowptr) + 9*deg (col, etype, w).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace ercg {
 
@@ -86,6 +87,58 @@ gather_fwd_kernel(const float* __restrict__ Y, long long ldy, const int* __restr
       st4(out + node * ldo + 4 * ch, r);
     }
   }
+}
+
+// Forward with a FLAT thread-per-chunk mapping: thread c owns float4 chunk c % (H/4) of node c / (H/4).  With H = 100 a warp
+// of the kernel above has 25 busy lanes of 32; here every lane is busy (a warp straddles two or three nodes: their edge
+// metadata is read per lane, 2-3 distinct addresses per warp).  Same edges in the same order with the same 4-way grouping,
+// so the result is bit-identical to gather_fwd_kernel.
+__global__ void __launch_bounds__(256)
+gather_fwd_flat_kernel(const float* __restrict__ Y, long long ldy, const int* __restrict__ rowptr,
+                       const int* __restrict__ col, const uint8_t* __restrict__ etype, const int* __restrict__ rel_slot,
+                       const float* __restrict__ w, int root_off, const float* __restrict__ bias, float* __restrict__ out,
+                       long long ldo, long long N, int H) {
+  const int nch = H >> 2;
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (c >= N * nch) return;
+  const long long node = c / nch;
+  const int ch = (int)(c - node * nch);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  int e = beg;
+  for (; e + 4 <= end; e += 4) {
+    const float* p[4];
+    float ww[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int s = col[e + u];
+      int t = etype ? (int)etype[e + u] : 0;
+      if (rel_slot) t = __ldg(rel_slot + t);
+      ww[u] = w ? w[e + u] : 1.f;
+      p[u] = Y + (long long)s * ldy + (long long)t * H + 4 * ch;
+    }
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld4(p[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) fma4(acc, ww[u], v[u]);
+  }
+  for (; e < end; ++e) {
+    const int s = col[e];
+    int t = etype ? (int)etype[e] : 0;
+    if (rel_slot) t = __ldg(rel_slot + t);
+    const float ww = w ? w[e] : 1.f;
+    fma4(acc, ww, ld4(Y + (long long)s * ldy + (long long)t * H + 4 * ch));
+  }
+  if (root_off >= 0) {
+    const float4 y = ld4(Y + node * ldy + root_off + 4 * ch);
+    acc.x += y.x; acc.y += y.y; acc.z += y.z; acc.w += y.w;
+  }
+  if (bias) {
+    const float4 b = ld4(bias + 4 * ch);
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  st4(out + node * ldo + 4 * ch, acc);
 }
 
 // by-source backward.  For every relation slot r the warp re-walks the out-edges of j (the dout rows
@@ -297,6 +350,14 @@ extern "C" int ercg_gather_fwd(const float* Y, int64_t ldy, const int32_t* rowpt
   if ((root_off >= 0 && (root_off & 3)) || (bias && !aligned16(bias))) return ERCG_EALIGN;
   const unsigned blocks = (unsigned)((N + GW - 1) / GW);
   cudaStream_t st = (cudaStream_t)stream;
+  const char* flat_env = getenv("ERCG_GATHER_FLAT");      // "0" forces the warp-per-node kernel (A/B tests; read per call)
+  const int flat = flat_env ? atoi(flat_env) : 1;
+  const long long chunks = N * (long long)(H >> 2);
+  if (flat && (H >> 2) % 32 != 0 && chunks < 2147483647LL * 256) {      // widths that leave lanes idle in the warp-per-node form
+    gather_fwd_flat_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(Y, ldy, rowptr, col, etype, etype ? rel_slot : nullptr,
+                                                                            w, root_off, bias, out, ldo, N, H);
+    return finish_launch();
+  }
   if (H <= 128) gather_fwd_kernel<1><<<blocks, GW * 32, 0, st>>>(Y, ldy, rowptr, col, etype, etype ? rel_slot : nullptr, w, root_off, bias, out, ldo, N, H);
   else gather_fwd_kernel<2><<<blocks, GW * 32, 0, st>>>(Y, ldy, rowptr, col, etype, etype ? rel_slot : nullptr, w, root_off, bias, out, ldo, N, H);
   return finish_launch();

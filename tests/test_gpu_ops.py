@@ -451,3 +451,30 @@ def test_gradient_tags_do_not_survive_inplace_accumulation():
     assert ops._tag_get(t, "_ercg_colsum") == "payload"
     t.add_(1.0)
     assert ops._tag_get(t, "_ercg_colsum") is None
+
+
+@pytest.mark.parametrize("H,wp,wf,n", [(100, 5, 5, 2), (100, 10, 10, 2), (200, 4, 9, 3), (36, -1, -1, 2)])
+def test_gather_forward_flat_mapping_is_bit_identical(H, wp, wf, n, monkeypatch):
+    """gather_fwd_flat_kernel (thread per float4 chunk, all lanes busy) vs the warp-per-node kernel: same bits."""
+    import erc_b200
+    from erc_b200 import _lib
+    from erc_b200.graph import build_graph
+    rng = np.random.default_rng(H + wp + n)
+    lens = torch.as_tensor(rng.integers(1, 50, size=41))
+    spk = torch.as_tensor(rng.integers(0, n, size=(41, int(lens.max()))))
+    g = build_graph(lens, spk.cuda(), wp, wf, n)
+    R = 2 * n * n
+    gen = torch.Generator().manual_seed(1)
+    Y = torch.randn(g.N, (R + 1) * H, generator=gen).cuda()
+    w = (torch.rand(g.E, generator=gen) + 0.1).cuda()
+    bias = torch.randn(H, generator=gen).cuda()
+    lib, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ERCG_GATHER_FLAT", flag)
+        o = torch.full((g.N, H), float("nan"), device="cuda")
+        _lib.check(lib.ercg_gather_fwd(Y.data_ptr(), Y.stride(0), g.rowptr.data_ptr(), g.col.data_ptr(), g.etype.data_ptr(), None,
+                                       w.data_ptr(), R * H, bias.data_ptr(), o.data_ptr(), H, g.N, H, st), "ercg_gather_fwd")
+        torch.cuda.synchronize()
+        outs.append(o)
+    assert not torch.isnan(outs[0]).any() and torch.equal(outs[0], outs[1])
