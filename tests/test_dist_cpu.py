@@ -77,3 +77,17 @@ def test_two_rank_sync_equals_single_rank():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_gradient_tag_helpers_follow_the_tensor_version():
+    """ops._tag_set / _tag_get (by-products hung on gradient tensors): valid until the tensor is written again."""
+    import erc_b200
+    from erc_b200 import ops
+    t = torch.zeros(8)
+    assert ops._tag_get(t, "_ercg_colsum") is None
+    ops._tag_set(t, "_ercg_colsum", "payload")
+    assert ops._tag_get(t, "_ercg_colsum") == "payload"
+    u = t.view(2, 4)                       # a view is another tensor object: no tag
+    assert ops._tag_get(u, "_ercg_colsum") is None
+    t.mul_(2.0)                            # any in-place write invalidates the tag
+    assert ops._tag_get(t, "_ercg_colsum") is None
