@@ -15,7 +15,6 @@ buffers (H2D of the inputs and D2H of the loss inside the timed region).
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

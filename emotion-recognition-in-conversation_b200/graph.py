@@ -9,7 +9,6 @@ import ctypes
 
 import torch
 
-from . import _lib
 from ._lib import lib, check, GraphOut
 
 

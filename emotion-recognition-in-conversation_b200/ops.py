@@ -4,12 +4,9 @@ Every forward/backward here is one or more calls into libercgraph.so on the curr
 PyTorch only owns the buffers.  Nothing in this file computes on the CPU or through ATen kernels
 except O(parameters) re-layouts of weights (transposes / concatenations of <= 600 KB tensors).
 """
-import math
-
 import torch
 
-from . import _lib
-from ._lib import lib, check, ACT_NONE, ACT_RELU, ACT_RELU_DROPOUT, ACT_MASK_POS
+from ._lib import lib, check, ACT_NONE, ACT_RELU, ACT_RELU_DROPOUT, ACT_MASK_POS  # noqa: F401  (ACT_* re-exported as ops.ACT_*)
 
 
 def _p(t):
