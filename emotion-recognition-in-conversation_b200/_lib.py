@@ -102,6 +102,8 @@ SIGNATURES = {
     "ercg_dag_dense_masks": (I, [P, I, I, I, P, P, P]),
     "ercg_dag_layer_fwd": (I, [POINTER(DagLayer), P]),
     "ercg_dag_layer_bwd": (I, [POINTER(DagLayer), P]),
+    "ercg_dag_gat_fwd": (I, [P, L, P, L, L, P, L, L, P, P, L, P, P, P, P, I, I, I, P]),
+    "ercg_dag_gat_bwd": (I, [P, L, L, P, L, P, P, P, P, P, P, P, P, I, I, I, P]),
 }
 
 _lib = None

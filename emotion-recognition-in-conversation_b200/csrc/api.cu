@@ -2,7 +2,7 @@
 #include "common.cuh"
 
 namespace ercg {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 }
 
 extern "C" const char* ercg_strerror(int code) {
@@ -19,4 +19,4 @@ extern "C" const char* ercg_strerror(int code) {
 
 extern "C" int ercg_version(void) { return 100; }
 
-extern "C" unsigned long long ercg_launch_count(void) { return ercg::g_launches; }
+extern "C" unsigned long long ercg_launch_count(void) { return ercg::g_launches.load(std::memory_order_relaxed); }

@@ -800,11 +800,11 @@ extern "C" int ercg_attn_window_fwd(const float* q, const float* k, const float*
   const size_t sm = attn_tile_smem(H, wlo, whi, 1, 2);
   const unsigned blocks = (unsigned)((N + WT - 1) / WT);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     cudaFuncSetAttribute(attn_fwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(attn_fwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr = true;
+    attr.mark();
   }
   if (wlo + whi + 1 <= 16) attn_fwd_tile_kernel<true><<<blocks, 256, sm, st>>>(q, k, v, s, ld, rowptr, col, scale, out, ldo, alpha, N, H, wlo, whi);
   else attn_fwd_tile_kernel<false><<<blocks, 256, sm, st>>>(q, k, v, s, ld, rowptr, col, scale, out, ldo, alpha, N, H, wlo, whi);
@@ -823,11 +823,11 @@ extern "C" int ercg_attn_window_bwd_dst(const float* dout, int64_t ldo, const fl
   const size_t sm = attn_tile_smem(H, wlo, whi, 1, 2);
   const unsigned blocks = (unsigned)((N + WT - 1) / WT);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     cudaFuncSetAttribute(attn_bwd_dst_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(attn_bwd_dst_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr = true;
+    attr.mark();
   }
   if (wlo + whi + 1 <= 16) attn_bwd_dst_tile_kernel<true><<<blocks, 256, sm, st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, colsum_partial, N, H, wlo, whi);
   else attn_bwd_dst_tile_kernel<false><<<blocks, 256, sm, st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, colsum_partial, N, H, wlo, whi);
@@ -845,10 +845,10 @@ extern "C" int ercg_attn_window_bwd_src(const float* dout, int64_t ldo, const fl
   ERCG_CHK(dout, ldo); ERCG_CHK(q, ld); ERCG_CHK(dk, ldd); ERCG_CHK(dv, ldd);
   const size_t sm = attn_tile_smem(H, wlo, whi, 0, 2);
   const unsigned blocks = (unsigned)((N + WT - 1) / WT);
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     cudaFuncSetAttribute(attn_bwd_src_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr = true;
+    attr.mark();
   }
   attn_bwd_src_tile_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(dout, ldo, q, ld, t_rowptr, t_col, t_eid, alpha, dsig, scale, dk, dv, ldd, colsum_partial, N, H, wlo, whi);
   return finish_launch();

@@ -1,15 +1,16 @@
 // Shared helpers for the libercgraph kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include "../../include/ercgraph.h"
 
 namespace ercg {
 
-extern unsigned long long g_launches;   // counted on the host side, one per kernel launch
+extern std::atomic<unsigned long long> g_launches;   // counted on the host side, one per kernel launch (any thread)
 
 inline int finish_launch() {
-  ++g_launches;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaPeekAtLastError() == cudaSuccess ? ERCG_OK : ERCG_ECUDA;
 }
 
@@ -77,5 +78,39 @@ __device__ __forceinline__ bool dropout_drop(uint64_t h, int lane4, unsigned thr
 }
 
 constexpr int kNumSMs = 148;   // B200
+constexpr int kMaxDevices = 64; // per-device caches of launch attributes are indexed by the CUDA device id
+
+// Per-device one-time setup (cudaFuncSetAttribute is per device context) and per-device attribute caches.  Function-local
+// `static bool done` flags made the second GPU of a process launch with the first GPU's setup; these are indexed by the
+// CUDA device id and safe to race on (worst case: the setup runs twice).
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+struct DeviceOnce {
+  std::atomic<unsigned char> done[kMaxDevices];
+  bool need() const {
+    const int d = current_device();
+    return d < 0 || d >= kMaxDevices || !done[d].load(std::memory_order_acquire);
+  }
+  void mark() {
+    const int d = current_device();
+    if (d >= 0 && d < kMaxDevices) done[d].store(1, std::memory_order_release);
+  }
+};
+inline int device_sm_count() {
+  static std::atomic<int> cache[kMaxDevices];
+  const int d = current_device();
+  if (d >= 0 && d < kMaxDevices) {
+    const int c = cache[d].load(std::memory_order_acquire);
+    if (c > 0) return c;
+  }
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+  if (n < 1) n = kNumSMs;
+  if (d >= 0 && d < kMaxDevices) cache[d].store(n, std::memory_order_release);
+  return n;
+}
 
 }  // namespace ercg

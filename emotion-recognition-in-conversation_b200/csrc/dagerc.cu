@@ -418,13 +418,7 @@ __global__ void dag_dense_kernel(const int* __restrict__ spk_pad, int B, int Lma
 }
 
 static int dag_units(int D, int* grid_out) {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms < 1) num_sms = kNumSMs;
-  }
+  const int num_sms = device_sm_count();
   const int UN = (D + num_sms - 1) / num_sms;
   *grid_out = (D + UN - 1) / UN;
   return UN;

@@ -45,6 +45,7 @@ gather_fwd_kernel(const float* __restrict__ Y, long long ldy, const int* __restr
       int t = etype ? (int)etype[e + u] : 0;
       if (rel_slot) t = __ldg(rel_slot + t);
       ww[u] = w ? w[e + u] : 1.f;
+      if (t < 0) { t = 0; ww[u] = 0.f; }                  // relation id without a slot in Y (layer has fewer relations): no message
       p[u] = Y + (long long)s * ldy + (long long)t * H;
     }
 #pragma unroll
@@ -63,7 +64,8 @@ gather_fwd_kernel(const float* __restrict__ Y, long long ldy, const int* __restr
     const int s = col[e];
     int t = etype ? (int)etype[e] : 0;
     if (rel_slot) t = __ldg(rel_slot + t);
-    const float ww = w ? w[e] : 1.f;
+    float ww = w ? w[e] : 1.f;
+    if (t < 0) { t = 0; ww = 0.f; }
     const float* p = Y + (long long)s * ldy + (long long)t * H;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -115,6 +117,7 @@ gather_fwd_flat_kernel(const float* __restrict__ Y, long long ldy, const int* __
       int t = etype ? (int)etype[e + u] : 0;
       if (rel_slot) t = __ldg(rel_slot + t);
       ww[u] = w ? w[e + u] : 1.f;
+      if (t < 0) { t = 0; ww[u] = 0.f; }                  // relation id without a slot in Y (layer has fewer relations): no message
       p[u] = Y + (long long)s * ldy + (long long)t * H + 4 * ch;
     }
     float4 v[4];
@@ -127,7 +130,8 @@ gather_fwd_flat_kernel(const float* __restrict__ Y, long long ldy, const int* __
     const int s = col[e];
     int t = etype ? (int)etype[e] : 0;
     if (rel_slot) t = __ldg(rel_slot + t);
-    const float ww = w ? w[e] : 1.f;
+    float ww = w ? w[e] : 1.f;
+    if (t < 0) { t = 0; ww = 0.f; }
     fma4(acc, ww, ld4(Y + (long long)s * ldy + (long long)t * H + 4 * ch));
   }
   if (root_off >= 0) {

@@ -68,21 +68,37 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Every wait is bounded in WALL TIME, not in polls: a pipeline bug must fail instead of hanging the GPU, but a slow and
+// legitimate wait (a pre-empted context, a debugger, a contended L2) must never be mistaken for one -- a __trap() poisons
+// the whole CUDA context.  The clock is read once per 65536 polls; the limit is 20 s, four orders of magnitude above
+// the longest wait of a healthy launch (~1 ms).  Build with -DERCG_NO_WAIT_LIMIT to remove the check altogether.
+__device__ __forceinline__ bool mbar_timed_out(unsigned long long& t0) {
+#ifdef ERCG_NO_WAIT_LIMIT
+  return false;
+#else
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (t0 == 0ull) { t0 = now; return false; }
+  return now - t0 > 20000000000ull;
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  unsigned long long t0 = 0ull;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > (1u << 24)) __trap();            // ~seconds: a broken pipeline must fail, not hang the GPU
+    if ((spin & 0xffffu) == 0xffffu && mbar_timed_out(t0)) __trap();
   }
 }
 // same wait for warps that are NOT on the latency-critical path (TMA producers): back off between polls so that the spin
 // loop does not eat the issue slots of the splitter / epilogue warps that share the SM sub-partition
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  unsigned long long t0 = 0ull;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -90,7 +106,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (!done) __nanosleep(96);
-    if (spin > (1u << 22)) __trap();
+    if ((spin & 0xffffu) == 0xffffu && mbar_timed_out(t0)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -1081,21 +1097,15 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   static const NnKernel kernels[4][2] = {
       {gemm_tc_nn_kernel<0, false>, gemm_tc_nn_kernel<0, true>}, {gemm_tc_nn_kernel<1, false>, gemm_tc_nn_kernel<1, true>},
       {gemm_tc_nn_kernel<2, false>, gemm_tc_nn_kernel<2, true>}, {gemm_tc_nn_kernel<3, false>, gemm_tc_nn_kernel<3, true>}};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;            // cudaFuncSetAttribute is per device context: once per DEVICE, not per process
+  if (attr_set.need()) {
     for (int i = 0; i < 4; ++i)
       for (int k = 0; k < 2; ++k)
         if (cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
           return ERCG_ECUDA;
-    attr_set = true;
+    attr_set.mark();
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms < 1) num_sms = kNumSMs;
-  }
+  const int num_sms = device_sm_count();
   const long long tiles = (M + TC_BM - 1) / TC_BM;          // a CTA owns whole M tiles (all their N tiles)
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   static int dbg = -1;
@@ -1174,11 +1184,11 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
   if (!make_map_plain(&tmW, W, M, Wc, ldw) ||
       !make_map(&tmN, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
       !make_map(&tmNp, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return ERCG_ECUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     if (cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
       return ERCG_ECUDA;
-    attr_set = true;
+    attr_set.mark();
   }
   cudaStream_t st = (cudaStream_t)stream;
   const long long units = (long long)wt * nt * S;

@@ -14,6 +14,7 @@
 //      by-source edge range lane-per-edge (coalesced 4/1/8-byte stores).
 // HBM traffic (algorithmic): 8B(lengths) + N speakers + 8(N+1) rowptrs + E*(4+1+4+1+4) (+4E inv_cnt,
 // +24E when the reference-layout int64 edge_index/edge_type are requested).
+#include <atomic>
 #include "common.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -111,17 +112,25 @@ __device__ __forceinline__ void fill_dialogue(const GraphifyParams& p, int d, I 
   const I F = (p.wf < 0 || (long long)p.wf > (long long)m) ? m : (I)p.wf;
   for (I k = lane; k < L; k += 32) {
     long long s;
+    int bad = 0;
+    // a dialogue longer than the padded width would read the next dialogue's speakers (or past the array) and emit pad_row
+    // values outside [0, B*Lmax): never dereference, clamp, and raise ERCG_GRAPH_ELENGTH in rel_info[513] (the reference
+    // raises IndexError here, cogmen_utils.py:131-132)
+    const long long kk = (p.spk_ld > 0 && (long long)k >= p.spk_ld) ? p.spk_ld - 1 : (long long)k;
+    if (kk != (long long)k) bad |= 1;
     if (p.spk_ld > 0) {
-      const long long idx = (long long)d * p.spk_ld + (long long)k;
+      const long long idx = (long long)d * p.spk_ld + kk;
       s = p.spk64 ? reinterpret_cast<const long long*>(p.speakers)[idx]
                   : (long long)reinterpret_cast<const int*>(p.speakers)[idx];
     } else {
       s = p.spk64 ? reinterpret_cast<const long long*>(p.speakers)[(long long)o + k]
                   : (long long)reinterpret_cast<const int*>(p.speakers)[(long long)o + k];
     }
+    if (s < 0 || s >= (long long)n_spk) { bad |= 2; s = 0; }       // would wrap in the uint8 relation id (reference: KeyError)
+    if (bad && p.o.rel_info) atomicOr(p.o.rel_info + 513, bad);
     p.o.spk[o + k] = (int)s;
     p.o.node_dlg[o + k] = d;
-    if (p.o.pad_row) p.o.pad_row[o + k] = (int)(p.spk_ld > 0 ? (long long)d * p.spk_ld + (long long)k : (long long)(o + k));
+    if (p.o.pad_row) p.o.pad_row[o + k] = (int)(p.spk_ld > 0 ? (long long)d * p.spk_ld + kk : (long long)(o + k));
     p.o.rowptr[o + k] = (int)(eo + deg_prefix_t<I>(L, P, F, k));
     p.o.t_rowptr[o + k] = (int)(eo + deg_prefix_t<I>(L, F, P, k));
   }
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(256) graphify_kernel(GraphifyParams p) {
   const int T = blockDim.x;
   const int numTiles = (p.B + T - 1) / T;
   if (p.o.rel_info && blockIdx.x == 0)       // [0] count, [1..256] id -> slot, [257..512] slot -> id: see rel_census_kernel
-    for (int i = threadIdx.x; i < 513; i += T) p.o.rel_info[i] = i == 0 ? 0 : -1;
+    for (int i = threadIdx.x; i < 516; i += T) p.o.rel_info[i] = (i == 0 || i >= 513) ? 0 : -1;   // [513] = input-error flags
 
   // ---- phase 1: tile aggregates
   for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
@@ -273,8 +282,10 @@ __global__ void __launch_bounds__(256) graphify_kernel(GraphifyParams p) {
     const long long L = load_len(p, (int)d);
     if (L == 0) continue;
     const long long o = p.o.node_off[d], eo = p.o.edge_off[d];
-    if (o + L > p.N) continue;                  // caller passed a too-small N: never write out of bounds
-    if (eo + dialog_edges(L, p.wp, p.wf) > p.E) continue;
+    if (o + L > p.N || eo + dialog_edges(L, p.wp, p.wf) > p.E) {   // caller passed too-small N / E: never write out of bounds
+      if (p.o.rel_info && (threadIdx.x & 31) == 0) atomicOr(p.o.rel_info + 513, 4);
+      continue;
+    }
     // every in-dialogue quantity fits 32 bits when L <= 46340 (L^2 < 2^31): the integer pipe is the bound of this kernel
     if (L <= 46340) fill_dialogue<int>(p, (int)d, (int)L, (int)o, (int)eo);
     else fill_dialogue<long long>(p, (int)d, L, o, eo);
@@ -402,15 +413,20 @@ extern "C" int ercg_graphify_csr(const void* lengths_dev, int lengths_is_i64, in
   p.speakers = speakers_dev; p.spk64 = speakers_is_i64; p.spk_ld = spk_ld;
   p.wp = wp; p.wf = wf; p.n_speakers = n_speakers; p.N = N; p.E = E; p.o = *out;
   p.tile_agg = reinterpret_cast<long long*>(workspace);
-  static int max_blocks_per_sm = 0;
-  static int num_sms = 0;
-  if (!max_blocks_per_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  // launch geometry is a property of the CURRENT device: cached per device id (read-mostly atomics, any thread may fill it)
+  static std::atomic<int> cache_bps[kMaxDevices], cache_sms[kMaxDevices];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+  int max_blocks_per_sm = cache_bps[slot].load(std::memory_order_acquire);
+  int num_sms = cache_sms[slot].load(std::memory_order_acquire);
+  if (!max_blocks_per_sm || !num_sms || slot != dev) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, graphify_kernel, 256, 0);
     if (max_blocks_per_sm < 1) max_blocks_per_sm = 1;
     if (num_sms < 1) num_sms = kNumSMs;
+    cache_sms[slot].store(num_sms, std::memory_order_release);
+    cache_bps[slot].store(max_blocks_per_sm, std::memory_order_release);
   }
   long long want = (B + 7) / 8;                       // one warp per dialogue
   long long cap = (long long)max_blocks_per_sm * num_sms;

@@ -256,6 +256,9 @@ ce_fwd_kernel(const float* __restrict__ logits, long long ld, const long long* _
     const bool ok = y >= 0 && y < C;
     const float w = ok ? (cw ? cw[y] : 1.f) : 0.f;
     if (ok) { num = w * (lse - z[y]); den = w; }
+    // a label outside [0, C) that is not F.cross_entropy's ignore_index (-100) is an input error (ATen raises a device
+    // assert): poison the loss with NaN instead of silently giving the row weight 0
+    else if (y != -100) num = __int_as_float(0x7fc00000);
     if (dlogits) {
       const float inv = 1.f / se;
       for (int c = 0; c < C; ++c) {

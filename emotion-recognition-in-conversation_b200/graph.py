@@ -65,6 +65,19 @@ class PackedGraph:
         self.edge_index._ercg_graph = core
         return self.edge_index
 
+    def check_inputs(self):
+        """Raise ValueError if K1 flagged its inputs (length beyond the padded width, speaker id out of range, sizes too
+        small).  Costs one wait for the 2 KB census copy that left the GPU right behind K1 -- not a stream drain."""
+        if self.rel_info is None:
+            return
+        if self._rel_cache is None and not _NO_CENSUS:
+            self.relation_slots()
+            return
+        if self._rel_event is not None:
+            self._rel_event.synchronize()
+            _raise_graph_errors(int(self.rel_info[513].item()) if _CENSUS_GEN.get(id(self._rel_host)) != self._rel_gen
+                                else int(self._rel_host[513]))
+
     def relation_slots(self):
         """K1's relation census: (ids, rel_slot) -- the sorted relation ids that occur on at least one edge (python list)
         and the device int32 table id -> compact slot (-1 = absent) -- or None for graphs that did not come from K1.
@@ -76,10 +89,25 @@ class PackedGraph:
             info = self._rel_host.tolist()          # read NOW: the ring buffer is reused by later graphs
             if _CENSUS_GEN.get(id(self._rel_host)) != self._rel_gen:
                 info = self.rel_info.cpu().tolist()  # the landing buffer was recycled before anyone asked: read the device copy
+            _raise_graph_errors(info[513])
             P = info[0]
             ids = info[257:257 + P]
             self._rel_cache = (ids, self.rel_info[1:1 + self.num_relations])
         return self._rel_cache
+
+
+def _raise_graph_errors(flags):
+    if not flags:
+        return
+    what = []
+    if flags & 1:
+        what.append("a dialogue is longer than the padded speaker width (text_length > speaker_tensor.size(1))")
+    if flags & 2:
+        what.append("a speaker id lies outside [0, n_speakers)")
+    if flags & 4:
+        what.append("the given (N, E) sizes are smaller than the lengths imply")
+    raise ValueError("batch_graphify: invalid input -- " + "; ".join(what) +
+                     " (the reference raises IndexError / KeyError at cogmen_utils.py:131-137)")
 
 
 def graph_sizes(lengths_cpu, wp, wf):
@@ -99,9 +127,21 @@ def build_graph(lengths, speakers, wp, wf, n_speakers, device=None, reference_la
     speakers  padded [B,Lmax] or packed [N] int64/int32 speaker ids
     sizes     optional (N, E) if the caller already knows them
     """
+    B = lengths.numel()
+    if not lengths.is_cuda and B:
+        # host-side validation where it costs nothing (B integers already on the host); device-resident inputs are
+        # checked by the kernel itself (flags in rel_info[513], raised by check_inputs() / relation_slots())
+        lmin, lmax = int(lengths.min()), int(lengths.max())
+        if lmin < 0:
+            raise ValueError("build_graph: negative dialogue length %d" % lmin)
+        if speakers.dim() == 2 and lmax > speakers.size(1):
+            raise ValueError("build_graph: dialogue length %d exceeds the padded speaker width %d" % (lmax, speakers.size(1)))
+    if not speakers.is_cuda and speakers.numel():
+        smin, smax = int(speakers.min()), int(speakers.max())
+        if smin < 0 or smax >= n_speakers:
+            raise ValueError("build_graph: speaker ids must lie in [0, %d), got [%d, %d]" % (n_speakers, smin, smax))
     if device is None:
         device = speakers.device if speakers.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    B = lengths.numel()
     if sizes is None:
         if lengths.is_cuda:
             tot = torch.empty(2, dtype=torch.int64, device=device)
@@ -150,7 +190,7 @@ def build_graph(lengths, speakers, wp, wf, n_speakers, device=None, reference_la
         g.edge_index = torch.empty((2, E), dtype=torch.int64, device=device)
         g.edge_type = torch.empty(E, dtype=torch.int64, device=device)
         g.edge_index_lengths = torch.empty(B, dtype=torch.int64, device=device)
-    g.rel_info = torch.empty(513, **i32)
+    g.rel_info = torch.empty(516, **i32)
     out = GraphOut(*[_p(getattr(g, n)) for n, _ in GraphOut._fields_])
     ws_bytes = lib().ercg_graphify_workspace_bytes(B)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
@@ -174,7 +214,7 @@ def _census_slot(depth=8):
     global _census_next
     if not _CENSUS_RING:
         for _ in range(depth):
-            _CENSUS_RING.append((torch.empty(513, dtype=torch.int32, pin_memory=True), torch.cuda.Event()))
+            _CENSUS_RING.append((torch.empty(516, dtype=torch.int32, pin_memory=True), torch.cuda.Event()))
         _census_next = 0
     host, ev = _CENSUS_RING[_census_next]
     _census_next = (_census_next + 1) % len(_CENSUS_RING)

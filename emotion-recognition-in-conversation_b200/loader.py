@@ -33,7 +33,8 @@ class DeviceFeeder:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.extra_streams = [torch.cuda.Stream(device=self.device) for _ in range(copy_streams - 1)]
         self.chunk_bytes = chunk_bytes
-        self._bufs = [dict() for _ in range(depth)]          # slot -> {key: device tensor}
+        self._store = [dict() for _ in range(depth)]         # slot -> {key: flat uint8 device storage (high-water mark)}
+        self._bufs = [dict() for _ in range(depth)]          # slot -> {key: view of the storage shaped like the last batch}
         self._free = [None] * depth                          # slot -> event after which the slot may be overwritten
         self._ready = deque()                                # (slot, event, keys) in submission order
         self._in_use = deque()                               # slots handed out by get() and not yet released
@@ -46,12 +47,29 @@ class DeviceFeeder:
             raise RuntimeError("DeviceFeeder: all %d buffer sets are in flight; call get()/release() first" % self.depth)
         slot = self._next
         self._next = (self._next + 1) % self.depth
-        bufs = self._bufs[slot]
-        for k, h in batch.items():                           # buffers live as long as the feeder (allocated on the
-            d = bufs.get(k)                                  # caller's stream, never returned to the allocator)
-            if d is None or d.shape != h.shape or d.dtype != h.dtype:
-                bufs[k] = torch.empty(h.shape, dtype=h.dtype, device=self.device)
+        store, bufs = self._store[slot], self._bufs[slot]
         streams = [self.copy_stream] + self.extra_streams
+        grew = False
+        for k, h in batch.items():
+            # Device storage is sized to the HIGH-WATER mark per key and handed out as views, so the reference collate's
+            # changing Lmax (mmbase.py:354-455 pads every batch to its own longest dialogue) does not reallocate.
+            nbytes = h.numel() * h.element_size()
+            flat = store.get(k)
+            if flat is None or flat.numel() < nbytes:
+                if flat is not None:
+                    for st in streams:                       # the outgoing block may still be read by queued copies
+                        flat.record_stream(st)
+                store[k] = flat = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+                grew = True
+            bufs[k] = flat[:nbytes].view(h.dtype).view(h.shape) if nbytes else torch.empty(h.shape, dtype=h.dtype, device=self.device)
+        if grew:
+            # The caching allocator may have handed back a block that kernels ALREADY QUEUED on the caller's stream still
+            # read (it was freed on that stream, which is all the allocator tracks).  The copies below run on other
+            # streams, so they must not start before the caller's stream has reached this point.
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            for st in streams:
+                st.wait_event(ev)
         for st in streams:
             if self._free[slot] is not None:
                 st.wait_event(self._free[slot])

@@ -144,9 +144,7 @@ class _LinearAct(torch.autograd.Function):
         dC = dC.contiguous()
         if ctx.act != ACT_NONE:
             scale = 1.0 / (1.0 - ctx.drop_p) if ctx.act == ACT_RELU_DROPOUT else 1.0
-            # the fused classifier-tail backward hands over the gradient already masked and scaled (and its column sums)
-            masked = _tag_get(dC, "_ercg_masked")
-            dZ = dC if masked == (C.data_ptr(), scale) else mask_pos(dC, C, scale)
+            dZ = mask_pos(dC, C, scale)
         else:
             dZ = dC
         dA = dB = dbias = None
@@ -171,26 +169,28 @@ def mask_pos(x, ref, scale=1.0):
     return out
 
 
-class _ClassifierTail(torch.autograd.Function):
-    """logits = h @ W3^T + b3 where h is the output of a Linear+ReLU(+dropout) epilogue (ops.linear(..., act=ACT_RELU*)).
+class _MlpHead(torch.autograd.Function):
+    """logits = Linear3(dropout(relu(Linear0(x))))  --  ``Linear -> ReLU -> Dropout -> Linear(H, C)``, the classifier of
+    cogmen.py:116-122 and dgcn_models.py:158-167, as ONE autograd node.
 
-    Backward is ONE kernel pass over h (ercg_cls_tail_bwd): it returns the gradient of that previous layer's PRE-activation
-    (mask and dropout scale applied) together with its column sums, tagged so that _LinearAct.backward skips its own mask
-    and bias-gradient passes, plus dW3 and db3."""
+    The hidden activation never leaves this node, so its backward can be one pass over it (ercg_cls_tail_bwd: the masked /
+    dropout-scaled gradient of Linear0's pre-activation, dW3, db3 and db0 together) without any contract between two
+    autograd nodes: no other consumer, hook or retain_grad can ever see -- or add to -- the intermediate gradient."""
 
     @staticmethod
-    def forward(ctx, h, weight, bias, scale):
-        logits = gemm_nn(h, weight.t().contiguous(), bias)
-        ctx.scale = scale
-        ctx.save_for_backward(h, weight)
+    def forward(ctx, x, W0, b0, W3, b3, drop_p, seed):
+        act = ACT_RELU_DROPOUT if drop_p > 0 else ACT_RELU
+        h = gemm_nn(x, W0.t().contiguous(), b0, act=act, drop_p=drop_p, seed=seed)
+        logits = gemm_nn(h, W3.t().contiguous(), b3)
+        ctx.scale = 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0
+        ctx.save_for_backward(x, W0, h, W3)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        h, weight = ctx.saved_tensors
-        h, ldh = _rows(h)
+        x, W0, h, W3 = ctx.saved_tensors
         N, K = h.shape
-        C = weight.size(0)
+        C = W3.size(0)
         dlogits = dlogits.contiguous()
         dev = h.device
         dZ = torch.empty((N, K), dtype=torch.float32, device=dev)
@@ -198,30 +198,21 @@ class _ClassifierTail(torch.autograd.Function):
         db3 = torch.empty(C, dtype=torch.float32, device=dev)
         db0 = torch.empty(K, dtype=torch.float32, device=dev)
         ws = _ws(lib().ercg_cls_tail_bwd_workspace_bytes(K, C), dev)
-        check(lib().ercg_cls_tail_bwd(_p(h), ldh, _p(dlogits), _p(weight.contiguous()), float(ctx.scale), _p(dZ), K, _p(dW3),
+        check(lib().ercg_cls_tail_bwd(_p(h), h.stride(0), _p(dlogits), _p(W3.contiguous()), float(ctx.scale), _p(dZ), K, _p(dW3),
                                       _p(db3), _p(db0), N, K, C, _p(ws), ws.numel(), _stream()), "ercg_cls_tail_bwd")
-        _tag_set(dZ, "_ercg_masked", (h.data_ptr(), float(ctx.scale)))
-        _tag_set(dZ, "_ercg_colsum", db0)
-        return dZ, dW3, db3, None
+        dx = gemm_nn(dZ, W0.contiguous(), want_colsum=True) if ctx.needs_input_grad[0] else None
+        dW0 = gemm_tn(dZ, x) if ctx.needs_input_grad[1] else None
+        return dx, dW0, db0, dW3, db3, None, None
 
 
-def classifier_tail(h, weight, bias, scale=None):
-    """Last Linear of  Linear -> ReLU -> Dropout -> Linear  (cogmen.py:116-122, dgcn_models.py:158-167).
-
-    The fused backward masks the gradient with ``h > 0`` and applies the dropout scale of the layer that PRODUCED ``h``, so
-    it is only taken when ``h`` is, verifiably, the contiguous output of ops.linear(..., act=ACT_RELU / ACT_RELU_DROPOUT)
-    (its autograd node says so and supplies the scale); anything else goes through the plain linear path."""
-    K, C = h.size(1), weight.size(0)
-    fn = h.grad_fn
-    fused = (bias is not None and (K & 3) == 0 and K <= 128 and C <= 8 and h.requires_grad and h.is_contiguous()
-             and fn is not None and type(fn).__name__ == "_LinearActBackward"
-             and getattr(fn, "act", ACT_NONE) in (ACT_RELU, ACT_RELU_DROPOUT))
-    if not fused:
-        return linear(h, weight, bias)
-    own = 1.0 / (1.0 - fn.drop_p) if fn.act == ACT_RELU_DROPOUT else 1.0
-    if scale is not None and abs(float(scale) - own) > 1e-12:
-        raise ValueError("classifier_tail: scale %r does not match the producing layer's dropout scale %r" % (scale, own))
-    return _ClassifierTail.apply(h, weight, bias, own)
+def mlp_head(x, W0, b0, W3, b3, drop_p=0.0, seed=0):
+    """``Linear(W0,b0) -> ReLU -> Dropout(drop_p) -> Linear(W3,b3)`` (nn.Linear weight layout [out,in]); pass drop_p = 0 in
+    eval mode.  Shapes the fused backward kernel does not cover go through two ordinary ops.linear nodes."""
+    K, C = W0.size(0), W3.size(0)
+    if b0 is None or b3 is None or (K & 3) or K > 128 or C > 8:
+        act = ACT_RELU_DROPOUT if drop_p > 0 else ACT_RELU
+        return linear(linear(x, W0, b0, act=act, drop_p=drop_p, seed=seed), W3, b3)
+    return _MlpHead.apply(x, W0, b0, W3, b3, float(drop_p), int(seed))
 
 
 def linear(x, weight, bias=None, act=ACT_NONE, a_rows=None, drop_p=0.0, seed=0):

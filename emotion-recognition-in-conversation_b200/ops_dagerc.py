@@ -104,3 +104,51 @@ def dag_layer(Hin, gat, gru_c, gru_p, dag):
     """One GNN layer of DAGERCModule.forward: H[l] [N,D] -> H[l+1] [N,D]."""
     return _DagLayer.apply(Hin, gat.linear.weight, gat.linear.bias, gat.Wr0.weight, gat.Wr1.weight, gru_c.weight_ih, gru_c.weight_hh,
                            gru_c.bias_ih, gru_c.bias_hh, gru_p.weight_ih, gru_p.weight_hh, gru_p.bias_ih, gru_p.bias_hh, dag)
+
+
+# ------------------------------------------------------------------------------------------- stand-alone GAT step
+class _GatStep(torch.autograd.Function):
+    """(alpha [B,N], S01 [B,2D]) = attention of B queries over N context rows (ercg_dag_gat_fwd); the Wr0 / Wr1 mix is a
+    dense transform on S01 applied by the caller (ops.linear), so its weight gradients come from the GEMM kernels."""
+
+    @staticmethod
+    def forward(ctx, Q, K, V, adj, s_mask, w_linear, b_linear):
+        B, N, D = K.shape
+        Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+        adj = adj.to(torch.float32).contiguous()
+        s_mask = s_mask.to(torch.float32).contiguous()
+        w = w_linear.reshape(-1).contiguous()
+        alpha = torch.empty((B, N), dtype=torch.float32, device=K.device)
+        S01 = torch.empty((B, 2 * D), dtype=torch.float32, device=K.device)
+        check(lib().ercg_dag_gat_fwd(_p(Q), D, _p(K), N * D, D, _p(V), N * D, D, _p(adj), _p(s_mask), N, _p(w),
+                                     _p(b_linear.contiguous()), _p(alpha), _p(S01), B, N, D, _stream()), "ercg_dag_gat_fwd")
+        ctx.save_for_backward(Q, K, V, s_mask, w, alpha)
+        ctx.wshape = w_linear.shape
+        return alpha, S01
+
+    @staticmethod
+    def backward(ctx, dalpha, dS01):
+        Q, K, V, s_mask, w, alpha = ctx.saved_tensors
+        B, N, D = K.shape
+        dev = K.device
+        dS01 = dS01.contiguous() if dS01 is not None else torch.zeros((B, 2 * D), dtype=torch.float32, device=dev)
+        dalpha = dalpha.contiguous() if dalpha is not None else None
+        de = torch.empty((B, N), dtype=torch.float32, device=dev)
+        dQ = torch.empty((B, D), dtype=torch.float32, device=dev)
+        dK = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+        dV = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+        check(lib().ercg_dag_gat_bwd(_p(V), N * D, D, _p(s_mask), N, _p(w), _p(alpha), _p(dalpha), _p(dS01), _p(de), _p(dQ),
+                                     _p(dK), _p(dV), B, N, D, _stream()), "ercg_dag_gat_bwd")
+        # Linear(2D,1): dw = [sum_b (sum_n de) Q_b | sum_{b,n} de K_{b,n}], db = sum de  -- transposed products through K2
+        de_col = de.reshape(B * N, 1)
+        ones = torch.ones((N, 1), dtype=torch.float32, device=dev)
+        rs = ops.gemm_nn(de, ones)                                          # [B,1] row sums of de
+        dwq = ops.gemm_tn(rs, Q)                                            # [1,D]
+        dwk = ops.gemm_tn(de_col, K.reshape(B * N, D))                      # [1,D]
+        dw = torch.cat([dwq, dwk], 1).reshape(ctx.wshape)
+        db = ops.colsum(de_col)
+        return dQ, dK, dV, None, None, dw, db
+
+
+def gat_step(Q, K, V, adj, s_mask, w_linear, b_linear):
+    return _GatStep.apply(Q, K, V, adj, s_mask, w_linear, b_linear)

@@ -42,6 +42,26 @@ class RGCNConv(nn.Module):
         R, H = self.num_relations, self.out_channels
         g = graph_from_edge_index(edge_index, edge_type, x.size(0), R)
         census = g.relation_slots()
+        if g.num_relations is not None and g.num_relations > R:
+            # The graph numbers more relation ids than this layer has weights: the reference builds GNN with the DEFAULT
+            # n_speakers = 2 whatever the data set (cogmen.py:114), so MELD batches (9 speakers, ids up to 161) meet an
+            # 8-relation RGCNConv.  PyG loops ``for i in range(num_relations)`` and never selects ids >= R: those edges
+            # carry no message.  Same here: ids >= R get slot -1, which every gather kernel skips.
+            if census is not None:
+                ids = [i for i in census[0] if i < R]
+            else:
+                ids = list(range(R))
+            P = len(ids)
+            if P == 0:                                   # no edge of this batch has a relation the layer knows
+                return ops.matmul_kn(x, self.root, self.bias)
+            table = torch.full((g.num_relations,), -1, dtype=torch.int32)
+            table[torch.tensor(ids, dtype=torch.int64)] = torch.arange(P, dtype=torch.int32)
+            rel_slot = table.to(x.device, non_blocking=True)
+            sel = torch.tensor(ids, dtype=torch.int64, device=x.device)
+            wrel = self.weight.index_select(0, sel)
+            wcat = torch.cat([wrel.permute(1, 0, 2).reshape(self.in_channels, P * H), self.root], dim=1)
+            y = ops.matmul_kn(x, wcat)
+            return ops.gather(y, g, H, R, w=g.mean_weight(), bias=self.bias, root_off=P * H, rel_slot=rel_slot, n_slots=P)
         if census is not None and g.num_relations == R and len(census[0]) < R:
             # only the relation ids that occur in this batch are transformed and gathered (one-speaker MOSEI batches use
             # 2 of the 8 ids): Y is [N, (P+1)*H]; the other weights get an exactly-zero gradient, as in the reference

@@ -77,7 +77,10 @@ class COGMENModule(nn.Module):
         mods.append(nn.Linear(input_size, hidden_size, bias=True))
         self.rnn = nn.ModuleList(mods)
         self.run_dead_encoder = run_dead_encoder and build_dead_encoder
-        self.gcn = GNN(hidden_size, hidden_size, hidden_size, n_speakers)
+        # reference quirk, reproduced (cogmen.py:114): GNN is built with its DEFAULT n_speakers = 2 -- conv1.weight is
+        # [8,100,100] for every data set, so reference checkpoints load unchanged (MELD, n_speakers = 9, included);
+        # relation ids >= 8 then carry no message (see pyg_nn.RGCNConv.forward)
+        self.gcn = GNN(hidden_size, hidden_size, hidden_size)
         self.cls = nn.Sequential(nn.Linear(100, 100), nn.ReLU(), nn.Dropout(p=0.5), nn.Linear(100, n_classes))
         self.n_speakers = n_speakers
         self.edge_type_to_idx = standard_edge_dict(n_speakers)
@@ -86,13 +89,9 @@ class COGMENModule(nn.Module):
     # -- pieces shared by the padded (reference) and packed (resident) entry points
     def _classify(self, graph_out):
         lin0, drop, lin3 = self.cls[0], self.cls[2], self.cls[3]
-        if self.training and drop.p > 0:
-            h = ops.linear(graph_out, lin0.weight, lin0.bias, act=ops.ACT_RELU_DROPOUT, drop_p=drop.p, seed=_fresh_seed())
-            scale = 1.0 / (1.0 - drop.p)
-        else:
-            h = ops.linear(graph_out, lin0.weight, lin0.bias, act=ops.ACT_RELU)
-            scale = 1.0
-        return ops.classifier_tail(h, lin3.weight, lin3.bias, scale)       # backward of both layers' tails in one kernel
+        p = drop.p if self.training else 0.0
+        # Linear -> ReLU -> Dropout -> Linear as one autograd node (one backward pass over the hidden activations)
+        return ops.mlp_head(graph_out, lin0.weight, lin0.bias, lin3.weight, lin3.bias, p, _fresh_seed() if p > 0 else 0)
 
     def _graph_forward(self, features, g):
         g.attach()

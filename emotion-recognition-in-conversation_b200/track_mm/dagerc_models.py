@@ -3,7 +3,8 @@ and ``attentive_node_features`` (:425-, identity for nodal_att_type=None which i
 
 In the reference the GAT is called once per utterance and layer from a Python loop (dagerc.py:174); here the whole loop
 is the persistent kernel K10 (csrc/dagerc.cu) driven by ``DAGERCModule``.  ``GAT_dialoggcn_v1`` keeps its parameters
-(``linear``, ``Wr0``, ``Wr1``: same state_dict keys) and K10 reads them."""
+(``linear``, ``Wr0``, ``Wr1``: same state_dict keys) and K10 reads them; called on its own, ``forward(Q, K, V, adj, s_mask)``
+runs the stand-alone step kernel (csrc/dag_gat.cu)."""
 import torch
 from torch import nn
 
@@ -21,9 +22,15 @@ class GAT_dialoggcn_v1(nn.Module):
         self.Wr1 = nn.Linear(hidden_size, hidden_size, bias=False)
 
     def forward(self, Q, K, V, adj, s_mask):
-        raise NotImplementedError(
-            "the per-utterance GAT step is fused into the persistent DAG layer kernel (erc_b200.ops_dagerc.dag_layer); "
-            "call DAGERCModule.forward, there is no stand-alone CPU/ATen path")
+        """Stand-alone step with the reference's signature (dagerc_models.py:326-365):
+        Q [B,D], K / V [B,N,D], adj [B,N], s_mask [B,N]  ->  (attn_weight [B,1,N], attn_sum [B,D]).
+        DAGERCModule does not come through here (its utterance loop is the fused layer kernel K10); this is for callers
+        that use the class on its own.  CUDA only: scores + mask + softmax + the two speaker-selected weighted sums are
+        one kernel (ercg_dag_gat_fwd), the Wr0 / Wr1 mix is one dense transform on the [B,2D] result."""
+        from .. import ops, ops_dagerc
+        alpha, s01 = ops_dagerc.gat_step(Q, K, V, adj, s_mask, self.linear.weight, self.linear.bias)
+        attn_sum = ops.linear(s01, torch.cat([self.Wr0.weight, self.Wr1.weight], 1))
+        return alpha.unsqueeze(1), attn_sum
 
 
 class attentive_node_features(nn.Module):

@@ -33,4 +33,5 @@ class DGCNModule(nn.Module):
         g.attach()
         graph_out = self.gcn(features, g.edge_index, edge_norm, g.edge_type)
         logits = self.clf(torch.cat([features, graph_out], dim=-1), text_length)
+        g.check_inputs()          # K1's input-error flags (length > padded width, speaker id out of range) -> ValueError
         return logits, graph_out

@@ -128,11 +128,6 @@ class Classifier(nn.Module):
         self.lin2 = nn.Linear(hidden_size, tag_size)
 
     def forward(self, h, text_len_tensor=None):
-        if self.training and self.drop.p > 0:
-            hidden = ops.linear(h, self.lin1.weight, self.lin1.bias, act=ops.ACT_RELU_DROPOUT, drop_p=self.drop.p,
-                                seed=_fresh_seed())
-            scale = 1.0 / (1.0 - self.drop.p)
-        else:
-            hidden = ops.linear(h, self.lin1.weight, self.lin1.bias, act=ops.ACT_RELU)
-            scale = 1.0
-        return ops.classifier_tail(hidden, self.lin2.weight, self.lin2.bias, scale)   # fused backward of the tail
+        p = self.drop.p if self.training else 0.0
+        return ops.mlp_head(h, self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias, p,
+                            _fresh_seed() if p > 0 else 0)

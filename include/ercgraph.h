@@ -36,6 +36,10 @@ extern "C" {
 #define ERCG_ECUDA (-4)    /* CUDA runtime reported an error at launch (cudaGetLastError) */
 #define ERCG_EWORKSPACE (-5) /* workspace too small */
 
+#define ERCG_GRAPH_ELENGTH 1   /* a dialogue is longer than the padded speaker width spk_ld */
+#define ERCG_GRAPH_ESPEAKER 2  /* a speaker id outside [0, n_speakers) */
+#define ERCG_GRAPH_ESIZE 4     /* the caller's N / E are smaller than the lengths imply: dialogues were skipped */
+
 #define ERCG_ACT_NONE 0
 #define ERCG_ACT_RELU 1
 #define ERCG_ACT_RELU_DROPOUT 2   /* relu then inverted dropout (mask from a counter hash of seed,row,col) */
@@ -85,9 +89,12 @@ typedef struct ercg_graph_out {
   int64_t* edge_index_lengths; /* [B] cogmen_utils.py:142 */
   int64_t* totals;     /* [2]   N, E as computed on the device (for validation) */
   int32_t* pad_row;    /* [N]   d*spk_ld + k: row of the node in a padded [B,spk_ld,*] tensor (node id if spk_ld=0) */
-  int32_t* rel_info;   /* [513] relation census: [0] = P = number of relation ids that occur on at least one edge,
+  int32_t* rel_info;   /* [516] relation census: [0] = P = number of relation ids that occur on at least one edge,
                           [1 + r] = compact slot of relation id r (-1 if no edge has it), [257 + s] = id of slot s (s < P).
-                          One-speaker data (MOSEI, mosei_feature.py:211) uses 2 of the 2n^2 = 8 ids of cogmen.py:64. */
+                          One-speaker data (MOSEI, mosei_feature.py:211) uses 2 of the 2n^2 = 8 ids of cogmen.py:64.
+                          [513] = input-error flags (0 = clean), OR of ERCG_GRAPH_E*: the kernel never reads or writes out
+                          of bounds on bad input, it clamps and reports here (the reference raises IndexError / KeyError
+                          at cogmen_utils.py:131-137); [514], [515] reserved (0). */
 } ercg_graph_out;
 
 /* speakers: padded [B, spk_ld] when spk_ld > 0 (reference layout), packed [N] when spk_ld == 0. */
@@ -417,6 +424,22 @@ typedef struct ercg_dag_layer {
 } ercg_dag_layer;
 int ercg_dag_layer_fwd(const ercg_dag_layer* args, void* stream);
 int ercg_dag_layer_bwd(const ercg_dag_layer* args, void* stream);
+
+/* Stand-alone attention step = GAT_dialoggcn_v1.forward(Q, K, V, adj, s_mask) (track_mm/dagerc_models.py:326-365, mask_logic
+ * :83-90) for B queries against N context rows each (the fused layer kernel above never materialises it):
+ *   e[b,n] = w_linear[:D].Q[b] + w_linear[D:].K[b,n] + b_linear - (1 - adj[b,n]) * 1e30;  alpha[b,:] = softmax_n e[b,:]
+ *   S01[b] = [ sum_n alpha*s*V[b,n] | sum_n alpha*(1-s)*V[b,n] ]   ([B, 2D]; attn_sum = S01 @ [Wr0 | Wr1]^T is a dense
+ *   transform done by the caller with ercg_gemm_nn).  Q [B,D] (ldq), K / V [B,N,D] with batch / row strides in elements,
+ *   adj / s_mask [B,N] fp32 (row stride ldm), alpha [B,N] and S01 [B,2D] contiguous.
+ * Backward: dalpha (may be NULL) and dS01 in; de [B,N] = gradient of the pre-softmax logits (dw_k = sum de*K, dw_q = sum_b
+ * (sum_n de) Q, db = sum de: the caller's transposed products), dQ [B,D], dK / dV [B,N,D] contiguous. */
+int ercg_dag_gat_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk_b, int64_t ldk_n, const float* V,
+                     int64_t ldv_b, int64_t ldv_n, const float* adj, const float* s_mask, int64_t ldm,
+                     const float* w_linear, const float* b_linear, float* alpha, float* S01, int B, int N, int D,
+                     void* stream);
+int ercg_dag_gat_bwd(const float* V, int64_t ldv_b, int64_t ldv_n, const float* s_mask, int64_t ldm,
+                     const float* w_linear, const float* alpha, const float* dalpha, const float* dS01, float* de,
+                     float* dQ, float* dK, float* dV, int B, int N, int D, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -59,7 +59,7 @@ class CogmenOracle(nn.Module):
     def __init__(self, input_size, hidden_size=100, n_speakers=2, n_classes=4, dropout=0.5, wp=5, wf=5):
         super().__init__()
         self.rnn = nn.ModuleDict({"1": nn.Linear(input_size, hidden_size)})   # key 'rnn.1.*'
-        self.gcn = CogmenGNN(hidden_size, hidden_size, hidden_size, n_speakers)
+        self.gcn = CogmenGNN(hidden_size, hidden_size, hidden_size)   # cogmen.py:114: DEFAULT n_speakers = 2, always 8 relations
         self.cls = nn.Sequential(nn.Linear(100, 100), nn.ReLU(), nn.Dropout(dropout), nn.Linear(100, n_classes))
         self.n_speakers, self.wp, self.wf = n_speakers, wp, wf
 
@@ -67,6 +67,19 @@ class CogmenOracle(nn.Module):
         feats = pack_nodes(self.rnn["1"](input_tensor), text_length)
         _, ei, et = _graph_tensors(text_length, speaker_tensor, self.wp, self.wf, self.n_speakers)
         return self.cls(self.gcn(feats, ei, et)), feats
+
+    def forward_packed(self, x_packed, speaker_packed, text_length, drop_mask=None):
+        """Same computation on rows that are already packed [N, hidden_all] (cogmen_utils.py:123,139 only re-packs the
+        padded tensor; Linear is row-wise, so packing before or after it is the same arithmetic).  ``drop_mask`` [N,100]
+        (entries 0 or 1/(1-p)) replaces nn.Dropout's own random mask in the classifier (cogmen.py:119), so a run of
+        the CUDA path WITH dropout can be checked by handing its mask to the oracle."""
+        feats = self.rnn["1"](x_packed)
+        _, ei, et = _graph_tensors(text_length, speaker_packed, self.wp, self.wf, self.n_speakers)
+        h = self.gcn(feats, ei, et)
+        if drop_mask is None:
+            return self.cls(h), feats
+        h = self.cls[1](self.cls[0](h)) * drop_mask.to(h.dtype)
+        return self.cls[3](h), feats
 
 
 class VendoredRGCNConv(nn.Module):

@@ -78,7 +78,7 @@ class CogmenRefPort(nn.Module):
         layer = nn.TransformerEncoderLayer(d_model=input_size, nhead=head, dropout=0.5, batch_first=True)
         self.rnn = nn.ModuleList([nn.TransformerEncoder(layer, num_layers=2, enable_nested_tensor=False),
                                   nn.Linear(input_size, hidden_size)])
-        self.gcn = CogmenGNN(hidden_size, hidden_size, hidden_size, n_speakers)
+        self.gcn = CogmenGNN(hidden_size, hidden_size, hidden_size)   # cogmen.py:114 (default n_speakers)
         self.cls = nn.Sequential(nn.Linear(100, 100), nn.ReLU(), nn.Dropout(0.5), nn.Linear(100, n_classes))
         self.rel_ids = {}
         for a in range(n_speakers):

@@ -5,11 +5,24 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import rel_err, check_grads
+import copy
+
+from conftest import rel_err, parity_check
 from oracle import modules as om
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+
+
+def _oracle_fp64(o, x, spk, lens, y, class_weight=None):
+    """The same oracle in double precision: the truth against which both fp32 results are measured (conftest.parity_check)."""
+    o64 = copy.deepcopy(o).double()
+    o64.zero_grad()
+    o64.train()
+    ol, of = o64(x.double(), spk, lens)
+    F.cross_entropy(ol, y, weight=None if class_weight is None else class_weight.double()).backward()
+    return ({"logits": ol.detach().numpy(), "features": of.detach().numpy()},
+            {k: p.grad.numpy() for k, p in o64.named_parameters() if p.grad is not None})
 
 
 def _run_ours(m, x, spk, lens, y, class_weight=None):
@@ -41,7 +54,12 @@ def test_cogmen_vs_reference_fixture(golden):
     assert abs(loss - float(fx["loss"])) < TOL * abs(float(fx["loss"]))
     want = {k[5:]: v for k, v in fx.items() if k.startswith("grad/")}
     assert not any(k.startswith("rnn.0") for k in grads)                          # dead encoder stays grad-free
-    check_grads(grads, want, 5 * TOL)
+    o = om.CogmenOracle(D, n_classes=C, dropout=0.0)
+    om.load_live(o, params)
+    out64, want64 = _oracle_fp64(o, x, spk, lens, y)
+    parity_check("cogmen/fixture/outputs", {"logits": logits.numpy(), "features": feats.numpy()},
+                 {"logits": fx["logits"], "features": fx["features"]}, out64)
+    parity_check("cogmen/fixture/grads", grads, want, want64)
     assert rel_err(m.gcn.bn.running_mean.cpu(), fx["bn_running_mean"]) < TOL
     assert rel_err(m.gcn.bn.running_var.cpu(), fx["bn_running_var"]) < TOL
     assert int(m.gcn.bn.num_batches_tracked) == 1
@@ -72,7 +90,10 @@ def test_cogmen_config1_shape_vs_oracle():
     assert rel_err(feats, of.detach()) < TOL
     assert rel_err(logits, ol.detach()) < TOL
     assert abs(loss - float(oloss)) < TOL * float(oloss)
-    check_grads(grads, {k: p.grad.numpy() for k, p in o.named_parameters()}, 5 * TOL)
+    out64, want64 = _oracle_fp64(o, batch["input_tensor"], batch["speaker_tensor"], batch["text_length"], batch["label"])
+    parity_check("cogmen/config1/outputs", {"logits": logits.numpy(), "features": feats.numpy()},
+                 {"logits": ol.detach().numpy(), "features": of.detach().numpy()}, out64)
+    parity_check("cogmen/config1/grads", grads, {k: p.grad.numpy() for k, p in o.named_parameters()}, want64)
 
 
 @pytest.mark.parametrize("speaker", [0, 1])
@@ -99,7 +120,8 @@ def test_cogmen_one_speaker_batch_relation_census_vs_oracle(speaker):
                                            batch["label"])
     assert rel_err(logits, ol.detach()) < TOL
     assert abs(loss - float(oloss)) < TOL * float(oloss)
-    check_grads(grads, {k: p.grad.numpy() for k, p in o.named_parameters()}, 5 * TOL)
+    _, want64 = _oracle_fp64(o, batch["input_tensor"], batch["speaker_tensor"], batch["text_length"], batch["label"])
+    parity_check("cogmen/one_speaker_%d/grads" % speaker, grads, {k: p.grad.numpy() for k, p in o.named_parameters()}, want64)
     gw = grads["gcn.conv1.weight"]
     live = [speaker * 6, speaker * 6 + 1]                      # ((s*2 + s)*2 + dir)
     assert all(np.abs(gw[r]).max() > 0 for r in live)

@@ -4,11 +4,24 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import rel_err, check_grads
+import copy
+
+from conftest import rel_err, parity_check
 from oracle import modules as om
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+
+
+def _oracle_fp64(o, x, spk, lens, y, w):
+    """DgcnOracle in double precision = the truth for conftest.parity_check."""
+    o64 = copy.deepcopy(o).double()
+    o64.zero_grad()
+    o64.train()
+    ol, og = o64(x.double(), spk, lens)
+    F.cross_entropy(ol, y, weight=w.double()).backward()
+    return ({"logits": ol.detach().numpy(), "graph_out": og.detach().numpy()},
+            {k: p.grad.numpy() for k, p in o64.named_parameters() if p.grad is not None})
 
 
 def _params(fx):
@@ -90,7 +103,12 @@ def test_dgcn_module_vs_reference_fixture(golden):
     assert rel_err(graph_out, fx["graph_out"]) < TOL
     assert abs(float(loss.detach()) - float(fx["loss"])) < TOL * float(fx["loss"])
     grads = {k: p.grad.cpu().numpy() for k, p in m.named_parameters() if p.grad is not None}
-    check_grads(grads, {k[5:]: v for k, v in fx.items() if k.startswith("grad/")}, 5 * TOL)
+    o = om.DgcnOracle(2, input_size=D, hidden_size=H, n_classes=6, dropout=0.0)
+    om.load_live(o, _params(fx))
+    out64, want64 = _oracle_fp64(o, x, spk, lens, y, torch.from_numpy(fx["class_weights"]))
+    parity_check("dgcn/fixture/outputs", {"logits": logits, "graph_out": graph_out},
+                 {"logits": fx["logits"], "graph_out": fx["graph_out"]}, out64)
+    parity_check("dgcn/fixture/grads", grads, {k[5:]: v for k, v in fx.items() if k.startswith("grad/")}, want64)
 
 
 def test_dgcn_config2_shape_vs_oracle():
@@ -119,7 +137,10 @@ def test_dgcn_config2_shape_vs_oracle():
     assert rel_err(logits, ol.detach()) < TOL
     assert abs(float(loss.detach()) - float(oloss.detach())) < TOL * float(oloss.detach())
     grads = {k: p.grad.cpu().numpy() for k, p in m.named_parameters() if p.grad is not None}
-    check_grads(grads, {k: p.grad.numpy() for k, p in o.named_parameters()}, 5 * TOL)
+    out64, want64 = _oracle_fp64(o, batch["input_tensor"], batch["speaker_tensor"], batch["text_length"], batch["label"], w)
+    parity_check("dgcn/config2/outputs", {"logits": logits, "graph_out": graph_out},
+                 {"logits": ol.detach(), "graph_out": og.detach()}, out64)
+    parity_check("dgcn/config2/grads", grads, {k: p.grad.numpy() for k, p in o.named_parameters()}, want64)
 
 
 def test_dropout_kernel_is_reproducible_and_unbiased():

@@ -315,6 +315,41 @@ def test_device_feeder_double_buffering(copy_streams, chunk_bytes):
     assert feeder.h2d_bytes == 7 * (4096 * 257 * 4 + 4096 * 8)
 
 
+def test_device_feeder_varying_shapes_with_compute_in_flight():
+    """Every batch has its own Lmax (the reference collate pads per batch, mmbase.py:354-455) while earlier steps' kernels
+    are still queued: buffers grow to a high-water mark and are handed out as views; a (re)allocation must not let the
+    H2D copy overwrite a recycled block that queued kernels still read.  Heavy temporaries are freed on the compute
+    stream right before each submit to give the caching allocator blocks to recycle."""
+    import erc_b200
+    from erc_b200.loader import DeviceFeeder, pin
+    dev = torch.device("cuda")
+    feeder = DeviceFeeder(dev, depth=2, copy_streams=2, chunk_bytes=1 << 20)
+    gen = torch.Generator().manual_seed(1)
+    shapes = [(64, 37, 300), (64, 80, 300), (64, 12, 300), (96, 110, 300), (8, 5, 300), (96, 110, 300), (64, 90, 300)]
+    batches = [pin({"x": torch.randn(*sh, generator=gen), "len": torch.randint(1, sh[1] + 1, (sh[0],), generator=gen)})
+               for sh in shapes]
+    w = torch.randn(300, 300, generator=gen).cuda()
+    results = []
+    feeder.submit(batches[0])
+    for i in range(len(batches)):
+        tmp = torch.randn(96 * 110 * 300, device=dev)            # a block about the size of the largest buffer ...
+        for _ in range(20):
+            tmp = tmp * 1.0001 + 1.0                               # ... kept busy by queued kernels, then freed
+        acc = tmp.sum()
+        del tmp
+        if i + 1 < len(batches):
+            feeder.submit(batches[i + 1])
+        d = feeder.get()
+        assert d["x"].shape == batches[i]["x"].shape and d["x"].is_contiguous()
+        y = (d["x"].reshape(-1, 300) @ w).sum() + d["len"].sum() + 0.0 * acc
+        feeder.release()
+        results.append(y)
+    for i, y in enumerate(results):
+        want = (batches[i]["x"].reshape(-1, 300).cuda() @ w).sum() + batches[i]["len"].sum().cuda()
+        assert torch.allclose(y, want, rtol=1e-4), i
+    assert len(feeder._store[0]) == 2 and feeder._store[0]["x"].numel() >= 96 * 110 * 300 * 4 or feeder._store[1]["x"].numel() >= 96 * 110 * 300 * 4
+
+
 @pytest.mark.parametrize("wp,wf,n,one_speaker", [(5, 5, 2, False), (5, 5, 2, True), (10, 10, 2, False), (3, 8, 3, False)])
 def test_gather_window_backward_is_bit_identical_to_generic(wp, wf, n, one_speaker):
     """CTA-tiled gather backward (window graphs) vs the generic warp-per-node kernel: same dY bit for bit, with and
@@ -355,9 +390,10 @@ def test_gather_window_backward_is_bit_identical_to_generic(wp, wf, n, one_speak
 
 
 @pytest.mark.parametrize("N,C,p", [(37, 6, 0.0), (5000, 6, 0.5), (70001, 4, 0.5), (4096, 7, 0.0)])
-def test_classifier_tail_fused_backward(N, C, p):
-    """Linear -> ReLU -> Dropout -> Linear: the fused tail backward (one pass over the hidden activations) gives the same
-    gradients as the unfused chain (mask kernel, skinny GEMMs, column sums) and as fp64 autograd on the same dropout mask."""
+def test_mlp_head_fused_backward(N, C, p):
+    """Linear -> ReLU -> Dropout -> Linear as ONE autograd node (ops.mlp_head): the fused backward (one pass over the hidden
+    activations) gives the same gradients as the chain of two ops.linear nodes (mask kernel, skinny GEMMs, column sums) and as
+    fp64 autograd on the same dropout mask."""
     import erc_b200
     from erc_b200 import ops, _lib
     K = 100
@@ -372,18 +408,21 @@ def test_classifier_tail_fused_backward(N, C, p):
     def run(fused):
         for t in (x, W0, b0, W3, b3):
             t.grad = None
-        h = ops.linear(x, W0, b0, act=act, drop_p=p, seed=77)
-        out = ops.classifier_tail(h, W3, b3, scale) if fused else ops.linear(h, W3, b3)
+        if fused:
+            out = ops.mlp_head(x, W0, b0, W3, b3, p, 77)
+        else:
+            out = ops.linear(ops.linear(x, W0, b0, act=act, drop_p=p, seed=77), W3, b3)
         n0 = _lib.launch_count()
         out.backward(dl)
         launches = _lib.launch_count() - n0
-        return h.detach(), out.detach(), [t.grad.clone() for t in (x, W0, b0, W3, b3)], launches
+        return out.detach(), [t.grad.clone() for t in (x, W0, b0, W3, b3)], launches
 
-    h, out_f, gf, lf = run(True)
-    _, out_u, gu, lu = run(False)
+    out_f, gf, lf = run(True)
+    out_u, gu, lu = run(False)
     assert torch.equal(out_f, out_u)
     assert lf < lu                                   # fewer kernels, not just different ones
     # fp64 autograd with the mask the kernel drew (h > 0 after relu+dropout)
+    h = ops.linear(x.detach(), W0.detach(), b0.detach(), act=act, drop_p=p, seed=77)
     mask = (h > 0).double() * scale
     xd, W0d, b0d, W3d, b3d = (t.detach().double().cpu().requires_grad_() for t in (x, W0, b0, W3, b3))
     hd = (xd @ W0d.t() + b0d) * mask.cpu()         # the mask IS relu' x dropout (no clamp: fp64 could flip a borderline sign)
@@ -394,38 +433,31 @@ def test_classifier_tail_fused_backward(N, C, p):
         assert rel_err(a, b) < 2e-5
 
 
-def test_classifier_tail_only_fuses_behind_a_relu_linear():
-    """The fused tail backward masks with h > 0: it must NOT be taken when h is not the output of a ReLU(+dropout) Linear
-    (plain Linear output, arbitrary tensor, non-contiguous view) -- those go through the ordinary linear path."""
+def test_mlp_head_input_with_a_second_consumer():
+    """The node's input may have other consumers (COGMEN returns graph features next to the logits): the engine sums the
+    gradients; nothing about the fused tail leaks out of the node."""
     import erc_b200
     from erc_b200 import ops
     g = torch.Generator().manual_seed(3)
     N, K, C = 4000, 100, 6
-    x = torch.randn(N, K, generator=g).cuda().requires_grad_()
-    W0, b0 = (torch.randn(K, K, generator=g) * 0.1).cuda(), torch.randn(K, generator=g).cuda()
+    x0 = torch.randn(N, K, generator=g).cuda().requires_grad_()
+    Wp = (torch.randn(K, K, generator=g) * 0.1).cuda().requires_grad_()
+    W0, b0 = (torch.randn(K, K, generator=g) * 0.1).cuda().requires_grad_(), torch.randn(K, generator=g).cuda().requires_grad_()
     W3, b3 = (torch.randn(C, K, generator=g) * 0.1).cuda().requires_grad_(), torch.randn(C, generator=g).cuda().requires_grad_()
-    dl = torch.randn(N, C, generator=g).cuda()
-    for make_h in (lambda: ops.linear(x, W0, b0),                          # no activation: gradient must NOT be masked
-                   lambda: (x * 1.0),                                       # not a Linear at all
-                   lambda: ops.linear(x, W0, b0, act=ops.ACT_RELU)[:, :]):  # a view of a ReLU Linear is still fine either way
-        for t in (x, W3, b3):
-            t.grad = None
-        h = make_h()
-        ops.classifier_tail(h, W3, b3).backward(dl)
-        got = [t.grad.clone() for t in (x, W3, b3)]
-        for t in (x, W3, b3):
-            t.grad = None
-        h2 = make_h()
-        ops.linear(h2, W3, b3).backward(dl)
-        for a, b in zip(got, (x.grad, W3.grad, b3.grad)):
-            assert rel_err(a, b) < 2e-5
-    h = ops.linear(x, W0, b0, act=ops.ACT_RELU_DROPOUT, drop_p=0.5, seed=1)
-    with pytest.raises(ValueError):
-        ops.classifier_tail(h, W3, b3, scale=1.0)
+    dl, extra = torch.randn(N, C, generator=g).cuda(), torch.randn(N, K, generator=g).cuda()
+    f = ops.linear(x0, Wp)                                      # produced by one of our nodes, consumed twice
+    ((ops.mlp_head(f, W0, b0, W3, b3, 0.5, 5) * dl).sum() + (f * extra).sum()).backward()
+    h = ops.linear(f.detach(), W0.detach(), b0.detach(), act=ops.ACT_RELU_DROPOUT, drop_p=0.5, seed=5)
+    mask = ((h > 0).double() * 2.0).cpu()
+    d = [t.detach().double().cpu().requires_grad_() for t in (x0, Wp, W0, b0, W3, b3)]
+    fd = d[0] @ d[1].t()
+    ((((fd @ d[2].t() + d[3]) * mask) @ d[4].t() + d[5]) * dl.double().cpu()).sum().add((fd * extra.double().cpu()).sum()).backward()
+    for a, w in zip((x0, Wp, W0, b0, W3, b3), d):
+        assert rel_err(a.grad, w.grad) < 2e-5
 
 
 def test_gradient_tags_do_not_survive_inplace_accumulation():
-    """The by-products hung on gradient tensors (fused column sums, "already masked") are tied to the tensor's version
+    """The by-products hung on gradient tensors (fused column sums) are tied to the tensor's version
     counter.  A feature tensor with TWO consumers makes the autograd engine add a second gradient to the tagged one; the
     bias gradient of the producing Linear must then be the column sums of the SUM, not the stale fused ones."""
     import erc_b200
