@@ -4,13 +4,18 @@
   python bench.py --gpus N --steps K --warmup W            our arm (libercgraph kernels)
   python bench.py --impl reference --gpus N ...            the reference's CPU path (oracle port), rank 0 only
 
-Workload ("config.workload"): COGMEN train step (graphify + forward + cross entropy + backward + gradient
-all-reduce + Adam) on ~2^20 synthetic MOSEI-shaped utterances (hidden_all = 768+640+35 = 1443, one speaker id,
-dialogue lengths 1+Geometric(1/7) clipped to 40, 6 classes) PER GPU, whole dialogues per GPU, no data-path collective
-(weak scaling, the default; ``--scaling strong`` splits one ~2^20-utterance set over the GPUs instead -- measured
-numbers for both are in DESIGN.md).  One "step" = one pass over a GPU's utterances as ONE batch.
-``value`` = utterances / second with inputs resident in HBM; ``e2e`` = the same step fed from pinned HOST
-buffers (H2D of the inputs and D2H of the loss inside the timed region).
+Workload ("config.workload"): COGMEN train step (graphify + forward + cross entropy + backward + gradient all-reduce +
+Adam, dropout on) on ~2^20 synthetic MOSEI-shaped utterances IN TOTAL (hidden_all = 768+640+35 = 1443, one speaker id,
+dialogue lengths 1+Geometric(1/7) clipped to 40, 6 classes), whole dialogues sharded over the N GPUs, no data-path collective:
+BASELINE.json configs[4] as written, i.e. STRONG scaling (the default).  With N > 1 the same run also measures the
+weak-scaling point (2^20 utterances PER GPU) and reports it under "weak_scaling"; ``--scaling weak`` makes that the headline.
+One "step" = one pass over a GPU's utterances as ONE batch.
+
+``value``  = utterances / second with inputs resident in HBM, the step replayed as ONE CUDA graph (train_step.CogmenTrainStep:
+             K1 + forward + backward + NCCL all-reduces + Adam captured once; ``--mode eager`` launches kernel by kernel).
+``kernels`` / ``roofline`` = per-kernel CUDA-event times of the same steps run eagerly (events cannot bracket kernels inside
+             a graph replay), K steps, inputs resident; ``eager`` holds that loop's own step time.
+``e2e``    = the same step fed from pinned HOST buffers (H2D of the inputs and D2H of the loss inside the timed region).
 """
 import argparse
 import json
@@ -29,7 +34,7 @@ METRIC = "COGMEN fwd+bwd utterances/sec"
 UNIT = "utterances/s"
 HIDDEN = 1443
 N_CLASSES = 6
-WORKLOAD = "cogmen-train-step mosei-emo-sbert-fbank-6 shape (hidden_all=1443, 1 speaker id, window 5/5), ~2^20 utterances per GPU per step, whole dialogues sharded over the GPUs"
+WORKLOAD = "cogmen-train-step mosei-emo-sbert-fbank-6 shape (hidden_all=1443, 1 speaker id, window 5/5), ~2^20 utterances per step in total, whole dialogues sharded over the GPUs"
 
 
 def measured_traffic():
@@ -198,13 +203,46 @@ def kernel_label(name, args):
     return name[5:] if name.startswith("ercg_") else name
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and allocate its pinned host buffers) on the NUMA node its GPU hangs off: with 8 ranks feeding 8 GPUs
+    from one host, cross-socket pinned buffers halve the per-rank H2D rate.  Best effort; returns a description."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis else local_rank
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa_node=-1 (single node or not reported)"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "node %d, %d cpus" % (node, len(allowed))
+        return "node %d has no allowed cpus" % node
+    except Exception as e:
+        return "unavailable (%s)" % type(e).__name__
+
+
 def run_ours(args):
+    import gc
     import torch.distributed as dist
-    import erc_b200
-    from erc_b200 import _lib, ops, synth
-    from erc_b200.graph import build_graph, graph_sizes
+    import erc_b200  # noqa: F401
+    from erc_b200 import _lib, synth
+    from erc_b200.graph import graph_sizes
     from erc_b200.track_mm.cogmen import COGMENModule
-    from erc_b200.dist import shard_dialogues, StatSync, LossSync, GradSync
+    from erc_b200.dist import shard_dialogues
+    from erc_b200.train_step import CogmenTrainStep
+    from erc_b200.loader import DeviceFeeder
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -213,179 +251,198 @@ def run_ours(args):
         raise SystemExit("bench.py (our arm) needs a GPU: libercgraph has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single rank)"
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")      # NCCL collectives are captured into the step's CUDA graph
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()                                            # fail loudly now if the .so is missing
-
-    # ---- workload
-    # weak scaling (default): every GPU gets its own ~args.total_utts utterances -- whole dialogues, no data-path collective
-    # (SURVEY.md 8e); strong scaling: the same ~args.total_utts utterances are split over the GPUs
-    weak = args.scaling == "weak"
-    lengths_all = synth.config5_lengths(args.total_utts * (world if weak else 1), seed=0)
-    total_utts = int(lengths_all.sum())
-    mine = shard_dialogues(lengths_all, world)[rank]
-    lengths = lengths_all[mine].contiguous()
-    N = int(lengths.sum())
     ld = (HIDDEN + 3) // 4 * 4                            # 1444: rows 16-byte aligned in HBM
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x_store = torch.empty((N, ld), dtype=torch.float32, device=dev)
-    x_store.normal_(generator=gen)
-    x = x_store[:, :HIDDEN]
-    spk = torch.zeros(N, dtype=torch.int64, device=dev)   # MOSEI: a single speaker id (mosei_feature.py:211)
-    labels = torch.randint(0, N_CLASSES, (N,), device=dev, generator=gen)
-    sizes = graph_sizes(lengths, 5, 5)
-
-    torch.manual_seed(0)
-    model = COGMENModule(HIDDEN, 100, 17, 2, N_CLASSES).to(dev)
-    model.train()
-    # cogmen.py:50 (Adam, lr 1e-4, wd 1e-8); fused=True = ATen's single-kernel multi-tensor Adam, same arithmetic
-    optim = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8, fused=True)
-    loss_sync = grad_sync = None
-    if world > 1:
-        model.gcn.stat_sync = StatSync(global_count=total_utts)
-        loss_sync = LossSync()
-        grad_sync = GradSync(model)
-
-    trace = [] if os.environ.get("ERCG_BENCH_TRACE") else None      # diagnostics: host timestamps of the step's phases
-
-    def step(xi, spki, labi):
-        t = [time.perf_counter()] if trace is not None else None
-        g = build_graph(lengths, spki, 5, 5, 2, device=dev, sizes=sizes)
-        if t is not None:
-            t.append(time.perf_counter())
-            g.relation_slots()
-            t.append(time.perf_counter())
-        logits, _ = model.forward_packed(xi, spki, lengths, graph=g)
-        loss = ops.cross_entropy(logits, labi, reduce_sync=loss_sync)
-        if t is not None:
-            t.append(time.perf_counter())
-        optim.zero_grad(set_to_none=True)
-        loss.backward()
-        if t is not None:
-            t.append(time.perf_counter())
-        if grad_sync is not None:
-            grad_sync()
-        optim.step()
-        if t is not None:
-            t.append(time.perf_counter())
-            ms_ = torch.cuda.memory_stats(dev)
-            trace.append([round((b - a) * 1e3, 3) for a, b in zip(t[:-1], t[1:])] +
-                         [ms_.get("num_device_alloc", 0), ms_.get("allocated_bytes.all.current", 0) >> 20,
-                          ms_.get("reserved_bytes.all.current", 0) >> 20])
-        return loss
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up: spawning it inside the timed region stalls
-    # rank 0's launch thread for tens of ms, which the other ranks then wait out in the first all-reduce
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
-    import gc
-    loss = step(x, spk, labels)                          # first step: lazy initialisation, allocator growth
-    gc.collect()
-    gc.freeze()                                         # a gen-2 collection inside a 15 ms step shows up as a 30 ms step;
-    gc.disable()                                        # frozen BEFORE the warm-up so the caching allocator settles after it
-    for _ in range(max(args.warmup, 3)):
-        loss = step(x, spk, labels)                      # (keeps the previous step's loss alive exactly like the timed loop:
-    barrier()                                           #  same allocation pattern => no cudaMalloc inside the timed region)
+        sampler.start()                                  # before any warm-up: starting it later stalls rank 0's launch thread
+
+    def measure(scaling, steps, with_kernels, with_e2e):
+        """One workload (strong: args.total_utts in total; weak: per GPU) -> dict of measurements (same on every rank)."""
+        weak = scaling == "weak"
+        lengths_all = synth.config5_lengths(args.total_utts * (world if weak else 1), seed=0)
+        total_utts = int(lengths_all.sum())
+        mine = shard_dialogues(lengths_all, world)[rank]
+        lengths = lengths_all[mine].contiguous()
+        N = int(lengths.sum())
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        x_store = torch.empty((N, ld), dtype=torch.float32, device=dev)
+        x_store.normal_(generator=gen)
+        x = x_store[:, :HIDDEN]
+        spk = torch.zeros(N, dtype=torch.int64, device=dev)   # MOSEI: a single speaker id (mosei_feature.py:211)
+        labels = torch.randint(0, N_CLASSES, (N,), device=dev, generator=gen)
+        sizes = graph_sizes(lengths, 5, 5)
+        torch.manual_seed(0)
+        model = COGMENModule(HIDDEN, 100, 17, 2, N_CLASSES).to(dev)
+        model.train()
+        # cogmen.py:50: Adam(lr 1e-4, weight_decay 1e-8) -- here ercg_adam_step on the flat buffer of the live parameters
+        ts = CogmenTrainStep(model, lengths, speakers_present=(0,), lr=1e-4, weight_decay=1e-8, world=world,
+                             global_utterances=total_utts, bn_sync=args.bn_sync, overlap=not args.no_overlap)
+        out = {"scaling": scaling, "utterances_per_step": total_utts, "utterances_rank0": N, "edges_rank0": sizes[1],
+               "dialogues": int(lengths_all.numel())}
+
+        # ---- eager steps (kernel by kernel): warm-up, then K steps with every C-ABI call bracketed by CUDA events
+        loss = ts.step(x, spk, labels)
+        gc.collect()
+        gc.freeze()
+        gc.disable()
+        for _ in range(max(args.warmup, 3)):
+            loss = ts.step(x, spk, labels)
+        barrier()
+        if args.profile_step:
+            torch.cuda.profiler.start()
+            ts.step(x, spk, labels)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            return {"profile_step": True, "utterances_per_step": total_utts}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        def time_eager():
+            with _lib.KernelTimer(labeler=kernel_label):    # one more warm step WITH the event bracketing active (event pool)
+                ts.step(x, spk, labels)
+            barrier()
+            launches0 = _lib.launch_count()
+            timer = _lib.KernelTimer(labeler=kernel_label)
+            with timer:
+                barrier()
+                e0.record()
+                for _ in range(steps):
+                    last = ts.step(x, spk, labels)
+                e1.record()
+                barrier()
+            eager_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+            out["eager"] = {"ms_per_step": eager_ms, "value": total_utts / (eager_ms / 1e3),
+                            "launches_per_step": (_lib.launch_count() - launches0) / steps}
+            out["ksum"] = timer.summary()
+            out["step_kernel_ms"] = sum(t for _, t in out["ksum"].values()) / steps
+            return last
+
+        if with_kernels or args.mode == "eager":
+            loss = time_eager()
+
+        # ---- the step as ONE CUDA graph
+        graph_err = None
+        if args.mode == "graph":
+            try:
+                launches0 = _lib.launch_count()
+                ts.capture(x, spk, labels, warmup=2)
+                barrier()
+                for _ in range(max(args.warmup, 3)):
+                    ts.replay()
+                barrier()
+                if sampler and scaling == args.scaling:
+                    t_wait = time.perf_counter()
+                    while not sampler.samples and time.perf_counter() - t_wait < 2.0:
+                        time.sleep(0.01)
+                    sampler.mark = len(sampler.samples)      # only samples taken from here on are reported
+                mem_before = torch.cuda.memory_stats(dev)
+                lc0 = _lib.launch_count()
+                barrier()
+                e0.record()
+                marks = []
+                for _ in range(steps):
+                    loss = ts.replay()
+                    marks.append(torch.cuda.Event(enable_timing=True))
+                    marks[-1].record()
+                e1.record()
+                barrier()
+                mem_after = torch.cuda.memory_stats(dev)
+                ms = max_over_ranks(e0.elapsed_time(e1))
+                out["graph"] = {"ms_per_step": ms / steps, "value": total_utts * steps / (ms / 1e3),
+                                "step_ms": [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)],
+                                "host_launches_in_timed_region": _lib.launch_count() - lc0,
+                                "cuda_mallocs_in_timed_region": int(mem_after.get("num_device_alloc", 0) - mem_before.get("num_device_alloc", 0))}
+            except Exception as e:                             # report, and fall back to the eager numbers
+                graph_err = "%s: %s" % (type(e).__name__, str(e)[:300])
+                out["graph_error"] = graph_err
+        if "graph" not in out and "eager" not in out:
+            loss = time_eager()
+        out["loss"] = float(loss.item()) if loss is not None else None
+        if world > 1:
+            out["loss_global"] = float(ts.global_loss().item())
+
+        # ---- e2e: the step through the public API with HOST buffers; every step's inputs (features, speakers, labels) are
+        # copied from pinned host memory inside the timed region (DeviceFeeder: double-buffered, on copy streams, so the H2D of
+        # step i+1 overlaps the kernels of step i) and the loss is read back.  Eager steps: PCIe is the bound, not launches.
+        if with_e2e:
+            e2e_steps = max(1, args.e2e_steps)
+            hx = torch.empty((N, ld), dtype=torch.float32, pin_memory=True)
+            hx.copy_(x_store)
+            host = {"x": hx, "spk": torch.zeros(N, dtype=torch.int64).pin_memory(), "label": labels.cpu().pin_memory()}
+            feeder = DeviceFeeder(dev, depth=2, copy_streams=args.copy_streams)
+
+            def e2e_run(n):
+                feeder.submit(host)
+                for i in range(n):
+                    if i + 1 < n:
+                        feeder.submit(host)                      # prefetch the next step's inputs
+                    d = feeder.get()
+                    loss_i = ts.step(d["x"][:, :HIDDEN], d["spk"], d["label"])
+                    feeder.release()
+                    float(loss_i.item())                         # D2H of the step's result
+
+            e2e_run(2)
+            barrier()
+            b0 = feeder.h2d_bytes
+            e0.record()
+            e2e_run(e2e_steps)
+            e1.record()
+            barrier()
+            e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+            h2d = (feeder.h2d_bytes - b0) // e2e_steps
+            if world > 1:
+                b = torch.tensor([h2d], dtype=torch.float64, device=dev)
+                dist.all_reduce(b)
+                h2d = int(b.item())
+            out["e2e"] = {"value": total_utts * e2e_steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                          "d2h_bytes_per_step": 4 * world, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                          "how": "pinned host buffers -> DeviceFeeder (double-buffered, %d copy streams) -> eager step -> loss.item(); "
+                                 "all copies inside the timed region; host threads bound to the GPU's NUMA node: %s" % (args.copy_streams, numa)}
+            del feeder, host, hx
+        ts.check()                                             # K1's input-error flags of the last step
+        gc.enable()
+        gc.unfreeze()
+        out["x_bytes"] = x_store.numel() * 4
+        out["N"], out["E"], out["n_dialogues_rank0"] = N, sizes[1], int(lengths.numel())
+        del ts, model, x_store, x, spk, labels
+        gc.collect()
+        torch.cuda.empty_cache()
+        return out
+
+    head = measure(args.scaling, args.steps, with_kernels=True, with_e2e=True)
     if args.profile_step:
-        # ncu --profile-from-start off: exactly ONE warm step between cudaProfilerStart/Stop, no timing, no JSON value
-        torch.cuda.profiler.start()
-        step(x, spk, labels)
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
         if rank == 0:
-            emit({"profile_step": True, "utterances_per_step": total_utts})
+            emit(head)
         return
-    if sampler:
-        t_wait = time.perf_counter()
-        while not sampler.samples and time.perf_counter() - t_wait < 2.0:
-            time.sleep(0.01)
-        sampler.mark = len(sampler.samples)          # only samples taken from here on are reported
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with _lib.KernelTimer(labeler=kernel_label):        # one more warm step WITH the event bracketing active (event pool)
-        loss = step(x, spk, labels)
-    barrier()
-    launches0 = _lib.launch_count()
-    mem_before = torch.cuda.memory_stats(dev)
-    if trace is not None:
-        del trace[:]
-    timer = _lib.KernelTimer(labeler=kernel_label)      # GEMM records are split by shape
-    with timer:
-        barrier()
-        e0.record()
-        marks = []
-        for _ in range(args.steps):
-            loss = step(x, spk, labels)
-            marks.append(torch.cuda.Event(enable_timing=True))
-            marks[-1].record()
-        e1.record()
-        barrier()
-    gc.enable()
-    mem_after = torch.cuda.memory_stats(dev)
-    ms = e0.elapsed_time(e1)
-    step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
-    launches = _lib.launch_count() - launches0
     clocks = sampler.finish() if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = total_utts * args.steps / (ms / 1e3)
-    ksum = timer.summary()
-
-    # ---- e2e: the same step through the public API with HOST buffers: every step's inputs (6 GB of features, speakers,
-    # labels) are copied from pinned host memory inside the timed region and the loss is read back.  The copies go through
-    # the package's DeviceFeeder (loader.py): double-buffered, on a copy stream, so the H2D of step i+1 overlaps the kernels
-    # of step i -- what a training loop with a pinned-memory DataLoader does.  PCIe (~55 GB/s) is the bound.
-    from erc_b200.loader import DeviceFeeder
-    e2e_steps = max(1, args.e2e_steps)
-    hx = torch.empty((N, ld), dtype=torch.float32, pin_memory=True)
-    hx.copy_(x_store)
-    host = {"x": hx, "spk": torch.zeros(N, dtype=torch.int64).pin_memory(), "label": labels.cpu().pin_memory()}
-    feeder = DeviceFeeder(dev, depth=2, copy_streams=args.copy_streams)
-
-    def e2e_run(n):
-        losses = []
-        feeder.submit(host)
-        for i in range(n):
-            if i + 1 < n:
-                feeder.submit(host)                      # prefetch the next step's inputs
-            d = feeder.get()
-            loss_i = step(d["x"][:, :HIDDEN], d["spk"], d["label"])
-            feeder.release()
-            losses.append(float(loss_i.item()))          # D2H of the step's result
-        return losses
-
-    e2e_run(2)
-    barrier()
-    b0 = feeder.h2d_bytes
-    e0.record()
-    e2e_run(e2e_steps)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = total_utts * e2e_steps / (e2e_ms / 1e3)
-    h2d = (feeder.h2d_bytes - b0) // e2e_steps
-    if world > 1:
-        b = torch.tensor([h2d], dtype=torch.float64, device=dev)
-        dist.all_reduce(b)
-        h2d = int(b.item())
+    other = None
+    if world > 1 and not args.no_second_scaling:
+        other = measure("weak" if args.scaling == "strong" else "strong", max(args.steps // 2, 3), with_kernels=False, with_e2e=False)
 
     if rank == 0:
         peak, peak_src = peaks()
-        E = sizes[1]
+        N, E = head["N"], head["E"]
+        mode = "graph" if "graph" in head else "eager"
+        best = head[mode]
+        ksum = head["ksum"]
         per = {k: (c, tot / c) for k, (c, tot) in ksum.items()}          # kernel label -> (calls, avg ms)
-        step_kernel_ms = sum(tot for _, tot in ksum.values()) / args.steps
         H, P = 100, 2          # row width; relation ids that occur (1 speaker id -> 2 of 8): Y / dY hold P + 1 slots
+        nd = head["n_dialogues_rank0"]
 
         def alg_bytes(label):
             """Algorithmic (unique) HBM bytes of ONE launch on this rank (weights ignored)."""
@@ -398,57 +455,67 @@ def run_ours(args):
                 "attn_fwd": 5 * 4 * H * N + 4 * (N + 1) + 8 * E,
                 "attn_bwd_dst": 5 * 4 * H * N + 4 * (N + 1) + 12 * E,
                 "attn_bwd_src": 4 * 4 * H * N + 4 * (N + 1) + 16 * E,
-                "graphify_csr": 8 * lengths.numel() + 8 * N + 8 * (N + 1) + 12 * N + E * (4 + 1 + 4 + 1 + 4 + 4 + 24),
+                "attn_bwd": 8 * 4 * H * N + 8 * (N + 1) + 12 * E,
+                "graphify_csr": 8 * nd + 8 * N + 8 * (N + 1) + 12 * N + E * (4 + 1 + 4 + 1 + 4 + 4 + 24),
                 "bn_stats": 4 * H * N, "bn_act_fwd": 8 * H * N, "bn_act_bwd_reduce": 8 * H * N, "bn_act_bwd_apply": 12 * H * N,
                 "mask_pos": 12 * H * N, "colsum": None, "ce_fwd": (4 * N_CLASSES * 2 + 8) * N,
                 "cls_tail_bwd": (8 * H + 4 * N_CLASSES) * N,
             }.get(label)
 
         kernels = {}
+        tr_all = measured_traffic()
         for label, (calls, avg_ms) in sorted(per.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
             ab = alg_bytes(label)
             ent = {"calls_per_step": calls / args.steps, "avg_ms": round(avg_ms, 4)}
             if ab:
                 gbs = ab / (avg_ms * 1e-3) / 1e9
                 ent.update({"algorithmic_bytes": ab, "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)})
+            if label in tr_all and tr_all[label].get("utterances"):   # DRAM bytes per launch from the committed ncu capture
+                ent["traffic"] = int(tr_all[label]["bytes"] * (N / float(tr_all[label]["utterances"])))
             kernels[label] = ent
         dom_label = max(ksum.items(), key=lambda kv: kv[1][1])[0]
         dom_calls, dom_ms = per[dom_label]
         dom_bytes = alg_bytes(dom_label) or 0
-        tr = measured_traffic().get(dom_label)
-        traffic = None
-        if tr and tr.get("utterances"):
-            traffic = int(tr["bytes"] * (N / float(tr["utterances"])))      # ncu capture, scaled to this rank's utterance count
+        tr = tr_all.get(dom_label)
+        traffic = int(tr["bytes"] * (N / float(tr["utterances"]))) if tr and tr.get("utterances") else None
         roof = {"bound": "hbm", "kernel": dom_label, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                 "traffic_source": (tr or {}).get("source"), "peak_source": peak_src,
-                "avg_launch_ms": dom_ms, "launches_timed": dom_calls, "algorithmic_bytes_per_launch": dom_bytes}
-        tr_all = measured_traffic()
-        for k, ent in kernels.items():              # DRAM bytes per launch from the committed ncu capture, where one exists
-            if k in tr_all and tr_all[k].get("utterances"):
-                ent["traffic"] = int(tr_all[k]["bytes"] * (N / float(tr_all[k]["utterances"])))
-        graph_kernels = {k: kernels[k] for k in ("gather_fwd", "gather_bwd", "attn_fwd", "attn_bwd_dst", "attn_bwd_src",
+                "avg_launch_ms": dom_ms, "launches_timed": dom_calls, "algorithmic_bytes_per_launch": dom_bytes,
+                "timed_in": "the eager loop (CUDA events around each C-ABI call on the launching stream); the headline loop replays the same kernels as one CUDA graph"}
+        graph_kernels = {k: kernels[k] for k in ("gather_fwd", "gather_bwd", "attn_fwd", "attn_bwd_dst", "attn_bwd_src", "attn_bwd",
                                                  "graphify_csr") if k in kernels}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "utterances_per_step": total_utts, "dialogues": int(lengths_all.numel()),
-                           "edges_per_step_rank0": E, "parallelism": "dp%d (whole dialogues per GPU, %s scaling: %d utterances %s)" % (
-                               world, args.scaling, args.total_utts, "per GPU" if weak else "in total"),
-                           "l2": "inputs (%.1f GB/step/GPU) are larger than the 126 MB L2" % (x_store.numel() * 4 / 1e9),
-                           "dropout": "on (train mode)", "optimizer": "Adam inside the step", "dead_encoder": "not executed (cogmen.py:146-147 discards its output)"},
-                "roofline": roof, "graph_kernels": graph_kernels,
-                "kernels": kernels,
-                "kernel_time_share_of_step": round(step_kernel_ms / (ms / args.steps), 4), "step_ms": step_ms,
-                "cuda_mallocs_in_timed_region": int(mem_after.get("num_device_alloc", 0) - mem_before.get("num_device_alloc", 0)),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
-                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                        "how": "pinned host buffers -> DeviceFeeder (double-buffered, %d copy streams) -> step -> loss.item(); all copies inside the timed region" % args.copy_streams},
-                "gpu_launches": launches, "clocks": clocks, "loss": float(loss.item())}
-        if trace is not None:
-            line["host_trace_ms"] = {"phases": ["build_graph", "census_wait", "forward+loss", "backward", "optimizer",
-                                                "cudaMallocs so far", "allocated MiB", "reserved MiB"],
-                                     "steps": trace[:args.steps]}
+        launches_per_step = head["eager"]["launches_per_step"]
+        line = {"metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": best["ms_per_step"], "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "utterances_per_step": head["utterances_per_step"], "dialogues": head["dialogues"],
+                           "edges_per_step_rank0": E,
+                           "parallelism": "dp%d (whole dialogues per GPU, %s scaling: %d utterances %s)" % (
+                               world, args.scaling, args.total_utts, "per GPU" if args.scaling == "weak" else "in total"),
+                           "l2": "inputs (%.2f GB/step/GPU) are larger than the 126 MB L2" % (head["x_bytes"] / 1e9),
+                           "step": "one CUDA-graph replay per step" if mode == "graph" else "eager launches",
+                           "bn_statistics": "global (all-reduced)" if (world > 1 and args.bn_sync == "global") else "per rank",
+                           "dropout": "on (train mode)", "optimizer": "Adam inside the step (ercg_adam_step on the flat parameter buffer)",
+                           "dead_encoder": "not executed (cogmen.py:146-147 discards its output)"},
+                "roofline": roof, "graph_kernels": graph_kernels, "kernels": kernels,
+                "eager": head.get("eager"), "graph": head.get("graph"),
+                "kernel_time_share_of_eager_step": round(head["step_kernel_ms"] / head["eager"]["ms_per_step"], 4),
+                "kernel_time_share_of_step": round(head["step_kernel_ms"] / best["ms_per_step"], 4),
+                "e2e": head["e2e"],
+                "gpu_launches": int(round(launches_per_step * args.steps)),
+                "gpu_launches_how": "%d libercgraph kernel launches per step (counted in the eager loop) x %d steps%s" % (
+                    int(round(launches_per_step)), args.steps, "; in the headline loop they are nodes of the replayed CUDA graph" if mode == "graph" else ""),
+                "clocks": clocks, "loss": head["loss"]}
+        if "graph_error" in head:
+            line["graph_error"] = head["graph_error"]
+        if "loss_global" in head:
+            line["loss_global"] = head["loss_global"]
+        if other is not None:
+            ob = other.get("graph") or other.get("eager")
+            line[other["scaling"] + "_scaling"] = {"value": ob["value"], "ms_per_step": ob["ms_per_step"],
+                                                   "utterances_per_step": other["utterances_per_step"],
+                                                   "mode": "graph" if "graph" in other else "eager", "unit": UNIT}
         if world == 1 and not args.no_cpu_baseline:
             v, sample, _ = cpu_reference_rate(args.cpu_budget_s)
             v2, sample2, _ = cpu_reference_rate(args.cpu_budget_s / 2, skip_dead_encoder=True)
@@ -490,8 +557,13 @@ def main():
     ap.add_argument("--copy-streams", type=int, default=2, help="H2D copy streams of the e2e feeder (2: +3 % over one)")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run one step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: --total-utts utterances PER GPU (default); strong: --total-utts in total, sharded over the GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default, BASELINE configs[4]): --total-utts in total, sharded over the GPUs; weak: per GPU")
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"], help="headline loop: CUDA-graph replay or eager launches")
+    ap.add_argument("--bn-sync", default="global", choices=["global", "local"],
+                    help="BatchNorm statistics across ranks: global = all-reduced (N-GPU == 1-GPU result), local = per rank (the reference's DDP)")
+    ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of the two overlapped buckets")
+    ap.add_argument("--no-second-scaling", action="store_true", help="N > 1: skip the extra weak- (or strong-) scaling measurement")
     args = ap.parse_args()
     _quiet_stdout()
     if args.impl == "reference":

@@ -43,12 +43,13 @@ SIGNATURES = {
     "ercg_graphify_count": (I, [P, I, I, I, I, P, P]),
     "ercg_graphify_workspace_bytes": (SZ, [I]),
     "ercg_graphify_csr": (I, [P, I, I, P, I, L, I, I, I, L, L, POINTER(GraphOut), P, SZ, P]),
+    "ercg_graphify_check_census": (I, [P, I, P, P]),
     "ercg_pack_rows": (I, [P, L, L, I, I, P, P, P, L, L, I, P]),
     "ercg_unpack_rows": (I, [P, L, P, P, P, L, L, I, I, L, I, P]),
-    "ercg_gemm_nn": (I, [P, L, P, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P]),
+    "ercg_gemm_nn": (I, [P, L, P, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, P]),
     "ercg_gemm_nn_tc_workspace_bytes": (SZ, [I, I]),
     "ercg_gemm_nn_tc_supported": (I, [P, L, P, L, L, I, I]),
-    "ercg_gemm_nn_tc": (I, [P, L, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, P, SZ, P]),
+    "ercg_gemm_nn_tc": (I, [P, L, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, P, P, SZ, P]),
     "ercg_gemm_nn_tc_trace": (I, [P]),
     "ercg_gemm_tn_workspace_bytes": (SZ, [L, I, I]),
     "ercg_gemm_tn": (I, [P, L, P, P, L, P, L, L, I, I, P, SZ, P]),
@@ -85,6 +86,9 @@ SIGNATURES = {
     "ercg_ce_workspace_bytes": (SZ, [L]),
     "ercg_ce_fwd": (I, [P, L, P, P, P, P, L, L, I, P, SZ, P]),
     "ercg_scale_by_ratio": (I, [P, L, P, P, P]),
+    "ercg_sumsq_workspace_bytes": (SZ, [L]),
+    "ercg_sumsq": (I, [P, L, P, P, SZ, P]),
+    "ercg_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P, F, P, P]),
     # K7 / K8 (MMGCN)
     "ercg_mmgcn_block_offsets": (I, [P, I, P, P]),
     "ercg_mmgcn_adj_fwd": (I, [P, L, P, P, P, L, L, I, I, P, L, P, P, P, P, P]),

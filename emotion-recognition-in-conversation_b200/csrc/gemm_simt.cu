@@ -24,6 +24,7 @@ struct Epilogue {
   const float* bias; int act; const float* aux; long long ldaux; float aux_scale; float drop_p; unsigned long long seed;
   // GCNII epilogues (internal act codes, see ercg_gcnii_layer_fwd / ercg_gcnii_layer_bwd_input below)
   const float* aux2; long long ldaux2; float c_acc, c1, c2; int half;
+  const unsigned long long* seed_dev = nullptr;   // optional device word added to `seed` (a step counter: fresh mask per graph replay)
 };
 constexpr int ACT_GCNII_FWD = 16;   // x = [relu if half](c_acc*acc + c1*aux[m,n] + c2*aux2[m,n]) (+ inverted dropout)
 constexpr int ACT_GCNII_BWD = 17;   // x = c_acc*acc + (n < half ? c1*aux[m,n] : c2*aux[m,n-half])
@@ -157,7 +158,7 @@ gemm_nn_kernel(const float* __restrict__ A, long long lda, const int* __restrict
               x = fmaxf(x, 0.f);
             } else if (ep.act == ERCG_ACT_RELU_DROPOUT) {
               x = fmaxf(x, 0.f);
-              const bool drop = dropout_drop(dropout_group_hash(ep.seed, m, nn, N), nn & 3, dropout_thr16(ep.drop_p));
+              const bool drop = dropout_drop(dropout_group_hash(ep.seed + (ep.seed_dev ? __ldg(ep.seed_dev) : 0ull), m, nn, N), nn & 3, dropout_thr16(ep.drop_p));
               x = drop ? 0.f : x * (1.0f / (1.0f - ep.drop_p));
             } else if (ep.act == ERCG_ACT_MASK_POS) {
               x = __ldg(ep.aux + m * ep.ldaux + nn) > 0.f ? x * ep.aux_scale : 0.f;
@@ -426,7 +427,8 @@ using namespace ercg;
 
 extern "C" int ercg_gemm_nn(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb,
                             const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int act,
-                            const float* aux, int64_t ldaux, float aux_scale, float drop_p, uint64_t seed, void* stream) {
+                            const float* aux, int64_t ldaux, float aux_scale, float drop_p, uint64_t seed,
+                            const uint64_t* seed_dev, void* stream) {
   if (M < 0 || N < 0 || K < 0) return ERCG_EINVAL;
   if (M == 0 || N == 0) return ERCG_OK;
   if (!A || !B || !C || lda < K || ldb < N || ldc < N) return ERCG_EINVAL;
@@ -457,6 +459,7 @@ extern "C" int ercg_gemm_nn(const float* A, int64_t lda, const int32_t* a_rows, 
     }
   }
   Epilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, nullptr, 0, 1.f, 0.f, 0.f, 0};
+  ep.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   const bool va = ((lda & 3) == 0) && aligned16(A);
   const bool vb = ((ldb & 3) == 0) && aligned16(B);
   long long gm = (M + BM - 1) / BM;

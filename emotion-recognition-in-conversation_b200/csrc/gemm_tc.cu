@@ -43,6 +43,7 @@ struct TcEpilogue {
   const float* bias; int act; const float* aux; long long ldaux; float aux_scale; float drop_p; unsigned long long seed;
   int dbg;   // ERCG_TC_DBG: performance experiments only (1 no MMA, 8 no B loads)
   long long* trace;   // ERCG_TC_TRACE: CTA 0 records clock64() per role and k-chunk (pipeline timeline, diagnostics only)
+  const unsigned long long* seed_dev = nullptr;   // optional device word added to `seed` (fresh dropout mask per graph replay)
 };
 constexpr int TR_N = 160;          // traced chunks
 constexpr int TR_ROLES = 5;        // 0 A producer, 1 splitter, 2 MMA, 3 epilogue (per group), 4 B producer
@@ -282,7 +283,7 @@ __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, lon
   if (ACT == ERCG_ACT_RELU_DROPOUT) {
     const float sc = 1.0f / (1.0f - ep.drop_p);
     const unsigned thr = dropout_thr16(ep.drop_p);
-    const uint64_t h = dropout_group_hash(ep.seed, m, nn0, N);          // nn0 is a multiple of 4: one hash per float4
+    const uint64_t h = dropout_group_hash(ep.seed + (ep.seed_dev ? __ldg(ep.seed_dev) : 0ull), m, nn0, N);   // nn0 % 4 == 0: one hash per float4
     x.x = dropout_drop(h, 0, thr) ? 0.f : x.x * sc;
     x.y = dropout_drop(h, 1, thr) ? 0.f : x.y * sc;
     x.z = dropout_drop(h, 2, thr) ? 0.f : x.z * sc;
@@ -1065,8 +1066,8 @@ extern "C" int ercg_gemm_nn_tc_supported(const float* A, int64_t lda, const floa
 
 extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                                int64_t ldc, int64_t M, int N, int K, int act, const float* aux, int64_t ldaux,
-                               float aux_scale, float drop_p, uint64_t seed, float* colsum_out, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               float aux_scale, float drop_p, uint64_t seed, const uint64_t* seed_dev, float* colsum_out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
   if (M < 0 || N < 0 || K < 0) return ERCG_EINVAL;
   if (colsum_out && (N > TC_BN || bias || act != ERCG_ACT_NONE)) return ERCG_EINVAL;
   if (M == 0 && colsum_out && N > 0) cudaMemsetAsync(colsum_out, 0, (size_t)N * sizeof(float), (cudaStream_t)stream);
@@ -1119,6 +1120,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   long long* nn_trace = (trace_on & 1) ? trace_buf : nullptr;
   if (nn_trace) cudaMemsetAsync(nn_trace, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
   TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg, nn_trace};
+  ep.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;       // the whole K extent is one TMEM accumulation group
   float* partial = colsum_out ? reinterpret_cast<float*>(b16 + (size_t)N * Kc * 64) : nullptr;   // [grid][4][128], after the B copies
   kernels[act][smallk]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep, partial);

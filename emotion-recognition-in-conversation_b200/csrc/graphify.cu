@@ -324,6 +324,13 @@ __global__ void __launch_bounds__(256) rel_census_kernel(const uint8_t* __restri
   if ((bits[threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u) rel_info[1 + threadIdx.x] = 0;
 }
 
+// A caller that already knows which relation ids can occur (from the speaker ids on the host) supplies its own id -> slot
+// table and does not wait for the census; this check raises ERCG_GRAPH_ECENSUS if an edge carries an id the table lacks.
+__global__ void __launch_bounds__(256) rel_check_kernel(const int* __restrict__ allowed, int n_allowed, int* __restrict__ rel_info) {
+  const int t = threadIdx.x;
+  if (rel_info[1 + t] >= 0 && (t >= n_allowed || allowed[t] < 0)) atomicOr(rel_info + 513, 8);
+}
+
 __global__ void __launch_bounds__(256) rel_slots_kernel(int* __restrict__ rel_info) {
   __shared__ int wcnt[8];
   const int t = threadIdx.x, lane = t & 31;
@@ -448,6 +455,12 @@ extern "C" int ercg_graphify_csr(const void* lengths_dev, int lengths_is_i64, in
     return finish_launch();
   }
   return ERCG_OK;
+}
+
+extern "C" int ercg_graphify_check_census(const int32_t* allowed_slots, int n_allowed, int32_t* rel_info, void* stream) {
+  if (!allowed_slots || !rel_info || n_allowed < 0 || n_allowed > 256) return ERCG_EINVAL;
+  rel_check_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(allowed_slots, n_allowed, rel_info);
+  return finish_launch();
 }
 
 static int pack_launch(const float* padded, int64_t ld, int64_t Lmax, int B, int seq_first,

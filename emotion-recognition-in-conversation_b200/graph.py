@@ -29,7 +29,7 @@ class PackedGraph:
     __slots__ = ("B", "N", "E", "wp", "wf", "n_speakers", "num_relations", "device", "node_off", "edge_off",
                  "rowptr", "col", "etype", "t_rowptr", "t_col", "t_etype", "t_eid", "spk", "node_dlg", "inv_cnt",
                  "edge_index", "edge_type", "edge_index_lengths", "totals", "pad_row", "perm", "Lpad", "rel_info",
-                 "_rel_host", "_rel_event", "_rel_cache", "_rel_gen", "_core")
+                 "_rel_host", "_rel_event", "_rel_cache", "_rel_gen", "_rel_sel", "_core")
 
     def __init__(self):
         for s in self.__slots__:
@@ -73,10 +73,20 @@ class PackedGraph:
         if self._rel_cache is None and not _NO_CENSUS:
             self.relation_slots()
             return
+        if self._rel_event is None:              # host-supplied relation ids: no census copy in flight, read the flag word
+            _raise_graph_errors(int(self.rel_info[513].item()))
+            return
         if self._rel_event is not None:
             self._rel_event.synchronize()
             _raise_graph_errors(int(self.rel_info[513].item()) if _CENSUS_GEN.get(id(self._rel_host)) != self._rel_gen
                                 else int(self._rel_host[513]))
+
+    def relation_sel(self):
+        """Device int64 [P]: the relation ids behind the compact slots (index for selecting their weights)."""
+        if self._rel_sel is not None:
+            return self._rel_sel
+        ids, _ = self.relation_slots()
+        return self.rel_info[257:257 + len(ids)].long()
 
     def relation_slots(self):
         """K1's relation census: (ids, rel_slot) -- the sorted relation ids that occur on at least one edge (python list)
@@ -106,6 +116,8 @@ def _raise_graph_errors(flags):
         what.append("a speaker id lies outside [0, n_speakers)")
     if flags & 4:
         what.append("the given (N, E) sizes are smaller than the lengths imply")
+    if flags & 8:
+        what.append("an edge carries a relation id that is not in the relation_ids given to build_graph")
     raise ValueError("batch_graphify: invalid input -- " + "; ".join(what) +
                      " (the reference raises IndexError / KeyError at cogmen_utils.py:131-137)")
 
@@ -119,13 +131,38 @@ def graph_sizes(lengths_cpu, wp, wf):
     return n.value, e.value
 
 
+def relation_ids_for_speakers(present_speakers, n_speakers):
+    """Every relation id ((s_j * n + s_k) * 2 + dir) that edges between the given speaker ids can carry -- a superset of
+    what a batch uses, computed on the host from the data set's speaker ids (MOSEI: {0} -> [0, 1])."""
+    sp = sorted(set(int(v) for v in present_speakers))
+    return sorted(((a * n_speakers + b) * 2 + d) for a in sp for b in sp for d in (0, 1))
+
+
+_HINT_TABLES = {}       # (device, num_relations, ids) -> (id -> slot table int32 [num_relations], ids int64 [P]) on the device
+
+
+def _hint_tables(device, num_relations, ids):
+    key = (str(device), num_relations, tuple(ids))
+    t = _HINT_TABLES.get(key)
+    if t is None:
+        table = torch.full((num_relations,), -1, dtype=torch.int32)
+        table[torch.tensor(list(ids), dtype=torch.int64)] = torch.arange(len(ids), dtype=torch.int32)
+        t = (table.to(device), torch.tensor(list(ids), dtype=torch.int64).to(device))
+        _HINT_TABLES[key] = t
+    return t
+
+
 def build_graph(lengths, speakers, wp, wf, n_speakers, device=None, reference_layout=True, mean_weight=True,
-                sizes=None):
+                sizes=None, relation_ids=None):
     """Run K1.
 
     lengths   [B] int64/int32 (CPU or CUDA).  A CPU tensor avoids the single size sync.
     speakers  padded [B,Lmax] or packed [N] int64/int32 speaker ids
     sizes     optional (N, E) if the caller already knows them
+    relation_ids  optional list of the relation ids that CAN occur (relation_ids_for_speakers): RGCNConv then takes its
+              relation slots from this list instead of waiting for K1's census to reach the host -- nothing in the step
+              touches the host, so it can be captured in a CUDA graph.  A batch that uses an id outside the list is
+              flagged on the device (ERCG_GRAPH_ECENSUS, raised by check_inputs()).
     """
     B = lengths.numel()
     if not lengths.is_cuda and B:
@@ -197,6 +234,12 @@ def build_graph(lengths, speakers, wp, wf, n_speakers, device=None, reference_la
     check(lib().ercg_graphify_csr(_p(ldev), 1 if ldev.dtype == torch.int64 else 0, B, _p(sdev),
                                   1 if sdev.dtype == torch.int64 else 0, spk_ld, wp, wf, n_speakers, N, E,
                                   ctypes.byref(out), _p(ws), ws.numel(), _stream()), "ercg_graphify_csr")
+    if relation_ids is not None:
+        ids = [int(i) for i in relation_ids]
+        table, sel = _hint_tables(device, g.num_relations, ids)
+        check(lib().ercg_graphify_check_census(_p(table), table.numel(), _p(g.rel_info), _stream()), "ercg_graphify_check_census")
+        g._rel_cache, g._rel_sel = (ids, table), sel
+        return g
     g._rel_host, g._rel_event, g._rel_gen = _census_slot()
     g._rel_host.copy_(g.rel_info, non_blocking=True)
     g._rel_event.record()

@@ -59,6 +59,11 @@ def _tag_get(t, name):
     return tag[0]
 
 
+# Optional device word added to every dropout seed (see ercg_gemm_nn's seed_dev): a train step captured in a CUDA graph
+# points this at its device step counter so that each replay draws a fresh mask.  None = host seeds only.
+SEED_DEV = None
+
+
 def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_scale=1.0, drop_p=0.0, seed=0, out=None,
             want_colsum=False):
     """C = act(A[a_rows] @ Bm + bias).  ``want_colsum``: when the tensor-core kernel runs a plain product with N <= 128 it
@@ -82,14 +87,14 @@ def gemm_nn(A, Bm, bias=None, act=ACT_NONE, a_rows=None, M=None, aux=None, aux_s
         if want_colsum and N <= 128 and bias is None and act == ACT_NONE and out is None:
             cs = torch.empty(N, dtype=torch.float32, device=A.device)
         check(lib().ercg_gemm_nn_tc(_p(A), lda, _p(Bm), ldb, _p(bias), _p(C), ldc, M, N, K, act, _p(aux), ldaux,
-                                    float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _p(cs), _p(ws), ws.numel(),
-                                    _stream()), "ercg_gemm_nn_tc")
+                                    float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _p(SEED_DEV), _p(cs), _p(ws),
+                                    ws.numel(), _stream()), "ercg_gemm_nn_tc")
         if cs is not None:
             _tag_set(C, "_ercg_colsum", cs)
         return C
     check(lib().ercg_gemm_nn(_p(A), lda, _p(a_rows), _p(Bm), ldb, _p(bias), _p(C), C.stride(0) if M > 1 else N, M, N, K,
-                             act, _p(aux), ldaux, float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _stream()),
-          "ercg_gemm_nn")
+                             act, _p(aux), ldaux, float(aux_scale), float(drop_p), int(seed) & (2 ** 64 - 1), _p(SEED_DEV),
+                             _stream()), "ercg_gemm_nn")
     return C
 
 
@@ -430,7 +435,7 @@ def bn_leaky_relu(x, gamma, beta, mean, var, eps, slope, use_batch_stats, count=
 # ------------------------------------------------------------------------------------------- cross entropy
 class _CrossEntropy(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, labels, class_weight, reduce_sync):
+    def forward(ctx, logits, labels, class_weight, reduce_sync, denom, num_out):
         logits, ld = _rows(logits)
         N, C = logits.shape
         nd = torch.empty(2, dtype=torch.float32, device=logits.device)
@@ -438,6 +443,10 @@ class _CrossEntropy(torch.autograd.Function):
         ws = _ws(lib().ercg_ce_workspace_bytes(N), logits.device)
         check(lib().ercg_ce_fwd(_p(logits), ld, _p(labels), _p(class_weight), _p(nd), _p(dl), C, N, C, _p(ws), ws.numel(),
                                 _stream()), "ercg_ce_fwd")
+        if num_out is not None:
+            num_out.copy_(nd[:1])                      # local numerator rides along with the gradient all-reduce
+        if denom is not None:
+            nd[1:].fill_(float(denom))                 # host-known global normaliser (utterance count): no collective needed
         if reduce_sync is not None:
             nd = reduce_sync(nd)                       # global numerator / denominator across ranks
         ctx.save_for_backward(dl, nd)
@@ -449,13 +458,18 @@ class _CrossEntropy(torch.autograd.Function):
         out = dl.clone()
         g = g.contiguous().reshape(1)
         check(lib().ercg_scale_by_ratio(_p(out), out.numel(), _p(g), nd.data_ptr() + 4, _stream()), "ercg_scale_by_ratio")
-        return out, None, None, None
+        return out, None, None, None, None, None
 
 
-def cross_entropy(logits, labels, class_weight=None, reduce_sync=None):
-    """F.cross_entropy(logits, labels, weight=class_weight) with mean reduction."""
+def cross_entropy(logits, labels, class_weight=None, reduce_sync=None, denom=None, num_out=None):
+    """F.cross_entropy(logits, labels, weight=class_weight) with mean reduction.
+
+    Data-parallel use: ``reduce_sync`` all-reduces (numerator, denominator) so every rank sees the global mean; or, with no
+    collective at all, ``denom`` = the host-known GLOBAL sum of weights (the utterance count for unweighted CE) makes the
+    returned value this rank's share of the global mean (gradients are then exact after the summed gradient all-reduce)
+    and ``num_out`` (a 1-element device tensor, e.g. a ride-along slot of FlatAdam) receives the local numerator."""
     assert labels.dtype == torch.int64 and labels.is_cuda
-    return _CrossEntropy.apply(logits, labels.contiguous(), class_weight, reduce_sync)
+    return _CrossEntropy.apply(logits, labels.contiguous(), class_weight, reduce_sync, denom, num_out)
 
 
 # ------------------------------------------------------------------------------------------- pack rows

@@ -67,7 +67,7 @@ class RGCNConv(nn.Module):
             # 2 of the 8 ids): Y is [N, (P+1)*H]; the other weights get an exactly-zero gradient, as in the reference
             ids, rel_slot = census
             P = len(ids)
-            sel = g.rel_info[257:257 + P].long()
+            sel = g.relation_sel()
             wrel = self.weight.index_select(0, sel)
             wcat = torch.cat([wrel.permute(1, 0, 2).reshape(self.in_channels, P * H), self.root], dim=1)
             y = ops.matmul_kn(x, wcat)

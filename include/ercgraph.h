@@ -39,6 +39,7 @@ extern "C" {
 #define ERCG_GRAPH_ELENGTH 1   /* a dialogue is longer than the padded speaker width spk_ld */
 #define ERCG_GRAPH_ESPEAKER 2  /* a speaker id outside [0, n_speakers) */
 #define ERCG_GRAPH_ESIZE 4     /* the caller's N / E are smaller than the lengths imply: dialogues were skipped */
+#define ERCG_GRAPH_ECENSUS 8   /* an edge carries a relation id missing from the caller's table (ercg_graphify_check_census) */
 
 #define ERCG_ACT_NONE 0
 #define ERCG_ACT_RELU 1
@@ -103,6 +104,11 @@ int ercg_graphify_csr(const void* lengths_dev, int lengths_is_i64, int B,
                       int wp, int wf, int n_speakers, int64_t N, int64_t E,
                       const ercg_graph_out* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* For callers that know the possible relation ids up front (from the speaker ids on the host) and use their own
+ * id -> slot table instead of waiting for the census of rel_info: ORs ERCG_GRAPH_ECENSUS into rel_info[513] when an edge
+ * of the graph carries an id r with r >= n_allowed or allowed_slots[r] < 0.  Run it right after ercg_graphify_csr. */
+int ercg_graphify_check_census(const int32_t* allowed_slots, int n_allowed, int32_t* rel_info, void* stream);
+
 /* padded [B,Lmax,D] (row stride ld) -> packed [N,D]: the torch.cat of cogmen_utils.py:123,139 and
  * simple_batch_graphify (track_mm/mmgcn_utils.py:5-21, seq_first=1 for its [L,B,D] layout). */
 int ercg_pack_rows(const float* padded, int64_t ld, int64_t Lmax, int B, int seq_first,
@@ -123,7 +129,10 @@ int ercg_unpack_rows(const float* packed, int64_t ldp, const int32_t* node_off, 
  * ------------------------------------------------------------------------------------------- */
 int ercg_gemm_nn(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb,
                  const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int act,
-                 const float* aux, int64_t ldaux, float aux_scale, float drop_p, uint64_t seed, void* stream);
+                 const float* aux, int64_t ldaux, float aux_scale, float drop_p, uint64_t seed,
+                 const uint64_t* seed_dev, void* stream);
+/* seed_dev (optional, device): the dropout mask is drawn from seed + *seed_dev.  Point it at a device-resident step counter
+ * (ercg_adam_step's) and a train step captured once in a CUDA graph draws a fresh mask on every replay. */
 
 /* Tensor-core variant of ercg_gemm_nn (tcgen05 kind::tf32, TMA-staged 128-byte-swizzled tiles, TMEM
  * accumulators).  fp32-grade accuracy through the 3xTF32 split (hi/lo of both operands, fp32 accumulate);
@@ -133,8 +142,8 @@ size_t ercg_gemm_nn_tc_workspace_bytes(int N, int K);
 int ercg_gemm_nn_tc_supported(const float* A, int64_t lda, const float* C, int64_t ldc, int64_t M, int N, int K);
 int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                     int64_t ldc, int64_t M, int N, int K, int act, const float* aux, int64_t ldaux,
-                    float aux_scale, float drop_p, uint64_t seed, float* colsum_out, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    float aux_scale, float drop_p, uint64_t seed, const uint64_t* seed_dev, float* colsum_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
 /* colsum_out (optional, [N]; needs N <= 128, bias == NULL, act == ERCG_ACT_NONE): also returns the column sums of C,
  * reduced from the tiles while they sit in shared memory -- the bias gradient of the layer that produced A's operand
  * (the input gradient dX = dZ @ W^T of one Linear is the dZ whose column sums the previous Linear needs). */
@@ -376,6 +385,23 @@ int ercg_speaker_embed_add(const float* x, int64_t ldx, const float* qmask, int 
                            int D, void* stream);
 /* out = dropout(relu(x)) with the counter-hash mask (relu(dropout(x)) of mmgcn.py:117-118 is the same function) */
 int ercg_relu_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer tail of the train steps on ONE flat fp32 buffer of all live parameters and its gradient twin:
+ *   torch.optim.Adam(lr, weight_decay) .step()           track_mm/cogmen.py:50,187-189, dgcn.py:41,127-129, mmgcn.py:34
+ *   torch.optim.AdamW + clip_grad_norm_(params, 5)        track_mm/dagerc.py:39,229-231
+ * ercg_sumsq: out[0] = sum x^2 (fixed-order fp64 partials; the squared global gradient norm).
+ * ercg_adam_step: one launch updates p, m, v in place from g.  decoupled = 0: Adam (g += wd * p), 1: AdamW (p *= 1 - lr*wd).
+ *   grad_scale multiplies every gradient (1/world_size after a summed all-reduce of per-rank MEAN losses; 1 otherwise).
+ *   sumsq (optional, device): clip_grad_norm_ -- gradients are scaled by min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)).
+ *   step_dev: device int64 step counter; the update uses step + 1 for the bias corrections and a second tiny launch
+ *   increments it, so a captured CUDA graph advances the optimizer state on every replay without host arithmetic.
+ * ------------------------------------------------------------------------------------------- */
+size_t ercg_sumsq_workspace_bytes(int64_t n);
+int ercg_sumsq(const float* x, int64_t n, float* out, void* workspace, size_t workspace_bytes, void* stream);
+int ercg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int decoupled, float grad_scale, const float* sumsq,
+                   float max_norm, int64_t* step_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K9  DAG-ERC predecessor structure (DAGERCModule.get_adj_v1 / get_s_mask, track_mm/dagerc.py:109-154) on packed

@@ -68,18 +68,45 @@ class CogmenOracle(nn.Module):
         _, ei, et = _graph_tensors(text_length, speaker_tensor, self.wp, self.wf, self.n_speakers)
         return self.cls(self.gcn(feats, ei, et)), feats
 
-    def forward_packed(self, x_packed, speaker_packed, text_length, drop_mask=None):
+    def forward_packed(self, x_packed, speaker_packed, text_length, drop_mask=None, act_masks=None):
         """Same computation on rows that are already packed [N, hidden_all] (cogmen_utils.py:123,139 only re-packs the
-        padded tensor; Linear is row-wise, so packing before or after it is the same arithmetic).  ``drop_mask`` [N,100]
-        (entries 0 or 1/(1-p)) replaces nn.Dropout's own random mask in the classifier (cogmen.py:119), so a run of
-        the CUDA path WITH dropout can be checked by handing its mask to the oracle."""
+        padded tensor; Linear is row-wise, so packing before or after it is the same arithmetic).
+
+        ``drop_mask`` [N,100] (entries 0 or 1/(1-p)) replaces nn.Dropout's own random mask in the classifier (cogmen.py:119),
+        so a run of the CUDA path WITH dropout can be checked by handing its mask to the oracle.
+
+        ``act_masks`` = (leaky_pos [N,100] bool, relu_pos [N,100] bool) pins the branch of the two piecewise-linear
+        activations (LeakyReLU after the BatchNorm, cogmen.py:68,72; ReLU in the classifier, :118).  With ~10^6 x 100
+        activations some pre-activation lands within rounding distance of the kink, where two correct implementations may
+        pick different branches; the VALUE moves by ~1e-7 but the GRADIENT of that element jumps, which in a sum over N
+        rows shows up as a 1e-4 .. 1e-3 relative change of whole weight gradients (measured: fp32 vs fp64 of this very
+        oracle).  Pinning the branch compares the implementations on the same piecewise-linear piece; ``self.kinks``
+        records how many elements were on the other side and how far (they must be within rounding distance of 0)."""
         feats = self.rnn["1"](x_packed)
         _, ei, et = _graph_tensors(text_length, speaker_packed, self.wp, self.wf, self.n_speakers)
-        h = self.gcn(feats, ei, et)
-        if drop_mask is None:
-            return self.cls(h), feats
-        h = self.cls[1](self.cls[0](h)) * drop_mask.to(h.dtype)
-        return self.cls[3](h), feats
+        if drop_mask is None and act_masks is None:
+            return self.cls(self.gcn(feats, ei, et)), feats
+        g = self.gcn
+        y = g.bn(g.conv2(g.conv1(feats, ei, et), ei))
+        self.kinks = {}
+        if act_masks is None:
+            h = g.relu(y)
+        else:
+            pos = act_masks[0]
+            off = (y.detach() > 0) != pos
+            self.kinks["leaky"] = (int(off.sum()), float(y.detach()[off].abs().max()) if off.any() else 0.0)
+            h = y * torch.where(pos, torch.ones((), dtype=y.dtype), torch.full((), g.relu.negative_slope, dtype=y.dtype))
+        z = self.cls[0](h)
+        if act_masks is None:
+            a = self.cls[1](z)
+        else:
+            pos = act_masks[1]
+            off = (z.detach() > 0) != pos
+            self.kinks["relu"] = (int(off.sum()), float(z.detach()[off].abs().max()) if off.any() else 0.0)
+            a = z * pos.to(z.dtype)
+        if drop_mask is not None:
+            a = a * drop_mask.to(a.dtype)
+        return self.cls[3](a), feats
 
 
 class VendoredRGCNConv(nn.Module):
@@ -122,9 +149,9 @@ class EdgeAttOracle(nn.Module):
         u = x @ self.weight.t()                                 # u_k = W x_k  (dgcn_models.py:136-137)
         score = (x.index_select(0, src) * u.index_select(0, dst)).sum(-1)
         n = x.size(0)
-        smax = torch.full((n,), float("-inf")).scatter_reduce(0, src, score, reduce="amax", include_self=True)
+        smax = torch.full((n,), float("-inf"), dtype=x.dtype).scatter_reduce(0, src, score, reduce="amax", include_self=True)
         ex = (score - smax[src]).exp()
-        den = torch.zeros(n).index_add_(0, src, ex)
+        den = torch.zeros(n, dtype=x.dtype).index_add_(0, src, ex)
         return ex / den[src]
 
 

@@ -26,15 +26,18 @@ def _batch(total, seed):
     return synth.packed_batch(lengths, HIDDEN, 2, C, gen, one_speaker=True)
 
 
-def _oracle_run(o, b, dtype, drop_mask=None):
+def _oracle_run(o, b, dtype, drop_mask, act_masks):
     o = copy.deepcopy(o).to(dtype)
     o.train()
     logits, feats = o.forward_packed(b["x_packed"].to(dtype), b["speaker_packed"], b["text_length"],
-                                     None if drop_mask is None else drop_mask.to(dtype))
+                                     None if drop_mask is None else drop_mask.to(dtype), act_masks)
     loss = F.cross_entropy(logits, b["label"])
     loss.backward()
-    out = {"logits": logits.detach().numpy(), "features": feats.detach().numpy(), "loss": np.asarray(float(loss))}
-    return out, grads_of(o)
+    out = {"logits": logits.detach().numpy(), "features": feats.detach().numpy(), "loss": np.asarray(float(loss.detach()))}
+    # branch pinning (see CogmenOracle.forward_packed) may only ever touch elements within rounding distance of the kink
+    for name, (count, far) in o.kinks.items():
+        assert count <= 64 and far < 1e-4, (name, count, far)
+    return out, grads_of(o), dict(o.kinks)
 
 
 @pytest.mark.parametrize("total,seed", [(1 << 14, 0), (1 << 16, 1)])
@@ -63,7 +66,15 @@ def test_config5_forward_packed_vs_oracle(total, seed, dropout, monkeypatch):
         m.cls[2].p = 0.0
     before = _lib.launch_count()
     x = b["x_storage"].cuda()[:, :HIDDEN]                             # row pitch 1444 floats: the resident layout of the bench
+    seen = {}
+    hook = m.gcn.register_forward_hook(lambda mod, inp, out: seen.__setitem__("graph_out", out.detach()))
     logits, feats = m.forward_packed(x, b["speaker_packed"].cuda(), b["text_length"])
+    hook.remove()
+    # the branches the kernels took at the two piecewise-linear activations: sign of the LeakyReLU output, and the ReLU
+    # pattern of the classifier's hidden layer (recomputed with the same kernel and arguments the fused node uses)
+    lin0 = m.cls[0]
+    hid = ops.linear(seen["graph_out"], lin0.weight.detach(), lin0.bias.detach(), act=ops.ACT_RELU)
+    act_masks = ((seen["graph_out"] > 0).cpu(), (hid > 0).cpu())
     loss = ops.cross_entropy(logits, b["label"].cuda())
     loss.backward()
     torch.cuda.synchronize()
@@ -71,9 +82,10 @@ def test_config5_forward_packed_vs_oracle(total, seed, dropout, monkeypatch):
     got = {"logits": logits.detach().cpu().numpy(), "features": feats.detach().cpu().numpy(),
            "loss": np.asarray(float(loss))}
     ggrads = grads_of(m)
-    r32, g32 = _oracle_run(o, b, torch.float32, mask)
-    r64, g64 = _oracle_run(o, b, torch.float64, mask)
+    r32, g32, k32 = _oracle_run(o, b, torch.float32, mask, act_masks)
+    r64, g64, k64 = _oracle_run(o, b, torch.float64, mask, act_masks)
     case = "config5/N=%d/dropout=%s" % (N, "on" if dropout else "off")
+    print(case, "activations on the other side of a kink (count, max |pre-activation|): fp32 oracle", k32, "fp64 oracle", k64)
     parity_check(case + "/outputs", got, r32, r64)
     assert len(g32) == 19 and set(ggrads) == set(g32)
     parity_check(case + "/grads", ggrads, g32, g64)

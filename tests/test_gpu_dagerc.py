@@ -173,7 +173,7 @@ def test_gat_dialoggcn_v1_standalone_forward_backward_vs_oracle(B, N, D):
     gw, gs = torch.randn(B, 1, N, generator=gen), torch.randn(B, D, generator=gen)
     res = []
     for mod, dev, dt in ((o, "cpu", torch.float32), (copy.deepcopy(o).double(), "cpu", torch.float64), (m, "cuda", torch.float32)):
-        q, k = Q.to(dev, dt).requires_grad_(), K.to(dev, dt).requires_grad_()
+        q, k = Q.to(dev, dt).detach().clone().requires_grad_(), K.to(dev, dt).detach().clone().requires_grad_()
         w, s = mod(q, k, k, adj.to(dev, dt), sm.to(dev))
         assert w.shape == (B, 1, N) and s.shape == (B, D)
         ((w * gw.to(dev, dt)).sum() + (s * gs.to(dev, dt)).sum()).backward()

@@ -1,0 +1,97 @@
+"""The optimizer tail (FlatAdam: ercg_adam_step / ercg_sumsq on one flat buffer) against torch.optim, and the whole COGMEN
+train step as a replayed CUDA graph against the same steps run eagerly (cogmen.py:50,179-195,
+dagerc.py:39,229-231)."""
+import copy
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _mlp(seed):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.Tanh(), torch.nn.Linear(64, 5), torch.nn.Linear(5, 3, bias=False)).cuda()
+
+
+@pytest.mark.parametrize("decoupled,wd,max_norm", [(False, 1e-8, None), (False, 0.0, None), (True, 1e-2, None), (True, 1e-2, 5.0),
+                                                   (True, 1e-2, 0.05)])
+def test_flat_adam_matches_torch_optim(decoupled, wd, max_norm):
+    import erc_b200  # noqa: F401
+    from erc_b200.optim import FlatAdam
+    a, b = _mlp(0), _mlp(0)
+    dead = torch.nn.Parameter(torch.ones(7, device="cuda"))            # never gets a gradient, like the reference's dead encoder
+    ours = FlatAdam(list(a.parameters()) + [dead], lr=3e-3, weight_decay=wd, decoupled=decoupled, max_norm=max_norm)
+    cls = torch.optim.AdamW if decoupled else torch.optim.Adam
+    ref = cls(list(b.parameters()), lr=3e-3, weight_decay=wd, foreach=False, fused=False)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for it in range(12):
+        x = torch.randn(50, 37, device="cuda", generator=gen) * (10.0 if it == 5 else 1.0)   # one step with a large gradient norm
+        for m in (a, b):
+            for p in m.parameters():
+                p.grad = None
+            m(x).square().sum().backward()
+        if max_norm is not None:
+            want_norm = torch.nn.utils.clip_grad_norm_(b.parameters(), max_norm)
+        ours.step()
+        if max_norm is not None:
+            assert rel_err(ours.grad_norm(), want_norm) < 1e-6
+        ref.step()
+    assert int(ours.step_dev.item()) == 12 and dead.grad is None and torch.equal(dead.data, torch.ones(7, device="cuda"))
+    for (k, p), q in zip(a.named_parameters(), b.parameters()):
+        assert rel_err(p, q) < 2e-6, k
+        assert p.data_ptr() >= ours.flat_p.data_ptr() and p.data_ptr() < ours.flat_p.data_ptr() + 4 * ours.n   # lives in the flat buffer
+
+
+def _cogmen_setup(total, seed, p_drop):
+    import erc_b200  # noqa: F401
+    from erc_b200 import synth
+    from erc_b200.track_mm.cogmen import COGMENModule
+    lengths = synth.config5_lengths(total, seed=seed)
+    b = synth.packed_batch(lengths, 1443, 2, 6, torch.Generator().manual_seed(seed), one_speaker=True)
+    torch.manual_seed(seed)
+    m = COGMENModule(1443, 100, 17, 2, 6, build_dead_encoder=False).cuda()
+    m.cls[2].p = p_drop
+    m.train()
+    x = b["x_storage"].cuda()[:, :1443]
+    return m, lengths, x, b["speaker_packed"].cuda(), b["label"].cuda()
+
+
+def test_train_step_graph_replay_equals_eager_and_torch_adam():
+    from erc_b200 import ops
+    from erc_b200.train_step import CogmenTrainStep
+    m0, lengths, x, spk, y = _cogmen_setup(6000, 3, 0.0)
+    m1, m2 = copy.deepcopy(m0), copy.deepcopy(m0)
+    # (a) eager steps through the train-step object
+    ts0 = CogmenTrainStep(m0, lengths, (0,))
+    losses0 = [float(ts0.step(x, spk, y)) for _ in range(5)]
+    ts0.check()
+    # (b) the same five steps: two eager warm-up steps inside capture(), then three replays of the captured graph
+    ts1 = CogmenTrainStep(m1, lengths, (0,)).capture(x, spk, y, warmup=2)
+    losses1 = [float(ts1.replay()) for _ in range(3)]
+    assert losses1 == losses0[2:]                                      # same kernels, same order: bit-identical
+    for (k, p), q in zip(m0.named_parameters(), m1.parameters()):
+        assert torch.equal(p, q), k
+    assert int(ts1.opt.step_dev.item()) == 5
+    # (c) the reference formulation: ops.cross_entropy + torch.optim.Adam (cogmen.py:50,185-189) on the legacy module path
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-4, weight_decay=1e-8, foreach=False, fused=False)
+    for i in range(5):
+        logits, _ = m2.forward_packed(x, spk, lengths)
+        loss = ops.cross_entropy(logits, y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(float(loss) - losses0[i]) <= 2e-6 * abs(losses0[i])
+    for (k, p), q in zip(m0.named_parameters(), m2.parameters()):
+        assert rel_err(p, q) < 2e-6, k
+    assert losses0[-1] < losses0[0]
+
+
+def test_train_step_graph_replay_draws_a_fresh_dropout_mask_each_replay():
+    from erc_b200.train_step import CogmenTrainStep
+    m, lengths, x, spk, y = _cogmen_setup(3000, 4, 0.5)
+    ts = CogmenTrainStep(m, lengths, (0,), lr=0.0, weight_decay=0.0).capture(x, spk, y)       # lr 0: only the mask changes
+    losses = [float(ts.replay()) for _ in range(4)]
+    assert len(set(losses)) == 4 and all(l == l for l in losses)
