@@ -39,9 +39,10 @@ class FlatAdam:
         if order is not None:
             live = sorted(live, key=order)            # stable: lets a caller put early-available gradients first
         dev = live[0].device
-        n = sum(p.numel() for p in live)
+        ALIGN = 64                                     # every parameter starts on a 256-byte boundary of the flat buffers: the
+        n = sum((p.numel() + ALIGN - 1) // ALIGN * ALIGN for p in live)    # kernels read weights / biases as float4 and through TMA
         self.n = n
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)     # padding stays 0 under Adam (g = 0, p = 0)
         self.flat_g = torch.zeros(n + self.extra_slots, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -57,7 +58,7 @@ class FlatAdam:
                 p.data = view                          # the parameter now LIVES in the flat buffer (same Parameter object)
                 self.g_views.append(self.flat_g[off:off + k].view_as(p))
                 self.offsets.append(off)
-                off += k
+                off += (k + ALIGN - 1) // ALIGN * ALIGN
         self.live = live
         self._live_ids = {id(p) for p in live}
         return self
