@@ -252,21 +252,27 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single rank)"
+    ctl = None
+    if args.watchdog_s > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog_s, exit=True)      # a hung collective must end the run with a traceback
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")      # NCCL collectives are captured into the step's CUDA graph
         dist.init_process_group("nccl", device_id=dev)
+        ctl = dist.new_group(backend="gloo")              # control plane (barriers, max over ranks of the timings): host side
     _lib.lib()                                            # fail loudly now if the .so is missing
     ld = (HIDDEN + 3) // 4 * 4                            # 1444: rows 16-byte aligned in HBM
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=ctl)
         torch.cuda.synchronize()
 
     def max_over_ranks(v):
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        t = torch.tensor([v], dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=ctl)
         return float(t.item())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -292,8 +298,9 @@ def run_ours(args):
         model = COGMENModule(HIDDEN, 100, 17, 2, N_CLASSES).to(dev)
         model.train()
         # cogmen.py:50: Adam(lr 1e-4, weight_decay 1e-8) -- here ercg_adam_step on the flat buffer of the live parameters
+        data_group = dist.new_group(backend="nccl") if world > 1 else None     # the step's own communicator (captured in its graph)
         ts = CogmenTrainStep(model, lengths, speakers_present=(0,), lr=1e-4, weight_decay=1e-8, world=world,
-                             global_utterances=total_utts, bn_sync=args.bn_sync, overlap=not args.no_overlap)
+                             global_utterances=total_utts, bn_sync=args.bn_sync, overlap=not args.no_overlap, group=data_group)
         out = {"scaling": scaling, "utterances_per_step": total_utts, "utterances_rank0": N, "edges_rank0": sizes[1],
                "dialogues": int(lengths_all.numel())}
 
@@ -406,8 +413,8 @@ def run_ours(args):
             e2e_ms = max_over_ranks(e0.elapsed_time(e1))
             h2d = (feeder.h2d_bytes - b0) // e2e_steps
             if world > 1:
-                b = torch.tensor([h2d], dtype=torch.float64, device=dev)
-                dist.all_reduce(b)
+                b = torch.tensor([h2d], dtype=torch.float64)
+                dist.all_reduce(b, group=ctl)
                 h2d = int(b.item())
             out["e2e"] = {"value": total_utts * e2e_steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                           "d2h_bytes_per_step": 4 * world, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
@@ -523,7 +530,13 @@ def run_ours(args):
                                     "value_dead_encoder_skipped": v2}
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # no NCCL teardown: destroying communicators whose kernels were captured in CUDA graphs was seen to hang
+        # (gpurun_out/r02c_probe*.log); everything is synchronised, the line is out, leave through the gloo barrier
+        torch.cuda.synchronize()
+        dist.barrier(group=ctl)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 _REAL_STDOUT = None
@@ -563,6 +576,7 @@ def main():
     ap.add_argument("--bn-sync", default="global", choices=["global", "local"],
                     help="BatchNorm statistics across ranks: global = all-reduced (N-GPU == 1-GPU result), local = per rank (the reference's DDP)")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of the two overlapped buckets")
+    ap.add_argument("--watchdog-s", type=int, default=0, help="dump all Python stacks and exit if the run takes longer than this")
     ap.add_argument("--no-second-scaling", action="store_true", help="N > 1: skip the extra weak- (or strong-) scaling measurement")
     args = ap.parse_args()
     _quiet_stdout()

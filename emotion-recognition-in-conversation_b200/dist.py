@@ -53,7 +53,7 @@ class StatSync:
         buf = torch.empty(2 * H + 1, dtype=torch.float64, device=mean.device)
         buf[:H] = mean.double() * n_local
         buf[H:2 * H] = (var.double() + mean.double() ** 2) * n_local
-        buf[2 * H] = n_local
+        buf[2 * H:].fill_(float(n_local))           # (indexed assignment of a Python number is a CPU->GPU copy: not capturable)
         dist.all_reduce(buf, group=self.group)
         count = buf[2 * H]
         gmean = buf[:H] / count
