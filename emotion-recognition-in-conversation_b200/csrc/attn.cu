@@ -12,7 +12,9 @@
 // k_j and v_j rows are read once per edge from L1/L2, q_i/s_i/out_i once per node from HBM.
 // Algorithmic HBM bytes per node: 5*4H (q,k,v,s,out) + 4 (rowptr) + 8*deg (col, alpha).
 #include "common.cuh"
+#include "attn_blk.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace ercg {
 
@@ -782,9 +784,25 @@ extern "C" int ercg_attn_bwd_src(const float* dout, int64_t ldo, const float* q,
 
 // ---- window-graph variants (contract: the in-neighbours of node i lie in [i - wlo, i + whi]; violated -> trap)
 static size_t attn_tile_smem(int H, int wlo, int whi, int full_tiles /* tile-only matrices */, int halo_tiles) {
-  return (size_t)(H >> 2) * 16 * ((size_t)full_tiles * WT + (size_t)halo_tiles * (WT + wlo + whi));
+  const size_t rows = (size_t)(H >> 2) * 16 * ((size_t)full_tiles * WT + (size_t)halo_tiles * (WT + wlo + whi));
+  return rows < 8192 ? 8192 : rows;        // tile_colsum reuses the first 8 KB as its reduction buffer (narrow H: rows alone are smaller)
 }
 static bool attn_tile_ok(int H, int wlo, int whi) { return H <= 128 && (H & 3) == 0 && wlo >= 0 && whi >= 0 && wlo + whi + 1 <= 32; }
+
+static_assert(BT == WT, "the blocked kernels share the tile count (per-CTA column-sum partials) with the tile kernels");
+// ERCG_ATTN_BLK=0 forces the round-1 tile kernels (A/B tests; read per call)
+static bool attn_use_blk(int H, int wlo, int whi) {
+  const char* e = getenv("ERCG_ATTN_BLK");
+  return (!e || atoi(e) != 0) && attn_blk_ok(H, wlo, whi);
+}
+template <typename K>
+static bool blk_attr(K kernel, DeviceOnce& once) {
+  if (once.need()) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return false;
+    once.mark();
+  }
+  return true;
+}
 
 extern "C" int ercg_attn_window_supported(int H, int wlo, int whi) { return attn_tile_ok(H, wlo, whi) ? 1 : 0; }
 extern "C" int64_t ercg_attn_window_tiles(int64_t N) { return N <= 0 ? 0 : (N + WT - 1) / WT; }
@@ -800,6 +818,12 @@ extern "C" int ercg_attn_window_fwd(const float* q, const float* k, const float*
   const size_t sm = attn_tile_smem(H, wlo, whi, 1, 2);
   const unsigned blocks = (unsigned)((N + WT - 1) / WT);
   cudaStream_t st = (cudaStream_t)stream;
+  if (attn_use_blk(H, wlo, whi)) {
+    static DeviceOnce once;
+    if (!blk_attr(attn_fwd_blk_kernel<BTH_FWD>, once)) return ERCG_ECUDA;
+    attn_fwd_blk_kernel<BTH_FWD><<<blocks, BTH_FWD, attn_blk_smem(H, wlo, whi, 0), st>>>(q, k, v, s, ld, rowptr, col, scale, out, ldo, alpha, N, H, wlo, whi);
+    return finish_launch();
+  }
   static DeviceOnce attr;
   if (attr.need()) {
     cudaFuncSetAttribute(attn_fwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -823,6 +847,12 @@ extern "C" int ercg_attn_window_bwd_dst(const float* dout, int64_t ldo, const fl
   const size_t sm = attn_tile_smem(H, wlo, whi, 1, 2);
   const unsigned blocks = (unsigned)((N + WT - 1) / WT);
   cudaStream_t st = (cudaStream_t)stream;
+  if (attn_use_blk(H, wlo, whi)) {
+    static DeviceOnce once;
+    if (!blk_attr(attn_bwd_dst_blk_kernel<BTH_DST>, once)) return ERCG_ECUDA;
+    attn_bwd_dst_blk_kernel<BTH_DST><<<blocks, BTH_DST, attn_blk_smem(H, wlo, whi, 1), st>>>(dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, colsum_partial, N, H, wlo, whi);
+    return finish_launch();
+  }
   static DeviceOnce attr;
   if (attr.need()) {
     cudaFuncSetAttribute(attn_bwd_dst_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -845,6 +875,12 @@ extern "C" int ercg_attn_window_bwd_src(const float* dout, int64_t ldo, const fl
   ERCG_CHK(dout, ldo); ERCG_CHK(q, ld); ERCG_CHK(dk, ldd); ERCG_CHK(dv, ldd);
   const size_t sm = attn_tile_smem(H, wlo, whi, 0, 2);
   const unsigned blocks = (unsigned)((N + WT - 1) / WT);
+  if (attn_use_blk(H, wlo, whi)) {
+    static DeviceOnce once;
+    if (!blk_attr(attn_bwd_src_blk_kernel<BTH_SRC>, once)) return ERCG_ECUDA;
+    attn_bwd_src_blk_kernel<BTH_SRC><<<blocks, BTH_SRC, attn_blk_smem(H, wlo, whi, 2), (cudaStream_t)stream>>>(dout, ldo, q, ld, t_rowptr, t_col, t_eid, alpha, dsig, scale, dk, dv, ldd, colsum_partial, N, H, wlo, whi);
+    return finish_launch();
+  }
   static DeviceOnce attr;
   if (attr.need()) {
     cudaFuncSetAttribute(attn_bwd_src_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);

@@ -510,3 +510,42 @@ def test_gather_forward_flat_mapping_is_bit_identical(H, wp, wf, n, monkeypatch)
         torch.cuda.synchronize()
         outs.append(o)
     assert not torch.isnan(outs[0]).any() and torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("wp,wf,H", [(5, 5, 100), (0, 0, 100), (0, 3, 100), (3, 8, 100), (6, 6, 100), (12, 0, 100), (1, 11, 100),
+                                     (5, 5, 36), (5, 5, 128), (2, 2, 4)])
+def test_blocked_window_attention_matches_tile_kernels_and_fp64(wp, wf, H, monkeypatch):
+    """attn_*_blk_kernel (register-blocked: 4 destinations share their candidate sources) against the round-1 tile kernels
+    (ERCG_ATTN_BLK=0) and fp64, forward + backward + the fused bias-gradient column sums: many short dialogues (a tile spans
+    several), single-utterance dialogues, N not a multiple of the 32-row tile, first / last tiles with clipped halos."""
+    import erc_b200
+    from erc_b200 import ops
+    rng = np.random.default_rng(wp * 31 + wf * 7 + H)
+    lens = [int(v) for v in rng.integers(1, 41, size=57)] + [1, 1, 2, 33, 64, 1]
+    g, b = _graph(lens, wp=wp, wf=wf, seed=5)
+    N = b["N"]
+    gen = torch.Generator().manual_seed(H + wp)
+    qkvs = torch.randn(N, 4 * H, generator=gen)
+    dout = torch.randn(N, H, generator=gen)
+    src, dst = torch.from_numpy(b["edge_index"][0]), torch.from_numpy(b["edge_index"][1])
+    x = qkvs.double().requires_grad_()
+    q, k, v, s = x[:, :H], x[:, H:2 * H], x[:, 2 * H:3 * H], x[:, 3 * H:]
+    sc = (q[dst] * k[src]).sum(-1) / math.sqrt(H)
+    mx = torch.full((N,), -1e300, dtype=torch.float64).scatter_reduce(0, dst, sc, reduce="amax")
+    ex = (sc - mx[dst]).exp()
+    alpha = ex / (torch.zeros(N, dtype=torch.float64).index_add(0, dst, ex) + 1e-16)[dst]
+    want = torch.zeros(N, H, dtype=torch.float64).index_add(0, dst, alpha[:, None] * v[src]) + s
+    want.backward(dout.double())
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ERCG_ATTN_BLK", flag)
+        xc = qkvs.cuda().requires_grad_()
+        got = ops.edge_attention(xc, g, H, 1.0 / math.sqrt(H))
+        (d,) = torch.autograd.grad(got, xc, dout.cuda())
+        cs = ops._tag_get(d, "_ercg_colsum")
+        assert cs is not None                                    # window path taken: column sums came with the gradient
+        res[flag] = (got.detach(), d, cs)
+        assert rel_err(got, want) < TOL and rel_err(d, x.grad) < TOL
+        assert rel_err(cs, x.grad.sum(0)) < 1e-5
+    assert rel_err(res["1"][0], res["0"][0]) < 2e-6 and rel_err(res["1"][1], res["0"][1]) < 2e-6
+    assert not torch.isnan(res["1"][1]).any()
