@@ -44,6 +44,7 @@ SIGNATURES = {
     "ercg_graphify_workspace_bytes": (SZ, [I]),
     "ercg_graphify_csr": (I, [P, I, I, P, I, L, I, I, I, L, L, POINTER(GraphOut), P, SZ, P]),
     "ercg_graphify_check_census": (I, [P, I, P, P]),
+    "ercg_collate_masks": (I, [P, P, I, L, I, I, P, P, P, P]),
     "ercg_pack_rows": (I, [P, L, L, I, I, P, P, P, L, L, I, P]),
     "ercg_unpack_rows": (I, [P, L, P, P, P, L, L, I, I, L, I, P]),
     "ercg_gemm_nn": (I, [P, L, P, P, L, P, P, L, L, I, I, I, P, L, F, F, U64, P, P]),

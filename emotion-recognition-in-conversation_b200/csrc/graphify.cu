@@ -463,6 +463,38 @@ extern "C" int ercg_graphify_check_census(const int32_t* allowed_slots, int n_al
   return finish_launch();
 }
 
+// ---- ERCCollate's small tensors, built on the device from the packed layout (track_mm/mmbase.py:354-371,417-428)
+namespace ercg {
+__global__ void __launch_bounds__(256)
+collate_masks_kernel(const int* __restrict__ node_off, const long long* __restrict__ spk_packed, int B, long long Lmax, int seq_first,
+                     int n_onehot, float* __restrict__ attention_mask, long long* __restrict__ speaker_ids, float* __restrict__ speaker_onehot) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Lmax) return;
+  const int b = (int)(idx / Lmax);
+  const long long l = idx - (long long)b * Lmax;
+  const int o = node_off[b], len = node_off[b + 1] - o;
+  const bool in = l < len;
+  if (attention_mask) attention_mask[idx] = in ? 1.f : 0.f;                       // always [B, Lmax] (mmbase.py:361-363)
+  const long long s = in ? spk_packed[o + l] : 0;                                 // padding = speaker 0 (zeros().long(), :370)
+  const long long pos = seq_first ? l * B + b : idx;                              // transposed when not batch_first (:422-423)
+  if (speaker_ids) speaker_ids[pos] = s;
+  if (speaker_onehot)
+    for (int c = 0; c < n_onehot; ++c) speaker_onehot[pos * n_onehot + c] = c == s ? 1.f : 0.f;   // onehot(), :425-426
+}
+}  // namespace ercg
+
+extern "C" int ercg_collate_masks(const int32_t* node_off, const int64_t* speaker_packed, int B, int64_t Lmax, int seq_first,
+                                  int n_onehot, float* attention_mask, int64_t* speaker_ids, float* speaker_onehot, void* stream) {
+  if (B < 0 || Lmax < 0 || n_onehot < 0) return ERCG_EINVAL;
+  if (B == 0 || Lmax == 0) return ERCG_OK;
+  if (!node_off || !speaker_packed || (speaker_onehot && n_onehot < 1)) return ERCG_EINVAL;
+  const long long total = (long long)B * Lmax;
+  collate_masks_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      node_off, reinterpret_cast<const long long*>(speaker_packed), B, Lmax, seq_first, n_onehot, attention_mask,
+      reinterpret_cast<long long*>(speaker_ids), speaker_onehot);
+  return finish_launch();
+}
+
 static int pack_launch(const float* padded, int64_t ld, int64_t Lmax, int B, int seq_first,
                        const int32_t* node_off, const int32_t* node_dlg, float* packed, int64_t ldp,
                        int64_t N, int D, int unpack, void* stream) {

@@ -98,14 +98,25 @@ class COGMENModule(nn.Module):
         graph_out = self.gcn(features, g.edge_index, g.edge_type)
         return self._classify(graph_out), features
 
-    def forward(self, input_tensor, speaker_tensor, text_length, *args, **kwargs):
+    def forward(self, input_tensor=None, speaker_tensor=None, text_length=None, *args, x_packed=None, speaker_packed=None, **kwargs):
+        """Reference signature (cogmen.py:138-160): padded ``input_tensor [B,Lmax,hidden_all]``, ``speaker_tensor [B,Lmax]``,
+        ``text_length [B]``; extra batch keys are swallowed.  A batch from erc_b200.collate.DeviceCollate also carries the
+        packed rows (``x_packed``, ``speaker_packed``): then the padded tensors are never touched (nor built)."""
+        if x_packed is not None and speaker_packed is not None:
+            return self.forward_packed(x_packed, speaker_packed, text_length)
         if self.run_dead_encoder:
             self.rnn[0](input_tensor)                # result discarded, exactly like cogmen.py:146-147
         B, Lmax, D = input_tensor.shape
         g = build_graph(text_length, speaker_tensor, self.wp, self.wf, self.n_speakers, device=input_tensor.device)
         lin = self.rnn[1]
         flat = input_tensor.reshape(B * Lmax, D)
-        features = ops.linear(flat, lin.weight, lin.bias, a_rows=g.pad_row)   # Linear fused with the node packing
+        if (D & 3) == 0 and B * Lmax >= 8192 and B * Lmax <= 2 * g.N and ops.GEMM_ENGINE == "tc":
+            # big padded batches: tensor-core projection over ALL padded rows (padding wastes < 2x), then pack the 100-wide
+            # result rows.  Below ~8 k rows the step is launch-bound and the exact-fp32 gather GEMM is just as fast.
+            y = ops.linear(flat, lin.weight, lin.bias)
+            features = ops.pack_rows(y.view(B, Lmax, -1), g)
+        else:
+            features = ops.linear(flat, lin.weight, lin.bias, a_rows=g.pad_row)   # Linear fused with the node packing (SIMT)
         return self._graph_forward(features, g)
 
     def forward_packed(self, x_packed, speaker_packed, text_length, graph=None):

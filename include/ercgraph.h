@@ -118,6 +118,14 @@ int ercg_pack_rows(const float* padded, int64_t ld, int64_t Lmax, int B, int seq
 int ercg_unpack_rows(const float* packed, int64_t ldp, const int32_t* node_off, const int32_t* node_dlg,
                      float* padded, int64_t ld, int64_t Lmax, int B, int seq_first, int64_t N, int D, void* stream);
 
+/* ERCCollate's small tensors (track_mm/mmbase.py:354-371,417-428) built on the device from the packed layout: the host
+ * uploads packed rows only (no padding bytes cross PCIe) and the padded tensors the reference's batch dict carries are
+ * produced here -- ercg_unpack_rows for the feature tensors, this call for
+ *   attention_mask [B,Lmax] f32 (1 inside a dialogue), speaker ids [B,Lmax] int64 (padding = 0; [Lmax,B] when seq_first,
+ *   i.e. not batch_first) and/or their one-hot [.., n_onehot] f32 (speaker_onehot).  Any output may be NULL. */
+int ercg_collate_masks(const int32_t* node_off, const int64_t* speaker_packed, int B, int64_t Lmax, int seq_first,
+                       int n_onehot, float* attention_mask, int64_t* speaker_ids, float* speaker_onehot, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2  dense feature transforms.  C[M,N] = act(A[M,K] @ B[K,N] + bias[N]).
  * Replaces nn.Linear (cogmen.py:103-105,116-122), the per-relation weights of PyG RGCNConv

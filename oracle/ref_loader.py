@@ -108,3 +108,28 @@ def load():
     mods["rgcn"] = importlib.import_module("models.rgcn")
     _loaded.update(mods)
     return types.SimpleNamespace(**_loaded)
+
+
+def load_collate():
+    """The reference's own ``ERCCollate`` class (track_mm/mmbase.py:344-455).  mmbase.py itself cannot be imported (lumo,
+    dbrecord, mmdatasets are not installed), so the class statement is cut out of the file verbatim and executed with the
+    two names it needs from lumo: ``CollateBase`` (a do-nothing base) and ``onehot`` (lumo/contrib/torch/tensor.py:57-67,
+    restated: zeros(..., n).scatter_(-1, labels.unsqueeze(-1), 1))."""
+    import re
+    import torch
+    path = os.path.join(REF_ROOT, "track_mm", "mmbase.py")
+    with open(path) as f:
+        text = f.read()
+    m = re.search(r"^class ERCCollate\(CollateBase\):.*?(?=^class ERCDM)", text, flags=re.S | re.M)
+    assert m, "ERCCollate not found in the reference"
+
+    class CollateBase:
+        def __init__(self, params=None):
+            pass
+
+    def onehot(labels, label_num):
+        return torch.zeros(*labels.shape, label_num, device=labels.device).scatter_(-1, labels.unsqueeze(-1), 1)
+
+    ns = {"CollateBase": CollateBase, "onehot": onehot, "torch": torch, "ParamsType": object}
+    exec(compile(m.group(0), path, "exec"), ns)
+    return ns["ERCCollate"]

@@ -162,3 +162,34 @@ def test_cogmen_generic_edge_index_path_matches_attached_graph():
         perm = torch.randperm(g.E).cuda()
         b = gnn(x, g.edge_index[:, perm].contiguous(), g.edge_type[perm].contiguous())
     assert rel_err(b.cpu(), a.cpu()) < 1e-6
+
+
+def test_cogmen_large_padded_batch_uses_tensor_core_projection_and_matches_packed():
+    """Reference-layout (padded) input big enough for the tensor-core projection over the padded rows + row packing."""
+    import erc_b200
+    from erc_b200 import _lib, ops
+    from erc_b200.track_mm.cogmen import COGMENModule
+    from erc_b200 import synth
+    gen = torch.Generator().manual_seed(7)
+    lens = torch.randint(60, 111, (96,), generator=gen)
+    batch = synth.padded_batch(lens, 1380, 2, 4, gen)
+    torch.manual_seed(1)
+    m = COGMENModule(1380, 100, 17, 2, 4, build_dead_encoder=False).cuda()
+    m.cls[2].p = 0.0
+    m.train()
+    x, spk = batch["input_tensor"].cuda(), batch["speaker_tensor"].cuda()
+    with _lib.KernelTimer() as kt:
+        logits, _ = m(x, spk, lens)
+        loss = ops.cross_entropy(logits, batch["label"].cuda())
+        loss.backward()
+    assert "ercg_gemm_nn_tc" in kt.summary() and "ercg_pack_rows" in kt.summary()
+    ga = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    mask = torch.arange(x.size(1))[None, :] < lens[:, None]
+    lg2, _ = m.forward_packed(batch["input_tensor"][mask].contiguous().cuda(), batch["speaker_tensor"][mask].contiguous().cuda(), lens)
+    ops.cross_entropy(lg2, batch["label"].cuda()).backward()
+    assert rel_err(logits, lg2) < 1e-5
+    scale = max(float(p.grad.abs().max()) for p in m.parameters() if p.grad is not None)
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert rel_err(ga[k], p.grad, floor=1e-2 * scale) < 1e-5, k
