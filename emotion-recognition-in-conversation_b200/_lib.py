@@ -65,8 +65,8 @@ SIGNATURES = {
     "ercg_gather_fwd": (I, [P, L, P, P, P, P, P, I, P, P, L, L, I, P]),
     "ercg_gather_bwd": (I, [P, L, P, L, P, P, P, P, P, P, I, I, P, L, P, L, I, P]),
     "ercg_gather_window_bwd": (I, [P, L, P, P, P, P, P, P, I, I, P, L, L, I, I, I, P]),
-    "ercg_attn_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, L, I, P]),
-    "ercg_attn_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, L, I, P]),
+    "ercg_attn_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, P, L, I, P]),
+    "ercg_attn_bwd_dst": (I, [P, L, P, P, L, P, P, P, F, P, P, L, P, P, L, I, P]),
     "ercg_attn_bwd_src": (I, [P, L, P, L, P, P, P, P, P, F, P, P, L, L, I, P]),
     "ercg_attn_window_supported": (I, [I, I, I]),
     "ercg_attn_window_fwd": (I, [P, P, P, P, L, P, P, F, P, L, P, L, I, I, I, P]),
@@ -101,6 +101,8 @@ SIGNATURES = {
     "ercg_node_rows": (I, [P, P, L, I, I, I, P, P]),
     "ercg_speaker_embed_add": (I, [P, L, P, I, P, P, L, P, L, P, P, L, I, P]),
     "ercg_relu_dropout": (I, [P, P, L, F, U64, P]),
+    "ercg_masked_edge_att_fwd": (I, [P, L, P, P, P, P, L, I, I, P, P, L, P]),
+    "ercg_masked_edge_att_bwd": (I, [P, L, P, P, P, P, L, I, I, P, P, P, P, L, L, P]),
     # K9 / K10 (DAG-ERC)
     "ercg_dag_build_workspace_bytes": (SZ, [L]),
     "ercg_dag_build": (I, [P, P, P, L, I, P, P, P, P, P, SZ, P]),

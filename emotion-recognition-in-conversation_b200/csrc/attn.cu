@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(AW * 32)
 attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                 const float* __restrict__ s, long long ld, const int* __restrict__ rowptr,
                 const int* __restrict__ col, float scale, float* __restrict__ out, long long ldo,
-                float* __restrict__ alpha, long long N, int H) {
+                float* __restrict__ alpha, float* __restrict__ dact, long long N, int H) {
   const int lane = threadIdx.x & 31;
   const long long node = (long long)blockIdx.x * AW + (threadIdx.x >> 5);
   if (node >= N) return;
@@ -114,6 +114,10 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
 #pragma unroll
       for (int qq = 0; qq < 4; ++qq)
         if (lane == u + qq) my = d[qq] * scale;
+    }
+    if (dact && lane < cn) {                    // MatchingAttention 'general2' (dgcnv2_models.py:128-133): softmax of tanh(score)
+      my = tanhf(my);
+      dact[cb + lane] = 1.f - my * my;          // d tanh / d score, applied to dsig by the by-destination backward
     }
     const float cmax = warp_max(my);
     const float new_max = fmaxf(run_max, cmax);
@@ -169,7 +173,7 @@ attn_bwd_dst_kernel(const float* __restrict__ dout, long long ldo, const float* 
                     const float* __restrict__ v, long long ld, const int* __restrict__ rowptr,
                     const int* __restrict__ col, const float* __restrict__ alpha, float scale,
                     float* __restrict__ dq, float* __restrict__ ds, long long ldd, float* __restrict__ dsig,
-                    long long N, int H) {
+                    const float* __restrict__ dact, long long N, int H) {
   const int lane = threadIdx.x & 31;
   const long long node = (long long)blockIdx.x * AW + (threadIdx.x >> 5);
   if (node >= N) return;
@@ -198,7 +202,8 @@ attn_bwd_dst_kernel(const float* __restrict__ dout, long long ldo, const float* 
         if (lane == u + qq) my = d[qq];
     }
     const float D = warp_sum(al * my);
-    const float g = al * (my - D);
+    float g = al * (my - D);
+    if (dact && lane < cn) g *= dact[beg + lane];
     if (lane < cn) dsig[beg + lane] = g;
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -246,6 +251,7 @@ attn_bwd_dst_kernel(const float* __restrict__ dout, long long ldo, const float* 
     float g = 0.f;
     if (lane < cn) {
       g = alpha[cb + lane] * (dsig[cb + lane] - D);
+      if (dact) g *= dact[cb + lane];
       dsig[cb + lane] = g;
     }
     for (int u = 0; u < cn; ++u) {
@@ -730,7 +736,7 @@ edgeatt_bwd_dst_kernel(const float* __restrict__ dsig, const float* __restrict__
 }
 
 static int chk(const void* p, long long ld, int H) {
-  if ((H & 3) || H <= 0 || H > 256) return ERCG_EINVAL;
+  if ((H & 3) || H <= 0 || H > 384) return ERCG_EINVAL;
   if (!p) return ERCG_EINVAL;
   if ((ld & 3) || !aligned16(p)) return ERCG_EALIGN;
   return ERCG_OK;
@@ -745,30 +751,32 @@ using namespace ercg;
   do {                                                                                         \
     const unsigned blocks_ = (unsigned)((N + AW - 1) / AW);                                    \
     if (H <= 128) kernel<1><<<blocks_, AW * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);       \
-    else kernel<2><<<blocks_, AW * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                \
+    else if (H <= 256) kernel<2><<<blocks_, AW * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);  \
+    else kernel<3><<<blocks_, AW * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                \
     return finish_launch();                                                                    \
   } while (0)
 
 extern "C" int ercg_attn_fwd(const float* q, const float* k, const float* v, const float* s, int64_t ld,
                              const int32_t* rowptr, const int32_t* col, float scale,
-                             float* out, int64_t ldo, float* alpha, int64_t N, int H, void* stream) {
+                             float* out, int64_t ldo, float* alpha, float* dact, int64_t N, int H, void* stream) {
   if (N < 0) return ERCG_EINVAL;
   if (N == 0) return ERCG_OK;
   if (!rowptr || !col) return ERCG_EINVAL;
   ERCG_CHK(q, ld); ERCG_CHK(k, ld); ERCG_CHK(v, ld); ERCG_CHK(out, ldo);
   if (s) ERCG_CHK(s, ld);
-  ERCG_LAUNCH_NC(attn_fwd_kernel, q, k, v, s, ld, rowptr, col, scale, out, ldo, alpha, N, H);
+  ERCG_LAUNCH_NC(attn_fwd_kernel, q, k, v, s, ld, rowptr, col, scale, out, ldo, alpha, dact, N, H);
 }
 
 extern "C" int ercg_attn_bwd_dst(const float* dout, int64_t ldo, const float* k, const float* v, int64_t ld,
                                  const int32_t* rowptr, const int32_t* col, const float* alpha, float scale,
-                                 float* dq, float* ds, int64_t ldd, float* dsig, int64_t N, int H, void* stream) {
+                                 float* dq, float* ds, int64_t ldd, float* dsig, const float* dact, int64_t N, int H,
+                                 void* stream) {
   if (N < 0) return ERCG_EINVAL;
   if (N == 0) return ERCG_OK;
   if (!rowptr || !col || !alpha || !dsig) return ERCG_EINVAL;
   ERCG_CHK(dout, ldo); ERCG_CHK(k, ld); ERCG_CHK(v, ld); ERCG_CHK(dq, ldd);
   if (ds) ERCG_CHK(ds, ldd);
-  ERCG_LAUNCH_NC(attn_bwd_dst_kernel, dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, N, H);
+  ERCG_LAUNCH_NC(attn_bwd_dst_kernel, dout, ldo, k, v, ld, rowptr, col, alpha, scale, dq, ds, ldd, dsig, dact, N, H);
 }
 
 extern "C" int ercg_attn_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld,

@@ -306,7 +306,7 @@ class _Attn(torch.autograd.Function):
                                              _p(out), H, _p(alpha), N, H, win[0], win[1], _stream()), "ercg_attn_window_fwd")
         else:
             check(lib().ercg_attn_fwd(b, b + 4 * H, b + 8 * H, b + 12 * H, ld, _p(graph.rowptr), _p(graph.col), scale,
-                                      _p(out), H, _p(alpha), N, H, _stream()), "ercg_attn_fwd")
+                                      _p(out), H, _p(alpha), None, N, H, _stream()), "ercg_attn_fwd")
         ctx.graph, ctx.H, ctx.scale, ctx.win = graph, H, scale, win
         ctx.save_for_backward(qkvs, alpha)
         return out
@@ -336,7 +336,7 @@ class _Attn(torch.autograd.Function):
             _tag_set(d, "_ercg_colsum", torch.cat([cs_dst[:H], cs_src, cs_dst[H:]]))
             return d, None, None, None
         check(lib().ercg_attn_bwd_dst(_p(dout), ldo, b + 4 * H, b + 8 * H, ld, _p(g.rowptr), _p(g.col), _p(alpha), scale,
-                                      db, db + 12 * H, 4 * H, _p(dsig), N, H, _stream()), "ercg_attn_bwd_dst")
+                                      db, db + 12 * H, 4 * H, _p(dsig), None, N, H, _stream()), "ercg_attn_bwd_dst")
         check(lib().ercg_attn_bwd_src(_p(dout), ldo, b, ld, _p(g.t_rowptr), _p(g.t_col), _p(g.t_eid), _p(alpha), _p(dsig),
                                       scale, db + 4 * H, db + 8 * H, 4 * H, N, H, _stream()), "ercg_attn_bwd_src")
         return d, None, None, None
@@ -346,6 +346,49 @@ def edge_attention(qkvs, graph, H, scale):
     """qkvs = [q | k | v | skip] (each H wide); TransformerConv(heads=1) message+aggregate+skip."""
     assert qkvs.size(1) == 4 * H
     return _Attn.apply(qkvs, graph, H, float(scale))
+
+
+class _MatchAttn(torch.autograd.Function):
+    """out_t = sum_j softmax_j(tanh(<xt_t, e_j>)) e_j over the in-edges of t (generic K4 kernels with the tanh option)."""
+
+    @staticmethod
+    def forward(ctx, xe, graph, H):
+        """xe = [xt | e] ([N, 2H]): queries and keys = values side by side (one row stride)."""
+        xe, ld = _rows(xe)
+        N = xe.size(0)
+        out = torch.empty((N, H), dtype=torch.float32, device=xe.device)
+        alpha = torch.empty(graph.E, dtype=torch.float32, device=xe.device)
+        dact = torch.empty(graph.E, dtype=torch.float32, device=xe.device)
+        b = xe.data_ptr()
+        check(lib().ercg_attn_fwd(b, b + 4 * H, b + 4 * H, None, ld, _p(graph.rowptr), _p(graph.col), 1.0, _p(out), H, _p(alpha),
+                                  _p(dact), N, H, _stream()), "ercg_attn_fwd")
+        ctx.graph, ctx.H = graph, H
+        ctx.save_for_backward(xe, alpha, dact)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xe, alpha, dact = ctx.saved_tensors
+        g, H = ctx.graph, ctx.H
+        dout, ldo = _rows(dout)
+        N, ld = xe.size(0), xe.stride(0)
+        d = torch.empty((N, 3 * H), dtype=torch.float32, device=dout.device)           # [dq | dk | dv]
+        dsig = torch.empty(g.E, dtype=torch.float32, device=dout.device)
+        b, db = xe.data_ptr(), d.data_ptr()
+        check(lib().ercg_attn_bwd_dst(_p(dout), ldo, b + 4 * H, b + 4 * H, ld, _p(g.rowptr), _p(g.col), _p(alpha), 1.0, db, None,
+                                      3 * H, _p(dsig), _p(dact), N, H, _stream()), "ercg_attn_bwd_dst")
+        check(lib().ercg_attn_bwd_src(_p(dout), ldo, b, ld, _p(g.t_rowptr), _p(g.t_col), _p(g.t_eid), _p(alpha), _p(dsig), 1.0,
+                                      db + 4 * H, db + 8 * H, 3 * H, N, H, _stream()), "ercg_attn_bwd_src")
+        return torch.cat([d[:, :H], d[:, H:2 * H] + d[:, 2 * H:]], 1), None, None      # e is both key and value
+
+
+def matching_attention(xt, e, graph):
+    """Nodal MatchingAttention 'general2' (dgcnv2_models.py:119-148) on packed nodes: for node t of a dialogue,
+    alpha = softmax over the dialogue's nodes j of tanh(<xt_t, e_j>), out_t = sum_j alpha e_j.  ``graph`` = the fully connected
+    per-dialogue graph (window -1 / -1); xt = transform(e).  (The reference's masked softmax + renormalisation over the valid
+    positions of the padded dialogue is exactly the softmax over the dialogue's own nodes.)"""
+    H = e.size(1)
+    return _MatchAttn.apply(torch.cat([xt, e], 1), graph, H)
 
 
 # ------------------------------------------------------------------------------------------- K5 EdgeAtt

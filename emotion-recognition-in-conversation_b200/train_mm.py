@@ -1,4 +1,4 @@
-"""``train_mm.py --module=<cogmen|dgcn|mmgcn|dagerc> --dataset=... --modality=atv`` without lumo / accelerate
+"""``train_mm.py --module=<cogmen|dgcn|dgcnv2|mmgcn|dagerc> --dataset=... --modality=atv`` without lumo / accelerate
 (reference: train_mm.py:16-25 -> track_mm/<module>.main -> mmbase.main, mmbase.py:483-499).
 
 What is kept from the reference
@@ -28,7 +28,7 @@ import time
 import numpy as np
 import torch
 
-MODULES = ("cogmen", "dgcn", "mmgcn", "dagerc")
+MODULES = ("cogmen", "dgcn", "dgcnv2", "mmgcn", "dagerc")
 
 
 # ------------------------------------------------------------------------------------------------ parameters
@@ -74,6 +74,7 @@ def resolve_params(args):
     per_module = {
         "cogmen": dict(epoch=55, batch_size=32, optim="Adam", lr=1e-4, weight_decay=1e-8, num_heads=17),          # cogmen.py:36-52
         "dgcn": dict(epoch=55, batch_size=32, optim="Adam", lr=3e-4, weight_decay=0.0, loss_weights=True),        # dgcn.py:24-44
+        "dgcnv2": dict(epoch=55, batch_size=32, optim="Adam", lr=3e-4, weight_decay=0.0, loss_weights=True, base_model="LSTM"),   # dgcnv2.py:20-45
         "mmgcn": dict(epoch=60, batch_size=16, optim="Adam", lr=3e-4, weight_decay=3e-5),                          # mmgcn.py:22-40
         "dagerc": dict(epoch=30, batch_size=8, optim="AdamW", lr=1e-3, weight_decay=1e-2, gnn_layers=4, dropout=0.0),   # dagerc.py:25-41
     }[module]
@@ -109,8 +110,8 @@ def resolve_params(args):
     p["hidden_all"] = sum({"t": ht, "a": ha, "v": hv}[m] for m in set(p["modality"]))
     if module == "dagerc" and p["reimplement"] and "iemocap" in ds:                               # dagerc.py:45-50
         p.update(dropout=0.2, epoch=55, batch_size=16, lr=5e-4)
-    p["batch_first"] = module != "mmgcn"                                                          # mmgcn.py:39-40
-    p["speaker_onehot"] = module in ("mmgcn", "dagerc")                                           # mmgcn.py:39, dagerc.py:41
+    p["batch_first"] = module not in ("mmgcn", "dgcnv2")                                          # mmgcn.py:39-40, dgcnv2.py:45
+    p["speaker_onehot"] = module in ("mmgcn", "dagerc", "dgcnv2")                                 # mmgcn.py:39, dagerc.py:41, dgcnv2.py:44
     return p
 
 
@@ -164,6 +165,10 @@ def build_model(p, dev):
     elif p["module"] == "dgcn":
         from .track_mm.dgcn import DGCNModule
         m = DGCNModule(input_size=p["hidden_all"], hidden_size=200, n_speakers=p["n_speakers"], n_classes=p["n_classes"])
+    elif p["module"] == "dgcnv2":
+        from .track_mm.dgcnv2 import DGCNModule as DGCNv2Module
+        m = DGCNv2Module(base_model=p["base_model"], input_size=p["hidden_all"], hidden_size=100, n_speakers=p["n_speakers"],
+                         n_classes=p["n_classes"], context_attention="general")                      # dgcnv2.py:188-195
     elif p["module"] == "mmgcn":
         from .track_mm.mmgcn import MMGCNModule
         m = MMGCNModule(hidden_text=p["hidden_text"], hidden_visual=p["hidden_visual"], hidden_audio=p["hidden_audio"],
@@ -189,7 +194,7 @@ class Trainer:
         self.optim = FlatAdam(self.model.parameters(), lr=p["lr"], weight_decay=p["weight_decay"], decoupled=p["optim"] == "AdamW",
                               max_norm=5.0 if p["module"] == "dagerc" else None)                    # dagerc.py:229-231
         self.class_weight = None
-        if p["module"] == "dgcn" and p.get("loss_weights") and p["n_classes"] == 6:
+        if p["module"] in ("dgcn", "dgcnv2") and p.get("loss_weights") and p["n_classes"] == 6:
             self.class_weight = torch.tensor(DGCN_LOSS_WEIGHTS, device=self.dev)
         self.best = {}
 
@@ -199,6 +204,9 @@ class Trainer:
             return self.model(**batch.packed_kwargs())[0]
         if m == "dgcn":
             return self.model(input_tensor=batch["input_tensor"], speaker_tensor=batch["speaker_tensor"], text_length=batch["text_length"])[0]
+        if m == "dgcnv2":
+            return self.model(input_tensor=batch["input_tensor"], speaker_tensor=batch["speaker_tensor"],
+                              attention_mask=batch["attention_mask"], text_length=batch["text_length"])[0]
         if m == "mmgcn":
             return self.model(text_feature=batch["text_feature"], audio_feature=batch["audio_feature"],
                               visual_feature=batch["visual_feature"], speaker_tensor=batch["speaker_tensor"],

@@ -223,11 +223,14 @@ int ercg_gather_window_bwd(const float* dout, int64_t ldo, const int32_t* t_rowp
  * ------------------------------------------------------------------------------------------- */
 int ercg_attn_fwd(const float* q, const float* k, const float* v, const float* s, int64_t ld,
                   const int32_t* rowptr, const int32_t* col, float scale,
-                  float* out, int64_t ldo, float* alpha, int64_t N, int H, void* stream);
-/* by-destination half: dq[i], ds[i] = dout[i], dsig[e] = alpha_e (dalpha_e - sum alpha dalpha) */
+                  float* out, int64_t ldo, float* alpha, float* dact, int64_t N, int H, void* stream);
+/* dact (optional, [E]): the softmax runs over tanh(score) instead of the score -- nodal MatchingAttention 'general2' of the
+ * declare-lab DialogueGCN (track_mm/dgcnv2_models.py:119-146, used over fully connected per-dialogue graphs, s = NULL,
+ * scale = 1) -- and dact[e] = 1 - tanh^2 is saved for ercg_attn_bwd_dst, which folds it into dsig.  H <= 384. */
+/* by-destination half: dq[i], ds[i] = dout[i], dsig[e] = alpha_e (dalpha_e - sum alpha dalpha) [* dact_e] */
 int ercg_attn_bwd_dst(const float* dout, int64_t ldo, const float* k, const float* v, int64_t ld,
                       const int32_t* rowptr, const int32_t* col, const float* alpha, float scale,
-                      float* dq, float* ds, int64_t ldd, float* dsig, int64_t N, int H, void* stream);
+                      float* dq, float* ds, int64_t ldd, float* dsig, const float* dact, int64_t N, int H, void* stream);
 /* by-source half: dk[j] = scale * sum_i dsig q[i], dv[j] = sum_i alpha dout[i] */
 int ercg_attn_bwd_src(const float* dout, int64_t ldo, const float* q, int64_t ld,
                       const int32_t* t_rowptr, const int32_t* t_col, const int32_t* t_eid,
@@ -410,6 +413,22 @@ int ercg_sumsq(const float* x, int64_t n, float* out, void* workspace, size_t wo
 int ercg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int decoupled, float grad_scale, const float* sumsq,
                    float max_norm, int64_t* step_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K11  MaskedEdgeAttention 'attn1' of the declare-lab DialogueGCN (track_mm/dgcnv2_models.py:517-562) -- the edge weights of
+ * dgcnv2's batch_graphify (:638-690) -- in closed form on the packed graph.  S [B*Lmax, >= max_seq_len] (row b*Lmax + j',
+ * column i) = M @ scalar.weight^T from ercg_gemm_nn, M = the dialogue-major, full-length context rows.  Per source (b, i):
+ *   nu[i -> j] = e_j / (Z_win + 1e-10 (Z_all - Z_win)),  e_j' = exp(S[j', i] - max_j' S[., i]) over ALL Lmax positions,
+ *   Z_win over the targets j of i's window [max(0, i-wp), min(len-1, i+wf)] (wp / wf = -1: unbounded);
+ * nu is written in by-destination edge order (through t_rowptr / t_eid of ercg_graphify_csr); stat [N,2] keeps (max, Den).
+ * Backward: dS (zero-initialised by the caller, same layout as S) from dnu. */
+int ercg_masked_edge_att_fwd(const float* S, int64_t ldS, const int32_t* node_off, const int32_t* node_dlg,
+                             const int32_t* t_rowptr, const int32_t* t_eid, int64_t Lmax, int wp, int wf,
+                             float* nu, float* stat, int64_t N, void* stream);
+int ercg_masked_edge_att_bwd(const float* S, int64_t ldS, const int32_t* node_off, const int32_t* node_dlg,
+                             const int32_t* t_rowptr, const int32_t* t_eid, int64_t Lmax, int wp, int wf,
+                             const float* nu, const float* dnu, const float* stat, float* dS, int64_t ldd,
+                             int64_t N, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K9  DAG-ERC predecessor structure (DAGERCModule.get_adj_v1 / get_s_mask, track_mm/dagerc.py:109-154) on packed

@@ -263,10 +263,37 @@ def dagerc_fixture(ref):
           max(float(np.abs(v).max()) for v in grads.values()))
 
 
+DGCNV2_SEED = 53
+
+
+def dgcnv2_fixture(ref):
+    """Real dgcnv2.DGCNModule('LSTM') (dgcnv2.py:54-181) with MaskedEdgeAttention / GraphNetwork / nodal MatchingAttention of
+    dgcnv2_models.py; dropout 0; weights by seeded.fill_by_name; class-weighted CE as in the trainer (dgcnv2.py:200-217)."""
+    from oracle import dgcnv2_oracle
+    r = ref_loader.load_dgcnv2()
+    D, C, lengths = 36, 6, [9, 3, 14, 1, 6]
+    torch.manual_seed(0)
+    m = r.dgcnv2.DGCNModule("LSTM", input_size=D, hidden_size=100, n_speakers=2, n_classes=C, dropout=0.0)
+    m.graph_net.dropout.p = 0.0
+    seeded.fill_by_name(m, DGCNV2_SEED)
+    m.train()
+    b = dgcnv2_oracle.inputs(lengths, D, 2, C, seed=77)
+    w = torch.tensor([1 / 0.086747, 1 / 0.144406, 1 / 0.227883, 1 / 0.160585, 1 / 0.127711, 1 / 0.252668])
+    logits, feats = m(**{k: v for k, v in b.items() if k != "label"})
+    loss = F.cross_entropy(logits, b["label"], weight=w)
+    loss.backward()
+    grads = _grads(m)
+    out = {k: _np(v) for k, v in b.items()}
+    out.update(logits=_np(logits), features=_np(feats), loss=_np(loss), class_weights=_np(w), live=np.array(sorted(grads)))
+    _store_grads(out, grads)
+    np.savez_compressed(os.path.join(OUT, "dgcnv2_small.npz"), **out)
+    print("dgcnv2_small.npz loss", float(loss), "live grads", len(grads), sorted(grads)[:6])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["graph", "cogmen", "dgcn", "mmgcn", "dagerc"]
+    which = sys.argv[1:] or ["graph", "cogmen", "dgcn", "mmgcn", "dagerc", "dgcnv2"]
     if "graph" in which:
         graph_fixtures(ref)
     if "cogmen" in which:
@@ -277,6 +304,8 @@ def main():
         mmgcn_fixture(ref)
     if "dagerc" in which:
         dagerc_fixture(ref)
+    if "dgcnv2" in which:
+        dgcnv2_fixture(ref)
 
 
 if __name__ == "__main__":

@@ -110,6 +110,41 @@ def load():
     return types.SimpleNamespace(**_loaded)
 
 
+def load_dgcnv2():
+    """The declare-lab DialogueGCN variant (track_mm/dgcnv2_models.py, dgcnv2.py).  Compat patch (iii) of SURVEY.md 8c:
+    ``mask[edge_ind_] = 1`` with an ndarray ``edge_ind_`` of shape [3,E] (dgcnv2_models.py:557-559) relied on old numpy /
+    torch treating the ndarray as a tuple of index arrays; it is read as ``mask[tuple(edge_ind_)] = 1``."""
+    import re
+    ns = load()
+    if "dgcnv2" in _loaded:
+        return types.SimpleNamespace(**_loaded)
+    lumo = sys.modules["lumo"]
+    contrib = sys.modules["lumo.contrib"]
+    torch_pkg = _placeholder("lumo.contrib.torch")
+    import torch
+
+    def onehot(labels, label_num):
+        return torch.zeros(*labels.shape, label_num, device=labels.device).scatter_(-1, labels.unsqueeze(-1), 1)
+
+    tensor_mod = _placeholder("lumo.contrib.torch.tensor", onehot=onehot)
+    contrib.torch = torch_pkg
+    torch_pkg.tensor = tensor_mod
+    path = os.path.join(REF_ROOT, "track_mm", "dgcnv2_models.py")
+    with open(path) as f:
+        text = f.read()
+    assert "mask[edge_ind_] = 1" in text and "mask_copy[edge_ind_] = 1" in text
+    text = text.replace("mask[edge_ind_] = 1", "mask[tuple(edge_ind_)] = 1").replace("mask_copy[edge_ind_] = 1", "mask_copy[tuple(edge_ind_)] = 1")
+    spec = importlib.util.spec_from_loader("track_mm.dgcnv2_models", loader=None, origin=path)
+    mod = importlib.util.module_from_spec(spec)
+    mod.__file__ = path
+    mod.__package__ = "track_mm"
+    sys.modules["track_mm.dgcnv2_models"] = mod
+    exec(compile(text, path, "exec"), mod.__dict__)
+    _loaded["dgcnv2_models"] = mod
+    _loaded["dgcnv2"] = importlib.import_module("track_mm.dgcnv2")
+    return types.SimpleNamespace(**_loaded)
+
+
 def load_collate():
     """The reference's own ``ERCCollate`` class (track_mm/mmbase.py:344-455).  mmbase.py itself cannot be imported (lumo,
     dbrecord, mmdatasets are not installed), so the class statement is cut out of the file verbatim and executed with the

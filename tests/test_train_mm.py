@@ -27,7 +27,7 @@ def test_params_follow_the_reference_rules():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("module,extra", [("cogmen", ["--dataset=iemocap-cogmen-sbert-4"]), ("dgcn", ["--dataset=iemocap-cogmen-6"]),
+@pytest.mark.parametrize("module,extra", [("cogmen", ["--dataset=iemocap-cogmen-sbert-4"]), ("dgcn", ["--dataset=iemocap-cogmen-6"]), ("dgcnv2", ["--dataset=iemocap-cogmen-6", "--max_len=40"]),
                                           ("mmgcn", ["--dataset=iemocap-cogmen-6"]), ("dagerc", ["--dataset=iemocap-cogmen-6", "--max_len=24"])])
 def test_synthetic_epochs_run_end_to_end(module, extra, tmp_path):
     import erc_b200  # noqa: F401
