@@ -194,6 +194,10 @@ def kernel_label(name, args):
             return "gemm_nn_tc[K=%d,N=%d]" % (args[9], args[8])
         if name == "ercg_gemm_tn_tc":
             return "gemm_tn_tc[K1=%d,N1=%d]" % (args[7], args[8])
+        if name == "ercg_gemm_nn_tc_bf16a":
+            return "gemm_nn_tc_bf16a[K=%d,N=%d]" % (args[9], args[8])
+        if name == "ercg_gemm_tn_tc_bf16a":
+            return "gemm_tn_tc_bf16a[K1=%d,N1=%d]" % (args[7], args[8])
         if name == "ercg_gemm_tn":
             return "gemm_tn[K1=%d,N1=%d]" % (args[8], args[9])
     except Exception:
@@ -279,8 +283,9 @@ def run_ours(args):
     if sampler:
         sampler.start()                                  # before any warm-up: starting it later stalls rank 0's launch thread
 
-    def measure(scaling, steps, with_kernels, with_e2e):
-        """One workload (strong: args.total_utts in total; weak: per GPU) -> dict of measurements (same on every rank)."""
+    def measure(scaling, steps, with_kernels, with_e2e, in_dtype="f32"):
+        """One workload (strong: args.total_utts in total; weak: per GPU) -> dict of measurements (same on every rank).
+        in_dtype "bf16": the bf16 input-feature mode (features stored in bf16, row pitch 1448 elements; everything else fp32)."""
         weak = scaling == "weak"
         lengths_all = synth.config5_lengths(args.total_utts * (world if weak else 1), seed=0)
         total_utts = int(lengths_all.sum())
@@ -290,7 +295,11 @@ def run_ours(args):
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
         x_store = torch.empty((N, ld), dtype=torch.float32, device=dev)
         x_store.normal_(generator=gen)
-        x = x_store[:, :HIDDEN]
+        if in_dtype == "bf16":
+            x = synth.to_bf16_rows(x_store[:, :HIDDEN])          # [N, 1443] view of a [N, 1448] bf16 buffer
+            x_store = x._base if x._base is not None else x
+        else:
+            x = x_store[:, :HIDDEN]
         spk = torch.zeros(N, dtype=torch.int64, device=dev)   # MOSEI: a single speaker id (mosei_feature.py:211)
         labels = torch.randint(0, N_CLASSES, (N,), device=dev, generator=gen)
         sizes = graph_sizes(lengths, 5, 5)
@@ -388,7 +397,7 @@ def run_ours(args):
         # step i+1 overlaps the kernels of step i) and the loss is read back.  Eager steps: PCIe is the bound, not launches.
         if with_e2e:
             e2e_steps = max(1, args.e2e_steps)
-            hx = torch.empty((N, ld), dtype=torch.float32, pin_memory=True)
+            hx = torch.empty(tuple(x_store.shape), dtype=x_store.dtype, pin_memory=True)
             hx.copy_(x_store)
             host = {"x": hx, "spk": torch.zeros(N, dtype=torch.int64).pin_memory(), "label": labels.cpu().pin_memory()}
             feeder = DeviceFeeder(dev, depth=2, copy_streams=args.copy_streams)
@@ -424,7 +433,7 @@ def run_ours(args):
         ts.check()                                             # K1's input-error flags of the last step
         gc.enable()
         gc.unfreeze()
-        out["x_bytes"] = x_store.numel() * 4
+        out["x_bytes"] = x_store.numel() * x_store.element_size()
         out["N"], out["E"], out["n_dialogues_rank0"] = N, sizes[1], int(lengths.numel())
         del ts, model, x_store, x, spk, labels
         gc.collect()
@@ -440,6 +449,9 @@ def run_ours(args):
     other = None
     if world > 1 and not args.no_second_scaling:
         other = measure("weak" if args.scaling == "strong" else "strong", max(args.steps // 2, 3), with_kernels=False, with_e2e=False)
+    bf16 = None
+    if world == 1 and not args.no_bf16_mode:
+        bf16 = measure(args.scaling, max(args.steps // 2, 3), with_kernels=True, with_e2e=True, in_dtype="bf16")
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -455,6 +467,8 @@ def run_ours(args):
             """Algorithmic (unique) HBM bytes of ONE launch on this rank (weights ignored)."""
             if label.startswith("gemm_"):
                 a, b = (int(v.split("=")[1]) for v in label[label.index("[") + 1:-1].split(","))
+                if "bf16a" in label:
+                    return N * (2 * a + 4 * b)            # the wide / streamed operand is stored in bf16
                 return 4 * N * (a + b)
             return {
                 "gather_fwd": 4 * H * P * N + 4 * H * N + 4 * H * N + 4 * (N + 1) + 9 * E,
@@ -523,6 +537,21 @@ def run_ours(args):
             line[other["scaling"] + "_scaling"] = {"value": ob["value"], "ms_per_step": ob["ms_per_step"],
                                                    "utterances_per_step": other["utterances_per_step"],
                                                    "mode": "graph" if "graph" in other else "eager", "unit": UNIT}
+        if bf16 is not None:
+            bb = bf16.get("graph") or bf16.get("eager")
+            bper = {k: (c, tot / c) for k, (c, tot) in bf16["ksum"].items()}
+            bk = {}
+            for label in ("gemm_nn_tc_bf16a[K=1443,N=100]", "gemm_tn_tc_bf16a[K1=1443,N1=100]"):
+                if label in bper:
+                    ab, ms_ = alg_bytes(label), bper[label][1]
+                    bk[label] = {"avg_ms": round(ms_, 4), "algorithmic_bytes": ab, "achieved_gbs": round(ab / (ms_ * 1e-3) / 1e9, 1),
+                                 "frac_of_hbm_peak": round(ab / (ms_ * 1e-3) / 1e9 / peak, 4)}
+            line["bf16_input_mode"] = {
+                "what": "utterance features stored in bf16 (row pitch 1448 elements); weights, activations, gradients, accumulation fp32",
+                "value": bb["value"], "ms_per_step": bb["ms_per_step"], "unit": UNIT, "mode": "graph" if "graph" in bf16 else "eager",
+                "e2e": bf16.get("e2e"), "kernels": bk, "loss": bf16["loss"],
+                "tolerance": "equals the fp32 path run on the bf16-rounded features to the fp32 parity bars; vs the original features: "
+                             "logits within 1e-2 relative (tests/test_gpu_bf16_mode.py)"}
         if world == 1 and not args.no_cpu_baseline:
             v, sample, _ = cpu_reference_rate(args.cpu_budget_s)
             v2, sample2, _ = cpu_reference_rate(args.cpu_budget_s / 2, skip_dead_encoder=True)
@@ -577,6 +606,7 @@ def main():
                     help="BatchNorm statistics across ranks: global = all-reduced (N-GPU == 1-GPU result), local = per rank (the reference's DDP)")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of the two overlapped buckets")
     ap.add_argument("--watchdog-s", type=int, default=0, help="dump all Python stacks and exit if the run takes longer than this")
+    ap.add_argument("--no-bf16-mode", action="store_true", help="N = 1: skip the extra bf16 input-feature-mode measurement")
     ap.add_argument("--no-second-scaling", action="store_true", help="N > 1: skip the extra weak- (or strong-) scaling measurement")
     args = ap.parse_args()
     _quiet_stdout()

@@ -57,6 +57,9 @@ SIGNATURES = {
     "ercg_gemm_tn_tc_workspace_bytes": (SZ, [L, I, I]),
     "ercg_gemm_tn_tc_supported": (I, [P, L, P, L, L, I, I]),
     "ercg_gemm_tn_tc": (I, [P, L, P, L, P, L, L, I, I, P, SZ, P]),
+    "ercg_gemm_bf16a_supported": (I, [P, L, L, I]),
+    "ercg_gemm_nn_tc_bf16a": (I, [P, L, P, L, P, P, L, L, I, I, P, SZ, P]),
+    "ercg_gemm_tn_tc_bf16a": (I, [P, L, P, L, P, L, L, I, I, P, SZ, P]),
     "ercg_cls_tail_bwd_workspace_bytes": (SZ, [I, I]),
     "ercg_cls_tail_bwd": (I, [P, L, P, P, F, P, L, P, P, P, L, I, I, P, SZ, P]),
     "ercg_mask_pos": (I, [P, L, P, L, F, P, L, L, I, P]),

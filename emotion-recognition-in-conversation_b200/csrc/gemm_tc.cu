@@ -214,6 +214,11 @@ __device__ __forceinline__ float4 lds4(uint32_t saddr) {
 __device__ __forceinline__ void sts4(uint32_t saddr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+  uint16_t r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(saddr) : "memory");
+  return (uint32_t)r;
+}
 __device__ __forceinline__ float lds1(uint32_t saddr) {
   float r;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(saddr) : "memory");
@@ -299,7 +304,12 @@ __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, lon
   return x;
 }
 
-template <int ACT, bool SMALLK>
+// ABF16: the streamed operand A is STORED in bf16 (bf16 input-feature mode: half the HBM bytes of the projection).  Its raw
+// tile is 128 rows x 32 bf16 = 64-byte rows (TMA 64-byte swizzle); the splitter copies the 16 words of its row -- already the
+// "two k-elements per 32-bit column" packing the bf16 MMAs read -- straight into TMEM; there is no A_lo, and B comes as
+// bf16_rn(B) | bf16_rn(B - bf16_rn(B)) (16 significant bits of every weight): 4 bf16 MMAs per 32-k chunk instead of 4 tf32 +
+// 4 bf16, and no fp32 B tile.  The arithmetic is exact products of bf16 A with 16-bit B, accumulated in fp32.
+template <int ACT, bool SMALLK, bool ABF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                   const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
@@ -354,7 +364,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             TC_TRACE(0, n, 0);
             mbar_wait_relaxed(BAR(BAR_R_FREE + r), ((n / TC_R) & 1) ^ 1);
             TC_TRACE(0, n, 1);
-            mbar_expect_tx(BAR(BAR_A_FULL + r), TC_A_BYTES);
+            mbar_expect_tx(BAR(BAR_A_FULL + r), ABF16 ? TC_A_BYTES / 2 : TC_A_BYTES);
             tma_load_2d(raw_base + r * TC_A_BYTES, &tmA, kc * TC_BK, m0, BAR(BAR_A_FULL + r));
           }
       }
@@ -372,8 +382,8 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait_relaxed(BAR(BAR_Q_FREE + q), ((n / TC_Q) & 1) ^ 1);
             TC_TRACE(4, n, 1);
             if (ep.dbg & 8) { mbar_arrive(BAR(BAR_B_FULL + q)); continue; }
-            mbar_expect_tx(BAR(BAR_B_FULL + q), tx);
-            tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
+            mbar_expect_tx(BAR(BAR_B_FULL + q), ABF16 ? tx / 2 : tx);
+            if (!ABF16) tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
             tma_load_2d(B_LO(q), &tmBl, kc * 64, nt * bn, BAR(BAR_B_FULL + q));      // bf16(B_hi) | bf16(B_lo) of this chunk
           }
     }
@@ -415,6 +425,16 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ah0 = TA_HI(s);
           const uint64_t bh0 = desc_hi | (uint64_t)((B_HI(q) >> 4) & 0x3FFF), b16 = desc_hi | (uint64_t)((B_LO(q) >> 4) & 0x3FFF);
           if (elect_one()) {
+            if (ABF16) {
+              // A (bf16, exact) * (bf16(B) + bf16(B - bf16(B))): two bf16 MMAs per 16 k
+#pragma unroll
+              for (int j = 0; j < TC_BK / 16; ++j) {
+                if (j < k16_n) {
+                  tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(j * 2), idesc16, (in_group | j) ? 1u : 0u);
+                  tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);
+                }
+              }
+            } else {
             // A_hi * B_hi in tf32 (exact products); the two 2^-11-sized correction terms A_lo * B_hi + A_hi * B_lo in bf16
             // at twice the rate: 4 + 4 instructions per 32-k chunk instead of 12 tf32 ones (see top of file)
 #pragma unroll
@@ -426,6 +446,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);        // bf16(A_lo) * bf16(B_hi)
                 tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);    // bf16(A_hi) * bf16(B_lo)
               }
+            }
             }
             tc_commit(BAR(BAR_Q_FREE + q));
             if (!resident || nt == n_tiles - 1) tc_commit(BAR(BAR_TA_FREE + s));
@@ -451,8 +472,19 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (threadIdx.x == 0) TC_TRACE(1, n, 0);
           mbar_wait(BAR(BAR_A_FULL + r), (n / TC_R) & 1);          // raw tile landed
           if (threadIdx.x == 0) TC_TRACE(1, n, 1);
-          const uint32_t src = raw_base + r * TC_A_BYTES + row * 128;
+          const uint32_t src = raw_base + r * TC_A_BYTES + (ABF16 ? row * 64 : row * 128);
           uint32_t hi[32], p16[32];                                // tf32 A_hi | bf16 pairs: [0,16) A_hi, [16,32) A_lo
+          if (ABF16) {
+            // 64-byte rows, TMA 64-byte swizzle: logical 16-byte chunk c sits at position c ^ ((row >> 1) & 3)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 x = lds4(src + ((c ^ ((row >> 1) & 3)) << 4));
+              p16[4 * c + 0] = __float_as_uint(x.x); p16[4 * c + 1] = __float_as_uint(x.y);
+              p16[4 * c + 2] = __float_as_uint(x.z); p16[4 * c + 3] = __float_as_uint(x.w);
+            }
+#pragma unroll
+            for (int c = 16; c < 32; ++c) p16[c] = 0u;
+          } else {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                            // logical 16-byte chunk c sits at position c ^ (row & 7)
             const float4 x = lds4(src + ((c ^ (row & 7)) << 4));
@@ -466,10 +498,11 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             p16[16 + 2 * c + 0] = pack_bf16x2(__uint_as_float(l0), __uint_as_float(l1));
             p16[16 + 2 * c + 1] = pack_bf16x2(__uint_as_float(l2), __uint_as_float(l3));
           }
+          }
           mbar_wait(BAR(BAR_TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
           if (threadIdx.x == 0) TC_TRACE(1, n, 2);
           tc_fence_after();
-          tc_st32(TA_HI(s) + lane_addr, hi);
+          if (!ABF16) tc_st32(TA_HI(s) + lane_addr, hi);
           tc_st32(TA_HI(s) + 32 + lane_addr, p16);
           tc_wait_st();
           // The raw stage is released only HERE: the TMEM stores above consume every loaded register, so the
@@ -659,6 +692,10 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
          ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 
+// WBF16: the wide operand W is stored in bf16 (the input features of the projection's weight gradient): raw tile 32 rows x 128
+// bf16 columns (256-byte rows), W_hi = the value itself (exact in tf32), no W_lo => 4 tf32 + 2 bf16 MMAs per chunk instead of
+// 4 + 4 and half the HBM bytes of the wide stream.
+template <bool WBF16>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                   float* __restrict__ P /* [S][Wc][Nc] */, long long M, int Wc /* columns of the wide operand */,
@@ -732,7 +769,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           const int r = n % TN_R;
           mbar_wait_relaxed(BAR(TN_W_FREE + r), ((n / TN_R) & 1) ^ 1);
           TN_TRACE(0, n, 1);
-          mbar_expect_tx(BAR(TN_W_FULL + r), TC_A_BYTES);
+          mbar_expect_tx(BAR(TN_W_FULL + r), WBF16 ? TC_A_BYTES / 2 : TC_A_BYTES);
           tma_load_2d(raw_base + r * TC_A_BYTES, &tmW, w0, (int)m, BAR(TN_W_FULL + r));
         }
       }
@@ -791,7 +828,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             tc_mma_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 64), idesc, (in_group | ks) ? 1u : 0u);   // 8 rows = 1024 B
 #pragma unroll
           for (int j = 0; j < TC_BK / 16; ++j) {
-            tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);        // bf16(W_lo) * bf16(N_hi)
+            if (!WBF16) tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);   // bf16(W_lo) * bf16(N_hi)
             tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);    // bf16(W_hi) * bf16(N_lo)
           }
           tc_commit(BAR(TN_TA_FREE + s));
@@ -815,8 +852,18 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // raw [32 rows][128 columns] -> this thread's column, rows along the TMEM columns
         mbar_wait(BAR(TN_W_FULL + r), (n / TN_R) & 1);
         if (tid == 0) TN_TRACE(1, n, 1);
-        const uint32_t src = raw_base + r * TC_A_BYTES + tid * 4;
+        const uint32_t src = raw_base + r * TC_A_BYTES + (WBF16 ? tid * 2 : tid * 4);
         uint32_t hi[32], p16[32];                        // tf32 W_hi | bf16 pairs along the rows: [0,16) W_hi, [16,32) W_lo
+        if (WBF16) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {               // raw [32 rows][128 bf16]: 256-byte rows
+            const uint32_t b0 = lds_u16(src + j * 256), b1 = lds_u16(src + (j + 1) * 256);
+            hi[j] = b0 << 16;                              // bf16 -> fp32 bit pattern: exact, and exact as a tf32 operand
+            hi[j + 1] = b1 << 16;
+            p16[j >> 1] = b0 | (b1 << 16);                 // element j at the even k position (low half)
+            p16[16 + (j >> 1)] = 0u;
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           uint32_t l0, l1;
@@ -824,6 +871,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           split_tf32(lds1(src + (j + 1) * 512), hi[j + 1], l1);
           p16[j >> 1] = pack_bf16x2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1]));
           p16[16 + (j >> 1)] = pack_bf16x2(__uint_as_float(l0), __uint_as_float(l1));
+        }
         }
         mbar_wait(BAR(TN_TA_FREE + s), ((n / TN_TA) & 1) ^ 1);
         if (tid == 0) TN_TRACE(1, n, 2);
@@ -958,7 +1006,7 @@ static void tn_tc_plan(int64_t M, int K1, int N1, bool& swap, int& w_tiles, int&
 // per chunk the 32 values bf16(B_hi) followed by the 32 values bf16(B - B_hi), i.e. one 128-byte row per (n, chunk) so that
 // a {64 x bn} TMA box lands as a 128-byte-swizzled K-major tile with the two bf16 operands side by side
 __global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int K, int N, int Kp, int Kc, float* __restrict__ hi,
-                                __nv_bfloat16* __restrict__ b16) {
+                                __nv_bfloat16* __restrict__ b16, int abf16 = 0) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -970,9 +1018,15 @@ __global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int 
     const int n = n0 + i, k = k0 + threadIdx.x;
     if (n < N) {
       const float x = tile[threadIdx.x][i];                 // zero beyond K
+      __nv_bfloat16* row = b16 + ((long long)n * Kc + blockIdx.x) * 64;
+      if (abf16) {                                          // bf16-A kernel: B = b1 + b2, 16 significant bits, no fp32 copy
+        const __nv_bfloat16 b1 = __float2bfloat16_rn(x);
+        row[threadIdx.x] = b1;
+        row[32 + threadIdx.x] = __float2bfloat16_rn(x - __bfloat162float(b1));
+        continue;
+      }
       const float h = rn_tf32(x);
       if (k < Kp) hi[(long long)n * Kp + k] = h;
-      __nv_bfloat16* row = b16 + ((long long)n * Kc + blockIdx.x) * 64;
       row[threadIdx.x] = __float2bfloat16_rn(h);
       row[32 + threadIdx.x] = __float2bfloat16_rn(x - h);
     }
@@ -1003,6 +1057,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode() {
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on the calling thread.  PyTorch runs backward passes on
+  // its own autograd threads, where a tensor-core GEMM can be the first CUDA call (torch.empty served from the caching
+  // allocator makes none) -> CUDA_ERROR_INVALID_CONTEXT (201).  One runtime call binds the primary context to the thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -1096,8 +1158,8 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   typedef void (*NnKernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, float*, long long, long long, int, int, int,
                            TcEpilogue, float*);
   static const NnKernel kernels[4][2] = {
-      {gemm_tc_nn_kernel<0, false>, gemm_tc_nn_kernel<0, true>}, {gemm_tc_nn_kernel<1, false>, gemm_tc_nn_kernel<1, true>},
-      {gemm_tc_nn_kernel<2, false>, gemm_tc_nn_kernel<2, true>}, {gemm_tc_nn_kernel<3, false>, gemm_tc_nn_kernel<3, true>}};
+      {gemm_tc_nn_kernel<0, false, false>, gemm_tc_nn_kernel<0, true, false>}, {gemm_tc_nn_kernel<1, false, false>, gemm_tc_nn_kernel<1, true, false>},
+      {gemm_tc_nn_kernel<2, false, false>, gemm_tc_nn_kernel<2, true, false>}, {gemm_tc_nn_kernel<3, false, false>, gemm_tc_nn_kernel<3, true, false>}};
   static DeviceOnce attr_set;            // cudaFuncSetAttribute is per device context: once per DEVICE, not per process
   if (attr_set.need()) {
     for (int i = 0; i < 4; ++i)
@@ -1188,7 +1250,7 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
       !make_map(&tmNp, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return ERCG_ECUDA;
   static DeviceOnce attr_set;
   if (attr_set.need()) {
-    if (cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
       return ERCG_ECUDA;
     attr_set.mark();
   }
@@ -1203,10 +1265,112 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
   }
   long long* tr = (tn_trace_on & 2) ? trace_buf : nullptr;          // ERCG_TC_TRACE=2: trace the TN kernel instead of the NN one
   if (tr) cudaMemsetAsync(tr, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
-  gemm_tc_tn_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr, tmNp);
+  gemm_tc_tn_kernel<false><<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr, tmNp);
   int rc = finish_launch();
   if (rc) return rc;
   const long long tot = (long long)K1 * N1;
   tn_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tot, S, C, ldc, K1, N1, swap ? 1 : 0);
+  return finish_launch();
+}
+
+
+// ---------------------------------------------------------------------------------------------- bf16 input-feature mode
+// The streamed operand of the input projection (x [N, hidden_all], 5.8 of the ~21 KB/utterance the step has to move) stored
+// in bf16: ercg_gemm_nn_tc_bf16a = x @ W + b (forward), ercg_gemm_tn_tc_bf16a = x^T @ dF (weight gradient).  fp32
+// accumulation, fp32 outputs, weights / gradients fp32 in HBM; the only approximation relative to the fp32 path is the
+// rounding of x itself (done once, where the data set is stored) plus 16-bit weights inside the forward product.
+namespace ercg {
+static int g_last_map_result = 0;
+static bool make_map_bf16_rows(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems,
+                               int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  g_last_map_result = (int)enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return g_last_map_result == 0;
+}
+}  // namespace ercg
+
+extern "C" int ercg_gemm_bf16a_supported(const void* A, int64_t lda, int64_t M, int K) {
+  if (M < 1 || K < 1 || !A) return 0;
+  if ((lda & 7) || !aligned16(A) || lda < K) return 0;            // 16-byte aligned bf16 rows
+  if (M >= 2147483647LL || K >= (1 << 30)) return 0;
+  return 1;
+}
+
+extern "C" int ercg_gemm_nn_tc_bf16a(const void* A_bf16, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                                     int64_t ldc, int64_t M, int N, int K, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  if (M < 0 || N < 0 || K < 0) return ERCG_EINVAL;
+  if (M == 0 || N == 0) return ERCG_OK;
+  if (!A_bf16 || !B || !C || ldb < N || ldc < N || K == 0) return ERCG_EINVAL;
+  if (!ercg_gemm_bf16a_supported(A_bf16, lda, M, K) || (ldc & 3) || !aligned16(C) || (bias && !aligned16(bias))) return ERCG_EALIGN;
+  if (workspace_bytes < ercg_gemm_nn_tc_workspace_bytes(N, K) || !workspace) return ERCG_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = (K + 3) / 4 * 4;
+  const int Kc = (K + TC_BK - 1) / TC_BK;
+  float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(
+      (reinterpret_cast<uintptr_t>(bhi + (size_t)N * Kp) + 255) & ~uintptr_t(255));
+  split_bt_kernel<<<dim3(Kc, (N + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Kp, Kc, bhi, b16, 1);
+  int rc = finish_launch();
+  if (rc) return rc;
+  int bn = 128;
+  if (N <= 128) bn = (N + 15) / 16 * 16;
+  CUtensorMap tmA, tmBl, tmC;
+  if (!make_map_bf16_rows(&tmA, A_bf16, M, K, lda, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_64B) ||
+      !make_map_b16(&tmBl, b16, N, Kc, bn) || !make_map(&tmC, C, M, N, ldc, 32))
+    return ERCG_ECUDA;
+  typedef void (*NnKernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, float*, long long, long long, int, int, int,
+                           TcEpilogue, float*);
+  static const NnKernel kernels[2] = {gemm_tc_nn_kernel<0, false, true>, gemm_tc_nn_kernel<0, true, true>};
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
+    for (int k = 0; k < 2; ++k)
+      if (cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) return ERCG_ECUDA;
+    attr_set.mark();
+  }
+  const int num_sms = device_sm_count();
+  const long long tiles = (M + TC_BM - 1) / TC_BM;
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  TcEpilogue ep{bias, ERCG_ACT_NONE, nullptr, 0, 1.f, 0.f, 0ull, 0, nullptr};
+  const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;
+  kernels[smallk]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBl /* unused fp32 slot */, tmBl, tmC, C, ldc, M, N, K, bn, ep, nullptr);
+  return finish_launch();
+}
+
+extern "C" int ercg_gemm_tn_tc_bf16a(const void* A_bf16, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                                     int64_t M, int K1, int N1, void* workspace, size_t workspace_bytes, void* stream) {
+  if (M < 1 || K1 < 1 || N1 < 1 || !A_bf16 || !B || !C || ldb < N1 || ldc < N1) return ERCG_EINVAL;
+  if (N1 > K1 || N1 > 128) return ERCG_EINVAL;                    // the bf16 operand must be the wide one (K1 >= N1), one narrow tile
+  if (!ercg_gemm_bf16a_supported(A_bf16, lda, M, K1) || (ldb & 3) || !aligned16(B)) return ERCG_EALIGN;
+  if (workspace_bytes < ercg_gemm_tn_tc_workspace_bytes(M, K1, N1) || !workspace) return ERCG_EWORKSPACE;
+  bool swap; int wt, nt, bn, S; long long rps;
+  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps);
+  if (swap) return ERCG_EINVAL;
+  float* P = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  CUtensorMap tmW, tmN, tmNp;
+  if (!make_map_bf16_rows(&tmW, A_bf16, M, K1, lda, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return ERCG_ECUDA;
+  if (!make_map(&tmN, B, M, N1, ldb, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map(&tmNp, B, M, N1, ldb, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return ERCG_ECUDA;
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
+    if (cudaFuncSetAttribute(gemm_tc_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
+      return ERCG_ECUDA;
+    attr_set.mark();
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long units = (long long)wt * nt * S;
+  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
+  gemm_tc_tn_kernel<true><<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, K1, N1, bn, wt, nt, S, rps, nullptr, tmNp);
+  int rc = finish_launch();
+  if (rc) return rc;
+  const long long tot = (long long)K1 * N1;
+  tn_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tot, S, C, ldc, K1, N1, 0);
   return finish_launch();
 }

@@ -220,8 +220,50 @@ def mlp_head(x, W0, b0, W3, b3, drop_p=0.0, seed=0):
     return _MlpHead.apply(x, W0, b0, W3, b3, float(drop_p), int(seed))
 
 
+class _LinearBf16In(torch.autograd.Function):
+    """y = x @ Bm + bias with the input rows x STORED in bf16 (bf16 input-feature mode, include/ercgraph.h): tensor-core
+    kernels with a bf16 streamed operand for the forward and the weight gradient; x itself gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, Bm, bias):
+        assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+        M, K = x.shape
+        lda = x.stride(0) if M > 1 else max(K, x.stride(0))
+        if not lib().ercg_gemm_bf16a_supported(_p(x), lda, M, K):
+            raise ValueError("bf16 input rows must be 16-byte aligned with a row pitch that is a multiple of 8 elements "
+                             "(got pitch %d): store them with synth.to_bf16_rows / a padded pitch" % lda)
+        Bm, ldb = _rows(Bm)
+        N = Bm.size(1)
+        C = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        ws = _ws(lib().ercg_gemm_nn_tc_workspace_bytes(N, K), x.device)
+        check(lib().ercg_gemm_nn_tc_bf16a(_p(x), lda, _p(Bm), ldb, _p(bias), _p(C), N, M, N, K, _p(ws), ws.numel(), _stream()),
+              "ercg_gemm_nn_tc_bf16a")
+        ctx.save_for_backward(x)
+        ctx.lda, ctx.has_bias = lda, bias is not None
+        return C
+
+    @staticmethod
+    def backward(ctx, dC):
+        (x,) = ctx.saved_tensors
+        dC, ldb = _rows(dC.contiguous())
+        M, K = x.shape
+        N = dC.size(1)
+        dB = dbias = None
+        if ctx.needs_input_grad[1]:
+            dB = torch.empty((K, N), dtype=torch.float32, device=x.device)
+            ws = _ws(lib().ercg_gemm_tn_tc_workspace_bytes(M, K, N), x.device)
+            check(lib().ercg_gemm_tn_tc_bf16a(_p(x), ctx.lda, _p(dC), ldb, _p(dB), N, M, K, N, _p(ws), ws.numel(), _stream()),
+                  "ercg_gemm_tn_tc_bf16a")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dbias = colsum(dC)
+        return None, dB, dbias
+
+
 def linear(x, weight, bias=None, act=ACT_NONE, a_rows=None, drop_p=0.0, seed=0):
-    """nn.Linear semantics (weight [out,in]) on 2-D row-major input."""
+    """nn.Linear semantics (weight [out,in]) on 2-D row-major input.  bf16 input rows select the bf16 input-feature mode."""
+    if x.dtype == torch.bfloat16:
+        assert act == ACT_NONE and a_rows is None, "bf16 input rows: plain projection only"
+        return _LinearBf16In.apply(x, weight.t().contiguous(), bias)
     return _LinearAct.apply(x, weight.t().contiguous(), bias, act, a_rows, drop_p, seed)
 
 

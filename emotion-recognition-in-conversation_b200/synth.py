@@ -71,3 +71,13 @@ MOSEI_HIDDEN = 1443      # t=768 + a=640 + v=35  (mmbase.py:93,97-98,103-104)
 def config5_lengths(total=1 << 20, seed=0):
     gen = torch.Generator().manual_seed(seed)
     return mosei_lengths(total, gen)
+
+
+def to_bf16_rows(x, pitch_multiple=8):
+    """[N, D] fp32 rows -> bf16 storage with a row pitch that is a multiple of 8 elements (16-byte aligned rows: what the
+    bf16 input-feature kernels read through TMA).  Returns the [N, D] view of the padded buffer (round-to-nearest-even)."""
+    N, D = x.shape
+    ld = (D + pitch_multiple - 1) // pitch_multiple * pitch_multiple
+    buf = torch.zeros((N, ld), dtype=torch.bfloat16, device=x.device)
+    buf[:, :D] = x.to(torch.bfloat16)
+    return buf[:, :D]

@@ -174,6 +174,21 @@ int ercg_gemm_tn_tc_supported(const float* A, int64_t lda, const float* B, int64
 int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                     int K1, int N1, void* workspace, size_t workspace_bytes, void* stream);
 
+/* bf16 INPUT-FEATURE MODE (BASELINE.json north_star: "stated separately for bf16").  The streamed operand A -- the
+ * utterance features x [N, hidden_all] of the input projection nn.Linear(hidden_all, 100) (cogmen.py:103-105,146-147), 5.8 of
+ * the ~21 KB/utterance a train step has to move -- is STORED in bf16 (uint16 bit patterns, row pitch lda ELEMENTS, a multiple
+ * of 8 so rows are 16-byte aligned); weights, bias, outputs and gradients stay fp32, accumulation is fp32.
+ *   ercg_gemm_nn_tc_bf16a   C[M,N]   = A @ B + bias        (forward; B enters with 16 significant bits)
+ *   ercg_gemm_tn_tc_bf16a   C[K1,N1] = A^T @ Bg            (weight gradient; Bg fp32 through the hi/lo split; K1 >= N1, N1 <= 128)
+ * Half the HBM (and host->device) bytes of the two largest kernels of the COGMEN step; results equal the fp32 path run on the
+ * bf16-ROUNDED features to ~1e-5 (tests/test_gpu_bf16_mode.py), i.e. the mode's error is the rounding of the stored features.
+ * Workspaces: ercg_gemm_nn_tc_workspace_bytes(N, K) / ercg_gemm_tn_tc_workspace_bytes(M, K1, N1). */
+int ercg_gemm_bf16a_supported(const void* A_bf16, int64_t lda, int64_t M, int K);
+int ercg_gemm_nn_tc_bf16a(const void* A_bf16, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                          int64_t ldc, int64_t M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
+int ercg_gemm_tn_tc_bf16a(const void* A_bf16, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                          int64_t M, int K1, int N1, void* workspace, size_t workspace_bytes, void* stream);
+
 /* out = ref > 0 ? x * scale : 0  -- backward of ReLU / ReLU+inverted-dropout given the forward OUTPUT
  * (cls of cogmen.py:116-122, Classifier of dgcn_models.py:163-170). */
 int ercg_mask_pos(const float* x, int64_t ldx, const float* ref, int64_t ldr, float scale,
