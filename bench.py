@@ -568,6 +568,76 @@ def run_ours(args):
         os._exit(0)
 
 
+def run_library_yardstick(args):
+    """NOT the product path: times what a library gives for the two projection GEMMs of the workload on this box --
+    cuBLAS through torch.matmul in exact fp32 (allow_tf32 off), in TF32 (10-bit mantissa: 1e-3 accuracy, outside the 1e-5 bar)
+    and in bf16 -- next to libercgraph's split-precision tcgen05 kernels.  One JSON line."""
+    import erc_b200  # noqa: F401
+    from erc_b200 import ops, synth
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    M, K, N = args.total_utts, HIDDEN, 100
+    ld = (K + 3) // 4 * 4
+    xs = torch.randn((M, ld), device=dev)
+    x = xs[:, :K]
+    W = torch.randn((N, K), device=dev) / K ** 0.5
+    dF = torch.randn((M, N), device=dev)
+    xb = synth.to_bf16_rows(x)
+    Wt = W.t().contiguous()
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ref_nn = (x[:4096].double() @ Wt.double())
+    ref_tn = None
+    out = {"shape": {"M": M, "K": K, "N": N}, "unit": "ms per launch", "nn": {}, "tn": {}}
+
+    def err(y):
+        return float((y[:4096].double() - ref_nn).abs().max() / ref_nn.abs().max())
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["nn"]["cublas_fp32"] = {"ms": timeit(lambda: torch.matmul(x, Wt)), "rel_err": err(torch.matmul(x, Wt))}
+    out["tn"]["cublas_fp32"] = {"ms": timeit(lambda: torch.matmul(x.t(), dF))}
+    torch.backends.cuda.matmul.allow_tf32 = True
+    out["nn"]["cublas_tf32"] = {"ms": timeit(lambda: torch.matmul(x, Wt)), "rel_err": err(torch.matmul(x, Wt))}
+    out["tn"]["cublas_tf32"] = {"ms": timeit(lambda: torch.matmul(x.t(), dF))}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Wb, dFb = Wt.to(torch.bfloat16), dF.to(torch.bfloat16)
+    out["nn"]["cublas_bf16"] = {"ms": timeit(lambda: torch.matmul(xb, Wb)), "rel_err": err(torch.matmul(xb, Wb).float())}
+    out["tn"]["cublas_bf16"] = {"ms": timeit(lambda: torch.matmul(xb.t(), dFb))}
+    out["nn"]["libercgraph_fp32_split"] = {"ms": timeit(lambda: ops.gemm_nn(x, Wt)), "rel_err": err(ops.gemm_nn(x, Wt))}
+    out["tn"]["libercgraph_fp32_split"] = {"ms": timeit(lambda: ops.gemm_tn(x, dF))}
+    Wp = W.clone().requires_grad_()
+
+    def bf_nn():
+        return ops.linear(xb, Wp)
+
+    y = bf_nn()
+    out["nn"]["libercgraph_bf16_input"] = {"ms": timeit(bf_nn), "rel_err_vs_rounded_features": float(
+        (y[:4096].double() - xb[:4096].double() @ Wt.double()).abs().max() / ref_nn.abs().max())}
+
+    def bf_tn():
+        (g,) = torch.autograd.grad(ops.linear(xb, Wp), Wp, dF)
+        return g
+
+    t_both = timeit(bf_tn)
+    out["tn"]["libercgraph_bf16_input"] = {"ms": t_both - out["nn"]["libercgraph_bf16_input"]["ms"], "how": "forward+wgrad minus forward"}
+    a = ops.gemm_tn(x, dF)[:64].double().cpu()
+    r = (x[:, :64].double().t() @ dF.double()).cpu()
+    out["tn"]["libercgraph_fp32_split"]["rel_err"] = float((a - r).abs().max() / r.abs().max())
+    out["note"] = "cuBLAS fp32 = SIMT FFMA path; TF32 and bf16 do not meet the 1e-5 parity bar of BASELINE.json (rel_err column)"
+    emit({"library_yardstick": out})
+
+
 _REAL_STDOUT = None
 
 
@@ -606,11 +676,15 @@ def main():
                     help="BatchNorm statistics across ranks: global = all-reduced (N-GPU == 1-GPU result), local = per rank (the reference's DDP)")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of the two overlapped buckets")
     ap.add_argument("--watchdog-s", type=int, default=0, help="dump all Python stacks and exit if the run takes longer than this")
+    ap.add_argument("--library-yardstick", action="store_true",
+                    help="time cuBLAS (fp32 / TF32 / bf16) on the projection GEMM shapes next to libercgraph's kernels and exit")
     ap.add_argument("--no-bf16-mode", action="store_true", help="N = 1: skip the extra bf16 input-feature-mode measurement")
     ap.add_argument("--no-second-scaling", action="store_true", help="N > 1: skip the extra weak- (or strong-) scaling measurement")
     args = ap.parse_args()
     _quiet_stdout()
-    if args.impl == "reference":
+    if args.library_yardstick:
+        run_library_yardstick(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
