@@ -391,6 +391,30 @@ def run_ours(args):
         out["loss"] = float(loss.item()) if loss is not None else None
         if world > 1:
             out["loss_global"] = float(ts.global_loss().item())
+            # Where does the time over (1-GPU time / N) go?  Every rank replays ITS shard as a stand-alone step (no collective,
+            # no waiting for anybody) while all the others do the same, i.e. in the same power / thermal state as the
+            # distributed run; the distributed step cannot be faster than the slowest of these.
+            try:
+                torch.manual_seed(0)
+                solo_model = COGMENModule(HIDDEN, 100, 17, 2, N_CLASSES).to(dev)
+                solo_model.train()
+                solo = CogmenTrainStep(solo_model, lengths, speakers_present=(0,), lr=1e-4, weight_decay=1e-8, world=1)
+                solo.capture(x, spk, labels, warmup=2)
+                for _ in range(3):
+                    solo.replay()
+                barrier()
+                e0.record()
+                for _ in range(steps):
+                    solo.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                mine_ms = e0.elapsed_time(e1) / steps
+                all_ms = [None] * world
+                dist.all_gather_object(all_ms, mine_ms, group=ctl)
+                out["solo_ms_per_rank"] = [round(v, 4) for v in all_ms]
+                del solo, solo_model
+            except Exception as e:
+                out["solo_error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
 
         # ---- e2e: the step through the public API with HOST buffers; every step's inputs (features, speakers, labels) are
         # copied from pinned host memory inside the timed region (DeviceFeeder: double-buffered, on copy streams, so the H2D of
@@ -412,6 +436,16 @@ def run_ours(args):
                     feeder.release()
                     float(loss_i.item())                         # D2H of the step's result
 
+            # ceiling of the host->device path on this box: every rank copies its pinned feature buffer, nothing else running
+            probe = torch.empty_like(x_store)
+            barrier()
+            e0.record()
+            for _ in range(3):
+                probe.copy_(hx, non_blocking=True)
+            e1.record()
+            barrier()
+            h2d_probe_ms = max_over_ranks(e0.elapsed_time(e1)) / 3
+            del probe
             e2e_run(2)
             barrier()
             b0 = feeder.h2d_bytes
@@ -427,6 +461,9 @@ def run_ours(args):
                 h2d = int(b.item())
             out["e2e"] = {"value": total_utts * e2e_steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                           "d2h_bytes_per_step": 4 * world, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                          "h2d_copy_only_ms": h2d_probe_ms,
+                          "h2d_copy_only_gbs_all_ranks": round(world * hx.numel() * hx.element_size() / (h2d_probe_ms * 1e-3) / 1e9, 1),
+                          "h2d_share_of_step": round(h2d_probe_ms / (e2e_ms / e2e_steps), 3),
                           "how": "pinned host buffers -> DeviceFeeder (double-buffered, %d copy streams) -> eager step -> loss.item(); "
                                  "all copies inside the timed region; host threads bound to the GPU's NUMA node: %s" % (args.copy_streams, numa)}
             del feeder, host, hx
@@ -532,11 +569,22 @@ def run_ours(args):
             line["graph_error"] = head["graph_error"]
         if "loss_global" in head:
             line["loss_global"] = head["loss_global"]
+        if "solo_ms_per_rank" in head:
+            sm = head["solo_ms_per_rank"]
+            line["scaling_breakdown"] = {
+                "solo_ms_per_rank": sm,
+                "what": "each rank's own shard replayed as a stand-alone step (no collectives, no waiting), all ranks at once",
+                "slowest_rank_solo_ms": max(sm), "fastest_rank_solo_ms": min(sm),
+                "collectives_and_skew_ms": round(best["ms_per_step"] - max(sm), 4),
+                "collectives_per_step": "BN statistics (2H+1 doubles, forward) + their backward sums (2H floats) + flat gradients "
+                                        "in two overlapped buckets (NCCL, captured in the step's CUDA graph)" if args.bn_sync == "global"
+                                        else "flat gradients in two overlapped buckets (NCCL, captured in the step's CUDA graph)"}
         if other is not None:
             ob = other.get("graph") or other.get("eager")
             line[other["scaling"] + "_scaling"] = {"value": ob["value"], "ms_per_step": ob["ms_per_step"],
                                                    "utterances_per_step": other["utterances_per_step"],
-                                                   "mode": "graph" if "graph" in other else "eager", "unit": UNIT}
+                                                   "mode": "graph" if "graph" in other else "eager", "unit": UNIT,
+                                                   "solo_ms_per_rank": other.get("solo_ms_per_rank")}
         if bf16 is not None:
             bb = bf16.get("graph") or bf16.get("eager")
             bper = {k: (c, tot / c) for k, (c, tot) in bf16["ksum"].items()}
