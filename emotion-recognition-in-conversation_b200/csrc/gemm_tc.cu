@@ -270,6 +270,60 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) helpers: the two CTAs of a cluster on one TPC run ONE MMA of M = 256; each CTA keeps its 128
+// rows of A / D in its own tensor memory and HALF of the B tile in its own shared memory (the hardware feeds both tensor
+// cores from both halves), so the shared-memory and L2 -> SM bytes of the B operand per SM halve.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t saddr, uint32_t rank) {   // shared::cta address -> shared::cluster address in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): what the peer's tensor core reads
+  // was ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync (tensor memory) or fence.proxy.async (shared memory)
+  // before this arrive; a .release.cluster here costs a cluster-wide memory barrier per arrival (measured: ~1500 clk)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope (peer arrivals)
+  uint32_t done = 0;
+  unsigned long long t0 = 0ull;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if ((spin & 0xffffu) == 0xffffu && mbar_timed_out(t0)) __trap();
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+
 template <int ACT>
 __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, long long m, int nn0, int N) {
   if (ep.bias) {
@@ -664,15 +718,32 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #define TN_R_ 4
 #endif
 #ifndef TN_Q_
-#define TN_Q_ 3
+#define TN_Q_ 4
 #endif
-constexpr int TN_R = TN_R_;       // raw W stages, 16 KB each ([32 rows][128 columns], no swizzle)
-constexpr int TN_Q = TN_Q_;       // narrow-operand stages: swizzled fp32 tile 16 KB + plain fp32 tile 16 KB + bf16 tile 16 KB
 constexpr int TN_TA = 4;          // TMEM stages of W: tf32 hi 32 + bf16 pairs (hi 16, lo 16) columns
-constexpr uint32_t TN_SMEM_BYTES = TN_R * TC_A_BYTES + TN_Q * 3 * TC_B_BYTES + 1024 + 512;
-constexpr int TN_W_FULL = 0, TN_W_FREE = TN_W_FULL + TN_R, TN_TA_FULL = TN_W_FREE + TN_R, TN_TA_FREE = TN_TA_FULL + TN_TA,
-              TN_B_FULL = TN_TA_FREE + TN_TA, TN_B_SPLIT = TN_B_FULL + TN_Q, TN_B_FREE = TN_B_SPLIT + TN_Q,
-              TN_ACC_FULL = TN_B_FREE + TN_Q, TN_ACC_EMPTY = TN_ACC_FULL + 2, TN_BARS = TN_ACC_EMPTY + 2;
+#ifndef TN_R2_
+#define TN_R2_ 6
+#endif
+#ifndef TN_Q2_
+#define TN_Q2_ 6
+#endif
+// Ring geometry.  Single CTA: R raw W stages of 16 KB ([32 rows][128 columns], no swizzle) and Q narrow stages of
+// (swizzled fp32 tile 16 KB + bf16 tile 16 KB).  CTA pair: each CTA holds HALF of the narrow tile (64 columns: 8 + 8 KB per
+// stage), so the narrow ring can be twice as deep in the same shared memory -- the pipeline trace of the single-CTA kernel
+// (profiles/r02n_tn_trace.txt) has the narrow ring as the critical loop: stage freed by the MMAs -> TMA (~3100 clk under
+// load) -> bf16 conversion (~600 clk) -> MMAs (~550 clk), i.e. ~4250 clk around a 4-stage ring.
+template <bool TWO>
+struct TnCfg {
+  static constexpr int R = TWO ? TN_R2_ : TN_R_;
+  static constexpr int Q = TWO ? TN_Q2_ : TN_Q_;
+  static constexpr uint32_t NT_BYTES = TWO ? TC_B_BYTES / 2 : TC_B_BYTES;     // one narrow tile (fp32 or bf16) of this CTA
+  static constexpr uint32_t SMEM_BYTES = R * TC_A_BYTES + Q * 2 * NT_BYTES + 1024 + 512;
+  static constexpr int W_FULL = 0, W_FREE = W_FULL + R, TA_FULL = W_FREE + R, TA_FREE = TA_FULL + TN_TA,
+                       B_FULL = TA_FREE + TN_TA, B_SPLIT = B_FULL + Q, B_FREE = B_SPLIT + Q, ACC_FULL = B_FREE + Q,
+                       ACC_EMPTY = ACC_FULL + 2, BARS = ACC_EMPTY + 2;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(BARS * 8 + 8 <= 512, "barrier area");
+};
 constexpr int TN_THREADS = 352;   // 4 splitter + 4 epilogue warps, W producer, MMA, narrow-operand producer
 #ifndef TN_GROUP_
 #define TN_GROUP_ 8
@@ -695,13 +766,18 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
 // WBF16: the wide operand W is stored in bf16 (the input features of the projection's weight gradient): raw tile 32 rows x 128
 // bf16 columns (256-byte rows), W_hi = the value itself (exact in tf32), no W_lo => 4 tf32 + 2 bf16 MMAs per chunk instead of
 // 4 + 4 and half the HBM bytes of the wide stream.
-template <bool WBF16>
+// TWO: CTA pairs (cluster of 2, cta_group::2).  Work unit = (PAIR of adjacent W tiles, slab): CTA rank r streams and splits
+// W tile 2p + r into its own tensor memory, loads and converts the narrow columns [64 r, 64 r + 64) only, and the leader's MMA
+// warp issues M = 256, N = 128 instructions for both.  Arrivals that the MMA warp waits for (TMEM operand written, narrow
+// half converted, accumulator drained) go to the LEADER's barriers from both CTAs; everything the MMAs release (TMEM
+// operand stages, narrow stages, accumulator stages) is a multicast commit to both CTAs.
+template <bool WBF16, bool TWO>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                   float* __restrict__ P /* [S][Wc][Nc] */, long long M, int Wc /* columns of the wide operand */,
                   int Nc /* columns of the narrow operand */, int bn /* narrow columns per unit: multiple of 32, <= 128 */,
-                  int w_tiles, int n_tiles, int S, long long rows_per_slab, long long* trace,
-                  const __grid_constant__ CUtensorMap tmNp /* the narrow operand again, unswizzled boxes */) {
+                  int w_tiles, int n_tiles, int S, long long rows_per_slab, long long* trace) {
+  using Cfg = TnCfg<TWO>;
   extern __shared__ uint8_t smem_raw[];
 #ifdef ERCG_TRACE
 #define TN_TRACE(role, idx, slot)                                                                                     \
@@ -712,47 +788,66 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #define TN_TRACE(role, idx, slot) do { } while (0)
 #endif
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* nring = smem + TN_R * TC_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(nring + TN_Q * 3 * TC_B_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TN_BARS);
+  uint8_t* nring = smem + Cfg::R * TC_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nring + Cfg::Q * 2 * Cfg::NT_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::BARS);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
+  // barriers the MMA warp waits on collect both CTAs' warps: in pair mode ONE arrival per warp (lane 0, after __syncwarp)
+  const uint32_t pair_arrivals = TWO ? 8u : 128u;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TN_R; ++i) { mbar_init(BAR(TN_W_FULL + i), 1); mbar_init(BAR(TN_W_FREE + i), 128); }
-    for (int i = 0; i < TN_TA; ++i) { mbar_init(BAR(TN_TA_FULL + i), 128); mbar_init(BAR(TN_TA_FREE + i), 1); }
-    for (int i = 0; i < TN_Q; ++i) {
-      mbar_init(BAR(TN_B_FULL + i), 1);
-      mbar_init(BAR(TN_B_SPLIT + i), 128);
-      mbar_init(BAR(TN_B_FREE + i), 1);
+    for (int i = 0; i < Cfg::R; ++i) { mbar_init(BAR(Cfg::W_FULL + i), 1); mbar_init(BAR(Cfg::W_FREE + i), 128); }
+    for (int i = 0; i < TN_TA; ++i) { mbar_init(BAR(Cfg::TA_FULL + i), pair_arrivals); mbar_init(BAR(Cfg::TA_FREE + i), 1); }
+    for (int i = 0; i < Cfg::Q; ++i) {
+      mbar_init(BAR(Cfg::B_FULL + i), 1);
+      mbar_init(BAR(Cfg::B_SPLIT + i), TWO ? 4u : 128u);     // pair mode: two conversion warps per CTA per chunk (teams)
+      mbar_init(BAR(Cfg::B_FREE + i), 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(TN_ACC_FULL + i), 1); mbar_init(BAR(TN_ACC_EMPTY + i), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Cfg::ACC_FULL + i), 1); mbar_init(BAR(Cfg::ACC_EMPTY + i), pair_arrivals); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();      // the peer's barriers are initialised before anything arrives there
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long units = (long long)w_tiles * n_tiles * S;
-  const int nb = bn / 32;                              // 32-wide boxes of the narrow operand per unit
-  const int mma_n = n_tiles == 1 ? (Nc + 15) / 16 * 16 : bn;   // UMMA N
+  const int w_units = TWO ? (w_tiles + 1) / 2 : w_tiles;   // W tiles, or pairs of W tiles
+  const long long units = (long long)w_units * n_tiles * S;
+  const int nb = TWO ? bn / 64 : bn / 32;              // 32-wide boxes of the narrow operand THIS CTA loads and converts
+  const int mma_n = TWO ? bn : (n_tiles == 1 ? (Nc + 15) / 16 * 16 : bn);   // UMMA N
+  const long long u_first = TWO ? blockIdx.x / 2 : blockIdx.x, u_step = TWO ? gridDim.x / 2 : gridDim.x;
+  // barriers of the leader as seen from this CTA (for the leader itself: its own)
+  auto LBAR = [&](int i) { return TWO ? mapa_cta(BAR(i), 0u) : BAR(i); };
+  auto arrive_leader = [&](uint32_t lbar) {
+    if (TWO) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lbar);
+    } else {
+      mbar_arrive(lbar);
+    }
+  };
   const uint32_t raw_base = smem_u32(smem), n_base = smem_u32(nring);
-  // per narrow stage: [fp32 tile, MN-major swizzled: B of the tf32 MMAs] [fp32 tile, plain boxes: source of the conversion]
+  // per narrow stage: [fp32 tile, MN-major swizzled: B of the tf32 MMAs AND the source of the bf16 conversion]
   //                   [bf16 tile, K-major 128-byte rows: bf16(hi) | bf16(lo) -- B of the bf16 MMAs, as in the NN kernel]
-  auto N_HI = [&](int q) { return n_base + q * 3 * TC_B_BYTES; };
-  auto N_PL = [&](int q) { return n_base + q * 3 * TC_B_BYTES + TC_B_BYTES; };
-  auto N_16 = [&](int q) { return n_base + q * 3 * TC_B_BYTES + 2 * TC_B_BYTES; };
+  auto N_HI = [&](int q) { return n_base + q * 2 * Cfg::NT_BYTES; };
+  auto N_16 = [&](int q) { return n_base + q * 2 * Cfg::NT_BYTES + Cfg::NT_BYTES; };
   auto TA_HI = [&](int s) { return tmem_base + 2 * TC_BN + (uint32_t)s * 64u; };
   // unit -> (W tile, narrow tile, slab); slab fastest so that concurrently running CTAs stream different rows
   auto decode = [&](long long u, int& w0, int& n0, long long& mbeg, long long& mend, int& slab) {
     slab = (int)(u % S);
     const long long kn = u / S;
-    w0 = (int)(kn / n_tiles) * TC_BM;
+    w0 = TWO ? ((int)(kn / n_tiles) * 2 + (int)rank) * TC_BM : (int)(kn / n_tiles) * TC_BM;
     n0 = (int)(kn % n_tiles) * bn;
     mbeg = (long long)slab * rows_per_slab;
     mend = mbeg + rows_per_slab < M ? mbeg + rows_per_slab : M;
@@ -762,47 +857,46 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   if (warp == 8) {
     if (lane == 0) {   // ---------------------------------------------------- wide-operand producer (HBM stream)
       uint32_t n = 0;
-      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      for (long long u = u_first; u < units; u += u_step) {
         int w0, n0, slab; long long mbeg, mend;
         decode(u, w0, n0, mbeg, mend, slab);
         for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
-          const int r = n % TN_R;
-          mbar_wait_relaxed(BAR(TN_W_FREE + r), ((n / TN_R) & 1) ^ 1);
+          const int r = n % Cfg::R;
+          mbar_wait_relaxed(BAR(Cfg::W_FREE + r), ((n / Cfg::R) & 1) ^ 1);
           TN_TRACE(0, n, 1);
-          mbar_expect_tx(BAR(TN_W_FULL + r), WBF16 ? TC_A_BYTES / 2 : TC_A_BYTES);
-          tma_load_2d(raw_base + r * TC_A_BYTES, &tmW, w0, (int)m, BAR(TN_W_FULL + r));
+          mbar_expect_tx(BAR(Cfg::W_FULL + r), WBF16 ? TC_A_BYTES / 2 : TC_A_BYTES);
+          tma_load_2d(raw_base + r * TC_A_BYTES, &tmW, w0, (int)m, BAR(Cfg::W_FULL + r));
         }
       }
     }
   } else if (warp == 10) {
     if (lane == 0) {   // ---------------------------------------------------- narrow-operand producer (mostly L2)
       uint32_t n = 0;
-      const uint32_t tx = 2u * (uint32_t)nb * 4096u;
-      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const uint32_t tx = (uint32_t)nb * 4096u;
+      for (long long u = u_first; u < units; u += u_step) {
         int w0, n0, slab; long long mbeg, mend;
         decode(u, w0, n0, mbeg, mend, slab);
         for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
-          const int q = n % TN_Q;
-          mbar_wait_relaxed(BAR(TN_B_FREE + q), ((n / TN_Q) & 1) ^ 1);
+          const int q = n % Cfg::Q;
+          mbar_wait_relaxed(BAR(Cfg::B_FREE + q), ((n / Cfg::Q) & 1) ^ 1);
           TN_TRACE(4, n, 1);
-          mbar_expect_tx(BAR(TN_B_FULL + q), tx);
-          for (int i = 0; i < nb; ++i) {
-            tma_load_2d(N_HI(q) + i * 4096, &tmN, n0 + 32 * i, (int)m, BAR(TN_B_FULL + q));
-            tma_load_2d(N_PL(q) + i * 4096, &tmNp, n0 + 32 * i, (int)m, BAR(TN_B_FULL + q));
-          }
+          mbar_expect_tx(BAR(Cfg::B_FULL + q), tx);
+          for (int i = 0; i < nb; ++i)
+            tma_load_2d(N_HI(q) + i * 4096, &tmN, n0 + (int)rank * (bn / 2) + 32 * i, (int)m, BAR(Cfg::B_FULL + q));
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 9 && rank == 0) {
     // ------------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane)
+    constexpr uint32_t MMA_M = TWO ? 2 * TC_BM : TC_BM;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) /* B is MN-major */ |
-                           ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                           ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+    const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
     const uint64_t desc_k = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
     uint32_t n = 0;
     int a = 0;
     uint32_t aph = 0;
-    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    for (long long u = u_first; u < units; u += u_step) {
       int w0, n0, slab; long long mbeg, mend;
       decode(u, w0, n0, mbeg, mend, slab);
       const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
@@ -810,11 +904,12 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int in_group = (int)(kc % TN_GROUP);
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
         if (lane == 0) TN_TRACE(2, n, 0);
-        if (in_group == 0) mbar_wait(BAR(TN_ACC_EMPTY + a), aph ^ 1);
-        const int s = n % TN_TA, q = n % TN_Q;
-        mbar_wait(BAR(TN_TA_FULL + s), (n / TN_TA) & 1);
+        if (in_group == 0) { if (TWO) mbar_wait_cluster(BAR(Cfg::ACC_EMPTY + a), aph ^ 1); else mbar_wait(BAR(Cfg::ACC_EMPTY + a), aph ^ 1); }
+        if (lane == 0) TN_TRACE(2, n, 1);
+        const int s = n % TN_TA, q = n % Cfg::Q;
+        if (TWO) mbar_wait_cluster(BAR(Cfg::TA_FULL + s), (n / TN_TA) & 1); else mbar_wait(BAR(Cfg::TA_FULL + s), (n / TN_TA) & 1);
         if (lane == 0) TN_TRACE(2, n, 2);
-        mbar_wait(BAR(TN_B_SPLIT + q), (n / TN_Q) & 1);
+        if (TWO) mbar_wait_cluster(BAR(Cfg::B_SPLIT + q), (n / Cfg::Q) & 1); else mbar_wait(BAR(Cfg::B_SPLIT + q), (n / Cfg::Q) & 1);
         if (lane == 0) TN_TRACE(2, n, 3);
         tc_fence_after();
         const uint32_t ah0 = TA_HI(s);
@@ -824,16 +919,29 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (elect_one()) {
           // W_hi * N_hi in tf32 (the fp32 tile is read with tf32 truncation = hi); the two correction terms in bf16
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks)
-            tc_mma_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 64), idesc, (in_group | ks) ? 1u : 0u);   // 8 rows = 1024 B
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {   // 8 rows = 1024 B
+            if (TWO) tc_mma2_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 64), idesc, (in_group | ks) ? 1u : 0u);
+            else tc_mma_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 64), idesc, (in_group | ks) ? 1u : 0u);
+          }
 #pragma unroll
           for (int j = 0; j < TC_BK / 16; ++j) {
-            if (!WBF16) tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);   // bf16(W_lo) * bf16(N_hi)
-            tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);    // bf16(W_hi) * bf16(N_lo)
+            if (TWO) {
+              if (!WBF16) tc_mma2_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);
+              tc_mma2_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);
+            } else {
+              if (!WBF16) tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);   // bf16(W_lo) * bf16(N_hi)
+              tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);    // bf16(W_hi) * bf16(N_lo)
+            }
           }
-          tc_commit(BAR(TN_TA_FREE + s));
-          tc_commit(BAR(TN_B_FREE + q));
-          if (last) tc_commit(BAR(TN_ACC_FULL + a));
+          if (TWO) {
+            tc_commit2(BAR(Cfg::TA_FREE + s));
+            tc_commit2(BAR(Cfg::B_FREE + q));
+            if (last) tc_commit2(BAR(Cfg::ACC_FULL + a));
+          } else {
+            tc_commit(BAR(Cfg::TA_FREE + s));
+            tc_commit(BAR(Cfg::B_FREE + q));
+            if (last) tc_commit(BAR(Cfg::ACC_FULL + a));
+          }
         }
         __syncwarp();
         if (last) { if (++a == 2) { a = 0; aph ^= 1; } }
@@ -844,13 +952,14 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int tid = threadIdx.x;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     uint32_t n = 0;
-    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    for (long long u = u_first; u < units; u += u_step) {
       int w0, n0, slab; long long mbeg, mend;
       decode(u, w0, n0, mbeg, mend, slab);
       for (long long m = mbeg; m < mend; m += TC_BK, ++n) {
-        const int r = n % TN_R, s = n % TN_TA;
+        const int r = n % Cfg::R, s = n % TN_TA;
         // raw [32 rows][128 columns] -> this thread's column, rows along the TMEM columns
-        mbar_wait(BAR(TN_W_FULL + r), (n / TN_R) & 1);
+        if (tid == 0) TN_TRACE(1, n, 0);
+        mbar_wait(BAR(Cfg::W_FULL + r), (n / Cfg::R) & 1);
         if (tid == 0) TN_TRACE(1, n, 1);
         const uint32_t src = raw_base + r * TC_A_BYTES + (WBF16 ? tid * 2 : tid * 4);
         uint32_t hi[32], p16[32];                        // tf32 W_hi | bf16 pairs along the rows: [0,16) W_hi, [16,32) W_lo
@@ -873,15 +982,15 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           p16[16 + (j >> 1)] = pack_bf16x2(__uint_as_float(l0), __uint_as_float(l1));
         }
         }
-        mbar_wait(BAR(TN_TA_FREE + s), ((n / TN_TA) & 1) ^ 1);
+        mbar_wait(BAR(Cfg::TA_FREE + s), ((n / TN_TA) & 1) ^ 1);
         if (tid == 0) TN_TRACE(1, n, 2);
         tc_fence_after();
         tc_st32(TA_HI(s) + lane_addr, hi);
         tc_st32(TA_HI(s) + 32 + lane_addr, p16);
         tc_wait_st();
-        mbar_arrive(BAR(TN_W_FREE + r));                 // after the TMEM stores: every loaded register has been consumed
+        mbar_arrive(BAR(Cfg::W_FREE + r));                 // after the TMEM stores: every loaded register has been consumed
         tc_fence_before();
-        mbar_arrive(BAR(TN_TA_FULL + s));
+        arrive_leader(LBAR(Cfg::TA_FULL + s));
         if (tid == 0) TN_TRACE(1, n, 3);
       }
     }
@@ -894,7 +1003,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int ew = warp & 3;
     const int te = threadIdx.x - 128;                  // 0..127
     uint32_t n = 0;                                    // chunk counter (narrow-operand ring)
-    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    for (long long u = u_first; u < units; u += u_step) {
       int w0, n0, slab; long long mbeg, mend;
       decode(u, w0, n0, mbeg, mend, slab);
       const long long chunks = (mend - mbeg + TC_BK - 1) / TC_BK;
@@ -903,7 +1012,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
       for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
       auto drain = [&]() {
-        mbar_wait(BAR(TN_ACC_FULL + a), aph);
+        mbar_wait(BAR(Cfg::ACC_FULL + a), aph);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < TC_BN; c += 32) {
@@ -916,28 +1025,62 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           }
         }
         tc_fence_before();
-        mbar_arrive(BAR(TN_ACC_EMPTY + a));
+        arrive_leader(LBAR(Cfg::ACC_EMPTY + a));
         if (++a == 2) { a = 0; aph ^= 1; }
       };
       for (long long g = 0; g < n_groups; ++g) {
         const long long kc_end = (g + 1) * TN_GROUP < chunks ? (g + 1) * TN_GROUP : chunks;
         bool pending = g > 0;                          // group g-1 still has to be drained (its MMAs retired long ago)
         for (long long kc = g * TN_GROUP; kc < kc_end; ++kc, ++n) {
-          if (pending && kc - g * TN_GROUP == TN_DRAIN_AT) { drain(); pending = false; }
-          const int q = n % TN_Q;
-          mbar_wait(BAR(TN_B_FULL + q), (n / TN_Q) & 1);
+          // pair mode: the conversion loop (barrier wait -> loads -> split -> stores -> proxy fence -> remote arrive, ~950 clk
+          // per chunk for one warp however little it converts: profiles/r02o_tn_pair_trace.txt) was the slowest stage of the
+          // pipeline, so the four warps form two TEAMS that take alternate chunks (thread = column, 64 columns per CTA)
+          // (every warp still waits on EVERY chunk's B_FULL, in order: a parity wait that skipped a phase could mistake the
+          // phase before last for the one it wants while a slow TMA of the skipped chunk is still in flight)
+          const int q = n % Cfg::Q;
+          if (TWO && ((int)(kc & 1) != (ew >> 1))) { mbar_wait(BAR(Cfg::B_FULL + q), (n / Cfg::Q) & 1); continue; }
+          if (te == 0) TN_TRACE(3, n, 0);
+          if (pending && kc - g * TN_GROUP >= TN_DRAIN_AT) { drain(); pending = false; if (te == 0) TN_TRACE(3, n, 3); }
+          mbar_wait(BAR(Cfg::B_FULL + q), (n / Cfg::Q) & 1);
           if (te == 0) TN_TRACE(3, n, 1);
-          // thread te = column te of the narrow tile: its 32 rows come from the plain boxes (conflict-free 4-byte reads),
-          // are split hi / lo and go, as bf16 pairs along k, into row te of the K-major bf16 tile (128-byte rows, 16-byte
-          // chunks XOR-swizzled with the row like a 128-byte-swizzle TMA box: chunks 0-3 = bf16(hi), 4-7 = bf16(lo))
+          // thread te = column te of the narrow tile: its 32 rows are read from the SAME swizzled MN-major tile the tf32 MMAs
+          // use (layout type 1 = Swizzle<2,5,2>: the 32-byte atom index of a 128-byte row is XORed with the row index mod 4;
+          // a warp reads one whole row per load, so the permutation inside the row keeps the 4-byte reads conflict-free --
+          // a second, unswizzled TMA copy of the tile used to be the source: it doubled the L2 -> SM traffic of this operand,
+          // and the kernel is bound by L2 slice throughput), are split hi / lo and go, as bf16 pairs along k, into row te
+          // of the K-major bf16 tile (128-byte rows, 16-byte chunks XOR-swizzled with the row like a 128-byte-swizzle TMA
+          // box: chunks 0-3 = bf16(hi), 4-7 = bf16(lo))
+          if (TWO) {
+            const int col = te & 63;                     // this team's 64 threads <-> the 64 columns of this CTA's half
+            if (col < nb * 32) {
+              const uint32_t src = N_HI(q) + (uint32_t)(col >> 5) * 4096u;
+              const uint32_t cb = (uint32_t)(col & 31) * 4u;
+              uint32_t p[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                uint32_t h0, h1, l0, l1;
+                split_tf32(lds1(src + j * 128 + (cb ^ (uint32_t)((j & 3) << 5))), h0, l0);
+                split_tf32(lds1(src + (j + 1) * 128 + (cb ^ (uint32_t)(((j + 1) & 3) << 5))), h1, l1);
+                p[j >> 1] = pack_bf16x2(__uint_as_float(h0), __uint_as_float(h1));
+                p[16 + (j >> 1)] = pack_bf16x2(__uint_as_float(l0), __uint_as_float(l1));
+              }
+              const uint32_t dst = N_16(q) + (uint32_t)col * 128u;
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                sts4(dst + (uint32_t)((c ^ (col & 7)) << 4),
+                     make_float4(__uint_as_float(p[4 * c]), __uint_as_float(p[4 * c + 1]), __uint_as_float(p[4 * c + 2]),
+                                 __uint_as_float(p[4 * c + 3])));
+            }
+          } else
           if (te < nb * 32) {
-            const uint32_t src = N_PL(q) + (uint32_t)(te >> 5) * 4096u + (uint32_t)(te & 31) * 4u;
+            const uint32_t src = N_HI(q) + (uint32_t)(te >> 5) * 4096u;
+            const uint32_t cb = (uint32_t)(te & 31) * 4u;
             uint32_t p[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               uint32_t h0, h1, l0, l1;
-              split_tf32(lds1(src + j * 128), h0, l0);
-              split_tf32(lds1(src + (j + 1) * 128), h1, l1);
+              split_tf32(lds1(src + j * 128 + (cb ^ (uint32_t)((j & 3) << 5))), h0, l0);
+              split_tf32(lds1(src + (j + 1) * 128 + (cb ^ (uint32_t)(((j + 1) & 3) << 5))), h1, l1);
               p[j >> 1] = pack_bf16x2(__uint_as_float(h0), __uint_as_float(h1));
               p[16 + (j >> 1)] = pack_bf16x2(__uint_as_float(l0), __uint_as_float(l1));
             }
@@ -949,7 +1092,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                                __uint_as_float(p[4 * c + 3])));
           }
           fence_proxy_async();
-          mbar_arrive(BAR(TN_B_SPLIT + q));
+          arrive_leader(LBAR(Cfg::B_SPLIT + q));
           if (te == 0) TN_TRACE(3, n, 2);
         }
         if (pending) drain();                          // (group shorter than TN_DRAIN_AT chunks)
@@ -965,10 +1108,11 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -984,15 +1128,56 @@ __global__ void tn_reduce_kernel(const float* __restrict__ P, long long stride, 
   C[(long long)r * ldc + c] = s;
 }
 
-// wide operand = the one with more columns; its 128-column tiles x row slabs are the work units
-static void tn_tc_plan(int64_t M, int K1, int N1, bool& swap, int& w_tiles, int& n_tiles, int& bn, int& S, long long& rps) {
+// wide operand = the one with more columns; its 128-column tiles (or PAIRS of tiles, `two`) x row slabs are the work units
+static bool tn_pairs_enabled() {
+  static const bool on = [] { const char* e = getenv("ERCG_TN_PAIRS"); return !e || atoi(e) != 0; }();   // read once
+  return on;
+}
+// CTA pairs that can be resident at once (1 CTA / SM, both SMs of a TPC): per-device, queried once.  A grid with more
+// clusters than this runs in two waves.
+static int tn_pair_capacity() {
+  static std::atomic<int> cache[kMaxDevices];
+  const int d = current_device();
+  if (d >= 0 && d < kMaxDevices) {
+    const int c = cache[d].load(std::memory_order_acquire);
+    if (c != 0) return c > 0 ? c : 0;
+  }
+  int n = 0;
+  if (cudaFuncSetAttribute(gemm_tc_tn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TnCfg<true>::SMEM_BYTES) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs / 2 * 2, 1, 1);
+    cfg.blockDim = dim3(TN_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = TnCfg<true>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_tn_kernel<false, true>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  } else {
+    cudaGetLastError();
+  }
+  if (const char* e = getenv("ERCG_TN_PAIR_CAP")) n = atoi(e);      // experiments only
+  if (d >= 0 && d < kMaxDevices) cache[d].store(n > 0 ? n : -1, std::memory_order_release);
+  return n;
+}
+extern "C" __attribute__((visibility("default"))) int ercg_debug_tn_pair_capacity() { return tn_pair_capacity(); }
+
+static void tn_tc_plan(int64_t M, int K1, int N1, bool& swap, int& w_tiles, int& n_tiles, int& bn, int& S, long long& rps,
+                       bool& two) {
   swap = N1 > K1;
   const int Wc = swap ? N1 : K1, Nc = swap ? K1 : N1;
   w_tiles = (Wc + TC_BM - 1) / TC_BM;
+  const int cap = tn_pairs_enabled() && w_tiles % 2 == 0 ? tn_pair_capacity() : 0;
+  two = cap > 0 && cap >= w_tiles / 2 * ((Nc + 127) / 128);         // CTA pairs need an even number of W tiles (no idle half pair)
+  const int gran = two ? 64 : 32;                        // each CTA of a pair loads whole 32-column boxes of its half
   n_tiles = (Nc + 127) / 128;
-  bn = ((Nc + n_tiles - 1) / n_tiles + 31) / 32 * 32;
+  bn = ((Nc + n_tiles - 1) / n_tiles + gran - 1) / gran * gran;
   n_tiles = (Nc + bn - 1) / bn;
-  S = kNumSMs / (w_tiles * n_tiles);
+  const int w_units = two ? w_tiles / 2 : w_tiles;
+  S = (two ? cap : kNumSMs) / (w_units * n_tiles);
   if (S < 1) S = 1;
   const long long quantum = (long long)TC_BK * TN_GROUP;
   long long maxS = (M + quantum - 1) / quantum;
@@ -1000,6 +1185,45 @@ static void tn_tc_plan(int64_t M, int K1, int N1, bool& swap, int& w_tiles, int&
   if (S > maxS) S = (int)maxS;
   rps = ((M + S - 1) / S + quantum - 1) / quantum * quantum;
   S = (int)((M + rps - 1) / rps);
+}
+
+// launch of either form; pairs = clusters of two CTAs on one TPC
+template <bool WBF16>
+static int tn_launch(bool two, const CUtensorMap& tmW, const CUtensorMap& tmN, float* P, long long M, int Wc, int Nc, int bn,
+                     int wt, int nt, int S, long long rps, long long* tr, cudaStream_t st) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
+    if (cudaFuncSetAttribute(gemm_tc_tn_kernel<WBF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TnCfg<false>::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_tn_kernel<WBF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TnCfg<true>::SMEM_BYTES) != cudaSuccess)
+      return ERCG_ECUDA;
+    attr_set.mark();
+  }
+  if (!two) {
+    const long long units = (long long)wt * nt * S;
+    const int grid = (int)(units < kNumSMs ? units : kNumSMs);
+    gemm_tc_tn_kernel<WBF16, false><<<grid, TN_THREADS, TnCfg<false>::SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr);
+    return finish_launch();
+  }
+  const long long units = (long long)(wt / 2) * nt * S;
+  const int cap = tn_pair_capacity();
+  const int pairs = (int)(units < cap ? units : cap);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(TN_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = TnCfg<true>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, gemm_tc_tn_kernel<WBF16, true>, tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr) != cudaSuccess) {
+    cudaGetLastError();
+    return ERCG_ECUDA;
+  }
+  return finish_launch();
 }
 
 // B[K,N] (row-major, ldb) -> Bt_hi [N, Kp] fp32 (K-major, tf32-rounded) and B16 [N, Kc, 64] bf16 (Kc = chunks of 32 k):
@@ -1207,8 +1431,8 @@ extern "C" int ercg_gemm_nn_tc_trace(long long* host_out /* [5][160][4] clock64 
 
 extern "C" size_t ercg_gemm_tn_tc_workspace_bytes(int64_t M, int K1, int N1) {
   if (M <= 0 || K1 <= 0 || N1 <= 0) return 0;
-  bool swap; int wt, nt, bn, S; long long rps;
-  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps);
+  bool swap, two; int wt, nt, bn, S; long long rps;
+  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps, two);
   return (size_t)S * K1 * N1 * sizeof(float) + 256;
 }
 
@@ -1237,26 +1461,17 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
   if (M < 1 || K1 < 1 || N1 < 1 || !A || !B || !C || lda < K1 || ldb < N1 || ldc < N1) return ERCG_EINVAL;
   if (!ercg_gemm_tn_tc_supported(A, lda, B, ldb, M, K1, N1)) return ERCG_EALIGN;
   if (workspace_bytes < ercg_gemm_tn_tc_workspace_bytes(M, K1, N1) || !workspace) return ERCG_EWORKSPACE;
-  bool swap; int wt, nt, bn, S; long long rps;
-  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps);
+  bool swap, two; int wt, nt, bn, S; long long rps;
+  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps, two);
   float* P = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   const float* W = swap ? B : A;
   const float* Nw = swap ? A : B;
   const long long ldw = swap ? ldb : lda, ldn = swap ? lda : ldb;
   const int Wc = swap ? N1 : K1, Nc = swap ? K1 : N1;
-  CUtensorMap tmW, tmN, tmNp;
+  CUtensorMap tmW, tmN;
   if (!make_map_plain(&tmW, W, M, Wc, ldw) ||
-      !make_map(&tmN, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
-      !make_map(&tmNp, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return ERCG_ECUDA;
-  static DeviceOnce attr_set;
-  if (attr_set.need()) {
-    if (cudaFuncSetAttribute(gemm_tc_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
-      return ERCG_ECUDA;
-    attr_set.mark();
-  }
+      !make_map(&tmN, Nw, M, Nc, ldn, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ERCG_ECUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long units = (long long)wt * nt * S;
-  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
   static int tn_trace_on = -1;
   if (tn_trace_on < 0) {
     const char* e = getenv("ERCG_TC_TRACE");
@@ -1265,8 +1480,7 @@ extern "C" int ercg_gemm_tn_tc(const float* A, int64_t lda, const float* B, int6
   }
   long long* tr = (tn_trace_on & 2) ? trace_buf : nullptr;          // ERCG_TC_TRACE=2: trace the TN kernel instead of the NN one
   if (tr) cudaMemsetAsync(tr, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
-  gemm_tc_tn_kernel<false><<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr, tmNp);
-  int rc = finish_launch();
+  int rc = tn_launch<false>(two, tmW, tmN, P, M, Wc, Nc, bn, wt, nt, S, rps, tr, st);
   if (rc) return rc;
   const long long tot = (long long)K1 * N1;
   tn_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tot, S, C, ldc, K1, N1, swap ? 1 : 0);
@@ -1350,25 +1564,15 @@ extern "C" int ercg_gemm_tn_tc_bf16a(const void* A_bf16, int64_t lda, const floa
   if (N1 > K1 || N1 > 128) return ERCG_EINVAL;                    // the bf16 operand must be the wide one (K1 >= N1), one narrow tile
   if (!ercg_gemm_bf16a_supported(A_bf16, lda, M, K1) || (ldb & 3) || !aligned16(B)) return ERCG_EALIGN;
   if (workspace_bytes < ercg_gemm_tn_tc_workspace_bytes(M, K1, N1) || !workspace) return ERCG_EWORKSPACE;
-  bool swap; int wt, nt, bn, S; long long rps;
-  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps);
+  bool swap, two; int wt, nt, bn, S; long long rps;
+  tn_tc_plan(M, K1, N1, swap, wt, nt, bn, S, rps, two);
   if (swap) return ERCG_EINVAL;
   float* P = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-  CUtensorMap tmW, tmN, tmNp;
+  CUtensorMap tmW, tmN;
   if (!make_map_bf16_rows(&tmW, A_bf16, M, K1, lda, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return ERCG_ECUDA;
-  if (!make_map(&tmN, B, M, N1, ldb, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
-      !make_map(&tmNp, B, M, N1, ldb, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return ERCG_ECUDA;
-  static DeviceOnce attr_set;
-  if (attr_set.need()) {
-    if (cudaFuncSetAttribute(gemm_tc_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES) != cudaSuccess)
-      return ERCG_ECUDA;
-    attr_set.mark();
-  }
+  if (!make_map(&tmN, B, M, N1, ldb, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ERCG_ECUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long units = (long long)wt * nt * S;
-  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
-  gemm_tc_tn_kernel<true><<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(tmW, tmN, P, M, K1, N1, bn, wt, nt, S, rps, nullptr, tmNp);
-  int rc = finish_launch();
+  int rc = tn_launch<true>(two, tmW, tmN, P, M, K1, N1, bn, wt, nt, S, rps, nullptr, st);
   if (rc) return rc;
   const long long tot = (long long)K1 * N1;
   tn_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tot, S, C, ldc, K1, N1, 0);
