@@ -185,26 +185,44 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
 #ifndef TC_Q_
 #define TC_Q_ 3
 #endif
-constexpr int TC_R = TC_R_;       // raw A stages
-constexpr int TC_Q = TC_Q_;       // B stages
 constexpr int TC_TA = 4;          // TMEM A stages
 constexpr uint32_t TC_TMEM_A0 = 2 * TC_BN;                       // first A column
+constexpr int TC_SLABS = 4;                                     // 32-column slabs of a 128-column tile
 constexpr uint32_t TC_SLAB_BYTES = 32 * 128;                     // epilogue staging slab: 32 rows x 32 columns, 128-byte swizzle
-constexpr int TC_SLABS = 4;                                     // staging slabs per epilogue warp: the whole 128-column tile
-constexpr uint32_t TC_STAGE_BYTES = 4 * TC_SLABS * TC_SLAB_BYTES;   // 4 warps x 4 slabs = 64 KB
-constexpr uint32_t TC_SMEM_BYTES = TC_R * TC_A_BYTES + TC_Q * 2 * TC_B_BYTES + TC_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int TC_THREADS = 352;   // 4 splitter + 4 epilogue warps, A producer, MMA, B producer
-
-// barrier indices
-constexpr int BAR_A_FULL = 0;                    // [TC_R]  TMA bytes of the raw A tile landed
-constexpr int BAR_R_FREE = BAR_A_FULL + TC_R;    // [TC_R]  splitter has read the raw tile (128 arrivals)
-constexpr int BAR_TA_FULL = BAR_R_FREE + TC_R;   // [TC_TA] A_hi / A_lo written to TMEM (128 arrivals)
-constexpr int BAR_TA_FREE = BAR_TA_FULL + TC_TA; // [TC_TA] MMAs that read this TMEM A stage retired
-constexpr int BAR_B_FULL = BAR_TA_FREE + TC_TA;  // [TC_Q]  TMA bytes of B_hi/B_lo landed
-constexpr int BAR_Q_FREE = BAR_B_FULL + TC_Q;    // [TC_Q]  MMAs that read this B stage retired
-constexpr int BAR_ACC_FULL = BAR_Q_FREE + TC_Q;  // [2]
-constexpr int BAR_ACC_EMPTY = BAR_ACC_FULL + 2;  // [2]     (128 arrivals)
-constexpr int BAR_COUNT = BAR_ACC_EMPTY + 2;
+#ifndef TC_R2_
+#define TC_R2_ 6
+#endif
+#ifndef TC_Q2_
+#define TC_Q2_ 6
+#endif
+// Ring geometry and barrier indices.  Single CTA: R raw A stages of 16 KB, Q B stages of (B_hi 16 KB + B16 16 KB), staging
+// for all four 32-column slabs of a tile per epilogue warp (64 KB).  CTA pair (cta_group::2, one N tile, long K): each CTA
+// holds HALF of the B tile (8 + 8 KB per stage) and stages one slab at a time (16 KB), so both rings are deeper in the same
+// shared memory -- the pipeline trace of the single-CTA kernel on K = 1443 (profiles/r02o_nn_trace_single_cta.txt) has the
+// B ring as the critical loop: stage freed by the MMAs -> TMA from L2 (~2800 clk under load) -> MMAs (~500 clk) around a
+// 3-stage ring = ~1100 clk per chunk, with the tensor pipe busy 42 % of the time.
+template <bool TWO>
+struct NnCfg {
+  static constexpr int R = TWO ? TC_R2_ : TC_R_;
+  static constexpr int Q = TWO ? TC_Q2_ : TC_Q_;
+  static constexpr uint32_t BT_BYTES = TWO ? TC_B_BYTES / 2 : TC_B_BYTES;       // one B tile (fp32 hi, or bf16 pairs) of this CTA
+  static constexpr int SLABS = TWO ? 1 : 4;                                     // staging slabs per epilogue warp
+  static constexpr uint32_t STAGE_BYTES = 4 * SLABS * TC_SLAB_BYTES;
+  static constexpr uint32_t SMEM_BYTES = R * TC_A_BYTES + Q * 2 * BT_BYTES + STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int A_FULL = 0;                   // [R]  TMA bytes of the raw A tile landed
+  static constexpr int R_FREE = A_FULL + R;          // [R]  splitter has read the raw tile (128 arrivals)
+  static constexpr int TA_FULL = R_FREE + R;         // [TC_TA] A_hi / A_lo written to TMEM
+  static constexpr int TA_FREE = TA_FULL + TC_TA;    // [TC_TA] MMAs that read this TMEM A stage retired
+  static constexpr int B_FULL = TA_FREE + TC_TA;     // [Q]  TMA bytes of B_hi/B_lo landed (pair: both halves, on the leader)
+  static constexpr int Q_FREE = B_FULL + Q;          // [Q]  MMAs that read this B stage retired
+  static constexpr int ACC_FULL = Q_FREE + Q;        // [2]
+  static constexpr int ACC_EMPTY = ACC_FULL + 2;     // [2]
+  static constexpr int COUNT = ACC_EMPTY + 2;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(COUNT * 8 + 8 <= 512, "barrier area");
+};
+constexpr uint32_t TC_SMEM_BYTES = NnCfg<false>::SMEM_BYTES;
 
 __device__ __forceinline__ float4 lds4(uint32_t saddr) {
   float4 r;
@@ -301,6 +319,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     if ((spin & 0xffffu) == 0xffffu && mbar_timed_out(t0)) __trap();
   }
 }
+// TMA load of this CTA's part of a pair's tile; the bytes complete on `cluster_bar` (the leader's barrier, mapa'd)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -363,63 +387,91 @@ __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, lon
 // "two k-elements per 32-bit column" packing the bf16 MMAs read -- straight into TMEM; there is no A_lo, and B comes as
 // bf16_rn(B) | bf16_rn(B - bf16_rn(B)) (16 significant bits of every weight): 4 bf16 MMAs per 32-k chunk instead of 4 tf32 +
 // 4 bf16, and no fp32 B tile.  The arithmetic is exact products of bf16 A with 16-bit B, accumulated in fp32.
-template <int ACT, bool SMALLK, bool ABF16>
+// TWO: CTA pairs (cluster of 2, cta_group::2) for one N tile and a long K: CTA rank r owns M tile 2p + r (its A rows go to
+// its own tensor memory, its accumulator rows stay there), loads rows [bn/2 r, bn/2 r + bn/2) of the B tile, and the
+// leader's MMA warp issues M = 256 instructions for both.  The peer's TMA completes its bytes on the LEADER's B_FULL
+// barrier; splitter and epilogue warps of both CTAs arrive (one lane per warp) on the leader's TA_FULL / ACC_EMPTY; what
+// the MMAs release is a multicast commit to both CTAs.
+template <int ACT, bool SMALLK, bool ABF16, bool TWO = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                   const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
                   float* __restrict__ C, long long ldc, long long M, int N,
                   int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, TcEpilogue ep,
                   float* __restrict__ colsum_partial /* [gridDim.x][4][128] column sums of C (N <= 128 only), or NULL */) {
+  using Cfg = NnCfg<TWO>;
+  static_assert(!TWO || (!SMALLK && !ABF16), "pair mode: long K, fp32 features");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bring = smem + TC_R * TC_A_BYTES;
-  uint8_t* stage_all = bring + TC_Q * 2 * TC_B_BYTES;          // 1024-byte aligned (every ring is a multiple of 1 KB)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + TC_STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+  uint8_t* bring = smem + Cfg::R * TC_A_BYTES;
+  uint8_t* stage_all = bring + Cfg::Q * 2 * Cfg::BT_BYTES;          // 1024-byte aligned (every ring is a multiple of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + Cfg::STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::COUNT);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
+  const uint32_t pair_arrivals = TWO ? 8u : 128u;          // pair mode: one arrival per warp of both CTAs
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_R; ++i) { mbar_init(BAR(BAR_A_FULL + i), 1); mbar_init(BAR(BAR_R_FREE + i), 128); }
-    for (int i = 0; i < TC_TA; ++i) { mbar_init(BAR(BAR_TA_FULL + i), 128); mbar_init(BAR(BAR_TA_FREE + i), 1); }
-    for (int i = 0; i < TC_Q; ++i) { mbar_init(BAR(BAR_B_FULL + i), 1); mbar_init(BAR(BAR_Q_FREE + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_ACC_FULL + i), 1); mbar_init(BAR(BAR_ACC_EMPTY + i), 128); }
+    for (int i = 0; i < Cfg::R; ++i) { mbar_init(BAR(Cfg::A_FULL + i), 1); mbar_init(BAR(Cfg::R_FREE + i), 128); }
+    for (int i = 0; i < TC_TA; ++i) { mbar_init(BAR(Cfg::TA_FULL + i), pair_arrivals); mbar_init(BAR(Cfg::TA_FREE + i), 1); }
+    for (int i = 0; i < Cfg::Q; ++i) { mbar_init(BAR(Cfg::B_FULL + i), 1); mbar_init(BAR(Cfg::Q_FREE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Cfg::ACC_FULL + i), 1); mbar_init(BAR(Cfg::ACC_EMPTY + i), pair_arrivals); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {   // all 512 TMEM columns: 2 accumulator stages x 128 + TC_TA A stages x 64
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  auto LBAR = [&](int i) { return TWO ? mapa_cta(BAR(i), 0u) : BAR(i); };
+  auto arrive_leader = [&](uint32_t lbar) {
+    if (TWO) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lbar);
+    } else {
+      mbar_arrive(lbar);
+    }
+  };
 
-  const long long m_tiles = (M + TC_BM - 1) / TC_BM;
+  // tile walk: single CTA t = blockIdx.x, += gridDim.x; pair p = blockIdx.x / 2, += gridDim.x / 2 and t = 2 p + rank (a tile
+  // past the end is all zero-filled loads and clipped stores)
+  const long long m_tiles_real = (M + TC_BM - 1) / TC_BM;
+  const long long m_tiles = TWO ? (m_tiles_real + 1) / 2 : m_tiles_real;
+  const long long t_first = TWO ? blockIdx.x / 2 : blockIdx.x, t_step = TWO ? gridDim.x / 2 : gridDim.x;
+  auto TILE = [&](long long t) { return TWO ? 2 * t + (long long)rank : t; };
   const int n_tiles = (N + bn - 1) / bn;
   const int k_chunks = (K + TC_BK - 1) / TC_BK;
   const bool resident = n_tiles > 1 && k_chunks <= TC_TA;     // A stays in TMEM across the N tiles of an M tile
   const int a_reps = resident ? 1 : n_tiles;                  // A chunk loads per M tile = a_reps * k_chunks
   const uint32_t raw_base = smem_u32(smem), b_base = smem_u32(bring);
-  auto B_HI = [&](int q) { return b_base + q * 2 * TC_B_BYTES; };
-  auto B_LO = [&](int q) { return b_base + q * 2 * TC_B_BYTES + TC_B_BYTES; };
+  auto B_HI = [&](int q) { return b_base + q * 2 * Cfg::BT_BYTES; };
+  auto B_LO = [&](int q) { return b_base + q * 2 * Cfg::BT_BYTES + Cfg::BT_BYTES; };
   auto TA_HI = [&](int s) { return tmem_base + TC_TMEM_A0 + (uint32_t)s * 64u; };
 
   if (warp == 8) {
     // ------------------------------------------------------------------ A producer (HBM stream)
     if (lane == 0) {
       uint32_t n = 0;
-      for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-        const int m0 = (int)t * TC_BM;
+      for (long long t = t_first; t < m_tiles; t += t_step) {
+        const int m0 = (int)TILE(t) * TC_BM;
         for (int rep = 0; rep < a_reps; ++rep)
           for (int kc = 0; kc < k_chunks; ++kc, ++n) {
-            const int r = n % TC_R;
+            const int r = n % Cfg::R;
             TC_TRACE(0, n, 0);
-            mbar_wait_relaxed(BAR(BAR_R_FREE + r), ((n / TC_R) & 1) ^ 1);
+            mbar_wait_relaxed(BAR(Cfg::R_FREE + r), ((n / Cfg::R) & 1) ^ 1);
             TC_TRACE(0, n, 1);
-            mbar_expect_tx(BAR(BAR_A_FULL + r), ABF16 ? TC_A_BYTES / 2 : TC_A_BYTES);
-            tma_load_2d(raw_base + r * TC_A_BYTES, &tmA, kc * TC_BK, m0, BAR(BAR_A_FULL + r));
+            mbar_expect_tx(BAR(Cfg::A_FULL + r), ABF16 ? TC_A_BYTES / 2 : TC_A_BYTES);
+            tma_load_2d(raw_base + r * TC_A_BYTES, &tmA, kc * TC_BK, m0, BAR(Cfg::A_FULL + r));
           }
       }
     }
@@ -428,20 +480,28 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       uint32_t n = 0;
       const uint32_t tx = 2u * (uint32_t)bn * TC_BK * 4u;
-      for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x)
+      for (long long t = t_first; t < m_tiles; t += t_step)
         for (int nt = 0; nt < n_tiles; ++nt)
           for (int kc = 0; kc < k_chunks; ++kc, ++n) {
-            const int q = n % TC_Q;
+            const int q = n % Cfg::Q;
             TC_TRACE(4, n, 0);
-            mbar_wait_relaxed(BAR(BAR_Q_FREE + q), ((n / TC_Q) & 1) ^ 1);
+            mbar_wait_relaxed(BAR(Cfg::Q_FREE + q), ((n / Cfg::Q) & 1) ^ 1);
             TC_TRACE(4, n, 1);
-            if (ep.dbg & 8) { mbar_arrive(BAR(BAR_B_FULL + q)); continue; }
-            mbar_expect_tx(BAR(BAR_B_FULL + q), ABF16 ? tx / 2 : tx);
-            if (!ABF16) tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(BAR_B_FULL + q));
-            tma_load_2d(B_LO(q), &tmBl, kc * 64, nt * bn, BAR(BAR_B_FULL + q));      // bf16(B_hi) | bf16(B_lo) of this chunk
+            if (TWO) {
+              // this CTA's half of the B rows; the bytes of BOTH halves complete on the leader's barrier
+              const uint32_t lbar = mapa_cta(BAR(Cfg::B_FULL + q), 0u);
+              if (rank == 0) mbar_expect_tx(BAR(Cfg::B_FULL + q), tx);
+              tma_load_2d_pair(B_HI(q), &tmBh, kc * TC_BK, nt * bn + (int)rank * (bn / 2), lbar);
+              tma_load_2d_pair(B_LO(q), &tmBl, kc * 64, nt * bn + (int)rank * (bn / 2), lbar);
+              continue;
+            }
+            if (ep.dbg & 8) { mbar_arrive(BAR(Cfg::B_FULL + q)); continue; }
+            mbar_expect_tx(BAR(Cfg::B_FULL + q), ABF16 ? tx / 2 : tx);
+            if (!ABF16) tma_load_2d(B_HI(q), &tmBh, kc * TC_BK, nt * bn, BAR(Cfg::B_FULL + q));
+            tma_load_2d(B_LO(q), &tmBl, kc * 64, nt * bn, BAR(Cfg::B_FULL + q));      // bf16(B_hi) | bf16(B_lo) of this chunk
           }
     }
-  } else if (warp == 9) {
+  } else if (warp == 9 && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer
     // The whole warp runs this loop with warp-uniform control flow and one ELECTED lane issues the tcgen05 instructions
     // (profiles/r01_*: inside an `if (lane == 0)` region every descriptor had to be moved vector -> uniform register
@@ -449,29 +509,30 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // UMMA N per N tile: bn, except the LAST tile of a row of tiles, which only computes the columns that exist (rounded up
     // to 16) -- N = 400 is 3 x 128 + 16 and N = 300 is 2 x 128 + 44: the tail tile costs 1/8 resp. 3/8 of a full one
     const int n_tail = (N - (n_tiles - 1) * bn + 15) & ~15;
-    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
-    const uint32_t idesc16_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BM >> 4) << 24);   // bf16 x bf16 -> f32
+    constexpr uint32_t MMA_M = TWO ? 2 * TC_BM : TC_BM;
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MMA_M >> 4) << 24);
+    const uint32_t idesc16_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_M >> 4) << 24);   // bf16 x bf16 -> f32
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
     uint32_t a_base = 0, nb_ = 0;     // A chunk loads before this M tile; B chunk loads so far
     int a = 0;
     uint32_t aph = 0;
-    for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+    for (long long t = t_first; t < m_tiles; t += t_step) {
       for (int nt = 0; nt < n_tiles; ++nt) {
         for (int kc = 0; kc < k_chunks; ++kc, ++nb_) {
           const int in_group = kc % TC_GROUP;
           const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
           if (lane == 0) TC_TRACE(2, nb_, 0);
-          if (in_group == 0) mbar_wait(BAR(BAR_ACC_EMPTY + a), aph ^ 1);   // epilogue has drained this accumulator stage
+          if (in_group == 0) mbar_wait(BAR(Cfg::ACC_EMPTY + a), aph ^ 1);   // epilogue has drained this accumulator stage
           if (lane == 0) TC_TRACE(2, nb_, 1);
           const uint32_t an = a_base + (resident ? 0 : nt * k_chunks) + kc;
-          const int s = an % TC_TA, q = nb_ % TC_Q;
-          mbar_wait(BAR(BAR_TA_FULL + s), (an / TC_TA) & 1);        // A_hi / A_lo of this chunk are in TMEM
+          const int s = an % TC_TA, q = nb_ % Cfg::Q;
+          mbar_wait(BAR(Cfg::TA_FULL + s), (an / TC_TA) & 1);        // A_hi / A_lo of this chunk are in TMEM
           if (lane == 0) TC_TRACE(2, nb_, 2);
-          mbar_wait(BAR(BAR_B_FULL + q), (nb_ / TC_Q) & 1);         // B tiles landed
+          mbar_wait(BAR(Cfg::B_FULL + q), (nb_ / Cfg::Q) & 1);         // B tiles landed
           if (lane == 0) TC_TRACE(2, nb_, 3);
           tc_fence_after();
           // k-steps that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 tf32 steps of 8, not 16)
-          const uint32_t n_mma = (uint32_t)((nt == n_tiles - 1 ? n_tail : bn) >> 3) << 17;
+          const uint32_t n_mma = (uint32_t)((!TWO && nt == n_tiles - 1 ? n_tail : bn) >> 3) << 17;   // pairs: bn / 2 columns per CTA
           const uint32_t idesc = idesc_base | n_mma, idesc16 = idesc16_base | n_mma;
           const int krem = K - kc * TC_BK;
           const int ks_n = (ep.dbg & 1) ? 0 : min(TC_BK / 8, (krem + 7) >> 3);
@@ -493,18 +554,32 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // at twice the rate: 4 + 4 instructions per 32-k chunk instead of 12 tf32 ones (see top of file)
 #pragma unroll
             for (int ks = 0; ks < TC_BK / 8; ++ks)
-              if (ks < ks_n) tc_mma_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 2), idesc, (in_group | ks) ? 1u : 0u);
+              if (ks < ks_n) {
+                if (TWO) tc_mma2_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 2), idesc, (in_group | ks) ? 1u : 0u);
+                else tc_mma_tf32_ts(d_tmem, ah0 + ks * 8, bh0 + (uint64_t)(ks * 2), idesc, (in_group | ks) ? 1u : 0u);
+              }
 #pragma unroll
             for (int j = 0; j < TC_BK / 16; ++j) {
               if (j < k16_n) {
-                tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);        // bf16(A_lo) * bf16(B_hi)
-                tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);    // bf16(A_hi) * bf16(B_lo)
+                if (TWO) {
+                  tc_mma2_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);
+                  tc_mma2_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);
+                } else {
+                  tc_mma_bf16_ts(d_tmem, ah0 + 48 + j * 8, b16 + (uint64_t)(j * 2), idesc16, 1u);        // bf16(A_lo) * bf16(B_hi)
+                  tc_mma_bf16_ts(d_tmem, ah0 + 32 + j * 8, b16 + (uint64_t)(4 + j * 2), idesc16, 1u);    // bf16(A_hi) * bf16(B_lo)
+                }
               }
             }
             }
-            tc_commit(BAR(BAR_Q_FREE + q));
-            if (!resident || nt == n_tiles - 1) tc_commit(BAR(BAR_TA_FREE + s));
-            if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) tc_commit(BAR(BAR_ACC_FULL + a));   // partial sum -> epilogue
+            if (TWO) {
+              tc_commit2(BAR(Cfg::Q_FREE + q));
+              tc_commit2(BAR(Cfg::TA_FREE + s));
+              if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) tc_commit2(BAR(Cfg::ACC_FULL + a));
+            } else {
+            tc_commit(BAR(Cfg::Q_FREE + q));
+            if (!resident || nt == n_tiles - 1) tc_commit(BAR(Cfg::TA_FREE + s));
+            if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) tc_commit(BAR(Cfg::ACC_FULL + a));   // partial sum -> epilogue
+            }
           }
           __syncwarp();
           if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) {
@@ -519,12 +594,12 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = threadIdx.x;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     uint32_t n = 0;
-    for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+    for (long long t = t_first; t < m_tiles; t += t_step) {
       for (int rep = 0; rep < a_reps; ++rep)
         for (int kc = 0; kc < k_chunks; ++kc, ++n) {
-          const int r = n % TC_R, s = n % TC_TA;
+          const int r = n % Cfg::R, s = n % TC_TA;
           if (threadIdx.x == 0) TC_TRACE(1, n, 0);
-          mbar_wait(BAR(BAR_A_FULL + r), (n / TC_R) & 1);          // raw tile landed
+          mbar_wait(BAR(Cfg::A_FULL + r), (n / Cfg::R) & 1);          // raw tile landed
           if (threadIdx.x == 0) TC_TRACE(1, n, 1);
           const uint32_t src = raw_base + r * TC_A_BYTES + (ABF16 ? row * 64 : row * 128);
           uint32_t hi[32], p16[32];                                // tf32 A_hi | bf16 pairs: [0,16) A_hi, [16,32) A_lo
@@ -553,7 +628,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             p16[16 + 2 * c + 1] = pack_bf16x2(__uint_as_float(l2), __uint_as_float(l3));
           }
           }
-          mbar_wait(BAR(BAR_TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
+          mbar_wait(BAR(Cfg::TA_FREE + s), ((n / TC_TA) & 1) ^ 1);   // MMAs that read this TMEM stage retired
           if (threadIdx.x == 0) TC_TRACE(1, n, 2);
           tc_fence_after();
           if (!ABF16) tc_st32(TA_HI(s) + lane_addr, hi);
@@ -563,9 +638,9 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // shared-memory loads have returned.  (An arrive placed right after the loads was scheduled by ptxas before
           // their data came back -- SASS: LD.E.128 x8, SYNCS.ARRIVE, then the first use -- and a refill by TMA could
           // overtake a slow warp: rare wrong 32-row x 128-column blocks, caught by test_tc_gemm_race_stress.)
-          mbar_arrive(BAR(BAR_R_FREE + r));
+          mbar_arrive(BAR(Cfg::R_FREE + r));
           tc_fence_before();
-          mbar_arrive(BAR(BAR_TA_FULL + s));
+          arrive_leader(LBAR(Cfg::TA_FULL + s));
           if (threadIdx.x == 0) TC_TRACE(1, n, 3);
         }
     }
@@ -583,21 +658,21 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int a = 0;
     uint32_t aph = 0;
     const int ew = warp & 3;
-    const uint32_t stg_u32 = smem_u32(stage_all + ew * TC_SLABS * TC_SLAB_BYTES);     // this warp's 4 slabs of 32 x 32
+    const uint32_t stg_u32 = smem_u32(stage_all + ew * Cfg::SLABS * TC_SLAB_BYTES);     // this warp's 4 slabs of 32 x 32
     const uint32_t my_row = stg_u32 + lane * 128;
     const int n_groups = (k_chunks + TC_GROUP - 1) / TC_GROUP;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
     float colacc[TC_SLABS];                                        // lane = column of a slab: sums over this warp's rows
 #pragma unroll
     for (int sl = 0; sl < TC_SLABS; ++sl) colacc[sl] = 0.f;
-    for (long long t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-      const long long m0 = t * TC_BM + ew * 32;
+    for (long long t = t_first; t < m_tiles; t += t_step) {
+      const long long m0 = TILE(t) * TC_BM + ew * 32;
       const long long m = m0 + lane;                               // this thread's row (TMEM lane)
       const long long mrow = m < M ? m : M - 1;
       for (int nt = 0; nt < n_tiles; ++nt) {
         const int n0 = nt * bn;
         if (SMALLK) {
-          mbar_wait(BAR(BAR_ACC_FULL + a), aph);
+          mbar_wait(BAR(Cfg::ACC_FULL + a), aph);
           tc_fence_after();
           if (lane == 0) tma_store_wait_read();                    // the previous tile's bulk stores have read the slabs
           __syncwarp();
@@ -618,14 +693,14 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           tc_fence_before();
-          mbar_arrive(BAR(BAR_ACC_EMPTY + a));
+          mbar_arrive(BAR(Cfg::ACC_EMPTY + a));
           if (++a == 2) { a = 0; aph ^= 1; }
         } else {
           float acc[TC_BN];
           for (int g = 0; g < n_groups; ++g) {
-            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - blockIdx.x) / gridDim.x) * n_groups + g, 0);
-            mbar_wait(BAR(BAR_ACC_FULL + a), aph);
-            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - blockIdx.x) / gridDim.x) * n_groups + g, 1);
+            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - t_first) / t_step) * n_groups + g, 0);
+            mbar_wait(BAR(Cfg::ACC_FULL + a), aph);
+            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - t_first) / t_step) * n_groups + g, 1);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < TC_BN; c += 32) {
@@ -643,9 +718,38 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             tc_fence_before();
-            mbar_arrive(BAR(BAR_ACC_EMPTY + a));
-            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - blockIdx.x) / gridDim.x) * n_groups + g, 2);
+            arrive_leader(LBAR(Cfg::ACC_EMPTY + a));
+            if (threadIdx.x == 128) TC_TRACE(3, (int)((t - t_first) / t_step) * n_groups + g, 2);
             if (++a == 2) { a = 0; aph ^= 1; }
+          }
+          if (TWO) {
+            // one staging slab per warp: stage, store, (column sums), and only then re-use it for the next slab -- four
+            // short waits per 46-chunk tile, in exchange for 48 KB of shared memory that went into the rings
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+              const int c = 32 * sl;
+              if (c < bn && n0 + c < N) {
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 v = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
+                  if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N);
+                  sts4(my_row + (((j >> 2) ^ (lane & 7)) << 4), v);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { tma_store_2d(&tmC, stg_u32, n0 + c, (int)m0); tma_store_commit(); }
+                if (colsum_partial) {
+                  float sum = 0.f;
+#pragma unroll 8
+                  for (int r = 0; r < 32; ++r)
+                    sum += lds1(stg_u32 + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                  colacc[sl] += sum;
+                }
+              }
+            }
+            continue;
           }
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
@@ -696,10 +800,11 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) tma_store_wait_all();                           // global writes complete before the kernel exits
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -1163,7 +1268,6 @@ static int tn_pair_capacity() {
   if (d >= 0 && d < kMaxDevices) cache[d].store(n > 0 ? n : -1, std::memory_order_release);
   return n;
 }
-extern "C" __attribute__((visibility("default"))) int ercg_debug_tn_pair_capacity() { return tn_pair_capacity(); }
 
 static void tn_tc_plan(int64_t M, int K1, int N1, bool& swap, int& w_tiles, int& n_tiles, int& bn, int& S, long long& rps,
                        bool& two) {
@@ -1335,6 +1439,41 @@ using namespace ercg;
 
 static long long* trace_buf = nullptr;      // ERCG_TC_TRACE=1: device buffer of the pipeline timeline (diagnostics only)
 
+static bool nn_pairs_enabled() {
+  static const bool on = [] { const char* e = getenv("ERCG_NN_PAIRS"); return !e || atoi(e) != 0; }();   // read once
+  return on;
+}
+// CTA pairs of the NN kernel that can be resident at once (per device, queried once)
+static int nn_pair_capacity() {
+  static std::atomic<int> cache[kMaxDevices];
+  const int d = current_device();
+  if (d >= 0 && d < kMaxDevices) {
+    const int c = cache[d].load(std::memory_order_acquire);
+    if (c != 0) return c > 0 ? c : 0;
+  }
+  int n = 0;
+  auto kern = gemm_tc_nn_kernel<0, false, false, true>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true>::SMEM_BYTES) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs / 2 * 2, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = NnCfg<true>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  } else {
+    cudaGetLastError();
+  }
+  if (n > kNumSMs / 2) n = kNumSMs / 2;
+  if (d >= 0 && d < kMaxDevices) cache[d].store(n > 0 ? n : -1, std::memory_order_release);
+  return n;
+}
+
 extern "C" size_t ercg_gemm_nn_tc_workspace_bytes(int N, int K) {
   if (N <= 0 || K <= 0) return 0;
   const size_t Kp = (size_t)(K + 3) / 4 * 4, Kc = (size_t)(K + TC_BK - 1) / TC_BK;
@@ -1372,11 +1511,17 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   split_bt_kernel<<<dim3(Kc, (N + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Kp, Kc, bhi, b16);
   int rc = finish_launch();
   if (rc) return rc;
-  // UMMA N: multiple of 16, <= 128, chosen to waste the fewest columns
+  const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;       // the whole K extent is one TMEM accumulation group
+  const long long tiles = (M + TC_BM - 1) / TC_BM;          // a CTA owns whole M tiles (all their N tiles)
+  // CTA pairs (cta_group::2): one N tile, long K, enough M tiles to fill the machine with pairs
+  const int pair_cap = (!smallk && N <= TC_BN && tiles >= 2 * (kNumSMs / 2) && nn_pairs_enabled()) ? nn_pair_capacity() : 0;
+  const bool two = pair_cap >= kNumSMs / 2 - 8;
+  // UMMA N: multiple of 16 (pairs: of 32, half per CTA), <= 128, chosen to waste the fewest columns
   int bn = 128;
-  if (N <= 128) bn = (N + 15) / 16 * 16;
+  if (N <= 128) bn = two ? (N + 31) / 32 * 32 : (N + 15) / 16 * 16;
   CUtensorMap tmA, tmBh, tmBl, tmC;
-  if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, bn) || !make_map_b16(&tmBl, b16, N, Kc, bn) ||
+  const int b_box = two ? bn / 2 : bn;                      // B rows per TMA box: the whole tile, or this CTA's half
+  if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, b_box) || !make_map_b16(&tmBl, b16, N, Kc, b_box) ||
       !make_map(&tmC, C, M, N, ldc, 32))                     // output: boxes of 32 rows x 32 columns (TMA bulk stores)
     return ERCG_ECUDA;
   typedef void (*NnKernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, float*, long long, long long, int, int, int,
@@ -1384,17 +1529,21 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   static const NnKernel kernels[4][2] = {
       {gemm_tc_nn_kernel<0, false, false>, gemm_tc_nn_kernel<0, true, false>}, {gemm_tc_nn_kernel<1, false, false>, gemm_tc_nn_kernel<1, true, false>},
       {gemm_tc_nn_kernel<2, false, false>, gemm_tc_nn_kernel<2, true, false>}, {gemm_tc_nn_kernel<3, false, false>, gemm_tc_nn_kernel<3, true, false>}};
+  static const NnKernel pair_kernels[4] = {gemm_tc_nn_kernel<0, false, false, true>, gemm_tc_nn_kernel<1, false, false, true>,
+                                           gemm_tc_nn_kernel<2, false, false, true>, gemm_tc_nn_kernel<3, false, false, true>};
   static DeviceOnce attr_set;            // cudaFuncSetAttribute is per device context: once per DEVICE, not per process
   if (attr_set.need()) {
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
       for (int k = 0; k < 2; ++k)
         if (cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
           return ERCG_ECUDA;
+      if (cudaFuncSetAttribute(pair_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true>::SMEM_BYTES) != cudaSuccess)
+        return ERCG_ECUDA;
+    }
     attr_set.mark();
   }
   const int num_sms = device_sm_count();
-  const long long tiles = (M + TC_BM - 1) / TC_BM;          // a CTA owns whole M tiles (all their N tiles)
-  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  const int grid = two ? 2 * pair_cap : (int)(tiles < num_sms ? tiles : num_sms);
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("ERCG_TC_DBG"); dbg = e ? atoi(e) : 0; }
   static int trace_on = -1;
@@ -1407,9 +1556,28 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   if (nn_trace) cudaMemsetAsync(nn_trace, 0, sizeof(long long) * TR_ROLES * TR_N * 4, st);
   TcEpilogue ep{bias, act, aux, (long long)ldaux, aux_scale, drop_p, (unsigned long long)seed, dbg, nn_trace};
   ep.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
-  const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;       // the whole K extent is one TMEM accumulation group
   float* partial = colsum_out ? reinterpret_cast<float*>(b16 + (size_t)N * Kc * 64) : nullptr;   // [grid][4][128], after the B copies
-  kernels[act][smallk]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep, partial);
+  if (two) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = NnCfg<true>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const long long ldc_ll = ldc, M_ll = M;
+    if (cudaLaunchKernelEx(&cfg, pair_kernels[act], tmA, tmBh, tmBl, tmC, C, ldc_ll, M_ll, N, K, bn, ep, partial) != cudaSuccess) {
+      cudaGetLastError();
+      return ERCG_ECUDA;
+    }
+  } else {
+    kernels[act][smallk]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmC, C, ldc, M, N, K, bn, ep, partial);
+  }
   if (colsum_out) {
     rc = finish_launch();
     if (rc) return rc;
