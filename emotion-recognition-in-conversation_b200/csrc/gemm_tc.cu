@@ -202,12 +202,17 @@ constexpr int TC_THREADS = 352;   // 4 splitter + 4 epilogue warps, A producer, 
 // shared memory -- the pipeline trace of the single-CTA kernel on K = 1443 (profiles/r02o_nn_trace_single_cta.txt) has the
 // B ring as the critical loop: stage freed by the MMAs -> TMA from L2 (~2800 clk under load) -> MMAs (~500 clk) around a
 // 3-stage ring = ~1100 clk per chunk, with the tensor pipe busy 42 % of the time.
-template <bool TWO>
+#ifndef TC_R2S_
+#define TC_R2S_ 4
+#endif
+template <bool TWO, bool SMALLK = false>
 struct NnCfg {
-  static constexpr int R = TWO ? TC_R2_ : TC_R_;
+  // pair + small K (the K = 100 transforms: A resident across N tiles or 4 chunks per tile) keeps the 4-slab staging its
+  // streaming epilogue needs and spends the freed B bytes on ring depth only
+  static constexpr int R = TWO ? (SMALLK ? TC_R2S_ : TC_R2_) : TC_R_;
   static constexpr int Q = TWO ? TC_Q2_ : TC_Q_;
   static constexpr uint32_t BT_BYTES = TWO ? TC_B_BYTES / 2 : TC_B_BYTES;       // one B tile (fp32 hi, or bf16 pairs) of this CTA
-  static constexpr int SLABS = TWO ? 1 : 4;                                     // staging slabs per epilogue warp
+  static constexpr int SLABS = (TWO && !SMALLK) ? 1 : 4;                        // staging slabs per epilogue warp
   static constexpr uint32_t STAGE_BYTES = 4 * SLABS * TC_SLAB_BYTES;
   static constexpr uint32_t SMEM_BYTES = R * TC_A_BYTES + Q * 2 * BT_BYTES + STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int A_FULL = 0;                   // [R]  TMA bytes of the raw A tile landed
@@ -399,8 +404,8 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   float* __restrict__ C, long long ldc, long long M, int N,
                   int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, TcEpilogue ep,
                   float* __restrict__ colsum_partial /* [gridDim.x][4][128] column sums of C (N <= 128 only), or NULL */) {
-  using Cfg = NnCfg<TWO>;
-  static_assert(!TWO || (!SMALLK && !ABF16), "pair mode: long K, fp32 features");
+  using Cfg = NnCfg<TWO, SMALLK>;
+  static_assert(!TWO || !ABF16, "pair mode: fp32 features");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bring = smem + Cfg::R * TC_A_BYTES;
@@ -491,8 +496,10 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               // this CTA's half of the B rows; the bytes of BOTH halves complete on the leader's barrier
               const uint32_t lbar = mapa_cta(BAR(Cfg::B_FULL + q), 0u);
               if (rank == 0) mbar_expect_tx(BAR(Cfg::B_FULL + q), tx);
-              tma_load_2d_pair(B_HI(q), &tmBh, kc * TC_BK, nt * bn + (int)rank * (bn / 2), lbar);
-              tma_load_2d_pair(B_LO(q), &tmBl, kc * 64, nt * bn + (int)rank * (bn / 2), lbar);
+              // (the last N tile only has n_cur columns, half of THEM per CTA; the box still brings bn / 2 rows)
+              const int n_cur = nt == n_tiles - 1 ? ((N - nt * bn + 31) & ~31) : bn;
+              tma_load_2d_pair(B_HI(q), &tmBh, kc * TC_BK, nt * bn + (int)rank * (n_cur / 2), lbar);
+              tma_load_2d_pair(B_LO(q), &tmBl, kc * 64, nt * bn + (int)rank * (n_cur / 2), lbar);
               continue;
             }
             if (ep.dbg & 8) { mbar_arrive(BAR(Cfg::B_FULL + q)); continue; }
@@ -508,7 +515,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // per instruction and the issue loop itself, ~150 clk per UTCHMMA, was the bottleneck of the kernel).
     // UMMA N per N tile: bn, except the LAST tile of a row of tiles, which only computes the columns that exist (rounded up
     // to 16) -- N = 400 is 3 x 128 + 16 and N = 300 is 2 x 128 + 44: the tail tile costs 1/8 resp. 3/8 of a full one
-    const int n_tail = (N - (n_tiles - 1) * bn + 15) & ~15;
+    const int n_tail = TWO ? ((N - (n_tiles - 1) * bn + 31) & ~31) : ((N - (n_tiles - 1) * bn + 15) & ~15);
     constexpr uint32_t MMA_M = TWO ? 2 * TC_BM : TC_BM;
     const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MMA_M >> 4) << 24);
     const uint32_t idesc16_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_M >> 4) << 24);   // bf16 x bf16 -> f32
@@ -532,7 +539,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane == 0) TC_TRACE(2, nb_, 3);
           tc_fence_after();
           // k-steps that still hold real columns (TMA zero-fills the K tail: K = 100 needs 13 tf32 steps of 8, not 16)
-          const uint32_t n_mma = (uint32_t)((!TWO && nt == n_tiles - 1 ? n_tail : bn) >> 3) << 17;   // pairs: bn / 2 columns per CTA
+          const uint32_t n_mma = (uint32_t)((nt == n_tiles - 1 ? n_tail : bn) >> 3) << 17;   // pairs: half of it per CTA
           const uint32_t idesc = idesc_base | n_mma, idesc16 = idesc16_base | n_mma;
           const int krem = K - kc * TC_BK;
           const int ks_n = (ep.dbg & 1) ? 0 : min(TC_BK / 8, (krem + 7) >> 3);
@@ -573,7 +580,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (TWO) {
               tc_commit2(BAR(Cfg::Q_FREE + q));
-              tc_commit2(BAR(Cfg::TA_FREE + s));
+              if (!resident || nt == n_tiles - 1) tc_commit2(BAR(Cfg::TA_FREE + s));
               if (in_group == TC_GROUP - 1 || kc == k_chunks - 1) tc_commit2(BAR(Cfg::ACC_FULL + a));
             } else {
             tc_commit(BAR(Cfg::Q_FREE + q));
@@ -693,7 +700,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           tc_fence_before();
-          mbar_arrive(BAR(Cfg::ACC_EMPTY + a));
+          arrive_leader(LBAR(Cfg::ACC_EMPTY + a));
           if (++a == 2) { a = 0; aph ^= 1; }
         } else {
           float acc[TC_BN];
@@ -1513,8 +1520,9 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   if (rc) return rc;
   const int smallk = (K + TC_BK - 1) / TC_BK <= TC_GROUP ? 1 : 0;       // the whole K extent is one TMEM accumulation group
   const long long tiles = (M + TC_BM - 1) / TC_BM;          // a CTA owns whole M tiles (all their N tiles)
-  // CTA pairs (cta_group::2): one N tile, long K, enough M tiles to fill the machine with pairs
-  const int pair_cap = (!smallk && N <= TC_BN && tiles >= 2 * (kNumSMs / 2) && nn_pairs_enabled()) ? nn_pair_capacity() : 0;
+  // CTA pairs (cta_group::2): one N tile, or several with A resident in tensor memory; enough M tiles to fill the machine
+  const bool pair_shape = N <= TC_BN || (K + TC_BK - 1) / TC_BK <= TC_TA;
+  const int pair_cap = (pair_shape && tiles >= 2 * (kNumSMs / 2) && nn_pairs_enabled()) ? nn_pair_capacity() : 0;
   const bool two = pair_cap >= kNumSMs / 2 - 8;
   // UMMA N: multiple of 16 (pairs: of 32, half per CTA), <= 128, chosen to waste the fewest columns
   int bn = 128;
@@ -1529,15 +1537,19 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   static const NnKernel kernels[4][2] = {
       {gemm_tc_nn_kernel<0, false, false>, gemm_tc_nn_kernel<0, true, false>}, {gemm_tc_nn_kernel<1, false, false>, gemm_tc_nn_kernel<1, true, false>},
       {gemm_tc_nn_kernel<2, false, false>, gemm_tc_nn_kernel<2, true, false>}, {gemm_tc_nn_kernel<3, false, false>, gemm_tc_nn_kernel<3, true, false>}};
-  static const NnKernel pair_kernels[4] = {gemm_tc_nn_kernel<0, false, false, true>, gemm_tc_nn_kernel<1, false, false, true>,
-                                           gemm_tc_nn_kernel<2, false, false, true>, gemm_tc_nn_kernel<3, false, false, true>};
+  static const NnKernel pair_kernels[4][2] = {
+      {gemm_tc_nn_kernel<0, false, false, true>, gemm_tc_nn_kernel<0, true, false, true>},
+      {gemm_tc_nn_kernel<1, false, false, true>, gemm_tc_nn_kernel<1, true, false, true>},
+      {gemm_tc_nn_kernel<2, false, false, true>, gemm_tc_nn_kernel<2, true, false, true>},
+      {gemm_tc_nn_kernel<3, false, false, true>, gemm_tc_nn_kernel<3, true, false, true>}};
   static DeviceOnce attr_set;            // cudaFuncSetAttribute is per device context: once per DEVICE, not per process
   if (attr_set.need()) {
     for (int i = 0; i < 4; ++i) {
       for (int k = 0; k < 2; ++k)
         if (cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
           return ERCG_ECUDA;
-      if (cudaFuncSetAttribute(pair_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true>::SMEM_BYTES) != cudaSuccess)
+      if (cudaFuncSetAttribute(pair_kernels[i][0], cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true, false>::SMEM_BYTES) != cudaSuccess ||
+          cudaFuncSetAttribute(pair_kernels[i][1], cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true, true>::SMEM_BYTES) != cudaSuccess)
         return ERCG_ECUDA;
     }
     attr_set.mark();
@@ -1561,7 +1573,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = NnCfg<true>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smallk ? NnCfg<true, true>::SMEM_BYTES : NnCfg<true, false>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1571,7 +1583,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const long long ldc_ll = ldc, M_ll = M;
-    if (cudaLaunchKernelEx(&cfg, pair_kernels[act], tmA, tmBh, tmBl, tmC, C, ldc_ll, M_ll, N, K, bn, ep, partial) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, pair_kernels[act][smallk], tmA, tmBh, tmBl, tmC, C, ldc_ll, M_ll, N, K, bn, ep, partial) != cudaSuccess) {
       cudaGetLastError();
       return ERCG_ECUDA;
     }

@@ -20,7 +20,11 @@ def _tc(fn):
 
 
 @pytest.mark.parametrize("M,K,N", [(256, 32, 16), (300, 100, 100), (1000, 1443, 100), (4096, 1380, 100), (777, 100, 900),
-                                   (2050, 900, 100), (513, 100, 400), (640, 400, 100), (33000, 1443, 100), (260, 200, 800)])
+                                   (2050, 900, 100), (513, 100, 400), (640, 400, 100), (33000, 1443, 100), (260, 200, 800),
+                                   # >= 148 row tiles: the CTA-pair (cta_group::2) kernels -- long K, small K with one N tile,
+                                   # A resident over several N tiles (tail tiles of 16 / 44 / 4 columns), odd tile count
+                                   (19000, 100, 400), (20000, 100, 300), (33100, 100, 100), (19071, 128, 900), (25000, 64, 132),
+                                   (40000, 400, 100), (19200, 300, 36)])
 def test_tc_gemm_matches_fp64(M, K, N):
     g = torch.Generator().manual_seed(M + K + N)
     ld = (K + 3) // 4 * 4
