@@ -205,14 +205,16 @@ constexpr int TC_THREADS = 352;   // 4 splitter + 4 epilogue warps, A producer, 
 #ifndef TC_R2S_
 #define TC_R2S_ 4
 #endif
-template <bool TWO, bool SMALLK = false>
+template <bool TWO, bool WIDE = false>
 struct NnCfg {
-  // pair + small K (the K = 100 transforms: A resident across N tiles or 4 chunks per tile) keeps the 4-slab staging its
-  // streaming epilogue needs and spends the freed B bytes on ring depth only
-  static constexpr int R = TWO ? (SMALLK ? TC_R2S_ : TC_R2_) : TC_R_;
+  // pair + short tiles (WIDE: K <= 512, i.e. the K = 100 transforms with A resident across N tiles and the K = 300 / 400 input
+  // gradients) keep the 4-slab staging -- with 4-16 chunks per tile the epilogue is a large share of a tile and staging slab
+  // by slab, with its column sums in between, measured slower in the step -- and spend the freed B bytes on ring depth only;
+  // pair + long K (K = 1443: 46 chunks per tile) stages one slab at a time and takes two more A stages
+  static constexpr int R = TWO ? (WIDE ? TC_R2S_ : TC_R2_) : TC_R_;
   static constexpr int Q = TWO ? TC_Q2_ : TC_Q_;
   static constexpr uint32_t BT_BYTES = TWO ? TC_B_BYTES / 2 : TC_B_BYTES;       // one B tile (fp32 hi, or bf16 pairs) of this CTA
-  static constexpr int SLABS = (TWO && !SMALLK) ? 1 : 4;                        // staging slabs per epilogue warp
+  static constexpr int SLABS = (TWO && !WIDE) ? 1 : 4;                          // staging slabs per epilogue warp
   static constexpr uint32_t STAGE_BYTES = 4 * SLABS * TC_SLAB_BYTES;
   static constexpr uint32_t SMEM_BYTES = R * TC_A_BYTES + Q * 2 * BT_BYTES + STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int A_FULL = 0;                   // [R]  TMA bytes of the raw A tile landed
@@ -353,25 +355,34 @@ __device__ __forceinline__ void tc_mma2_bf16_ts(uint32_t d_tmem, uint32_t a_tmem
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
 
-template <int ACT>
-__device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, long long m, int nn0, int N) {
+// bias of four consecutive columns (zeros without a bias): fetched BEFORE the loop that applies it -- the staging stores of the
+// epilogue are asm volatile with a memory clobber, so a load inside that loop is issued, waited for and used one at a time
+__device__ __forceinline__ float4 tc_bias4(const TcEpilogue& ep, int nn0, int N) {
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ep.bias) {
     if (nn0 + 4 <= N) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nn0));   // bias is 16-byte aligned (checked on host)
-      x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+      b = __ldg(reinterpret_cast<const float4*>(ep.bias + nn0));   // bias is 16-byte aligned (checked on host)
     } else {
-      if (nn0 + 0 < N) x.x += __ldg(ep.bias + nn0 + 0);
-      if (nn0 + 1 < N) x.y += __ldg(ep.bias + nn0 + 1);
-      if (nn0 + 2 < N) x.z += __ldg(ep.bias + nn0 + 2);
+      if (nn0 + 0 < N) b.x = __ldg(ep.bias + nn0 + 0);
+      if (nn0 + 1 < N) b.y = __ldg(ep.bias + nn0 + 1);
+      if (nn0 + 2 < N) b.z = __ldg(ep.bias + nn0 + 2);
     }
   }
+  return b;
+}
+template <int ACT>
+__device__ __forceinline__ uint64_t tc_drop_hash(const TcEpilogue& ep, long long m, int nn0, int N) {
+  return ACT == ERCG_ACT_RELU_DROPOUT ? dropout_group_hash(ep.seed, m, nn0, N) : 0ull;   // nn0 % 4 == 0: one hash per float4
+}
+template <int ACT>
+__device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, long long m, int nn0, int N, float4 b, uint64_t h) {
+  x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
   if (ACT == ERCG_ACT_RELU || ACT == ERCG_ACT_RELU_DROPOUT) {
     x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
   }
   if (ACT == ERCG_ACT_RELU_DROPOUT) {
     const float sc = 1.0f / (1.0f - ep.drop_p);
     const unsigned thr = dropout_thr16(ep.drop_p);
-    const uint64_t h = dropout_group_hash(ep.seed + (ep.seed_dev ? __ldg(ep.seed_dev) : 0ull), m, nn0, N);   // nn0 % 4 == 0: one hash per float4
     x.x = dropout_drop(h, 0, thr) ? 0.f : x.x * sc;
     x.y = dropout_drop(h, 1, thr) ? 0.f : x.y * sc;
     x.z = dropout_drop(h, 2, thr) ? 0.f : x.z * sc;
@@ -397,15 +408,18 @@ __device__ __forceinline__ float4 tc_finish4(float4 x, const TcEpilogue& ep, lon
 // leader's MMA warp issues M = 256 instructions for both.  The peer's TMA completes its bytes on the LEADER's B_FULL
 // barrier; splitter and epilogue warps of both CTAs arrive (one lane per warp) on the leader's TA_FULL / ACC_EMPTY; what
 // the MMAs release is a multicast commit to both CTAs.
-template <int ACT, bool SMALLK, bool ABF16, bool TWO = false>
+template <int ACT, bool SMALLK, bool ABF16, bool TWO = false, bool ONESLAB = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                   const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
                   float* __restrict__ C, long long ldc, long long M, int N,
-                  int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, TcEpilogue ep,
+                  int K, int bn /* UMMA N for this launch: multiple of 16, <= 128 */, const TcEpilogue ep_in,
                   float* __restrict__ colsum_partial /* [gridDim.x][4][128] column sums of C (N <= 128 only), or NULL */) {
-  using Cfg = NnCfg<TWO, SMALLK>;
+  using Cfg = NnCfg<TWO, !ONESLAB>;
+  TcEpilogue ep = ep_in;                                   // the device seed word is read ONCE, not per float4 of the epilogue
+  if (ACT == ERCG_ACT_RELU_DROPOUT && ep.seed_dev) { ep.seed += *ep.seed_dev; ep.seed_dev = nullptr; }
   static_assert(!TWO || !ABF16, "pair mode: fp32 features");
+  static_assert(!ONESLAB || (TWO && !SMALLK), "one-slab staging: pair mode, long K");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bring = smem + Cfg::R * TC_A_BYTES;
@@ -689,12 +703,18 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (c < bn && n0 + c < N) {
               uint32_t rr[32];
               tc_ld32(tmem_lane + (uint32_t)(a * TC_BN + c), rr);
+              float4 bb[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) bb[j] = tc_bias4(ep, n0 + c + 4 * j, N);     // in flight with the TMEM load
+              uint64_t hh[8];                        // the eight hash chains of a slab interleave (one warp per scheduler: no
+#pragma unroll                                       // other warp hides the latency of a serial 64-bit multiply chain)
+              for (int j = 0; j < 8; ++j) hh[j] = tc_drop_hash<ACT>(ep, mrow, n0 + c + 4 * j, N);
               tc_wait_ld();
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 float4 v = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
                                        __uint_as_float(rr[j + 3]));
-                if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N);
+                if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N, bb[j >> 2], hh[j >> 2]);
                 sts4(my_row + sl * TC_SLAB_BYTES + (((j >> 2) ^ (lane & 7)) << 4), v);
               }
             }
@@ -729,7 +749,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (threadIdx.x == 128) TC_TRACE(3, (int)((t - t_first) / t_step) * n_groups + g, 2);
             if (++a == 2) { a = 0; aph ^= 1; }
           }
-          if (TWO) {
+          if (ONESLAB) {
             // one staging slab per warp: stage, store, (column sums), and only then re-use it for the next slab -- four
             // short waits per 46-chunk tile, in exchange for 48 KB of shared memory that went into the rings
 #pragma unroll
@@ -741,7 +761,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                   float4 v = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
-                  if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N);
+                  if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N, tc_bias4(ep, n0 + c + j, N), tc_drop_hash<ACT>(ep, mrow, n0 + c + j, N));
                   sts4(my_row + (((j >> 2) ^ (lane & 7)) << 4), v);
                 }
                 fence_proxy_async();
@@ -767,7 +787,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 float4 v = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
-                if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N);
+                if (ACT != ERCG_ACT_NONE || ep.bias) v = tc_finish4<ACT>(v, ep, mrow, n0 + c + j, N, tc_bias4(ep, n0 + c + j, N), tc_drop_hash<ACT>(ep, mrow, n0 + c + j, N));
                 sts4(my_row + sl * TC_SLAB_BYTES + (((j >> 2) ^ (lane & 7)) << 4), v);
               }
             }
@@ -1459,7 +1479,7 @@ static int nn_pair_capacity() {
     if (c != 0) return c > 0 ? c : 0;
   }
   int n = 0;
-  auto kern = gemm_tc_nn_kernel<0, false, false, true>;
+  auto kern = gemm_tc_nn_kernel<0, false, false, true, true>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true>::SMEM_BYTES) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kNumSMs / 2 * 2, 1, 1);
@@ -1537,11 +1557,13 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   static const NnKernel kernels[4][2] = {
       {gemm_tc_nn_kernel<0, false, false>, gemm_tc_nn_kernel<0, true, false>}, {gemm_tc_nn_kernel<1, false, false>, gemm_tc_nn_kernel<1, true, false>},
       {gemm_tc_nn_kernel<2, false, false>, gemm_tc_nn_kernel<2, true, false>}, {gemm_tc_nn_kernel<3, false, false>, gemm_tc_nn_kernel<3, true, false>}};
-  static const NnKernel pair_kernels[4][2] = {
-      {gemm_tc_nn_kernel<0, false, false, true>, gemm_tc_nn_kernel<0, true, false, true>},
-      {gemm_tc_nn_kernel<1, false, false, true>, gemm_tc_nn_kernel<1, true, false, true>},
-      {gemm_tc_nn_kernel<2, false, false, true>, gemm_tc_nn_kernel<2, true, false, true>},
-      {gemm_tc_nn_kernel<3, false, false, true>, gemm_tc_nn_kernel<3, true, false, true>}};
+  // [act][0 long K: one-slab staging | 1 small K | 2 medium K: wide staging]
+  static const NnKernel pair_kernels[4][3] = {
+      {gemm_tc_nn_kernel<0, false, false, true, true>, gemm_tc_nn_kernel<0, true, false, true>, gemm_tc_nn_kernel<0, false, false, true>},
+      {gemm_tc_nn_kernel<1, false, false, true, true>, gemm_tc_nn_kernel<1, true, false, true>, gemm_tc_nn_kernel<1, false, false, true>},
+      {gemm_tc_nn_kernel<2, false, false, true, true>, gemm_tc_nn_kernel<2, true, false, true>, gemm_tc_nn_kernel<2, false, false, true>},
+      {gemm_tc_nn_kernel<3, false, false, true, true>, gemm_tc_nn_kernel<3, true, false, true>, gemm_tc_nn_kernel<3, false, false, true>}};
+  const int pair_kind = smallk ? 1 : ((K + TC_BK - 1) / TC_BK > 16 ? 0 : 2);
   static DeviceOnce attr_set;            // cudaFuncSetAttribute is per device context: once per DEVICE, not per process
   if (attr_set.need()) {
     for (int i = 0; i < 4; ++i) {
@@ -1549,7 +1571,8 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
         if (cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
           return ERCG_ECUDA;
       if (cudaFuncSetAttribute(pair_kernels[i][0], cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true, false>::SMEM_BYTES) != cudaSuccess ||
-          cudaFuncSetAttribute(pair_kernels[i][1], cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true, true>::SMEM_BYTES) != cudaSuccess)
+          cudaFuncSetAttribute(pair_kernels[i][1], cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true, true>::SMEM_BYTES) != cudaSuccess ||
+          cudaFuncSetAttribute(pair_kernels[i][2], cudaFuncAttributeMaxDynamicSharedMemorySize, NnCfg<true, true>::SMEM_BYTES) != cudaSuccess)
         return ERCG_ECUDA;
     }
     attr_set.mark();
@@ -1573,7 +1596,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smallk ? NnCfg<true, true>::SMEM_BYTES : NnCfg<true, false>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = pair_kind == 0 ? NnCfg<true, false>::SMEM_BYTES : NnCfg<true, true>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1583,7 +1606,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const long long ldc_ll = ldc, M_ll = M;
-    if (cudaLaunchKernelEx(&cfg, pair_kernels[act][smallk], tmA, tmBh, tmBl, tmC, C, ldc_ll, M_ll, N, K, bn, ep, partial) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, pair_kernels[act][pair_kind], tmA, tmBh, tmBl, tmC, C, ldc_ll, M_ll, N, K, bn, ep, partial) != cudaSuccess) {
       cudaGetLastError();
       return ERCG_ECUDA;
     }

@@ -63,6 +63,23 @@ def main():
                         "gbs": round(4.0 * M * (K + N) / avg / 1e6, 1), "checksum_rel_err": err})
             print(json.dumps(out[-1]), flush=True)
             del A, B, C
+    if args.only in ("", "step"):
+        # the NN calls of the COGMEN step with their epilogues: forward transforms with bias / ReLU+dropout, input
+        # gradients with the fused bias-gradient column sums
+        cases = [("qkvs fwd", 100, 400, dict(bias=True)), ("rgcn fwd", 100, 300, dict()), ("cls0 fwd", 100, 100, dict(bias=True, act=ops.ACT_RELU_DROPOUT, drop_p=0.5)),
+                 ("qkvs dx", 400, 100, dict(want_colsum=True)), ("rgcn dx", 300, 100, dict(want_colsum=True)),
+                 ("cls0 dx", 100, 100, dict(want_colsum=True)), ("proj fwd", 1443, 100, dict(bias=True))]
+        for name, K, N, kw in cases:
+            ld = (K + 3) // 4 * 4
+            A = torch.randn(M, ld, device=dev, generator=g)[:, :K]
+            B = torch.randn(K, N, device=dev, generator=g) / K ** 0.5
+            bias = torch.randn(N, device=dev, generator=g) if kw.get("bias") else None
+            call = lambda: ops.gemm_nn(A, B, bias, act=kw.get("act", ops.ACT_NONE), drop_p=kw.get("drop_p", 0.0), seed=1,
+                                       want_colsum=kw.get("want_colsum", False))
+            avg, best = timeit(call, args.reps, flush)
+            out.append({"kernel": "nn-step", "call": name, "K": K, "N": N, "avg_ms": round(avg, 4), "min_ms": round(best, 4)})
+            print(json.dumps(out[-1]), flush=True)
+            del A, B
     if args.only in ("", "tn"):
         for K1, N1 in TN_SHAPES:
             ld = (K1 + 3) // 4 * 4
