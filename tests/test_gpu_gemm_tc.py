@@ -94,7 +94,9 @@ def test_tc_gemm_tn_matches_fp64(M, K1, N1):
     assert rel_err(r1, want) < TOL
 
 
-@pytest.mark.parametrize("M,K,N", [(1376, 800, 200), (8192, 1443, 100), (4096, 100, 900), (3000, 256, 384)])
+@pytest.mark.parametrize("M,K,N", [(1376, 800, 200), (8192, 1443, 100), (4096, 100, 900), (3000, 256, 384),
+                                   # CTA-pair kernels (>= 148 row tiles): long K, medium K, A resident over N tiles
+                                   (19200, 1443, 100), (19100, 400, 100), (19000, 100, 400)])
 def test_tc_gemm_race_stress(M, K, N):
     """The same product 25 times with other work in between: bit-identical and correct every time.  (A shared-memory
     stage that is released before its loads have returned shows up here as a rare, small mismatch.)"""
@@ -140,3 +142,26 @@ def test_tc_gemm_fused_column_sums(M, K, N):
     scale = float((A.double().abs() @ B.double().abs()).sum(0).max())
     assert float((cs.cpu().double() - want).abs().max()) < TOL * scale
     assert rel_err(cs, cs_plain) < 1e-6
+
+
+@pytest.mark.parametrize("M,K1,N1", [(40000, 1443, 100), (40000, 100, 400), (20000, 256, 100), (6000, 1443, 100)])
+def test_tc_gemm_tn_race_stress(M, K1, N1):
+    """Weight-gradient kernels (single CTA and CTA pairs: even numbers of 128-column tiles of the wide operand) 25 times with
+    other work in between: bit-identical and correct every time -- the pair protocol crosses CTAs (remote arrivals on the
+    leader's barriers, multicast commits, conversion teams that skip every other chunk)."""
+    g = torch.Generator().manual_seed(M + K1 + N1)
+    A, B = torch.randn(M, (K1 + 3) // 4 * 4, generator=g).cuda()[:, :K1], torch.randn(M, N1, generator=g).cuda()
+    want = A.double().t() @ B.double()
+
+    def run(ops):
+        outs = []
+        for i in range(25):
+            outs.append(ops.gemm_tn(A, B))
+            ops.gemm_tn(A[: M // 2], B[: M // 2])           # perturbs the timing of the next launch
+        torch.cuda.synchronize()
+        return outs
+
+    outs = _tc(run)
+    assert rel_err(outs[0], want) < TOL
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
