@@ -1166,11 +1166,16 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         for (long long kc = g * TN_GROUP; kc < kc_end; ++kc, ++n) {
           // pair mode: the conversion loop (barrier wait -> loads -> split -> stores -> proxy fence -> remote arrive, ~950 clk
           // per chunk for one warp however little it converts: profiles/r02o_tn_pair_trace.txt) was the slowest stage of the
-          // pipeline, so the four warps form two TEAMS that take alternate chunks (thread = column, 64 columns per CTA)
-          // (every warp still waits on EVERY chunk's B_FULL, in order: a parity wait that skipped a phase could mistake the
-          // phase before last for the one it wants while a slow TMA of the skipped chunk is still in flight)
+          // pipeline, so the four warps form two TEAMS that take alternate chunks (thread = column, 64 columns per CTA).
+          // Ownership goes by the parity of the GLOBAL chunk counter n and the ring depth is even, so a narrow stage
+          // (q = n % Q) always belongs to the same team and only that team ever waits on its B_FULL barrier -- in every
+          // phase.  (A first version had the other team wait on the skipped chunks' barriers "to keep the phase": a warp
+          // whose arrival is not needed for a stage's reuse can be lapped by two phases, and a parity wait then blocks for
+          // good.  It never happened in normal runs -- the conversion warps are ahead of the data -- but ncu's
+          // instrumented replay pass slowed the warps enough to hang the kernel; profiles/README.md.)
+          static_assert(!TWO || Cfg::Q % 2 == 0, "conversion teams own the narrow stages by parity");
           const int q = n % Cfg::Q;
-          if (TWO && ((int)(kc & 1) != (ew >> 1))) { mbar_wait(BAR(Cfg::B_FULL + q), (n / Cfg::Q) & 1); continue; }
+          if (TWO && ((int)(n & 1u) != (ew >> 1))) continue;
           if (te == 0) TN_TRACE(3, n, 0);
           if (pending && kc - g * TN_GROUP >= TN_DRAIN_AT) { drain(); pending = false; if (te == 0) TN_TRACE(3, n, 3); }
           mbar_wait(BAR(Cfg::B_FULL + q), (n / Cfg::Q) & 1);
