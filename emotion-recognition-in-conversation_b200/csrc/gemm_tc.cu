@@ -186,6 +186,10 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
 #define TC_Q_ 3
 #endif
 constexpr int TC_TA = 4;          // TMEM A stages
+#ifndef PAIR_N_GRAN_
+#define PAIR_N_GRAN_ 32
+#endif
+constexpr int PAIR_N_GRAN = PAIR_N_GRAN_;   // UMMA N granularity of the pair kernels (half of it per CTA)
 constexpr uint32_t TC_TMEM_A0 = 2 * TC_BN;                       // first A column
 constexpr int TC_SLABS = 4;                                     // 32-column slabs of a 128-column tile
 constexpr uint32_t TC_SLAB_BYTES = 32 * 128;                     // epilogue staging slab: 32 rows x 32 columns, 128-byte swizzle
@@ -511,7 +515,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t lbar = mapa_cta(BAR(Cfg::B_FULL + q), 0u);
               if (rank == 0) mbar_expect_tx(BAR(Cfg::B_FULL + q), tx);
               // (the last N tile only has n_cur columns, half of THEM per CTA; the box still brings bn / 2 rows)
-              const int n_cur = nt == n_tiles - 1 ? ((N - nt * bn + 31) & ~31) : bn;
+              const int n_cur = nt == n_tiles - 1 ? ((N - nt * bn + PAIR_N_GRAN - 1) / PAIR_N_GRAN * PAIR_N_GRAN) : bn;
               tma_load_2d_pair(B_HI(q), &tmBh, kc * TC_BK, nt * bn + (int)rank * (n_cur / 2), lbar);
               tma_load_2d_pair(B_LO(q), &tmBl, kc * 64, nt * bn + (int)rank * (n_cur / 2), lbar);
               continue;
@@ -529,7 +533,7 @@ gemm_tc_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // per instruction and the issue loop itself, ~150 clk per UTCHMMA, was the bottleneck of the kernel).
     // UMMA N per N tile: bn, except the LAST tile of a row of tiles, which only computes the columns that exist (rounded up
     // to 16) -- N = 400 is 3 x 128 + 16 and N = 300 is 2 x 128 + 44: the tail tile costs 1/8 resp. 3/8 of a full one
-    const int n_tail = TWO ? ((N - (n_tiles - 1) * bn + 31) & ~31) : ((N - (n_tiles - 1) * bn + 15) & ~15);
+    const int n_tail = TWO ? ((N - (n_tiles - 1) * bn + PAIR_N_GRAN - 1) / PAIR_N_GRAN * PAIR_N_GRAN) : ((N - (n_tiles - 1) * bn + 15) & ~15);
     constexpr uint32_t MMA_M = TWO ? 2 * TC_BM : TC_BM;
     const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MMA_M >> 4) << 24);
     const uint32_t idesc16_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_M >> 4) << 24);   // bf16 x bf16 -> f32
@@ -1551,7 +1555,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   const bool two = pair_cap >= kNumSMs / 2 - 8;
   // UMMA N: multiple of 16 (pairs: of 32, half per CTA), <= 128, chosen to waste the fewest columns
   int bn = 128;
-  if (N <= 128) bn = two ? (N + 31) / 32 * 32 : (N + 15) / 16 * 16;
+  if (N <= 128) bn = two ? (N + PAIR_N_GRAN - 1) / PAIR_N_GRAN * PAIR_N_GRAN : (N + 15) / 16 * 16;
   CUtensorMap tmA, tmBh, tmBl, tmC;
   const int b_box = two ? bn / 2 : bn;                      // B rows per TMA box: the whole tile, or this CTA's half
   if (!make_map(&tmA, A, M, K, lda, TC_BM) || !make_map(&tmBh, bhi, N, K, Kp, b_box) || !make_map_b16(&tmBl, b16, N, Kc, b_box) ||
