@@ -1300,7 +1300,6 @@ static int tn_pair_capacity() {
   } else {
     cudaGetLastError();
   }
-  if (const char* e = getenv("ERCG_TN_PAIR_CAP")) n = atoi(e);      // experiments only
   if (d >= 0 && d < kMaxDevices) cache[d].store(n > 0 ? n : -1, std::memory_order_release);
   return n;
 }
