@@ -549,3 +549,61 @@ def test_blocked_window_attention_matches_tile_kernels_and_fp64(wp, wf, H, monke
         assert rel_err(cs, x.grad.sum(0)) < 1e-5
     assert rel_err(res["1"][0], res["0"][0]) < 2e-6 and rel_err(res["1"][1], res["0"][1]) < 2e-6
     assert not torch.isnan(res["1"][1]).any()
+
+
+@pytest.mark.parametrize("n,wp,wf,one_speaker", [(2, 5, 5, True), (2, 5, 5, False), (1, 3, 7, True), (3, 0, 4, False), (2, 10, 0, False)])
+def test_rgcn_aggregate_first_kernel_matches_transform_first_and_fp64(n, wp, wf, one_speaker):
+    """PyG RGCNConv on a K1 window graph as ONE aggregate-first tensor-core kernel per direction (ercg_rgcn_window) against
+    (a) the transform-first composition (GEMM + gather, the path every other test pins) and (b) an fp64 evaluation of the
+    layer's formula: output, input gradient, relation / root weight gradients (absent relations exactly zero), bias
+    gradient.  Sizes above the 148-tile threshold, dialogues of length 1, windows clipped at both ends."""
+    import erc_b200
+    from erc_b200 import ops
+    from erc_b200.graph import build_graph
+    from erc_b200.pyg_nn import RGCNConv
+    rng = np.random.default_rng(7 * n + wp + 3 * wf)
+    lens = torch.as_tensor(np.concatenate([[1, 1, 2, 40, 3], rng.integers(1, 41, size=1100)]))
+    spk = torch.as_tensor(rng.integers(0, 1 if one_speaker else n, size=(lens.numel(), int(lens.max()))))
+    g = build_graph(lens, spk.cuda(), wp, wf, n)
+    N, R, K, H = g.N, 2 * n * n, 100, 100
+    assert N >= 148 * 128
+    torch.manual_seed(3)
+    conv = RGCNConv(K, H, R).cuda()
+    with torch.no_grad():
+        conv.bias.normal_()
+    x0 = torch.randn(N, K, generator=torch.Generator().manual_seed(5)).cuda()
+    dout = torch.randn(N, H, generator=torch.Generator().manual_seed(6)).cuda()
+    edge_index, edge_type = g.attach(), g.edge_type
+
+    def run(fused):
+        ops.RGCN_FUSED = fused
+        try:
+            for p_ in conv.parameters():
+                p_.grad = None
+            x = x0.clone().requires_grad_()
+            with erc_b200._lib.KernelTimer() as kt:
+                out = conv(x, edge_index, edge_type)
+                out.backward(dout)
+            torch.cuda.synchronize()
+            return out.detach(), x.grad, conv.weight.grad.clone(), conv.root.grad.clone(), conv.bias.grad.clone(), set(kt.summary())
+        finally:
+            ops.RGCN_FUSED = False
+
+    fused, plain = run(True), run(False)
+    assert "ercg_rgcn_window" in fused[5] and "ercg_gather_fwd" not in fused[5]
+    assert "ercg_rgcn_window" not in plain[5] and "ercg_gather_fwd" in plain[5]
+    # fp64 formula on the CPU
+    src, dst, et = g.col.long().cpu(), edge_index[1].long().cpu(), g.etype.long().cpu()
+    xd = x0.double().cpu().requires_grad_()
+    Wd, rootd, bd = (t.detach().double().cpu().requires_grad_() for t in (conv.weight, conv.root, conv.bias))
+    wmean = g.mean_weight().double().cpu()
+    msg = torch.einsum("ek,ekh->eh", xd[src], Wd[et]) * wmean[:, None]
+    want = torch.zeros(N, H, dtype=torch.float64).index_add(0, dst, msg) + xd @ rootd + bd
+    want.backward(dout.double().cpu())
+    refs = (want.detach(), xd.grad, Wd.grad, rootd.grad, bd.grad)
+    for name, a, b, r in zip(("out", "dx", "dW", "droot", "dbias"), fused, plain, refs):
+        assert rel_err(a, r) < TOL, (name, "fused vs fp64", rel_err(a, r))
+        assert rel_err(b, r) < TOL, (name, "transform-first vs fp64", rel_err(b, r))
+    absent = [r_ for r_ in range(R) if not bool((et == r_).any())]
+    for r_ in absent:
+        assert float(fused[2][r_].abs().max()) == 0.0
