@@ -714,7 +714,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-budget-s", type=float, default=16.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--copy-streams", type=int, default=2, help="H2D copy streams of the e2e feeder (2: +3 % over one)")
+    ap.add_argument("--copy-streams", type=int, default=2, help="H2D copy streams of the e2e feeder (2: +3 %% over one)")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run one step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],

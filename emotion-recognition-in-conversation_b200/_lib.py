@@ -87,6 +87,9 @@ SIGNATURES = {
     "ercg_dropout": (I, [P, P, L, F, U64, P]),
     "ercg_bn_workspace_bytes": (SZ, [L, I]),
     "ercg_bn_stats": (I, [P, L, L, I, P, P, P, SZ, P]),
+    "ercg_bn_running_update": (I, [P, P, P, P, P, F, F, I, P]),
+    "ercg_bn_sync_pack": (I, [P, P, D, I, P, P]),
+    "ercg_bn_sync_unpack": (I, [P, I, P, P, P]),
     "ercg_bn_act_fwd": (I, [P, L, P, P, F, P, P, F, P, L, L, I, P]),
     "ercg_bn_act_bwd_reduce": (I, [P, L, P, L, P, P, F, P, P, F, P, L, I, P, SZ, P]),
     "ercg_bn_act_bwd_apply": (I, [P, L, P, L, P, P, F, P, P, F, P, D, I, P, L, L, I, P]),

@@ -27,6 +27,9 @@
 //     unroll factors (A/B runs with one .so per variant: forward / by-source weighted-sum loop not unrolled, by-destination x7;
 //     256-thread dot loop not unrolled; 128-thread kernels compiled for 5 CTAs/SM; streaming vs plain stores: no difference).
 //     Result: 0.559 / 0.528 / 0.590 ms = 0.59 / 0.63 / 0.47 of the HBM copy peak by each kernel's algorithmic bytes.
+//     * packed fp32 FMAs (fma.rn.f32x2 = SASS FFMA2; common.cuh) in the dot-product and weighted-sum loops: 45 -> 29
+//       instructions per weighted-sum iteration, yet forward 0.558 -> 0.539 ms, by-source 0.588 -> 0.584 ms (noise),
+//       by-destination 0.531 -> 0.596 ms (slower): issue slots are not what these kernels wait for.  Forward only.
 // Per-edge arithmetic (chunk order inside each half of the dot products, ascending-source order of the weighted sums) follows
 // the tile kernels; the two half dot products and the softmax denominator are combined in a different order, so results
 // agree with the tile / generic kernels to rounding (tests: 2e-6), not bit for bit; every order is fixed => run-to-run
@@ -150,13 +153,29 @@ __device__ __forceinline__ void blk_colsum_finish(const float4* red, int nch, fl
 // Banded products of one tile, score phase: sc[d] = <a_{i0+d}, b_cand>.  arows: [BT][nch] row-major (tile rows); bt: [nch][RP]
 // chunk-major.  GRP == 2 (256 threads): each thread group takes half of the chunks, group 1 hands its partial sums to group 0
 // through `spart` (one barrier); GRP == 1: the whole dot product, in chunk order.
-template <int GRP>
+template <int GRP, bool PK = false>
 __device__ __forceinline__ void blk_dots(const float4* __restrict__ arows, const float4* __restrict__ bt, int RP, int nch, int il0, int r,
                                          bool any, int grp, float4* __restrict__ spart, int slot, float sc[BD]) {
   const int cmid = (nch + 1) >> 1;
   const int c0 = (GRP == 2 && grp) ? cmid : 0, c1 = (GRP == 2 && !grp) ? cmid : nch;
   sc[0] = sc[1] = sc[2] = sc[3] = 0.f;
-  if (any) {
+  if (PK) {                      // packed FMAs (FFMA2): even / odd partial sums per destination, added at the end
+    float2 s2[BD];
+#pragma unroll
+    for (int d = 0; d < BD; ++d) s2[d] = make_float2(0.f, 0.f);
+    if (any) {
+      const float4* br = bt + r;
+      const float4* a0 = arows + il0 * nch;
+#pragma unroll 5
+      for (int c = c0; c < c1; ++c) {
+        const float4 bc = br[c * RP];
+#pragma unroll
+        for (int d = 0; d < BD; ++d) dot4_acc2(s2[d], a0[d * nch + c], bc);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < BD; ++d) sc[d] = s2[d].x + s2[d].y;
+  } else if (any) {
     const float4* br = bt + r;
     const float4* a0 = arows + il0 * nch;
     if (GRP == 2) {
@@ -219,7 +238,7 @@ attn_fwd_blk_kernel(const float* __restrict__ q, const float* __restrict__ k, co
   const int r = (int)min(max(cand - g.r0, 0LL), (long long)(g.R - 1));
   cp_wait_all();
   float sc[BD];
-  blk_dots<GRP>(sq, skt, RP, nch, il0, r, any, grp, spart, slot, sc);
+  blk_dots<GRP, true>(sq, skt, RP, nch, il0, r, any, grp, spart, slot, sc);
   if (!grp) {
     float al[BD];
 #pragma unroll
@@ -251,7 +270,7 @@ attn_fwd_blk_kernel(const float* __restrict__ q, const float* __restrict__ k, co
       const int rr = min(max(rb + j, 0), g.R - 1);
       const float4 a4 = sa[bb * BCAND + j];
       const float4 vv = sv[rr * nch + c];
-      fma4(acc[0], a4.x, vv); fma4(acc[1], a4.y, vv); fma4(acc[2], a4.z, vv); fma4(acc[3], a4.w, vv);
+      fma4_p(acc[0], a4.x, vv); fma4_p(acc[1], a4.y, vv); fma4_p(acc[2], a4.z, vv); fma4_p(acc[3], a4.w, vv);
     }
 #pragma unroll
     for (int d = 0; d < BD; ++d)

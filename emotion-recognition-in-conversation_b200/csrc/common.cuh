@@ -43,9 +43,61 @@ __device__ __forceinline__ void st4_stream(float* p, float4 v) {
 __device__ __forceinline__ void fma4(float4& a, float s, const float4& b) {
   a.x = fmaf(s, b.x, a.x); a.y = fmaf(s, b.y, a.y); a.z = fmaf(s, b.z, a.z); a.w = fmaf(s, b.w, a.w);
 }
+// Packed variants.  sm_100a has a packed fp32 FMA (fma.rn.f32x2 -> SASS FFMA2, one operand may be a broadcast scalar): two
+// IEEE FMAs per issue slot, bit-identical to two fmaf.  It does not raise the FMA pipe's peak, it halves the issue slots of
+// a weighted-sum / dot-product loop.  Measured on the graph kernels (tools/bench_graph.py, 2^20 nodes): window
+// attention forward 0.558 -> 0.539 ms, by-source backward and both gathers unchanged (they wait on loads, not on issue
+// slots), the 256-thread by-destination backward SLOWER (0.531 -> 0.596 ms) -- so only the forward kernel uses these.
+__device__ __forceinline__ void fma2_p(float& a0, float& a1, float s, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rs;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\t"
+      "fma.rn.f32x2 ra, rs, rb, ra;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1), "f"(s));
+}
+__device__ __forceinline__ void fma4_p(float4& a, float s, const float4& b) {
+  fma2_p(a.x, a.y, s, b.x, b.y);
+  fma2_p(a.z, a.w, s, b.z, b.w);
+}
+// acc (two partial sums: even / odd elements) += a . b as two packed FMAs; the caller adds acc.x + acc.y at the end
+__device__ __forceinline__ void dot4_acc2(float2& acc, const float4& a, const float4& b) {
+  asm("{\n\t.reg .b64 rc, ra, rb;\n\tmov.b64 rc, {%0, %1};\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 ra, {%6, %7};\n\tmov.b64 rb, {%8, %9};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(acc.x), "+f"(acc.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(a.z), "f"(a.w), "f"(b.z), "f"(b.w));
+}
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
+
+// Second level of the two-level column reductions (bias gradients, BatchNorm statistics and backward sums, classifier-tail
+// gradients): column c of out = sum over the nb block partials, fixed order, fp64.  A block is FIN_COLS columns x FIN_ROWS
+// row-lanes; a thread adds every FIN_ROWS-th partial of its column with four independent accumulators (four loads in
+// flight), then the FIN_ROWS lane sums are added in lane order.  The first version (32 columns x 8 row-lanes, one
+// accumulator) walked 600 partials in 75 load-latency-bound iterations: 11-19 us per launch, nine such launches per COGMEN
+// step -- nothing at 2^20 utterances per GPU, ~5 % of the step when the same batch is sharded over 8 GPUs.
+constexpr int FIN_COLS = 8, FIN_ROWS = 32;           // FIN_COLS * FIN_ROWS == 256 threads
+__device__ __forceinline__ double fin_reduce(const float* __restrict__ partial, int nb, long long ld, int c, bool ok,
+                                             double (*sm)[FIN_COLS + 1]) {
+  const int tx = threadIdx.x & (FIN_COLS - 1), ty = threadIdx.x / FIN_COLS;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (ok) {
+    const float* p = partial + c;
+    int b = ty;
+    for (; b + 3 * FIN_ROWS < nb; b += 4 * FIN_ROWS) {
+      const float v0 = p[(long long)b * ld], v1 = p[(long long)(b + FIN_ROWS) * ld], v2 = p[(long long)(b + 2 * FIN_ROWS) * ld],
+                  v3 = p[(long long)(b + 3 * FIN_ROWS) * ld];
+      s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
+    }
+    for (; b < nb; b += FIN_ROWS) s0 += (double)p[(long long)b * ld];
+  }
+  __syncthreads();                                   // sm may still be read by a previous call
+  sm[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int y = 0; y < FIN_ROWS; ++y) tot += sm[y][tx];
+  return tot;
+}
+static inline unsigned fin_blocks(int ncols) { return (unsigned)((ncols + FIN_COLS - 1) / FIN_COLS); }
 
 // counter-based hash RNG for dropout: uniform in [0,1) from (seed, element index)
 __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {

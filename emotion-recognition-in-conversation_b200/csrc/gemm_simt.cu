@@ -378,20 +378,10 @@ colsum_partial_v4_kernel(const float* __restrict__ A, long long lda, long long M
 }
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ out) {
-  __shared__ double sm[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  double s = 0.0;
-  if (c < N)
-    for (int b = ty; b < nblocks; b += 8) s += (double)partial[(long long)b * N + c];
-  sm[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && c < N) {
-    double tot = 0.0;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) tot += sm[y][tx];
-    out[c] = (float)tot;
-  }
+  __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
+  const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
+  const double tot = fin_reduce(partial, nblocks, N, c, c < N, sm);
+  if (threadIdx.x < FIN_COLS && c < N) out[c] = (float)tot;
 }
 
 // skinny weight gradient (N1 <= 16, K1 <= 256, no row gather): slabs of rows, one block each
@@ -586,7 +576,7 @@ extern "C" int ercg_colsum(const float* A, int64_t lda, int64_t M, int N, float*
     colsum_partial_kernel<<<nb, 256, 0, st>>>(A, lda, M, N, reinterpret_cast<float*>(workspace));
   int rc = finish_launch();
   if (rc != ERCG_OK) return rc;
-  colsum_final_kernel<<<(N + 31) / 32, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), nb, N, out);
+  colsum_final_kernel<<<fin_blocks(N), 256, 0, st>>>(reinterpret_cast<const float*>(workspace), nb, N, out);
   return finish_launch();
 }
 

@@ -1579,20 +1579,10 @@ __global__ void split_bt_kernel(const float* __restrict__ B, long long ldb, int 
 // out[c] = sum_b partial[b * ldp + c], fixed order, fp64 accumulation
 __global__ void __launch_bounds__(256)
 tc_colsum_final_kernel(const float* __restrict__ partial, int nblocks, int ldp, int N, float* __restrict__ out) {
-  __shared__ double sm[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  double s = 0.0;
-  if (c < N)
-    for (int b = ty; b < nblocks; b += 8) s += (double)partial[(long long)b * ldp + c];
-  sm[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && c < N) {
-    double tot = 0.0;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) tot += sm[y][tx];
-    out[c] = (float)tot;
-  }
+  __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
+  const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
+  const double tot = fin_reduce(partial, nblocks, ldp, c, c < N, sm);
+  if (threadIdx.x < FIN_COLS && c < N) out[c] = (float)tot;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1804,7 +1794,7 @@ extern "C" int ercg_gemm_nn_tc(const float* A, int64_t lda, const float* B, int6
   if (colsum_out) {
     rc = finish_launch();
     if (rc) return rc;
-    tc_colsum_final_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial, grid * 4, 128, N, colsum_out);
+    tc_colsum_final_kernel<<<fin_blocks(N), 256, 0, st>>>(partial, grid * 4, 128, N, colsum_out);
   }
   return finish_launch();
 }
@@ -1942,7 +1932,7 @@ extern "C" int ercg_rgcn_window(const float* x, int64_t ldx, const int32_t* rowp
   if (colsum_out) {
     rc = finish_launch();
     if (rc) return rc;
-    tc_colsum_final_kernel<<<(Nout + 31) / 32, 256, 0, st>>>(partial, grid * 4, 128, Nout, colsum_out);
+    tc_colsum_final_kernel<<<fin_blocks(Nout), 256, 0, st>>>(partial, grid * 4, 128, Nout, colsum_out);
   }
   return finish_launch();
 }

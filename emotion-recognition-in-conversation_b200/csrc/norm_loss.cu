@@ -130,31 +130,16 @@ col_partials_v4_kernel(const float* __restrict__ x, long long ldx, const float* 
   }
 }
 
-// fixed-order fp64 reduction of partial[nb][2H] column c: 8 row-lanes per column, then a fixed 8-term sum
-__device__ __forceinline__ double reduce_partials(const float* __restrict__ partial, int nb, int width, int c, bool ok,
-                                                  double (*sm)[33]) {
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  double s = 0.0;
-  if (ok)
-    for (int b = ty; b < nb; b += 8) s += (double)partial[(long long)b * width + c];
-  __syncthreads();
-  sm[ty][tx] = s;
-  __syncthreads();
-  double tot = 0.0;
-#pragma unroll
-  for (int y = 0; y < 8; ++y) tot += sm[y][tx];
-  return tot;
-}
-
+// second level of the BatchNorm reductions: fin_reduce (common.cuh) over partial[nb][2H]
 __global__ void __launch_bounds__(256)
 bn_stats_final_kernel(const float* __restrict__ partial, int nb, int H, long long N,
                       const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var) {
-  __shared__ double sm[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
+  const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
   const bool ok = c < H;
-  const double s0 = reduce_partials(partial, nb, 2 * H, c, ok, sm);
-  const double s1 = reduce_partials(partial, nb, 2 * H, H + c, ok, sm);
-  if (!ok || (threadIdx.x >> 5) != 0) return;
+  const double s0 = fin_reduce(partial, nb, 2 * H, c, ok, sm);
+  const double s1 = fin_reduce(partial, nb, 2 * H, H + c, ok, sm);
+  if (!ok || threadIdx.x >= FIN_COLS) return;
   const double m = s0 / (double)N;          // mean of (x - shift)
   double v = s1 / (double)N - m * m;
   if (v < 0.0) v = 0.0;
@@ -163,11 +148,48 @@ bn_stats_final_kernel(const float* __restrict__ partial, int nb, int H, long lon
 
 __global__ void __launch_bounds__(256)
 sums_final_kernel(const float* __restrict__ partial, int nb, int H, float* __restrict__ sums) {
-  __shared__ double sm[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
+  const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
   const bool ok = c < 2 * H;
-  const double s = reduce_partials(partial, nb, 2 * H, c, ok, sm);
-  if (ok && (threadIdx.x >> 5) == 0) sums[c] = (float)s;
+  const double s = fin_reduce(partial, nb, 2 * H, c, ok, sm);
+  if (ok && threadIdx.x < FIN_COLS) sums[c] = (float)s;
+}
+
+// explicit _rn intrinsics: no FMA contraction, so the values equal the elementwise fp64 expression they replace
+__global__ void __launch_bounds__(256)
+bn_sync_pack_kernel(const float* __restrict__ mean, const float* __restrict__ var, double n, int H, double* __restrict__ buf) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < H) {
+    const double m = (double)mean[c];
+    buf[c] = __dmul_rn(m, n);
+    buf[H + c] = __dmul_rn(__dadd_rn((double)var[c], __dmul_rn(m, m)), n);
+  } else if (c == H) {
+    buf[2 * H] = n;
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_sync_unpack_kernel(const double* __restrict__ buf, int H, float* __restrict__ mean, float* __restrict__ var) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= H) return;
+  const double count = buf[2 * H];
+  const double gm = __ddiv_rn(buf[c], count);
+  const double gv = __dsub_rn(__ddiv_rn(buf[H + c], count), __dmul_rn(gm, gm));
+  mean[c] = (float)gm;
+  var[c] = (float)(gv > 0.0 ? gv : 0.0);
+}
+
+__global__ void __launch_bounds__(256)
+bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ var, float* __restrict__ rmean,
+                         float* __restrict__ rvar, long long* __restrict__ nbt, float momentum, float count, int H) {
+  const long long seen = nbt ? nbt[0] + 1 : 1;
+  const float m = momentum >= 0.f ? momentum : (float)(1.0 / (double)seen);
+  const float unbias = m * count / fmaxf(count - 1.0f, 1.0f);
+  for (int c = threadIdx.x; c < H; c += 256) {
+    rmean[c] = fmaf(m, mean[c], rmean[c] * (1.0f - m));
+    rvar[c] = fmaf(unbias, var[c], rvar[c] * (1.0f - m));
+  }
+  __syncthreads();                       // every thread has read nbt[0]
+  if (threadIdx.x == 0 && nbt) nbt[0] = seen;
 }
 
 __global__ void __launch_bounds__(256)
@@ -276,13 +298,23 @@ ce_fwd_kernel(const float* __restrict__ logits, long long ld, const long long* _
   if (threadIdx.x == 0) { partial[2 * (long long)blockIdx.x] = s0[0]; partial[2 * (long long)blockIdx.x + 1] = s1[0]; }
 }
 
-__global__ void ce_final_kernel(const float* __restrict__ partial, long long nb, float* __restrict__ out) {
-  // one warp; fixed order: lane-strided fp64 sums then a fixed shuffle tree
+__global__ void __launch_bounds__(256)
+ce_final_kernel(const float* __restrict__ partial, long long nb, float* __restrict__ out) {
+  // fixed order: thread-strided fp64 sums (256 threads: 16 loads per thread for 4096 partials, not 128 on one warp), a fixed
+  // shuffle tree per warp, then the 8 warp sums in warp order
+  __shared__ double sa[8], sb[8];
   double a = 0.0, b = 0.0;
-  for (long long i = threadIdx.x; i < nb; i += 32) { a += (double)partial[2 * i]; b += (double)partial[2 * i + 1]; }
+  for (long long i = threadIdx.x; i < nb; i += 256) { a += (double)partial[2 * i]; b += (double)partial[2 * i + 1]; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-  if (threadIdx.x == 0) { out[0] = (float)a; out[1] = (float)b; }
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { ta += sa[w]; tb += sb[w]; }
+    out[0] = (float)ta; out[1] = (float)tb;
+  }
 }
 
 __global__ void scale_by_ratio_kernel(float* __restrict__ x, long long n, const float* __restrict__ num,
@@ -407,11 +439,11 @@ cls_tail_bwd_kernel(const float* __restrict__ h, long long ldh, const float* __r
 __global__ void __launch_bounds__(256)
 cls_tail_final_kernel(const float* __restrict__ partial, int nb, int width, int CK, int K, int C, float* __restrict__ dW3,
                       float* __restrict__ db0, float* __restrict__ db3) {
-  __shared__ double sm[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
+  const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
   const bool ok = c < CK + K + C;
-  const double s = reduce_partials(partial, nb, width, c, ok, sm);
-  if (!ok || (threadIdx.x >> 5) != 0) return;
+  const double s = fin_reduce(partial, nb, width, c, ok, sm);
+  if (!ok || threadIdx.x >= FIN_COLS) return;
   if (c < CK) dW3[c] = (float)s;
   else if (c < CK + K) db0[c - CK] = (float)s;
   else db3[c - CK - K] = (float)s;
@@ -458,7 +490,27 @@ extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, floa
     col_partials_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
   int rc = finish_launch();
   if (rc) return rc;
-  bn_stats_final_kernel<<<(H + 31) / 32, 256, 0, st>>>(part, nb, H, N, x, mean, var);
+  bn_stats_final_kernel<<<fin_blocks(H), 256, 0, st>>>(part, nb, H, N, x, mean, var);
+  return finish_launch();
+}
+
+extern "C" int ercg_bn_running_update(const float* mean, const float* var, float* running_mean, float* running_var,
+                                      int64_t* num_batches_tracked, float momentum, float count, int H, void* stream) {
+  if (H <= 0 || H > 1024 || !mean || !var || !running_mean || !running_var) return ERCG_EINVAL;
+  if (momentum < 0.f && !num_batches_tracked) return ERCG_EINVAL;
+  bn_running_update_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(mean, var, running_mean, running_var,
+                                                                reinterpret_cast<long long*>(num_batches_tracked), momentum, count, H);
+  return finish_launch();
+}
+
+extern "C" int ercg_bn_sync_pack(const float* mean, const float* var, double n_local, int H, double* buf, void* stream) {
+  if (H <= 0 || !mean || !var || !buf) return ERCG_EINVAL;
+  bn_sync_pack_kernel<<<(H + 1 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mean, var, n_local, H, buf);
+  return finish_launch();
+}
+extern "C" int ercg_bn_sync_unpack(const double* buf, int H, float* mean, float* var, void* stream) {
+  if (H <= 0 || !mean || !var || !buf) return ERCG_EINVAL;
+  bn_sync_unpack_kernel<<<(H + 255) / 256, 256, 0, (cudaStream_t)stream>>>(buf, H, mean, var);
   return finish_launch();
 }
 
@@ -496,7 +548,7 @@ extern "C" int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const floa
   }
   int rc = finish_launch();
   if (rc) return rc;
-  sums_final_kernel<<<(2 * H + 31) / 32, 256, 0, st>>>(part, nb, H, sums);
+  sums_final_kernel<<<fin_blocks(2 * H), 256, 0, st>>>(part, nb, H, sums);
   return finish_launch();
 }
 
@@ -539,7 +591,7 @@ extern "C" int ercg_ce_fwd(const float* logits, int64_t ld, const int64_t* label
                                              ldd, N, C, part);
   int rc = finish_launch();
   if (rc) return rc;
-  ce_final_kernel<<<1, 32, 0, st>>>(part, nb, lossnum_den);
+  ce_final_kernel<<<1, 256, 0, st>>>(part, nb, lossnum_den);
   return finish_launch();
 }
 
@@ -583,6 +635,6 @@ extern "C" int ercg_cls_tail_bwd(const float* h, int64_t ldh, const float* dlogi
   }
   int rc = finish_launch();
   if (rc) return rc;
-  cls_tail_final_kernel<<<(width + 31) / 32, 256, 0, st>>>(part, grid, width, C * K, K, C, dW3, db0, db3);
+  cls_tail_final_kernel<<<fin_blocks(width), 256, 0, st>>>(part, grid, width, C * K, K, C, dW3, db0, db3);
   return finish_launch();
 }

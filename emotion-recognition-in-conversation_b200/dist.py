@@ -50,6 +50,20 @@ class StatSync:
     def stats(self, mean, var, n_local):
         """local (mean, biased var, n) -> global (mean, biased var, count)."""
         H = mean.numel()
+        if mean.is_cuda:
+            # two launches around the collective (ercg_bn_sync_pack / _unpack) instead of a dozen elementwise ones: with the
+            # batch sharded over 8 GPUs the step is 1.7 ms and every 3 us launch on its critical path shows
+            from ._lib import lib, check
+            from .ops import _p, _stream
+            buf = torch.empty(2 * H + 1, dtype=torch.float64, device=mean.device)
+            mean, var = mean.contiguous(), var.contiguous()
+            check(lib().ercg_bn_sync_pack(_p(mean), _p(var), float(n_local), H, _p(buf), _stream()), "ercg_bn_sync_pack")
+            dist.all_reduce(buf, group=self.group)
+            gmean = torch.empty(H, dtype=torch.float32, device=mean.device)
+            gvar = torch.empty(H, dtype=torch.float32, device=mean.device)
+            check(lib().ercg_bn_sync_unpack(_p(buf), H, _p(gmean), _p(gvar), _stream()), "ercg_bn_sync_unpack")
+            return gmean, gvar, (float(self.global_count) if self.global_count else float(buf[2 * H].item()))
+        # CPU tensors (gloo tests of the host logic): the same arithmetic as elementwise torch expressions
         buf = torch.empty(2 * H + 1, dtype=torch.float64, device=mean.device)
         buf[:H] = mean.double() * n_local
         buf[H:2 * H] = (var.double() + mean.double() ** 2) * n_local

@@ -595,6 +595,13 @@ def bn_stats(x):
     return mean, var
 
 
+def bn_running_update(bn, mean, var, count):
+    """Train-mode bookkeeping of nn.BatchNorm1d (num_batches_tracked, running_mean, running_var) in ONE launch."""
+    check(lib().ercg_bn_running_update(_p(mean), _p(var), _p(bn.running_mean), _p(bn.running_var), _p(bn.num_batches_tracked),
+                                       float(bn.momentum) if bn.momentum is not None else -1.0, float(count),
+                                       mean.numel(), _stream()), "ercg_bn_running_update")
+
+
 def bn_leaky_relu(x, gamma, beta, mean, var, eps, slope, use_batch_stats, count=None, stat_sync=None):
     return _BnAct.apply(x, gamma, beta, mean, var, float(eps), float(slope), bool(use_batch_stats),
                         float(count if count is not None else x.size(0)), stat_sync)

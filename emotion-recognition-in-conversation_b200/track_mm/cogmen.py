@@ -43,11 +43,7 @@ class GNN(nn.Module):
             if self.stat_sync is not None:
                 mean, var, count = self.stat_sync.stats(mean, var, n_local)
             if bn.track_running_stats:
-                with torch.no_grad():
-                    bn.num_batches_tracked += 1
-                    m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                    bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                    bn.running_var.mul_(1 - m).add_(var, alpha=m * count / max(count - 1.0, 1.0))
+                ops.bn_running_update(bn, mean, var, count)     # one launch, no host read of num_batches_tracked
             return ops.bn_leaky_relu(x, bn.weight, bn.bias, mean, var, bn.eps, self.relu.negative_slope, True, count,
                                      self.stat_sync.grads if self.stat_sync is not None else None)
         return ops.bn_leaky_relu(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,

@@ -334,6 +334,18 @@ int ercg_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, 
 size_t ercg_bn_workspace_bytes(int64_t N, int H);
 int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, float* mean, float* var,
                   void* workspace, size_t workspace_bytes, void* stream);
+/* running statistics of nn.BatchNorm1d in train mode (cogmen.py:67; torch semantics): num_batches_tracked += 1;
+ * m = momentum, or 1 / num_batches_tracked when momentum < 0 (momentum=None);
+ * running_mean = (1 - m) running_mean + m mean;  running_var = (1 - m) running_var + m var count / max(count - 1, 1).
+ * ONE launch instead of five elementwise ones; count = rows behind the statistics (all ranks).  H <= 1024. */
+int ercg_bn_running_update(const float* mean, const float* var, float* running_mean, float* running_var,
+                           int64_t* num_batches_tracked, float momentum, float count, int H, void* stream);
+/* data-parallel BatchNorm statistics (global-batch mode): pack local (mean, biased var, n) into the fp64 all-reduce buffer
+ * buf[2H+1] = (mean n | (var + mean^2) n | n), and unpack the summed buffer into the global (mean, biased var) -- two
+ * launches around the collective instead of a dozen elementwise ones.  Same arithmetic, in fp64, as the reference-style
+ * torch expression it replaces (emotion-recognition-in-conversation_b200/dist.py). */
+int ercg_bn_sync_pack(const float* mean, const float* var, double n_local, int H, double* buf, void* stream);
+int ercg_bn_sync_unpack(const double* buf, int H, float* mean, float* var, void* stream);
 int ercg_bn_act_fwd(const float* x, int64_t ldx, const float* mean, const float* var, float eps,
                     const float* gamma, const float* beta, float slope,
                     float* out, int64_t ldo, int64_t N, int H, void* stream);

@@ -238,6 +238,49 @@ def test_bn_leaky_relu_fwd_bwd(N):
     assert rel_err(gc.grad, gd.grad, floor=1e-3) < TOL and rel_err(bc.grad, bd.grad) < TOL
 
 
+@pytest.mark.parametrize("momentum", [0.1, None])
+def test_bn_running_update_matches_torch_batchnorm(momentum):
+    """ercg_bn_running_update = the train-mode bookkeeping of nn.BatchNorm1d (num_batches_tracked, running_mean, running_var
+    with the unbiased-variance factor), momentum=None (cumulative average) included."""
+    import erc_b200
+    from erc_b200 import ops
+    H, gen = 100, torch.Generator().manual_seed(5)
+    ref = torch.nn.BatchNorm1d(H, momentum=momentum).double().train()
+    ours = torch.nn.BatchNorm1d(H, momentum=momentum).cuda().train()
+    for n in (700, 33, 1500):
+        x = torch.randn(n, H, generator=gen) * 3 + 1
+        ref(x.double())
+        m, v = ops.bn_stats(x.cuda())
+        ops.bn_running_update(ours, m, v, float(n))
+    assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == 3
+    assert rel_err(ours.running_mean, ref.running_mean) < TOL and rel_err(ours.running_var, ref.running_var) < TOL
+
+
+def test_bn_sync_pack_unpack_equal_the_elementwise_expression():
+    """The two kernels around the BatchNorm-statistics all-reduce (dist.StatSync.stats on CUDA) against the torch fp64
+    expression they replace, bit for bit, with two simulated ranks."""
+    import erc_b200
+    from erc_b200._lib import lib, check
+    H, gen = 100, torch.Generator().manual_seed(9)
+    parts, bufs = [], []
+    for n in (1234, 777):
+        mean, var = torch.randn(H, generator=gen), torch.rand(H, generator=gen) + 0.1
+        buf = torch.empty(2 * H + 1, dtype=torch.float64, device="cuda")
+        mc, vc = mean.cuda(), var.cuda()
+        check(lib().ercg_bn_sync_pack(mc.data_ptr(), vc.data_ptr(), float(n), H, buf.data_ptr(), None), "pack")
+        want = torch.cat([mean.double() * n, (var.double() + mean.double() ** 2) * n, torch.tensor([float(n)], dtype=torch.float64)])
+        assert torch.equal(buf.cpu(), want)
+        bufs.append(buf)
+        parts.append(want)
+    tot = bufs[0] + bufs[1]                      # what the all-reduce delivers
+    gm, gv = torch.empty(H, device="cuda"), torch.empty(H, device="cuda")
+    check(lib().ercg_bn_sync_unpack(tot.data_ptr(), H, gm.data_ptr(), gv.data_ptr(), None), "unpack")
+    w = parts[0] + parts[1]
+    wm = w[:H] / w[2 * H]
+    wv = (w[H:2 * H] / w[2 * H] - wm ** 2).clamp_(min=0)
+    assert torch.equal(gm.cpu(), wm.float()) and torch.equal(gv.cpu(), wv.float())
+
+
 @pytest.mark.parametrize("C,weighted", [(4, False), (6, True), (1, False), (7, True)])
 def test_cross_entropy(C, weighted):
     import erc_b200
