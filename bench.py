@@ -309,9 +309,10 @@ def run_ours(args):
         # cogmen.py:50: Adam(lr 1e-4, weight_decay 1e-8) -- here ercg_adam_step on the flat buffer of the live parameters
         data_group = dist.new_group(backend="nccl") if world > 1 else None     # the step's own communicator (captured in its graph)
         ts = CogmenTrainStep(model, lengths, speakers_present=(0,), lr=1e-4, weight_decay=1e-8, world=world,
-                             global_utterances=total_utts, bn_sync=args.bn_sync, overlap=not args.no_overlap, group=data_group)
+                             global_utterances=total_utts, bn_sync=args.bn_sync, overlap=not args.no_overlap, group=data_group,
+                             transport=args.transport)
         out = {"scaling": scaling, "utterances_per_step": total_utts, "utterances_rank0": N, "edges_rank0": sizes[1],
-               "dialogues": int(lengths_all.numel())}
+               "dialogues": int(lengths_all.numel()), "transport": ts.transport}
 
         # ---- eager steps (kernel by kernel): warm-up, then K steps with every C-ABI call bracketed by CUDA events
         loss = ts.step(x, spk, labels)
@@ -467,7 +468,11 @@ def run_ours(args):
                           "how": "pinned host buffers -> DeviceFeeder (double-buffered, %d copy streams) -> eager step -> loss.item(); "
                                  "all copies inside the timed region; host threads bound to the GPU's NUMA node: %s" % (args.copy_streams, numa)}
             del feeder, host, hx
-        ts.check()                                             # K1's input-error flags of the last step
+        ts.check()                                             # K1's input-error flags of the last step, peer-collective timeouts
+        if ts.comms:
+            barrier()                                          # nobody may still be reading a region that is about to be freed
+            for c in ts.comms:
+                c.close()
         gc.enable()
         gc.unfreeze()
         out["x_bytes"] = x_store.numel() * x_store.element_size()
@@ -554,6 +559,7 @@ def run_ours(args):
                            "l2": "inputs (%.2f GB/step/GPU) are larger than the 126 MB L2" % (head["x_bytes"] / 1e9),
                            "step": "one CUDA-graph replay per step" if mode == "graph" else "eager launches",
                            "bn_statistics": "global (all-reduced)" if (world > 1 and args.bn_sync == "global") else "per rank",
+                           "collectives": head.get("transport", "none") if world > 1 else "none (one GPU)",
                            "dropout": "on (train mode)", "optimizer": "Adam inside the step (ercg_adam_step on the flat parameter buffer)",
                            "dead_encoder": "not executed (cogmen.py:146-147 discards its output)"},
                 "roofline": roof, "graph_kernels": graph_kernels, "kernels": kernels,
@@ -576,9 +582,10 @@ def run_ours(args):
                 "what": "each rank's own shard replayed as a stand-alone step (no collectives, no waiting), all ranks at once",
                 "slowest_rank_solo_ms": max(sm), "fastest_rank_solo_ms": min(sm),
                 "collectives_and_skew_ms": round(best["ms_per_step"] - max(sm), 4),
-                "collectives_per_step": "BN statistics (2H+1 doubles, forward) + their backward sums (2H floats) + flat gradients "
-                                        "in two overlapped buckets (NCCL, captured in the step's CUDA graph)" if args.bn_sync == "global"
-                                        else "flat gradients in two overlapped buckets (NCCL, captured in the step's CUDA graph)"}
+                "collectives_per_step": ("BN statistics (2H+1 doubles, forward) + their backward sums (2H floats) + flat gradients "
+                                         "in two overlapped buckets" if args.bn_sync == "global"
+                                         else "flat gradients in two overlapped buckets") +
+                                        " (%s, nodes of the step's CUDA graph)" % head.get("transport", "torch.distributed")}
         if other is not None:
             ob = other.get("graph") or other.get("eager")
             line[other["scaling"] + "_scaling"] = {"value": ob["value"], "ms_per_step": ob["ms_per_step"],
@@ -722,6 +729,8 @@ def main():
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"], help="headline loop: CUDA-graph replay or eager launches")
     ap.add_argument("--bn-sync", default="global", choices=["global", "local"],
                     help="BatchNorm statistics across ranks: global = all-reduced (N-GPU == 1-GPU result), local = per rank (the reference's DDP)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: the step's all-reduces through libercgraph's peer-memory kernel (p2p), NCCL, or p2p when available")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of the two overlapped buckets")
     ap.add_argument("--watchdog-s", type=int, default=0, help="dump all Python stacks and exit if the run takes longer than this")
     ap.add_argument("--library-yardstick", action="store_true",

@@ -99,6 +99,14 @@ SIGNATURES = {
     "ercg_sumsq_workspace_bytes": (SZ, [L]),
     "ercg_sumsq": (I, [P, L, P, P, SZ, P]),
     "ercg_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P, F, P, P]),
+    # peer-memory all-reduce (csrc/p2p.cu)
+    "ercg_p2p_region_bytes": (SZ, [SZ]),
+    "ercg_p2p_alloc": (I, [SZ, P, P]),
+    "ercg_p2p_open": (I, [P, P]),
+    "ercg_p2p_close": (I, [P]),
+    "ercg_p2p_free": (I, [P]),
+    "ercg_p2p_status": (I, [P, P]),
+    "ercg_p2p_allreduce": (I, [P, I, I, P, P, L, I, SZ, P]),
     # K7 / K8 (MMGCN)
     "ercg_mmgcn_block_offsets": (I, [P, I, P, P]),
     "ercg_mmgcn_adj_fwd": (I, [P, L, P, P, P, L, L, I, I, P, L, P, P, P, P, P]),
@@ -164,7 +172,8 @@ class _Timed:
     def __getattr__(self, name):
         fn = getattr(self._h, name)
         if name.endswith("_bytes") or name.endswith("_supported") or name.endswith("_tiles") or name in ("ercg_strerror", "ercg_version", "ercg_launch_count",
-                                               "ercg_graphify_sizes_host"):
+                                               "ercg_graphify_sizes_host", "ercg_p2p_alloc", "ercg_p2p_open", "ercg_p2p_close",
+                                               "ercg_p2p_free", "ercg_p2p_status"):
             setattr(self, name, fn)
             return fn
 

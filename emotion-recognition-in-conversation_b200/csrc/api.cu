@@ -13,6 +13,7 @@ extern "C" const char* ercg_strerror(int code) {
     case ERCG_ERANGE: return "size exceeds the packed int32/uint8 format";
     case ERCG_ECUDA: return "CUDA launch error";
     case ERCG_EWORKSPACE: return "workspace too small";
+    case ERCG_P2P_ETIMEOUT: return "a peer did not arrive at a peer-memory collective";
     default: return "unknown error";
   }
 }

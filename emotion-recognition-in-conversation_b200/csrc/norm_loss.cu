@@ -165,6 +165,7 @@ bn_sync_pack_kernel(const float* __restrict__ mean, const float* __restrict__ va
     buf[H + c] = __dmul_rn(__dadd_rn((double)var[c], __dmul_rn(m, m)), n);
   } else if (c == H) {
     buf[2 * H] = n;
+    buf[2 * H + 1] = 0.0;                 // pad: the buffer is an even number of doubles = whole 16-byte units
   }
 }
 __global__ void __launch_bounds__(256)

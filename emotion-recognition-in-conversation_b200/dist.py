@@ -43,9 +43,11 @@ def shard_dialogues(lengths, world_size):
 class StatSync:
     """All-reduce hooks for BatchNorm statistics (see GNN._bn_relu in track_mm/cogmen.py of this package)."""
 
-    def __init__(self, group=None, global_count=None):
+    def __init__(self, group=None, global_count=None, reduce=None):
         self.group = group
         self.global_count = global_count       # host-known global utterance count: avoids a device sync
+        # in-place all-reduce(sum): torch.distributed on ``group``, or a p2p.Reducer (peer-memory kernel on one NVSwitch node)
+        self.reduce = reduce if reduce is not None else (lambda t: dist.all_reduce(t, group=self.group))
 
     def stats(self, mean, var, n_local):
         """local (mean, biased var, n) -> global (mean, biased var, count)."""
@@ -55,10 +57,10 @@ class StatSync:
             # batch sharded over 8 GPUs the step is 1.7 ms and every 3 us launch on its critical path shows
             from ._lib import lib, check
             from .ops import _p, _stream
-            buf = torch.empty(2 * H + 1, dtype=torch.float64, device=mean.device)
+            buf = torch.empty(2 * H + 2, dtype=torch.float64, device=mean.device)   # even count: whole 16-byte units for the peer kernel
             mean, var = mean.contiguous(), var.contiguous()
             check(lib().ercg_bn_sync_pack(_p(mean), _p(var), float(n_local), H, _p(buf), _stream()), "ercg_bn_sync_pack")
-            dist.all_reduce(buf, group=self.group)
+            self.reduce(buf)
             gmean = torch.empty(H, dtype=torch.float32, device=mean.device)
             gvar = torch.empty(H, dtype=torch.float32, device=mean.device)
             check(lib().ercg_bn_sync_unpack(_p(buf), H, _p(gmean), _p(gvar), _stream()), "ercg_bn_sync_unpack")
@@ -68,14 +70,14 @@ class StatSync:
         buf[:H] = mean.double() * n_local
         buf[H:2 * H] = (var.double() + mean.double() ** 2) * n_local
         buf[2 * H:].fill_(float(n_local))           # (indexed assignment of a Python number is a CPU->GPU copy: not capturable)
-        dist.all_reduce(buf, group=self.group)
+        self.reduce(buf)
         count = buf[2 * H]
         gmean = buf[:H] / count
         gvar = (buf[H:2 * H] / count - gmean ** 2).clamp_(min=0)
         return gmean.float(), gvar.float(), (float(self.global_count) if self.global_count else float(count.item()))
 
     def grads(self, sums):
-        dist.all_reduce(sums, group=self.group)
+        self.reduce(sums)
         return sums
 
 

@@ -27,14 +27,26 @@ from .optim import FlatAdam
 
 class CogmenTrainStep:
     def __init__(self, model, lengths, speakers_present=(0,), lr=1e-4, weight_decay=1e-8, world=1, global_utterances=None,
-                 bn_sync="global", overlap=True, group=None):
+                 bn_sync="global", overlap=True, group=None, transport="auto"):
         """lengths: CPU int64 [B] dialogue lengths of THIS rank's batch (a step re-run on new data of the same lengths reuses
-        the capture; new lengths need a new capture).  speakers_present: the speaker ids the data set uses."""
+        the capture; new lengths need a new capture).  speakers_present: the speaker ids the data set uses.
+        transport: "p2p" = peer-memory all-reduce kernels (ercg_p2p_allreduce, one NVSwitch node), "nccl" = torch.distributed
+        on ``group``, "auto" = p2p when every rank can set it up, else torch.distributed."""
         from .dist import StatSync
+        from .p2p import PeerComm, Reducer
         self.model, self.world, self.group = model, world, group
+        self.dev = next(model.parameters()).device
+        comms = None
+        if world > 1 and transport in ("auto", "p2p") and self.dev.type == "cuda":
+            # two communicators: the early gradient bucket runs on a side stream next to the main stream's collectives
+            comms = PeerComm.create(group, self.dev, max_bytes=8 << 20, n=2)
+            if comms is None and transport == "p2p":
+                raise RuntimeError("CogmenTrainStep: transport='p2p' but the peer-memory communicator could not be set up")
+        self.comms = comms
+        self.reduce_main = Reducer(group, comms[0] if comms else None)
+        self.reduce_side = Reducer(group, comms[1] if comms else None)
         self.lengths = lengths.to(torch.int64).cpu().contiguous()
         self.sizes = graph_sizes(self.lengths, model.wp, model.wf)
-        self.dev = next(model.parameters()).device
         self.lengths_dev = self.lengths.to(self.dev)
         self.rel_ids = relation_ids_for_speakers(speakers_present, model.n_speakers)
         self.global_utts = int(global_utterances if global_utterances is not None else self.sizes[0])
@@ -42,7 +54,7 @@ class CogmenTrainStep:
         self.overlap = bool(overlap) and world > 1
         self.side = torch.cuda.Stream(device=self.dev) if self.overlap else None
         if world > 1 and bn_sync == "global":
-            model.gcn.stat_sync = StatSync(group=group, global_count=self.global_utts)
+            model.gcn.stat_sync = StatSync(group=group, global_count=self.global_utts, reduce=self.reduce_main)
         self._graph = None
         self._static = None
         self._pending = 0
@@ -89,7 +101,7 @@ class CogmenTrainStep:
         ev.record()
         self.side.wait_event(ev)
         with torch.cuda.stream(self.side):
-            dist.all_reduce(opt.span(0, self._n_early), group=self.group)
+            self.reduce_side(opt.span(0, self._n_early))
 
     def step(self, x, spk, labels):
         """One eager step.  Returns this rank's share of the global mean loss (device scalar)."""
@@ -100,18 +112,18 @@ class CogmenTrainStep:
                 self.opt.extra.copy_(loss.detach().reshape(1) * float(self.global_utts))
             self.opt.gather()
             if self.world > 1:
-                dist.all_reduce(self.opt.flat_g, group=self.group)
+                self.reduce_main(self.opt.flat_g)
             self.opt.update()
             return loss.detach()
         opt = self.opt
         if self.world > 1:
             if self.overlap:
                 opt.gather(self._n_early, None)
-                dist.all_reduce(opt.flat_g[opt.offsets[self._n_early]:], group=self.group)    # projection bucket + loss slot
+                self.reduce_main(opt.flat_g[opt.offsets[self._n_early]:])                    # projection bucket + loss slot
                 torch.cuda.current_stream(self.dev).wait_stream(self.side)
             else:
                 opt.gather()
-                dist.all_reduce(opt.flat_g, group=self.group)
+                self.reduce_main(opt.flat_g)
         else:
             opt.gather()
         opt.update()
@@ -144,5 +156,12 @@ class CogmenTrainStep:
         return self._loss
 
     def check(self):
-        """Raise if K1 flagged the batch of the last step (bad lengths / speaker ids / relation id outside the hint)."""
+        """Raise if K1 flagged the batch of the last step (bad lengths / speaker ids / relation id outside the hint), or if
+        a peer-memory collective timed out."""
         self._last_graph.check_inputs()
+        for c in self.comms or ():
+            c.check()
+
+    @property
+    def transport(self):
+        return self.reduce_main.transport

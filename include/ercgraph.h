@@ -35,6 +35,7 @@ extern "C" {
 #define ERCG_ERANGE (-3)   /* size exceeds what the packed int32/uint8 formats can hold */
 #define ERCG_ECUDA (-4)    /* CUDA runtime reported an error at launch (cudaGetLastError) */
 #define ERCG_EWORKSPACE (-5) /* workspace too small */
+#define ERCG_P2P_ETIMEOUT (-6) /* a peer did not arrive at a peer-memory collective within 30 s (ercg_p2p_status) */
 
 #define ERCG_GRAPH_ELENGTH 1   /* a dialogue is longer than the padded speaker width spk_ld */
 #define ERCG_GRAPH_ESPEAKER 2  /* a speaker id outside [0, n_speakers) */
@@ -341,7 +342,7 @@ int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, float* mean, fl
 int ercg_bn_running_update(const float* mean, const float* var, float* running_mean, float* running_var,
                            int64_t* num_batches_tracked, float momentum, float count, int H, void* stream);
 /* data-parallel BatchNorm statistics (global-batch mode): pack local (mean, biased var, n) into the fp64 all-reduce buffer
- * buf[2H+1] = (mean n | (var + mean^2) n | n), and unpack the summed buffer into the global (mean, biased var) -- two
+ * buf[2H+2] = (mean n | (var + mean^2) n | n | 0), and unpack the summed buffer into the global (mean, biased var) -- two
  * launches around the collective instead of a dozen elementwise ones.  Same arithmetic, in fp64, as the reference-style
  * torch expression it replaces (emotion-recognition-in-conversation_b200/dist.py). */
 int ercg_bn_sync_pack(const float* mean, const float* var, double n_local, int H, double* buf, void* stream);
@@ -460,6 +461,33 @@ int ercg_sumsq(const float* x, int64_t n, float* out, void* workspace, size_t wo
 int ercg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int decoupled, float grad_scale, const float* sumsq,
                    float max_norm, int64_t* step_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Peer-memory all-reduce over NVLink / NVSwitch for the exchanges of the dialogue-sharded train step: BatchNorm statistics,
+ * their backward sums, the flat gradient buffer.  Replaces the bucketed NCCL all-reduce the reference reaches through
+ * accelerate / DDP (lumo/trainer/trainer.py:62-64,315-327, track_mm/cogmen.py:188) on ONE node.  One-shot: every rank stages
+ * its vector in a region that all peers have opened through CUDA IPC, raises a flag in every peer's region, waits for the
+ * peers' flags and adds the W staged vectors in rank order (bit-identical on all ranks, run to run).  See csrc/p2p.cu.
+ *
+ * Setup (the only entry points of this library that allocate or synchronise; call them once per communicator):
+ *   ercg_p2p_region_bytes(max_bytes): size of a region for payloads up to max_bytes per call;
+ *   ercg_p2p_alloc: cudaMalloc + zero a region on the current device, return it and its 64-byte IPC handle;
+ *   ercg_p2p_open / ercg_p2p_close: map / unmap a PEER's region from its handle (exchange the handles over any host channel);
+ *   ercg_p2p_free; ercg_p2p_status: copies the region's sticky status word to the host (0 or ERCG_P2P_ETIMEOUT).
+ * ercg_p2p_allreduce: out[i] = sum over ranks of in[i] (in == out allowed), n elements of fp32 (dtype 0) or fp64 (dtype 1);
+ *   regions_dev = DEVICE array of the W region base pointers as mapped in this process (own region at index rank).
+ *   Every rank must issue the same sequence of calls (same n) on a communicator, all on one stream (or otherwise
+ *   serialised); concurrent streams need one communicator each.  Plain kernel launch: capturable in a CUDA graph.
+ * ------------------------------------------------------------------------------------------- */
+#define ERCG_P2P_HANDLE_BYTES 64
+size_t ercg_p2p_region_bytes(size_t max_bytes);
+int ercg_p2p_alloc(size_t region_bytes, void** region, unsigned char* ipc_handle);
+int ercg_p2p_open(const unsigned char* ipc_handle, void** region);
+int ercg_p2p_close(void* peer_region);
+int ercg_p2p_free(void* region);
+int ercg_p2p_status(const void* region, int* status_host);
+int ercg_p2p_allreduce(void* const* regions_dev, int rank, int world, const void* in, void* out, int64_t n, int dtype,
+                       size_t max_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K11  MaskedEdgeAttention 'attn1' of the declare-lab DialogueGCN (track_mm/dgcnv2_models.py:517-562) -- the edge weights of

@@ -265,10 +265,10 @@ def test_bn_sync_pack_unpack_equal_the_elementwise_expression():
     parts, bufs = [], []
     for n in (1234, 777):
         mean, var = torch.randn(H, generator=gen), torch.rand(H, generator=gen) + 0.1
-        buf = torch.empty(2 * H + 1, dtype=torch.float64, device="cuda")
+        buf = torch.empty(2 * H + 2, dtype=torch.float64, device="cuda")
         mc, vc = mean.cuda(), var.cuda()
         check(lib().ercg_bn_sync_pack(mc.data_ptr(), vc.data_ptr(), float(n), H, buf.data_ptr(), None), "pack")
-        want = torch.cat([mean.double() * n, (var.double() + mean.double() ** 2) * n, torch.tensor([float(n)], dtype=torch.float64)])
+        want = torch.cat([mean.double() * n, (var.double() + mean.double() ** 2) * n, torch.tensor([float(n), 0.0], dtype=torch.float64)])
         assert torch.equal(buf.cpu(), want)
         bufs.append(buf)
         parts.append(want)
