@@ -52,6 +52,31 @@ class PeerComm:
             torch.cuda.synchronize(self.device)
 
     @classmethod
+    def simulate(cls, world, device, max_bytes=4 << 20):
+        """``world`` communicator endpoints inside ONE process on ONE device (their regions are plain allocations of this
+        process, no IPC): rank r's collective is launched on its own stream and the kernels meet through the same flag
+        protocol as across GPUs.  For tests of every world size on a one-GPU box; not a transport."""
+        device = torch.device(device)
+        L = lib()
+        nbytes = L.ercg_p2p_region_bytes(int(max_bytes))
+        bases = []
+        with torch.cuda.device(device):
+            for _ in range(world):
+                ptr = ctypes.c_void_p()
+                handle = (ctypes.c_ubyte * HANDLE_BYTES)()
+                check(L.ercg_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "ercg_p2p_alloc")
+                bases.append(ptr.value)
+            regions = torch.tensor(bases, dtype=torch.int64).to(device)
+            torch.cuda.synchronize(device)
+        out = []
+        for r in range(world):
+            c = cls.__new__(cls)
+            c.group, c.device, c.rank, c.world, c.max_bytes = None, device, r, world, int(max_bytes)
+            c._own, c._peers, c.regions = bases[r], [], regions
+            out.append(c)
+        return out
+
+    @classmethod
     def create(cls, group, device, max_bytes=4 << 20, n=1):
         """``n`` communicators, or None on EVERY rank if any rank could not set one up (no peer access, IPC refused, more than
         16 ranks, ERCG_P2P=0): the caller then stays on torch.distributed.  Collective."""

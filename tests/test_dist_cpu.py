@@ -67,6 +67,14 @@ def _worker(rank, world, port, out):
     ref.load_state_dict(lin.state_dict())
     (ref(x).sum() / 101).backward()
     ok = ok and n == 7 * 3 + 3 and torch.allclose(lin.weight.grad, ref.weight.grad, atol=1e-5) and dead.weight.grad is None
+    # the Reducer the train step hands to StatSync: without a peer-memory communicator (CPU tensors, or set-up refused on any
+    # rank) it is torch.distributed on the group -- and PeerComm.create must answer None on EVERY rank, not raise
+    from erc_b200.p2p import PeerComm, Reducer
+    os.environ["ERCG_P2P"] = "0"
+    comms = PeerComm.create(None, "cpu", n=2)
+    red = Reducer(None, None)
+    m2, v2, _ = StatSync(reduce=red).stats(xl.mean(0), xl.var(0, unbiased=False), xl.size(0))
+    ok = ok and comms is None and red.transport == "torch.distributed" and torch.equal(m2, m) and torch.equal(v2, v)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

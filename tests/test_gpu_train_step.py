@@ -101,3 +101,120 @@ def test_train_step_graph_replay_draws_a_fresh_dropout_mask_each_replay():
     ts = CogmenTrainStep(m, lengths, (0,), lr=0.0, weight_decay=0.0).capture(x, spk, y)       # lr 0: only the mask changes
     losses = [float(ts.replay()) for _ in range(4)]
     assert len(set(losses)) == 4 and all(l == l for l in losses)
+
+
+def _single_rank_group():
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        import socket
+        sk = socket.socket()
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+        sk.close()
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+    return dist.group.WORLD
+
+
+def test_peer_allreduce_single_rank_slots_flags_and_graph_replay():
+    """ercg_p2p_allreduce with a one-rank communicator (what a 1-GPU box can run): region set-up through CUDA IPC handles, the
+    staging slots / flag words / call counter over many calls of changing size (aligned, odd counts, offset views, fp64), a
+    second communicator on a side stream, and replays from a CUDA graph.  With one rank the sum is the input, bit for bit.
+    The multi-GPU behaviour is covered by tools/p2p_check.py (test below when the box has two GPUs)."""
+    import erc_b200
+    from erc_b200.p2p import PeerComm, Reducer
+    group = _single_rank_group()
+    comms = PeerComm.create(group, "cuda:0", max_bytes=1 << 20, n=2)
+    assert comms is not None and len(comms) == 2
+    comm, comm2 = comms
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    before = __import__("erc_b200")._lib.launch_count()
+    for it in range(40):
+        for n, dt in ((1, torch.float32), (202, torch.float64), (201, torch.float64), (200, torch.float32), (4097, torch.float32),
+                      (134913, torch.float32), (1 << 18, torch.float32)):
+            x = torch.randn(n + 1, device="cuda", dtype=dt, generator=gen)
+            for v in (x[:n], x[1:]):                                  # 16-byte aligned and offset views
+                want = v.clone()
+                assert comm.all_reduce(v) is v and torch.equal(v, want)
+        if it % 4 == 0:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            y = torch.randn(5000, device="cuda", generator=gen)
+            want = y.clone()
+            with torch.cuda.stream(s):
+                comm2.all_reduce(y)
+            torch.cuda.current_stream().wait_stream(s)
+            assert torch.equal(y, want)
+    assert __import__("erc_b200")._lib.launch_count() - before >= 40 * 14
+    with pytest.raises(Exception):
+        comm.all_reduce(torch.zeros((1 << 20) // 4 + 64, device="cuda"))   # payload larger than the region's slots
+    a = torch.zeros(1000, device="cuda")
+    out = torch.zeros(1000, device="cuda")
+    red = Reducer(group, comm)
+    assert "peer memory" in red.transport
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        red(out)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out.copy_(a)
+        red(out)
+    for it in range(5):
+        a.fill_(float(it))
+        g.replay()
+        torch.cuda.synchronize()
+        assert bool((out == float(it)).all())
+    assert comm.status() == 0 and comm2.status() == 0
+    for c in comms:
+        c.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 5, 8])
+def test_peer_allreduce_every_world_size_on_one_gpu(world):
+    """The flag / slot protocol and all three reduce-loop shapes (W <= 2, W <= 4, W > 4) with W endpoints inside one process:
+    rank r's kernel runs on its own stream, the W kernels meet through the flag words exactly as across GPUs
+    (PeerComm.simulate).  Result on every rank = the rank-ordered sum, bit for bit; alternating payloads reuse slots and
+    flags in every pattern; a late rank (a sleep kernel ahead of its collective) must be waited for."""
+    import erc_b200
+    from erc_b200.p2p import PeerComm
+    comms = PeerComm.simulate(world, "cuda:0", max_bytes=2 << 20)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    gen = torch.Generator(device="cuda").manual_seed(world)
+    sizes = [(202, torch.float64), (200, torch.float32), (3, torch.float32), (134913, torch.float32), (4097, torch.float64),
+             (144401, torch.float32), (1 << 19, torch.float32)]
+    for it in range(6):
+        for n, dt in sizes:
+            xs = [torch.randn(n, device="cuda", dtype=dt, generator=gen) for _ in range(world)]
+            want = xs[0].clone()
+            for x in xs[1:]:
+                want += x
+            torch.cuda.synchronize()
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    if r == (it + n) % world:
+                        torch.cuda._sleep(300000)                      # this rank arrives ~0.15 ms late
+                    comms[r].all_reduce(xs[r])
+            torch.cuda.synchronize()
+            for r in range(world):
+                assert torch.equal(xs[r], want), (world, it, n, dt, r)
+    assert all(c.status() == 0 for c in comms)
+    for c in comms:
+        c.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_allreduce_two_gpus_equals_rank_ordered_sum():
+    """tools/p2p_check.py on two GPUs: bit-exact against the rank-ordered sum, skewed stress, graph replays, no time-outs."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29547", os.path.join(root, "tools", "p2p_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line.get("mismatches_all_ranks") == 0 and line.get("status") == 0, line
