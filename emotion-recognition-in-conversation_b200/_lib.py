@@ -107,6 +107,8 @@ SIGNATURES = {
     "ercg_p2p_free": (I, [P]),
     "ercg_p2p_status": (I, [P, P]),
     "ercg_p2p_allreduce": (I, [P, I, I, P, P, L, I, SZ, P]),
+    "ercg_p2p_bn_stats": (I, [P, I, I, P, L, L, I, D, P, P, P, P, P, F, P, SZ, SZ, P]),
+    "ercg_p2p_bn_act_bwd_reduce": (I, [P, I, I, P, L, P, L, P, P, F, P, P, F, P, P, L, I, P, SZ, SZ, P]),
     # K7 / K8 (MMGCN)
     "ercg_mmgcn_block_offsets": (I, [P, I, P, P]),
     "ercg_mmgcn_adj_fwd": (I, [P, L, P, P, P, L, L, I, I, P, L, P, P, P, P, P]),

@@ -4,6 +4,7 @@
 // summing the partials in fp64) => bit-reproducible and independent of scheduling.
 #include "common.cuh"
 #include "col_stream.cuh"
+#include "p2p_dev.cuh"
 #include <math.h>
 
 namespace ercg {
@@ -146,6 +147,65 @@ bn_stats_final_kernel(const float* __restrict__ partial, int nb, int H, long lon
   mean[c] = (float)(m + (double)x[c]); var[c] = (float)v;
 }
 
+// Data-parallel BatchNorm statistics in ONE kernel: the second level of the column reduction (as bn_stats_final_kernel), the
+// exchange of the per-rank statistics over peer memory (p2p_dev.cuh), the global mean / biased variance and the running
+// statistics of nn.BatchNorm1d -- instead of final-reduce, pack, all-reduce, unpack and running-update launches in a row on
+// the critical path of the forward pass.  A CTA owns FIN_COLS columns from the partial sums to the result: it stages
+// (mean n, (var + mean^2) n) of its columns in this rank's region, raises its flag in every peer's region, waits for the
+// peers' CTA of the same index and adds the W staged values in rank order.  Arithmetic = ercg_bn_stats (fp32 results) then
+// ercg_bn_sync_pack / all-reduce / ercg_bn_sync_unpack in fp64, step by step, so the result equals the unfused path bit for
+// bit (and is the same on every rank).  count = rows over all ranks (host-known).
+__global__ void __launch_bounds__(256)
+bn_stats_final_p2p_kernel(const float* __restrict__ partial, int nb, int H, long long N, const float* __restrict__ x,
+                          unsigned char* const* __restrict__ regions, int rank, int world, size_t slot_bytes, double count,
+                          float* __restrict__ mean, float* __restrict__ var, float* __restrict__ rmean, float* __restrict__ rvar,
+                          long long* __restrict__ nbt, float momentum) {
+  __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
+  const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
+  const bool ok = c < H, owner = ok && threadIdx.x < FIN_COLS;
+  const double s0 = fin_reduce(partial, nb, 2 * H, c, ok, sm);
+  const double s1 = fin_reduce(partial, nb, 2 * H, H + c, ok, sm);
+  const P2pCall k = p2p_begin(regions, rank, slot_bytes);
+  if (owner) {
+    const double m = s0 / (double)N;
+    double v = s1 / (double)N - m * m;
+    if (v < 0.0) v = 0.0;
+    const double md = (double)(float)(m + (double)x[c]), vd = (double)(float)v, n = (double)N;   // the fp32 local statistics
+    double* mine = reinterpret_cast<double*>(regions[rank] + k.slot_off);
+    mine[c] = __dmul_rn(md, n);
+    mine[H + c] = __dmul_rn(__dadd_rn(vd, __dmul_rn(md, md)), n);
+  }
+  p2p_signal_wait(regions, rank, world, blockIdx.x, k);
+  if (owner) {
+    double a[P2P_MAX_WORLD], b[P2P_MAX_WORLD];
+#pragma unroll
+    for (int p = 0; p < P2P_MAX_WORLD; ++p)
+      if (p < world) {
+        const double* d = reinterpret_cast<const double*>(regions[p] + k.slot_off);
+        a[p] = ld_peer(d + c);
+        b[p] = ld_peer(d + H + c);
+      }
+    double sa = a[0], sb = b[0];
+#pragma unroll
+    for (int p = 1; p < P2P_MAX_WORLD; ++p)
+      if (p < world) { sa += a[p]; sb += b[p]; }
+    const double gm = __ddiv_rn(sa, count);
+    const double gv = __dsub_rn(__ddiv_rn(sb, count), __dmul_rn(gm, gm));
+    const float m32 = (float)gm, v32 = (float)(gv > 0.0 ? gv : 0.0);
+    mean[c] = m32;
+    var[c] = v32;
+    if (rmean) {                                              // = bn_running_update_kernel
+      const long long seen = nbt ? nbt[0] + 1 : 1;            // nbt is bumped below, after every CTA has passed this point
+      const float mom = momentum >= 0.f ? momentum : (float)(1.0 / (double)seen);
+      const float cf = (float)count;
+      const float unbias = mom * cf / fmaxf(cf - 1.0f, 1.0f);
+      rmean[c] = fmaf(mom, m32, rmean[c] * (1.0f - mom));
+      rvar[c] = fmaf(unbias, v32, rvar[c] * (1.0f - mom));
+    }
+  }
+  if (p2p_close_call(k, gridDim.x) && rmean && nbt) nbt[0] += 1;
+}
+
 __global__ void __launch_bounds__(256)
 sums_final_kernel(const float* __restrict__ partial, int nb, int H, float* __restrict__ sums) {
   __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
@@ -191,6 +251,37 @@ bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict
   }
   __syncthreads();                       // every thread has read nbt[0]
   if (threadIdx.x == 0 && nbt) nbt[0] = seen;
+}
+
+// BatchNorm backward sums (sum dy, sum dy * xhat) fused with their exchange: second level of the column reduction, then the
+// per-rank sums meet over peer memory; `sums` keeps this rank's own values (= its dbeta / dgamma, which travel with the
+// gradient all-reduce later), `gsums` the rank-ordered total the input gradient needs.  = sums_final_kernel + all-reduce.
+__global__ void __launch_bounds__(256)
+sums_final_p2p_kernel(const float* __restrict__ partial, int nb, int H, unsigned char* const* __restrict__ regions, int rank,
+                      int world, size_t slot_bytes, float* __restrict__ sums, float* __restrict__ gsums) {
+  __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
+  const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
+  const bool ok = c < 2 * H, owner = ok && threadIdx.x < FIN_COLS;
+  const double s = fin_reduce(partial, nb, 2 * H, c, ok, sm);
+  const P2pCall k = p2p_begin(regions, rank, slot_bytes);
+  if (owner) {
+    const float v = (float)s;
+    sums[c] = v;
+    reinterpret_cast<float*>(regions[rank] + k.slot_off)[c] = v;
+  }
+  p2p_signal_wait(regions, rank, world, blockIdx.x, k);
+  if (owner) {
+    float a[P2P_MAX_WORLD];
+#pragma unroll
+    for (int p = 0; p < P2P_MAX_WORLD; ++p)
+      if (p < world) a[p] = ld_peer(reinterpret_cast<const float*>(regions[p] + k.slot_off) + c);
+    float t = a[0];
+#pragma unroll
+    for (int p = 1; p < P2P_MAX_WORLD; ++p)
+      if (p < world) t += a[p];
+    gsums[c] = t;
+  }
+  p2p_close_call(k, gridDim.x);
 }
 
 __global__ void __launch_bounds__(256)
@@ -474,13 +565,9 @@ extern "C" size_t ercg_bn_workspace_bytes(int64_t N, int H) {
   return a > b ? a : b;
 }
 
-extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, float* mean, float* var,
-                             void* workspace, size_t workspace_bytes, void* stream) {
-  if (N <= 0 || H <= 0 || !x || !mean || !var || ldx < H) return ERCG_EINVAL;
-  if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
+// first level of the BatchNorm statistics: per-block partial sums of (x - x[0,c]) and its square -> part[nb][2H]
+static int bn_stats_partials(const float* x, int64_t ldx, int64_t N, int H, float* part, cudaStream_t st) {
   int nb = (int)((N + RPB - 1) / RPB);
-  cudaStream_t st = (cudaStream_t)stream;
-  float* part = reinterpret_cast<float*>(workspace);
   if (col_stream_ok(x, ldx, H, N)) {      // contiguous rows: flat float4 stream, every lane busy
     const long long total4 = N * (long long)(H >> 2);
     nb = col_stream_blocks(H >> 2, total4);
@@ -489,9 +576,42 @@ extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, floa
     col_partials_v4_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
   else
     col_partials_kernel<0><<<nb, 256, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, N, H, part);
+  return nb;
+}
+
+extern "C" int ercg_bn_stats(const float* x, int64_t ldx, int64_t N, int H, float* mean, float* var,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0 || H <= 0 || !x || !mean || !var || ldx < H) return ERCG_EINVAL;
+  if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(workspace);
+  const int nb = bn_stats_partials(x, ldx, N, H, part, st);
   int rc = finish_launch();
   if (rc) return rc;
   bn_stats_final_kernel<<<fin_blocks(H), 256, 0, st>>>(part, nb, H, N, x, mean, var);
+  return finish_launch();
+}
+
+extern "C" int ercg_p2p_bn_stats(void* const* regions_dev, int rank, int world, const float* x, int64_t ldx, int64_t N, int H,
+                                 double count_global, float* mean, float* var, float* running_mean, float* running_var,
+                                 int64_t* num_batches_tracked, float momentum, void* workspace, size_t workspace_bytes,
+                                 size_t max_bytes, void* stream) {
+  if (!regions_dev || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return ERCG_EINVAL;
+  if (N <= 0 || H <= 0 || !x || !mean || !var || ldx < H || !(count_global >= (double)N)) return ERCG_EINVAL;
+  if ((running_mean == nullptr) != (running_var == nullptr)) return ERCG_EINVAL;
+  if (running_mean && momentum < 0.f && !num_batches_tracked) return ERCG_EINVAL;
+  if (fin_blocks(H) > (unsigned)P2P_MAX_CTAS) return ERCG_ERANGE;          // one flag word per CTA
+  const size_t slot = (max_bytes + 255) / 256 * 256;
+  if ((size_t)2 * H * sizeof(double) > slot) return ERCG_EWORKSPACE;
+  if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(workspace);
+  const int nb = bn_stats_partials(x, ldx, N, H, part, st);
+  int rc = finish_launch();
+  if (rc) return rc;
+  bn_stats_final_p2p_kernel<<<fin_blocks(H), 256, 0, st>>>(part, nb, H, N, x, reinterpret_cast<unsigned char* const*>(regions_dev),
+                                                          rank, world, slot, count_global, mean, var, running_mean, running_var,
+                                                          reinterpret_cast<long long*>(num_batches_tracked), momentum);
   return finish_launch();
 }
 
@@ -529,15 +649,11 @@ extern "C" int ercg_bn_act_fwd(const float* x, int64_t ldx, const float* mean, c
   return finish_launch();
 }
 
-extern "C" int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const float* x, int64_t ldx,
-                                      const float* mean, const float* var, float eps,
-                                      const float* gamma, const float* beta, float slope,
-                                      float* sums, int64_t N, int H, void* workspace, size_t workspace_bytes, void* stream) {
-  if (N <= 0 || H <= 0 || !dout || !x || !mean || !var || !gamma || !beta || !sums) return ERCG_EINVAL;
-  if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
+// first level of the BatchNorm backward sums -> part[nb][2H]
+static int bn_bwd_partials(const float* dout, int64_t ldo, const float* x, int64_t ldx, const float* mean, const float* var,
+                           float eps, const float* gamma, const float* beta, float slope, int64_t N, int H, float* part,
+                           cudaStream_t st) {
   int nb = (int)((N + RPB - 1) / RPB);
-  cudaStream_t st = (cudaStream_t)stream;
-  float* part = reinterpret_cast<float*>(workspace);
   if (col_stream_ok(x, ldx, H, N) && col_stream_ok(dout, ldo, H, N) && aligned16(mean) && aligned16(var) && aligned16(gamma) &&
       aligned16(beta)) {
     const long long total4 = N * (long long)(H >> 2);
@@ -547,9 +663,42 @@ extern "C" int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const floa
     // (the row-per-warp float4 variant measured slower for this two-input mode: 0.33 vs 0.29 ms at 2^20 x 100)
     col_partials_kernel<1><<<nb, 256, 0, st>>>(x, ldx, dout, ldo, mean, var, eps, gamma, beta, slope, N, H, part);
   }
+  return nb;
+}
+
+extern "C" int ercg_bn_act_bwd_reduce(const float* dout, int64_t ldo, const float* x, int64_t ldx,
+                                      const float* mean, const float* var, float eps,
+                                      const float* gamma, const float* beta, float slope,
+                                      float* sums, int64_t N, int H, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0 || H <= 0 || !dout || !x || !mean || !var || !gamma || !beta || !sums) return ERCG_EINVAL;
+  if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(workspace);
+  const int nb = bn_bwd_partials(dout, ldo, x, ldx, mean, var, eps, gamma, beta, slope, N, H, part, st);
   int rc = finish_launch();
   if (rc) return rc;
   sums_final_kernel<<<fin_blocks(2 * H), 256, 0, st>>>(part, nb, H, sums);
+  return finish_launch();
+}
+
+extern "C" int ercg_p2p_bn_act_bwd_reduce(void* const* regions_dev, int rank, int world, const float* dout, int64_t ldo,
+                                          const float* x, int64_t ldx, const float* mean, const float* var, float eps,
+                                          const float* gamma, const float* beta, float slope, float* sums, float* sums_global,
+                                          int64_t N, int H, void* workspace, size_t workspace_bytes, size_t max_bytes,
+                                          void* stream) {
+  if (!regions_dev || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return ERCG_EINVAL;
+  if (N <= 0 || H <= 0 || !dout || !x || !mean || !var || !gamma || !beta || !sums || !sums_global) return ERCG_EINVAL;
+  if (fin_blocks(2 * H) > (unsigned)P2P_MAX_CTAS) return ERCG_ERANGE;      // one flag word per CTA
+  const size_t slot = (max_bytes + 255) / 256 * 256;
+  if ((size_t)2 * H * sizeof(float) > slot) return ERCG_EWORKSPACE;
+  if (workspace_bytes < ercg_bn_workspace_bytes(N, H) || !workspace) return ERCG_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(workspace);
+  const int nb = bn_bwd_partials(dout, ldo, x, ldx, mean, var, eps, gamma, beta, slope, N, H, part, st);
+  int rc = finish_launch();
+  if (rc) return rc;
+  sums_final_p2p_kernel<<<fin_blocks(2 * H), 256, 0, st>>>(part, nb, H, reinterpret_cast<unsigned char* const*>(regions_dev), rank,
+                                                          world, slot, sums, sums_global);
   return finish_launch();
 }
 

@@ -20,47 +20,9 @@
 // wait for each other inside a grid, only for the same-index CTA of the peers, so no co-residency of the grid is assumed.
 // Every wait is bounded (30 s): on timeout the kernel records ERCG_P2P_ETIMEOUT in the region header and carries on with
 // whatever is there -- a dead peer makes the step wrong and says so (ercg_p2p_status), it does not hang the GPU.
-#include "common.cuh"
+#include "p2p_dev.cuh"
 
 namespace ercg {
-
-constexpr int P2P_MAX_CTAS = 128;
-constexpr int P2P_MAX_WORLD = 16;
-constexpr int P2P_THREADS = 128;
-constexpr unsigned long long P2P_TIMEOUT_NS = 30ull * 1000000000ull;   // ranks may be seconds apart at start-up (lazy library init)
-
-struct P2pHeader {
-  unsigned long long call;                                   // calls completed by this rank
-  unsigned int done;                                         // CTAs of the running call that have finished
-  int status;                                                // 0, or ERCG_P2P_ETIMEOUT (sticky)
-  unsigned int pad[60];                                     // header = 256 bytes + the flag words
-  unsigned int flag[2][P2P_MAX_WORLD][P2P_MAX_CTAS];         // [parity][writer rank][CTA] = call number (low 32 bits)
-};
-static_assert(sizeof(P2pHeader) % 256 == 0, "data slots start 256-byte aligned");
-
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ld_peer16(const void* p) {   // peer memory: never through L1
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-template <typename T>
-__device__ __forceinline__ T ld_peer(const T* p) {
-  return *reinterpret_cast<const volatile T*>(p);
-}
-__device__ __forceinline__ void add16(float4& a, const float4& b, float) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-__device__ __forceinline__ void add16(float4& a, const float4& b, double) {
-  double2& x = reinterpret_cast<double2&>(a);
-  const double2& y = reinterpret_cast<const double2&>(b);
-  x.x += y.x; x.y += y.y;
-}
 
 // B units per thread per round, at most WP peers each (B * WP == 8 loads in flight); returns the first unit not processed
 template <typename T, int B, int WP>
@@ -94,15 +56,12 @@ p2p_allreduce_kernel(unsigned char* const* __restrict__ regions, int rank, int w
                      long long n, long long units, size_t slot_bytes) {
   const int c = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
   unsigned char* self = regions[rank];
-  P2pHeader* hdr = reinterpret_cast<P2pHeader*>(self);
-  const unsigned long long call = *reinterpret_cast<volatile unsigned long long*>(&hdr->call) + 1;   // same on every rank
-  const int par = (int)(call & 1);
-  const unsigned int tag = (unsigned int)call;
+  const P2pCall k = p2p_begin(regions, rank, slot_bytes);
+  const size_t slot_off = k.slot_off;
   constexpr int EPV = 16 / sizeof(T);                         // elements per 16-byte unit
   const long long per = (units + G - 1) / G;
   const long long u0 = min(units, (long long)c * per), u1 = min(units, u0 + per);
   const long long e0 = c == G - 1 ? units * EPV : n, e1 = n;  // scalar tail (last CTA only)
-  const size_t slot_off = sizeof(P2pHeader) + (size_t)par * slot_bytes;
   // 1. stage this CTA's chunk in the local region
   {
     float4* dst = reinterpret_cast<float4*>(self + slot_off);
@@ -116,27 +75,8 @@ p2p_allreduce_kernel(unsigned char* const* __restrict__ regions, int rank, int w
     T* dste = reinterpret_cast<T*>(self + slot_off);
     for (long long e = e0 + tid; e < e1; e += P2P_THREADS) dste[e] = in[e];
   }
-  __syncthreads();                                            // the release stores below are cumulative over the CTA's writes
-  // 2. tell every peer (and ourselves) that chunk c of call `call` is in place; 3. wait for everybody's chunk c
-  if (tid < world) {
-    P2pHeader* peer = reinterpret_cast<P2pHeader*>(regions[tid]);
-    st_release_sys(&peer->flag[par][rank][c], tag);
-    const unsigned int* mine = &hdr->flag[par][tid][c];
-    unsigned int spins = 0;
-    unsigned long long t0 = 0;
-    while (ld_acquire_sys(mine) != tag) {
-      if (++spins < (1u << 14)) continue;                     // the usual case: the peers are a few microseconds apart
-      __nanosleep(500);
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      if (now - t0 > P2P_TIMEOUT_NS) {                        // the peer is not coming
-        hdr->status = ERCG_P2P_ETIMEOUT;
-        break;
-      }
-    }
-  }
-  __syncthreads();
+  // 2. tell every peer (and ourselves) that chunk c of this call is in place; 3. wait for everybody's chunk c
+  p2p_signal_wait(regions, rank, world, c, k);
   // 4. add the W staged chunks in rank order; the peers' copies are read over NVLink, up to eight loads in flight per thread
   //    (a load costs ~2 us: issuing them one by one would make the kernel W times slower)
   {
@@ -168,15 +108,7 @@ p2p_allreduce_kernel(unsigned char* const* __restrict__ regions, int rank, int w
     }
   }
   // 5. the last CTA to finish closes the call
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    if (atomicAdd(&hdr->done, 1u) == (unsigned int)G - 1) {
-      hdr->done = 0;
-      __threadfence();
-      *reinterpret_cast<volatile unsigned long long*>(&hdr->call) = call;
-    }
-  }
+  p2p_close_call(k, G);
 }
 
 }  // namespace ercg

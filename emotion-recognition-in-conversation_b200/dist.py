@@ -49,6 +49,17 @@ class StatSync:
         # in-place all-reduce(sum): torch.distributed on ``group``, or a p2p.Reducer (peer-memory kernel on one NVSwitch node)
         self.reduce = reduce if reduce is not None else (lambda t: dist.all_reduce(t, group=self.group))
 
+    def fused_stats(self, x, bn=None):
+        """(global mean, global biased var, global count) of the rows of x over all ranks in ONE collective kernel
+        (ops.bn_stats_sync), running statistics of ``bn`` included -- or None when there is no peer-memory communicator
+        or the global count is not known on the host (the caller then goes bn_stats -> stats())."""
+        comm = getattr(self.reduce, "comm", None)
+        if comm is None or not x.is_cuda or not self.global_count:
+            return None
+        from .ops import bn_stats_sync
+        mean, var = bn_stats_sync(x, comm, self.global_count, bn)
+        return mean, var, float(self.global_count)
+
     def stats(self, mean, var, n_local):
         """local (mean, biased var, n) -> global (mean, biased var, count)."""
         H = mean.numel()

@@ -572,11 +572,22 @@ class _BnAct(torch.autograd.Function):
         ldx = x.stride(0)
         sums = torch.empty(2 * H, dtype=torch.float32, device=x.device)
         ws = _ws(lib().ercg_bn_workspace_bytes(N, H), x.device)
-        check(lib().ercg_bn_act_bwd_reduce(_p(dout), ldo, _p(x), ldx, _p(mean), _p(var), ctx.eps, _p(gamma), _p(beta), ctx.slope,
-                                           _p(sums), N, H, _p(ws), ws.numel(), _stream()), "ercg_bn_act_bwd_reduce")
-        local = sums
-        if ctx.stat_sync is not None and ctx.use_batch_stats:
-            sums = ctx.stat_sync(sums.clone())         # all-reduce(sum) of (sum dy, sum dy*xhat) across ranks
+        sync = ctx.stat_sync if ctx.use_batch_stats else None
+        comm = getattr(getattr(sync, "__self__", None), "reduce", None)      # StatSync.grads -> its Reducer -> PeerComm
+        comm = getattr(comm, "comm", None)
+        if comm is not None and 2 * H <= 8 * 128:
+            # reduction and exchange over peer memory in one kernel: this rank's sums (dbeta | dgamma) and the global ones
+            local = sums
+            sums = torch.empty(2 * H, dtype=torch.float32, device=x.device)
+            check(lib().ercg_p2p_bn_act_bwd_reduce(comm.regions.data_ptr(), comm.rank, comm.world, _p(dout), ldo, _p(x), ldx, _p(mean),
+                                                   _p(var), ctx.eps, _p(gamma), _p(beta), ctx.slope, _p(local), _p(sums), N, H,
+                                                   _p(ws), ws.numel(), comm.max_bytes, _stream()), "ercg_p2p_bn_act_bwd_reduce")
+        else:
+            check(lib().ercg_bn_act_bwd_reduce(_p(dout), ldo, _p(x), ldx, _p(mean), _p(var), ctx.eps, _p(gamma), _p(beta), ctx.slope,
+                                               _p(sums), N, H, _p(ws), ws.numel(), _stream()), "ercg_bn_act_bwd_reduce")
+            local = sums
+            if sync is not None:
+                sums = sync(sums.clone())              # all-reduce(sum) of (sum dy, sum dy*xhat) across ranks
         dx = torch.empty((N, H), dtype=torch.float32, device=x.device)
         check(lib().ercg_bn_act_bwd_apply(_p(dout), ldo, _p(x), ldx, _p(mean), _p(var), ctx.eps, _p(gamma), _p(beta), ctx.slope,
                                           _p(sums), float(ctx.count), 1 if ctx.use_batch_stats else 0, _p(dx), H, N, H,
@@ -592,6 +603,24 @@ def bn_stats(x):
     var = torch.empty(H, dtype=torch.float32, device=x.device)
     ws = _ws(lib().ercg_bn_workspace_bytes(N, H), x.device)
     check(lib().ercg_bn_stats(_p(x), ldx, N, H, _p(mean), _p(var), _p(ws), ws.numel(), _stream()), "ercg_bn_stats")
+    return mean, var
+
+
+def bn_stats_sync(x, comm, count_global, bn=None):
+    """Data-parallel BatchNorm statistics fused with their exchange (ercg_p2p_bn_stats): (mean[H], biased var[H]) over the rows
+    of ALL ranks, the same on every rank; ``bn`` (an nn.BatchNorm1d in train mode) also gets its running statistics updated.
+    ``comm``: p2p.PeerComm; collective -- every rank of the communicator calls it at the same point of its stream."""
+    x, ldx = _rows(x)
+    N, H = x.shape
+    mean = torch.empty(H, dtype=torch.float32, device=x.device)
+    var = torch.empty(H, dtype=torch.float32, device=x.device)
+    ws = _ws(lib().ercg_bn_workspace_bytes(N, H), x.device)
+    run = bn is not None and bn.track_running_stats
+    check(lib().ercg_p2p_bn_stats(comm.regions.data_ptr(), comm.rank, comm.world, _p(x), ldx, N, H, float(count_global), _p(mean),
+                                  _p(var), _p(bn.running_mean) if run else None, _p(bn.running_var) if run else None,
+                                  _p(bn.num_batches_tracked) if run else None,
+                                  (float(bn.momentum) if bn.momentum is not None else -1.0) if run else 0.0,
+                                  _p(ws), ws.numel(), comm.max_bytes, _stream()), "ercg_p2p_bn_stats")
     return mean, var
 
 

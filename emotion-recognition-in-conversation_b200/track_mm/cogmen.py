@@ -38,12 +38,16 @@ class GNN(nn.Module):
         bn = self.bn
         n_local = x.size(0)
         if self.training or not bn.track_running_stats:
-            mean, var = ops.bn_stats(x)
-            count = float(n_local)
-            if self.stat_sync is not None:
-                mean, var, count = self.stat_sync.stats(mean, var, n_local)
-            if bn.track_running_stats:
-                ops.bn_running_update(bn, mean, var, count)     # one launch, no host read of num_batches_tracked
+            fused = self.stat_sync.fused_stats(x, bn) if self.stat_sync is not None else None
+            if fused is not None:                               # reduction + exchange over peer memory + running statistics
+                mean, var, count = fused
+            else:
+                mean, var = ops.bn_stats(x)
+                count = float(n_local)
+                if self.stat_sync is not None:
+                    mean, var, count = self.stat_sync.stats(mean, var, n_local)
+                if bn.track_running_stats:
+                    ops.bn_running_update(bn, mean, var, count)     # one launch, no host read of num_batches_tracked
             return ops.bn_leaky_relu(x, bn.weight, bn.bias, mean, var, bn.eps, self.relu.negative_slope, True, count,
                                      self.stat_sync.grads if self.stat_sync is not None else None)
         return ops.bn_leaky_relu(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,

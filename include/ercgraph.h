@@ -479,6 +479,12 @@ int ercg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
  *   Every rank must issue the same sequence of calls (same n) on a communicator, all on one stream (or otherwise
  *   serialised); concurrent streams need one communicator each.  Plain kernel launch: capturable in a CUDA graph.
  * ------------------------------------------------------------------------------------------- */
+/* ercg_p2p_bn_stats: the data-parallel BatchNorm statistics of GNN.forward (cogmen.py:67,72 under DDP with the statistics
+ *   taken over the GLOBAL batch) fused with their exchange: column reduction of this rank's rows, exchange over peer memory,
+ *   global mean / biased variance (the same on every rank) and, when running_mean / running_var are given, the train-mode
+ *   running statistics (as ercg_bn_running_update) -- two launches in all.  count_global = rows over all ranks.  Equals
+ *   ercg_bn_stats + ercg_bn_sync_pack + all-reduce + ercg_bn_sync_unpack + ercg_bn_running_update bit for bit.
+ *   workspace as for ercg_bn_stats; H <= 1024. */
 #define ERCG_P2P_HANDLE_BYTES 64
 size_t ercg_p2p_region_bytes(size_t max_bytes);
 int ercg_p2p_alloc(size_t region_bytes, void** region, unsigned char* ipc_handle);
@@ -488,6 +494,17 @@ int ercg_p2p_free(void* region);
 int ercg_p2p_status(const void* region, int* status_host);
 int ercg_p2p_allreduce(void* const* regions_dev, int rank, int world, const void* in, void* out, int64_t n, int dtype,
                        size_t max_bytes, void* stream);
+/* ercg_p2p_bn_act_bwd_reduce: ercg_bn_act_bwd_reduce fused with the exchange of its result: sums[2H] = this rank's
+ * (sum dy, sum dy*xhat) (its dbeta / dgamma), sums_global[2H] = the rank-ordered total over all ranks (what
+ * ercg_bn_act_bwd_apply needs when the statistics were global).  H <= 512. */
+int ercg_p2p_bn_act_bwd_reduce(void* const* regions_dev, int rank, int world, const float* dout, int64_t ldo,
+                               const float* x, int64_t ldx, const float* mean, const float* var, float eps,
+                               const float* gamma, const float* beta, float slope, float* sums, float* sums_global,
+                               int64_t N, int H, void* workspace, size_t workspace_bytes, size_t max_bytes, void* stream);
+int ercg_p2p_bn_stats(void* const* regions_dev, int rank, int world, const float* x, int64_t ldx, int64_t N, int H,
+                      double count_global, float* mean, float* var, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, float momentum, void* workspace, size_t workspace_bytes,
+                      size_t max_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K11  MaskedEdgeAttention 'attn1' of the declare-lab DialogueGCN (track_mm/dgcnv2_models.py:517-562) -- the edge weights of

@@ -204,6 +204,118 @@ def test_peer_allreduce_every_world_size_on_one_gpu(world):
         c.close()
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_fused_bn_statistics_exchange_equals_the_unfused_path(world):
+    """ercg_p2p_bn_stats (column reduction + exchange over peer memory + global statistics + running statistics in one
+    kernel) on W simulated ranks with shards of different sizes: identical on every rank, bit-identical to bn_stats ->
+    pack -> rank-ordered sum -> unpack -> running update, equal to the statistics of the concatenated batch, and the running
+    statistics equal nn.BatchNorm1d's on that batch."""
+    import erc_b200
+    from erc_b200 import ops
+    from erc_b200._lib import lib, check
+    from erc_b200.p2p import PeerComm
+    H = 100
+    comms = PeerComm.simulate(world, "cuda:0", max_bytes=1 << 16)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    gen = torch.Generator(device="cuda").manual_seed(11 * world)
+    ref = torch.nn.BatchNorm1d(H).double().train()
+    bns = [torch.nn.BatchNorm1d(H).cuda().train() for _ in range(world)]
+    bn_unfused = torch.nn.BatchNorm1d(H).cuda().train()
+    for it in range(3):
+        shards = [torch.randn(2000 + 977 * r + 131 * it, H, device="cuda", generator=gen) * (1 + r) + 0.3 * r for r in range(world)]
+        total = sum(x.size(0) for x in shards)
+        torch.cuda.synchronize()
+        got = [None] * world
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                got[r] = ops.bn_stats_sync(shards[r], comms[r], total, bns[r])
+        torch.cuda.synchronize()
+        # unfused: local statistics, pack, sum in rank order, unpack, running update
+        acc = None
+        for r in range(world):
+            m, v = ops.bn_stats(shards[r])
+            buf = torch.empty(2 * H + 2, dtype=torch.float64, device="cuda")
+            check(lib().ercg_bn_sync_pack(m.data_ptr(), v.data_ptr(), float(shards[r].size(0)), H, buf.data_ptr(), None), "pack")
+            acc = buf if acc is None else acc + buf
+        gm, gv = torch.empty(H, device="cuda"), torch.empty(H, device="cuda")
+        check(lib().ercg_bn_sync_unpack(acc.data_ptr(), H, gm.data_ptr(), gv.data_ptr(), None), "unpack")
+        ops.bn_running_update(bn_unfused, gm, gv, float(total))
+        allx = torch.cat(shards).double().cpu()
+        ref(allx)
+        for r in range(world):
+            assert torch.equal(got[r][0], gm) and torch.equal(got[r][1], gv), (world, it, r)
+            assert torch.equal(bns[r].running_mean, bn_unfused.running_mean) and torch.equal(bns[r].running_var, bn_unfused.running_var)
+            assert int(bns[r].num_batches_tracked) == it + 1
+        assert rel_err(gm, allx.mean(0)) < 1e-5 and rel_err(gv, allx.var(0, unbiased=False)) < 1e-5
+        assert rel_err(bns[0].running_mean, ref.running_mean) < 1e-5 and rel_err(bns[0].running_var, ref.running_var) < 1e-5
+    assert all(c.status() == 0 for c in comms)
+    for c in comms:
+        c.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_bn_backward_sums_exchange_equals_the_unfused_path(world):
+    """BatchNorm + LeakyReLU backward through ops.bn_leaky_relu with a StatSync whose Reducer owns a peer-memory communicator
+    (ercg_p2p_bn_act_bwd_reduce: reduction + exchange in one kernel) on W simulated ranks: the input gradients and the
+    dgamma / dbeta of every rank are bit-identical to the unfused path (local sums, rank-ordered total), and their totals
+    equal the fp64 gradients of the concatenated batch."""
+    import erc_b200
+    from erc_b200 import ops
+    from erc_b200.dist import StatSync
+    from erc_b200.p2p import PeerComm, Reducer
+    H = 100
+    comms = PeerComm.simulate(world, "cuda:0", max_bytes=1 << 16)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    gen = torch.Generator(device="cuda").manual_seed(7 * world)
+    shards = [torch.randn(1500 + 611 * r, H, device="cuda", generator=gen) * (1 + 0.5 * r) + 0.2 * r for r in range(world)]
+    douts = [torch.randn(x.size(0), H, device="cuda", generator=gen) for x in shards]
+    gamma = torch.rand(H, device="cuda", generator=gen) + 0.5
+    beta = torch.randn(H, device="cuda", generator=gen)
+    total = sum(x.size(0) for x in shards)
+    allx = torch.cat(shards).double().cpu().requires_grad_()
+    gd, bd = gamma.double().cpu().requires_grad_(), beta.double().cpu().requires_grad_()
+    mean64, var64 = allx.mean(0), allx.var(0, unbiased=False)
+    want = torch.nn.functional.leaky_relu((allx - mean64) / (var64 + 1e-5).sqrt() * gd + bd, 0.01)
+    want.backward(torch.cat(douts).double().cpu())
+    mean, var = mean64.detach().float().cuda(), var64.detach().float().cuda()
+
+    class OrderedSum:                      # stands in for the all-reduce of the unfused path: rank-ordered total, computed up front
+        def __init__(self, tot):
+            self.tot = tot
+
+        def grads(self, sums):
+            return self.tot.clone()
+
+    def run(r, sync):
+        x, g, b = shards[r].clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+        out = ops.bn_leaky_relu(x, g, b, mean, var, 1e-5, 0.01, True, float(total), sync)
+        out.backward(douts[r])
+        return x.grad, g.grad, b.grad
+
+    # unfused reference: every rank's local sums first (dgamma | dbeta with a no-op sync), then the rank-ordered total
+    local = [run(r, None) for r in range(world)]
+    tot = None
+    for r in range(world):
+        s_r = torch.cat([local[r][2], local[r][1]])           # sums = (sum dy | sum dy*xhat) = (dbeta | dgamma)
+        tot = s_r.clone() if tot is None else tot + s_r
+    unfused = [run(r, OrderedSum(tot).grads) for r in range(world)]
+    torch.cuda.synchronize()
+    fused = [None] * world
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            fused[r] = run(r, StatSync(global_count=total, reduce=Reducer(None, comms[r])).grads)
+    torch.cuda.synchronize()
+    for r in range(world):
+        for a, b in zip(fused[r], unfused[r]):
+            assert torch.equal(a, b), (world, r)
+    dx = torch.cat([f[0] for f in fused]).double().cpu()
+    assert rel_err(dx, allx.grad) < 5e-5
+    assert rel_err(sum(f[1] for f in fused), gd.grad, floor=1e-3) < 1e-5 and rel_err(sum(f[2] for f in fused), bd.grad) < 1e-5
+    assert all(c.status() == 0 for c in comms)
+    for c in comms:
+        c.close()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_peer_allreduce_two_gpus_equals_rank_ordered_sum():
     """tools/p2p_check.py on two GPUs: bit-exact against the rank-ordered sum, skewed stress, graph replays, no time-outs."""
