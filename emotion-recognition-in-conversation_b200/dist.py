@@ -9,8 +9,10 @@ no data-path exchange; what crosses GPUs per step is
      backward, so that N-GPU results equal the 1-GPU result on the same global batch (the reference's DDP
      uses per-rank statistics; ``global_stats=False`` reproduces that),
   3. the loss numerator/denominator (2 floats) so the mean is over the global utterance count.
-All of them are torch.distributed collectives (NCCL on GPUs, gloo in the CPU tests); none is fused with
-compute because none follows a compute tile -- they are latency-bound scalars/vectors.
+On one NVSwitch node they go through libercgraph's own peer-memory kernels (p2p.py / csrc/p2p.cu: a one-shot all-reduce over
+CUDA-IPC regions; the BatchNorm statistics and their backward sums are exchanged by the very kernels that reduce them,
+``StatSync.fused_stats`` / ``ops._BnAct.backward``); torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the fallback
+transport and the set-up channel.
 """
 import torch
 import torch.distributed as dist

@@ -5,12 +5,15 @@ track_mm/cogmen.py:179-195, under accelerate/DDP, lumo/trainer/trainer.py:62-64,
 
 * Nothing in the step touches the host: sizes and the possible relation ids come from the host-side batch description,
   the loss normaliser is the host-known global utterance count, the optimizer's step counter and the dropout seed live on
-  the device.  ``capture()`` records the step once into a CUDA graph (NCCL collectives included) and ``replay()`` relaunches
+  the device.  ``capture()`` records the step once into a CUDA graph (collectives included) and ``replay()`` relaunches
   it: ~50 kernel launches + autograd bookkeeping per step become one graph launch -- what makes 2^20 utterances split over
   8 GPUs (1.7 ms of kernels per rank) scale.
 * Collectives per step with world > 1: BatchNorm statistics (2H+1 doubles, forward), their backward sums (2H floats) --
   both only in ``bn_sync="global"`` mode; ``"local"`` is the reference's DDP behaviour (per-rank statistics) -- and the flat
   gradient buffer.  The loss numerator rides in the tail of the gradient buffer; there is no separate loss collective.
+* Transport: libercgraph's peer-memory kernels over NVLink (p2p.PeerComm: ercg_p2p_allreduce for the gradient buckets,
+  ercg_p2p_bn_stats / ercg_p2p_bn_act_bwd_reduce = the BatchNorm reductions fused with their exchange) when every rank can set
+  them up, else torch.distributed on ``group`` -- the results are the same to the last bit (rank-ordered sums).
 * The gradient all-reduce is bucketed in two: everything except the input projection is reduced on a side stream as soon as
   those gradients exist, under the projection's weight-gradient GEMM (the longest kernel of the step); the projection's own
   gradient follows on the main stream.
