@@ -1,12 +1,12 @@
 // Peer-memory all-reduce for the exchanges of the dialogue-sharded train step (reference: DDP's bucketed NCCL
 // all-reduce under accelerate, lumo/trainer/trainer.py:62-64,315-327).
 //
-// What crosses GPUs per COGMEN step is small and latency-bound: BatchNorm statistics (2H+1 doubles), their backward sums
+// What crosses GPUs per COGMEN step is small and latency-bound: BatchNorm statistics (2H doubles), their backward sums
 // (2H floats) and the flat gradient buffer in two buckets (0.53 + 0.58 MB).  With the batch sharded over 8 GPUs the whole
 // step is 1.7 ms and four NCCL launches cost ~10 % of it.  On one NVSwitch node every GPU can load every peer's memory at
 // NVLink speed, so the exchange is ONE-SHOT:
 //   1. a CTA copies its chunk of the local vector into this rank's REGION (cudaMalloc'ed once, opened by every peer through
-//      CUDA IPC) and, after a system-scope fence, writes the call number into its flag word in EVERY peer's region;
+//      CUDA IPC) and writes the call number into its flag word in EVERY peer's region (system-scope release store);
 //   2. it waits until all W flag words of its own region show that call number (acquire loads of local memory);
 //   3. it adds the W staged chunks in rank order, loading the peers' copies straight over NVLink.
 // Every rank adds the same values in the same order: results are bit-identical across ranks and run to run.  There is no
@@ -20,6 +20,8 @@
 // wait for each other inside a grid, only for the same-index CTA of the peers, so no co-residency of the grid is assumed.
 // Every wait is bounded (30 s): on timeout the kernel records ERCG_P2P_ETIMEOUT in the region header and carries on with
 // whatever is there -- a dead peer makes the step wrong and says so (ercg_p2p_status), it does not hang the GPU.
+// The same protocol is the tail of two reducing kernels in norm_loss.cu (BatchNorm statistics and their backward sums are
+// exchanged by the kernels that reduce them); p2p_dev.cuh holds the device side.
 #include "p2p_dev.cuh"
 
 namespace ercg {
