@@ -159,13 +159,13 @@ __global__ void __launch_bounds__(256)
 bn_stats_final_p2p_kernel(const float* __restrict__ partial, int nb, int H, long long N, const float* __restrict__ x,
                           unsigned char* const* __restrict__ regions, int rank, int world, size_t slot_bytes, double count,
                           float* __restrict__ mean, float* __restrict__ var, float* __restrict__ rmean, float* __restrict__ rvar,
-                          long long* __restrict__ nbt, float momentum) {
+                          long long* __restrict__ nbt, float momentum, unsigned long long timeout_ns) {
   __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
   const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
   const bool ok = c < H, owner = ok && threadIdx.x < FIN_COLS;
   const double s0 = fin_reduce(partial, nb, 2 * H, c, ok, sm);
   const double s1 = fin_reduce(partial, nb, 2 * H, H + c, ok, sm);
-  const P2pCall k = p2p_begin(regions, rank, slot_bytes);
+  const P2pCall k = p2p_begin(regions, rank, slot_bytes, timeout_ns);
   if (owner) {
     const double m = s0 / (double)N;
     double v = s1 / (double)N - m * m;
@@ -258,12 +258,13 @@ bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict
 // gradient all-reduce later), `gsums` the rank-ordered total the input gradient needs.  = sums_final_kernel + all-reduce.
 __global__ void __launch_bounds__(256)
 sums_final_p2p_kernel(const float* __restrict__ partial, int nb, int H, unsigned char* const* __restrict__ regions, int rank,
-                      int world, size_t slot_bytes, float* __restrict__ sums, float* __restrict__ gsums) {
+                      int world, size_t slot_bytes, float* __restrict__ sums, float* __restrict__ gsums,
+                      unsigned long long timeout_ns) {
   __shared__ double sm[FIN_ROWS][FIN_COLS + 1];
   const int c = blockIdx.x * FIN_COLS + (threadIdx.x & (FIN_COLS - 1));
   const bool ok = c < 2 * H, owner = ok && threadIdx.x < FIN_COLS;
   const double s = fin_reduce(partial, nb, 2 * H, c, ok, sm);
-  const P2pCall k = p2p_begin(regions, rank, slot_bytes);
+  const P2pCall k = p2p_begin(regions, rank, slot_bytes, timeout_ns);
   if (owner) {
     const float v = (float)s;
     sums[c] = v;
@@ -611,7 +612,7 @@ extern "C" int ercg_p2p_bn_stats(void* const* regions_dev, int rank, int world, 
   if (rc) return rc;
   bn_stats_final_p2p_kernel<<<fin_blocks(H), 256, 0, st>>>(part, nb, H, N, x, reinterpret_cast<unsigned char* const*>(regions_dev),
                                                           rank, world, slot, count_global, mean, var, running_mean, running_var,
-                                                          reinterpret_cast<long long*>(num_batches_tracked), momentum);
+                                                          reinterpret_cast<long long*>(num_batches_tracked), momentum, p2p_timeout_ns());
   return finish_launch();
 }
 
@@ -698,7 +699,7 @@ extern "C" int ercg_p2p_bn_act_bwd_reduce(void* const* regions_dev, int rank, in
   int rc = finish_launch();
   if (rc) return rc;
   sums_final_p2p_kernel<<<fin_blocks(2 * H), 256, 0, st>>>(part, nb, H, reinterpret_cast<unsigned char* const*>(regions_dev), rank,
-                                                          world, slot, sums, sums_global);
+                                                          world, slot, sums, sums_global, p2p_timeout_ns());
   return finish_launch();
 }
 

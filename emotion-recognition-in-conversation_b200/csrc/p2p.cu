@@ -55,10 +55,10 @@ __device__ __forceinline__ long long reduce_rounds(unsigned char* const* __restr
 template <typename T>
 __global__ void __launch_bounds__(P2P_THREADS, 10)
 p2p_allreduce_kernel(unsigned char* const* __restrict__ regions, int rank, int world, const T* __restrict__ in, T* __restrict__ out,
-                     long long n, long long units, size_t slot_bytes) {
+                     long long n, long long units, size_t slot_bytes, unsigned long long timeout_ns) {
   const int c = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
   unsigned char* self = regions[rank];
-  const P2pCall k = p2p_begin(regions, rank, slot_bytes);
+  const P2pCall k = p2p_begin(regions, rank, slot_bytes, timeout_ns);
   const size_t slot_off = k.slot_off;
   constexpr int EPV = 16 / sizeof(T);                         // elements per 16-byte unit
   const long long per = (units + G - 1) / G;
@@ -182,8 +182,8 @@ extern "C" int ercg_p2p_allreduce(void* const* regions_dev, int rank, int world,
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* const* regs = reinterpret_cast<unsigned char* const*>(regions_dev);
   if (dtype == 0)
-    p2p_allreduce_kernel<float><<<grid, P2P_THREADS, 0, st>>>(regs, rank, world, (const float*)in, (float*)out, n, units, slot);
+    p2p_allreduce_kernel<float><<<grid, P2P_THREADS, 0, st>>>(regs, rank, world, (const float*)in, (float*)out, n, units, slot, p2p_timeout_ns());
   else
-    p2p_allreduce_kernel<double><<<grid, P2P_THREADS, 0, st>>>(regs, rank, world, (const double*)in, (double*)out, n, units, slot);
+    p2p_allreduce_kernel<double><<<grid, P2P_THREADS, 0, st>>>(regs, rank, world, (const double*)in, (double*)out, n, units, slot, p2p_timeout_ns());
   return finish_launch();
 }

@@ -1,12 +1,13 @@
 // Device side of the peer-memory exchange protocol (see p2p.cu for the design): the region header, the system-scope flag
 // operations and the three steps a kernel wraps around its own staging / combining code:
-//     P2pCall k = p2p_begin(regions, rank, slot_bytes);   // call number, parity, data-slot offset
+//     P2pCall k = p2p_begin(regions, rank, slot_bytes, timeout_ns);   // call number, parity, data-slot offset
 //     ... write this CTA's values into regions[rank] + k.slot_off ...
 //     p2p_signal_wait(regions, rank, world, blockIdx.x, k);   // flag to every peer, wait for every peer's flag (bounded)
 //     ... read regions[p] + k.slot_off for p = 0 .. world-1 (ld_peer*), combine in rank order ...
 //     if (p2p_close_call(k, gridDim.x)) { ... exactly one thread of the grid, after every CTA is done ... }
 // Used by the all-reduce kernel (p2p.cu) and by kernels that fuse their own reduction tail with the exchange (norm_loss.cu).
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ercg {
@@ -14,7 +15,17 @@ namespace ercg {
 constexpr int P2P_MAX_CTAS = 128;
 constexpr int P2P_MAX_WORLD = 16;
 constexpr int P2P_THREADS = 128;
-constexpr unsigned long long P2P_TIMEOUT_NS = 30ull * 1000000000ull;   // ranks may be seconds apart at start-up (lazy library init)
+// Bound of every wait for a peer: 30 s (ranks may be seconds apart at start-up: lazy library initialisation); the environment
+// variable ERCG_P2P_TIMEOUT_MS (read once per process) overrides it -- the test of the failure path uses 300 ms.
+inline unsigned long long p2p_timeout_ns() {
+  static const unsigned long long v = [] {
+    const char* e = getenv("ERCG_P2P_TIMEOUT_MS");
+    long long ms = e ? atoll(e) : 30000;
+    if (ms < 1) ms = 1;
+    return (unsigned long long)ms * 1000000ull;
+  }();
+  return v;
+}
 
 struct P2pHeader {
   unsigned long long call;                                   // calls completed by this rank
@@ -54,12 +65,15 @@ struct P2pCall {
   P2pHeader* hdr;
   unsigned long long call;
   size_t slot_off;      // byte offset of this call's data slot inside every region
+  unsigned long long timeout_ns;
   unsigned int tag;
   int par;
 };
 // every thread of every CTA of the grid; the value is the same on every rank (each rank has completed the same calls)
-__device__ __forceinline__ P2pCall p2p_begin(unsigned char* const* __restrict__ regions, int rank, size_t slot_bytes) {
+__device__ __forceinline__ P2pCall p2p_begin(unsigned char* const* __restrict__ regions, int rank, size_t slot_bytes,
+                                             unsigned long long timeout_ns) {
   P2pCall k;
+  k.timeout_ns = timeout_ns;
   k.hdr = reinterpret_cast<P2pHeader*>(regions[rank]);
   k.call = *reinterpret_cast<volatile unsigned long long*>(&k.hdr->call) + 1;
   k.par = (int)(k.call & 1);
@@ -84,7 +98,7 @@ __device__ __forceinline__ void p2p_signal_wait(unsigned char* const* __restrict
       unsigned long long now;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
-      if (now - t0 > P2P_TIMEOUT_NS) {                        // the peer is not coming
+      if (now - t0 > k.timeout_ns) {                          // the peer is not coming
         k.hdr->status = ERCG_P2P_ETIMEOUT;
         break;
       }

@@ -478,6 +478,8 @@ int ercg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
  *   regions_dev = DEVICE array of the W region base pointers as mapped in this process (own region at index rank).
  *   Every rank must issue the same sequence of calls (same n) on a communicator, all on one stream (or otherwise
  *   serialised); concurrent streams need one communicator each.  Plain kernel launch: capturable in a CUDA graph.
+ *   Every wait for a peer is bounded (30 s; the environment variable ERCG_P2P_TIMEOUT_MS, read once per process, overrides
+ *   it): a peer that never arrives makes the kernel return with the region's status word set to ERCG_P2P_ETIMEOUT.
  * ------------------------------------------------------------------------------------------- */
 /* ercg_p2p_bn_stats: the data-parallel BatchNorm statistics of GNN.forward (cogmen.py:67,72 under DDP with the statistics
  *   taken over the GLOBAL batch) fused with their exchange: column reduction of this rank's rows, exchange over peer memory,

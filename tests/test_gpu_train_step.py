@@ -316,6 +316,43 @@ def test_fused_bn_backward_sums_exchange_equals_the_unfused_path(world):
         c.close()
 
 
+def test_peer_allreduce_missing_peer_times_out_and_reports():
+    """The failure path: a peer that never arrives.  With the wait bound lowered to 300 ms (ERCG_P2P_TIMEOUT_MS, read once
+    per process -- hence a subprocess) rank 0 of a two-endpoint communicator runs its collective ALONE: the kernel must
+    return (no hang), the communicator's sticky status must say ERCG_P2P_ETIMEOUT, check() must raise, and the GPU must
+    still run kernels afterwards."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, time, torch
+sys.path.insert(0, %r)
+import erc_b200
+from erc_b200.p2p import PeerComm
+from erc_b200._lib import ErcgError
+comms = PeerComm.simulate(2, "cuda:0", max_bytes=1 << 16)
+x = torch.ones(1000, device="cuda")
+t0 = time.time()
+comms[0].all_reduce(x)                  # rank 1 never calls
+torch.cuda.synchronize()
+dt = time.time() - t0
+st = comms[0].status()
+try:
+    comms[0].check()
+    raised = False
+except ErcgError:
+    raised = True
+y = (torch.arange(10, device="cuda") * 2).sum().item()      # the device is alive
+print("RESULT", st, raised, round(dt, 2), y)
+""" % root
+    env = dict(os.environ, ERCG_P2P_TIMEOUT_MS="300")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+    assert int(line[1]) == -6 and line[2] == "True" and 0.25 < float(line[3]) < 20.0 and int(line[4]) == 90, r.stdout
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_peer_allreduce_two_gpus_equals_rank_ordered_sum():
     """tools/p2p_check.py on two GPUs: bit-exact against the rank-ordered sum, skewed stress, graph replays, no time-outs."""
